@@ -1,0 +1,171 @@
+/*
+ * b2jpeg.h -- C-ABI of the B200-native JPEG engine (libb2jpeg.so).
+ *
+ * This is the drop-in boundary for the reference's hot path. Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository, OroChippw/Nvjpeg-ImageCompressor):
+ *
+ *   b2j_create / b2j_destroy      NvjpegCompressRunnerImpl::initCompressEnv / initDecodeEnv /
+ *                                 destoryCompressEnv / destoryDecodeEnv
+ *                                 (src/ImageCompressorDll/ImageCompressorImpl.cu:19-45, 47-65, 67-95, 97-117)
+ *   b2j_encode                    NvjpegCompressRunnerImpl::CompressWorker  (ImageCompressorImpl.cu:269-294:
+ *                                 cv::split + 3x cudaMemcpy + nvjpegEncodeImage + nvjpegEncodeRetrieveBitstream)
+ *   b2j_encode_device             the cudaEvent bracket of the same function (ImageCompressorImpl.cu:279-281):
+ *                                 input already on the device, bitstream left on the device
+ *   b2j_decode / b2j_peek         NvjpegCompressRunnerImpl::DecodeWorker (ImageCompressorImpl.cu:311-385:
+ *                                 nvjpegGetImageInfo, nvjpegDecodeJpegHost/TransferToDevice/Device) and
+ *                                 getCVImageOnCPU (:184-232; the planar->interleaved step is fused into the store)
+ *   b2j_diff / b2j_psnr /         the README's "difference map / secondary compression / PSNR" bullet
+ *   b2j_secondary                 (README.md:8, PSNR column README.md:45) -- absent from the reference code,
+ *                                 defined in SURVEY.md section 8 row a-12
+ *
+ * Conventions: plain pointers and sizes only (no cv::Mat, no torch types); pixels are 8-bit BGR interleaved
+ * (cv::Mat CV_8UC3) with a row pitch `step` in bytes; every function returns 0 on success or a negative
+ * B2J_E* code and never calls exit() (the reference's CHECK_CUDA/CHECK_NVJPEG exit(1),
+ * ImageCompressorImpl.cuh:16-34, is deliberately not reproduced). One context = one encoder/decoder state on
+ * one GPU, not thread-safe, synchronous at return unless stated otherwise (as the reference,
+ * SURVEY.md 8b "Threading").
+ */
+#ifndef B2JPEG_H_
+#define B2JPEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2J_API __declspec(dllexport)
+#else
+#define B2J_API __attribute__((visibility("default")))
+#endif
+
+/* nvjpegChromaSubsampling_t values the reference's README sweeps (README.md:44-51) */
+enum { B2J_CSS_444 = 0, B2J_CSS_422 = 1, B2J_CSS_440 = 2, B2J_CSS_420 = 3, B2J_CSS_411 = 4 };
+
+enum {
+    B2J_OK = 0,
+    B2J_EINVAL = -1,     /* bad argument */
+    B2J_ECUDA = -2,      /* CUDA runtime error (b2j_last_error has the text) */
+    B2J_ENOMEM = -3,
+    B2J_ECAPACITY = -4,  /* output buffer too small */
+    B2J_EFORMAT = -5,    /* not a baseline 3-component JPEG this decoder handles */
+    B2J_EINTERNAL = -6,  /* a device-side consistency check failed */
+    B2J_ESIZE = -7       /* image does not match the context's width/height */
+};
+
+/* b2j_diff modes */
+enum { B2J_DIFF_ABS = 0, B2J_DIFF_OFFSET128 = 1 };
+
+typedef struct b2j_ctx b2j_ctx;
+
+/* Mirrors NvjpegCompressRunner's constructor (ImageCompressor.h:27) plus the sampling factor the reference
+ * hard-codes at ImageCompressorImpl.cu:31. */
+typedef struct b2j_params {
+    int width;     /* default 8320  */
+    int height;    /* default 40000 */
+    int quality;   /* default 95    */
+    int optimize;  /* optimized Huffman, default 1 */
+    int css;       /* B2J_CSS_*, README default 422 */
+    int device;    /* CUDA device ordinal; -1 = current device */
+    int flags;     /* B2J_FLAG_* */
+} b2j_params;
+
+enum {
+    B2J_FLAG_NO_PINNED = 1,  /* do not allocate pinned host staging (device-resident use only) */
+    B2J_FLAG_ENCODE = 2,     /* allocate encoder state at create (else lazily on first encode) */
+    B2J_FLAG_DECODE = 4      /* allocate decoder state at create (else lazily on first decode) */
+};
+
+B2J_API void b2j_default_params(b2j_params *p);
+B2J_API int b2j_create(const b2j_params *p, b2j_ctx **out);
+B2J_API void b2j_destroy(b2j_ctx *ctx);
+B2J_API const char *b2j_last_error(const b2j_ctx *ctx);
+B2J_API const char *b2j_version(void);
+
+/* The caller's CUDA stream (cudaStream_t as void*); NULL = the context's own stream. */
+B2J_API int b2j_set_stream(b2j_ctx *ctx, void *cuda_stream);
+
+/* Upper bound of the JPEG size b2j_encode can produce for this context. */
+B2J_API size_t b2j_encode_bound(const b2j_ctx *ctx);
+
+/* Host -> host. bgr: host pointer (pageable or pinned). out: host buffer of `cap` bytes. */
+B2J_API int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out,
+                       size_t cap, size_t *len);
+
+/* Device -> device, asynchronous on the context's stream. d_bgr: device pointer. On return *d_out points at
+ * the context-owned device buffer that will hold the complete JPEG; its length is written to the device word
+ * *d_len (uint64). b2j_encode_finish synchronises and returns the length. */
+B2J_API int b2j_encode_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int height,
+                              const uint8_t **d_out, const uint64_t **d_len);
+B2J_API int b2j_encode_finish(b2j_ctx *ctx, size_t *len);
+
+/* Header probe (nvjpegGetImageInfo, ImageCompressorImpl.cu:335). */
+B2J_API int b2j_peek(const uint8_t *jpg, size_t len, int *width, int *height, int *css);
+
+/* Host -> host decode to BGR interleaved. */
+B2J_API int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *width,
+                       int *height);
+/* Host JPEG bytes -> device BGR (d_bgr: device pointer, pitch step); asynchronous after the header parse. */
+B2J_API int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_bgr, size_t step,
+                              int *width, int *height);
+
+/* Difference map and PSNR over n bytes (host pointers). */
+B2J_API int b2j_diff(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int mode, uint8_t *out);
+B2J_API int b2j_psnr(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, double *psnr, uint64_t *ssd);
+/* Same on device pointers, asynchronous; *d_ssd is a device uint64 owned by the context. */
+B2J_API int b2j_diff_psnr_device(b2j_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t n, int mode,
+                                 uint8_t *d_out, const uint64_t **d_ssd);
+
+/* Secondary compression: encode -> reconstruct -> difference map -> encode(diff), plus PSNR(orig, recon),
+ * device resident between the steps. Any output pointer may be NULL. */
+B2J_API int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, int diff_mode,
+                          uint8_t *jpg1, size_t cap1, size_t *len1, uint8_t *jpg2, size_t cap2, size_t *len2,
+                          uint8_t *recon, size_t recon_step, double *psnr);
+
+/* ---- staged (strip) interface used by the multi-GPU host: one MCU-row strip per context/GPU -------------
+ * phase1: colour/downsample/FDCT/quant (+ symbol histograms when optimize) of a device-resident strip.
+ * Between phases the host runs the collectives on the device words exposed by b2j_strip_state. */
+typedef struct b2j_strip_state {
+    uint32_t *d_hist;       /* [4][257] symbol counts: DC0, AC0, DC1, AC1 (allreduce SUM target) */
+    int16_t *d_last_dc;     /* [3] quantised DC of the strip's last Y, Cb, Cr blocks (allgather source) */
+    int16_t *d_pred_in;     /* [3] DC predictors at the strip start (host fills from the previous rank) */
+    uint64_t *d_strip_bits; /* [2]: entropy bits of this strip (unstuffed), first 32 bits of its bit string */
+    uint64_t *d_out_len;    /* bytes this strip produced in d_out (header included on first strip) */
+    uint8_t *d_out;
+} b2j_strip_state;
+
+B2J_API int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st);
+B2J_API int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows);
+/* DC-difference symbols at the strip start need d_pred_in: counted here, after the last-DC exchange. */
+B2J_API int b2j_strip_phase1b(b2j_ctx *ctx);
+/* tables from d_hist (after allreduce) + entropy-code the strip at bit phase 0 */
+B2J_API int b2j_strip_phase2(b2j_ctx *ctx, int full_width, int full_height);
+/* shift to the global bit phase, byte-stuff. skip_bits = (8 - global_start_bit%8)%8, ext_byte = next strip's
+ * first 8 bits (0xFF for the last strip). flags: bit0 = emit headers first, bit1 = append EOI. */
+B2J_API int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags);
+
+/* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
+enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4 };
+B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len);
+
+/* per-stage device times (ms) of the last encode/decode, measured with CUDA events on the context stream */
+typedef struct b2j_timings {
+    float h2d, fdct, hist_edge, tables, pack, scan, stuff, d2h, total;
+    float dec_parse, dec_sync, dec_write, dec_idct, dec_color;
+} b2j_timings;
+B2J_API int b2j_last_timings(b2j_ctx *ctx, b2j_timings *t);
+B2J_API int b2j_enable_timing(b2j_ctx *ctx, int on);
+
+/* number of kernels this library launched since the context was created */
+B2J_API uint64_t b2j_launch_count(const b2j_ctx *ctx);
+
+/* pinned host memory helpers for callers that want zero-copy-staged uploads */
+B2J_API void *b2j_host_alloc(size_t bytes);
+B2J_API void b2j_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2JPEG_H_ */

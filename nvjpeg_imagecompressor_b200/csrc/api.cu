@@ -1,0 +1,591 @@
+// api.cu -- the extern "C" boundary of libb2jpeg.so (include/b2jpeg.h): context, device buffers, stage sequencing.
+// Host-side mirror of NvjpegCompressRunnerImpl (reference src/ImageCompressorDll/ImageCompressorImpl.cu:19-117
+// env setup/teardown, :269-294 CompressWorker, :311-385 DecodeWorker) with nvJPEG replaced by this library's kernels.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/b2jpeg.h"
+#include "common.cuh"
+#include "dec.h"
+#include "kernels.h"
+
+using namespace b2j;
+
+namespace {
+
+struct Ctrl {  // zeroed before every encode with one memset
+    uint32_t hist[4 * 257];
+    uint32_t ticket;
+    uint32_t err;
+    uint64_t out_len;
+    uint64_t strip_bits[2];
+    uint64_t ssd;
+    int16_t last_dc[4];
+};
+
+struct HostRet {  // pinned
+    uint64_t out_len;
+    uint64_t strip_bits[2];
+    uint64_t ssd;
+    uint32_t err;
+    uint32_t huff_err;
+};
+
+}  // namespace
+
+struct b2j_ctx {
+    b2j_params p;
+    int device;
+    cudaStream_t own_stream, copy_stream, stream;
+    Geom cap_g;  // geometry of the configured (maximum) image
+    Geom g;      // geometry of the current image / strip
+    QuantDev hq;
+    // encoder state
+    bool enc_ready;
+    uint8_t *d_img;
+    size_t d_img_bytes;
+    int16_t *d_coef;
+    uint32_t *d_slots, *d_tile_bits;
+    uint64_t *d_tile_off, *d_desc;
+    size_t ndesc;
+    Ctrl *d_ctrl;
+    int16_t *d_pred_in;
+    HuffDev *d_huff;
+    QuantDev *d_quant;
+    uint8_t *d_out;
+    size_t out_cap;
+    HostRet *h_ret;
+    cudaEvent_t ev[12], ev_copy[64];
+    bool timing;
+    b2j_timings tm;
+    uint64_t launches;
+    char err[256];
+    // decoder + secondary state
+    b2j::Decoder *dec;
+    uint8_t *d_recon, *d_diff;
+    size_t d_recon_bytes;
+    b2j_ctx *second;  // encoder for the difference image (secondary compression)
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            snprintf(ctx->err, sizeof(ctx->err), "%s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B2J_ECUDA;                                                                           \
+        }                                                                                               \
+    } while (0)
+
+static int make_geom(int W, int H, int css, Geom *g) {
+    static const int HS[5] = {1, 2, 1, 2, 4}, VS[5] = {1, 1, 2, 2, 1};
+    if (W <= 0 || H <= 0 || W > 65535 || H > 65535 || css < 0 || css > 4) return B2J_EINVAL;
+    memset(g, 0, sizeof(*g));
+    g->W = W; g->H = H; g->hs = HS[css]; g->vs = VS[css];
+    g->mcux = (W + 8 * g->hs - 1) / (8 * g->hs);
+    g->mcuy = (H + 8 * g->vs - 1) / (8 * g->vs);
+    g->bpm = g->hs * g->vs + 2;
+    for (int c = 0; c < 3; c++) {
+        const int h = c ? 1 : g->hs, v = c ? 1 : g->vs;
+        g->dw[c] = (W * h + g->hs - 1) / g->hs;
+        g->dh[c] = (H * v + g->vs - 1) / g->vs;
+        g->wib[c] = (g->dw[c] + 7) / 8;
+        g->hib[c] = (g->dh[c] + 7) / 8;
+    }
+    const long long nb = (long long)g->mcux * g->mcuy * g->bpm;
+    if (nb > 0x7fffffffLL / 64) return B2J_EINVAL;
+    g->nblocks = (int)nb;
+    g->ntiles = (g->nblocks + PACK_BLOCKS - 1) / PACK_BLOCKS;
+    // fdct tiles: as even as possible, an even MCU count per tile (16-byte alignment of the bulk copies)
+    const int tmax = fdct_tm_max(g->hs, g->vs);
+    g->tiles_x = (g->mcux + tmax - 1) / tmax;
+    int tm = (g->mcux + g->tiles_x - 1) / g->tiles_x;
+    tm = (tm + 1) & ~1;
+    if (tm > tmax) tm = tmax;
+    g->tm = tm;
+    g->tiles_x = (g->mcux + tm - 1) / tm;
+    return B2J_OK;
+}
+
+// jcparam.c jpeg_set_quality + exact reciprocals for the forward quantiser
+static void make_quant(int quality, QuantDev *q) {
+    static const uint8_t L[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                  14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                  18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                  49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const uint8_t Cq[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99,
+                                   99, 99, 47, 66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                   99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+    int ql = quality < 1 ? 1 : (quality > 100 ? 100 : quality);
+    const int scale = ql < 50 ? 5000 / ql : 200 - 2 * ql;
+    for (int t = 0; t < 2; t++)
+        for (int i = 0; i < 64; i++) {
+            long v = ((long)(t ? Cq[i] : L[i]) * scale + 50) / 100;
+            if (v < 1) v = 1;
+            if (v > 255) v = 255;
+            const uint32_t d = 8u * (uint32_t)v;
+            q->q[t][i] = (uint16_t)v;
+            q->half[t][i] = d >> 1;
+            q->recip[t][i] = (uint32_t)((1ull << 32) / d) + 1u;  // exact floor(x/d) for x*d < 2^32
+        }
+}
+
+extern "C" {
+
+void b2j_default_params(b2j_params *p) {
+    p->width = 8320; p->height = 40000; p->quality = 95; p->optimize = 1; p->css = B2J_CSS_422; p->device = -1; p->flags = 0;
+}
+
+const char *b2j_version(void) { return "b2jpeg 0.1 (sm_100a)"; }
+
+const char *b2j_last_error(const b2j_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+static int enc_alloc(b2j_ctx *ctx) {
+    if (ctx->enc_ready) return B2J_OK;
+    const Geom &g = ctx->cap_g;
+    CK(cudaMalloc(&ctx->d_coef, (size_t)g.nblocks * 128));
+    CK(cudaMalloc(&ctx->d_slots, (size_t)g.ntiles * SLOT_WORDS * 4));
+    CK(cudaMalloc(&ctx->d_tile_bits, (size_t)(g.ntiles + 1) * 4));
+    CK(cudaMalloc(&ctx->d_tile_off, (size_t)(g.ntiles + 2) * 8));
+    ctx->out_cap = (size_t)g.nblocks * 208 + 4096;
+    CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
+    ctx->ndesc = ctx->out_cap / STUFF_CHUNK + 4;
+    CK(cudaMalloc(&ctx->d_desc, ctx->ndesc * 8));
+    CK(cudaMalloc(&ctx->d_ctrl, sizeof(Ctrl)));
+    CK(cudaMalloc(&ctx->d_pred_in, 16));
+    CK(cudaMemset(ctx->d_pred_in, 0, 16));
+    CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
+    CK(cudaMalloc(&ctx->d_quant, sizeof(QuantDev)));
+    CK(cudaMemcpy(ctx->d_quant, &ctx->hq, sizeof(QuantDev), cudaMemcpyHostToDevice));
+    ctx->enc_ready = true;
+    return B2J_OK;
+}
+
+int b2j_create(const b2j_params *p, b2j_ctx **out) {
+    if (!p || !out) return B2J_EINVAL;
+    b2j_ctx *ctx = new (std::nothrow) b2j_ctx();
+    if (!ctx) return B2J_ENOMEM;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->p = *p;
+    int rc = make_geom(p->width, p->height, p->css, &ctx->cap_g);
+    if (rc) { delete ctx; return rc; }
+    ctx->g = ctx->cap_g;
+    make_quant(p->quality, &ctx->hq);
+    cudaError_t e;
+    if (p->device >= 0) {
+        e = cudaSetDevice(p->device);
+        if (e != cudaSuccess) { delete ctx; return B2J_ECUDA; }
+    }
+    e = cudaGetDevice(&ctx->device);
+    if (e != cudaSuccess) { delete ctx; return B2J_ECUDA; }  // no CUDA device: fail loudly, there is no CPU path
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B2J_ECUDA; }
+    ctx->stream = ctx->own_stream;
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto &ev : ctx->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (cudaHostAlloc(&ctx->h_ret, sizeof(HostRet), cudaHostAllocDefault) != cudaSuccess) { b2j_destroy(ctx); return B2J_ECUDA; }
+    *out = ctx;
+    if (p->flags & B2J_FLAG_ENCODE) { rc = enc_alloc(ctx); if (rc) { b2j_destroy(ctx); *out = nullptr; return rc; } }
+    return B2J_OK;
+}
+
+void b2j_destroy(b2j_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->second) b2j_destroy(ctx->second);
+    if (ctx->dec) dec_destroy(ctx->dec);
+    cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
+    cudaFree(ctx->d_tile_off); cudaFree(ctx->d_desc); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_pred_in);
+    cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
+    if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int b2j_set_stream(b2j_ctx *ctx, void *s) {
+    if (!ctx) return B2J_EINVAL;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return B2J_OK;
+}
+
+size_t b2j_encode_bound(const b2j_ctx *ctx) { return ctx ? (size_t)ctx->cap_g.nblocks * 208 + 4096 : 0; }
+uint64_t b2j_launch_count(const b2j_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int b2j_enable_timing(b2j_ctx *ctx, int on) { if (!ctx) return B2J_EINVAL; ctx->timing = on != 0; return B2J_OK; }
+
+void *b2j_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+void b2j_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------ staged encode
+static int set_strip_geom(b2j_ctx *ctx, int width, int rows) {
+    Geom g;
+    int rc = make_geom(width, rows, ctx->p.css, &g);
+    if (rc) return rc;
+    if (g.nblocks > ctx->cap_g.nblocks) { snprintf(ctx->err, sizeof(ctx->err), "image %dx%d exceeds the context's %dx%d", width, rows, ctx->p.width, ctx->p.height); return B2J_ESIZE; }
+    ctx->g = g;
+    return B2J_OK;
+}
+
+static int enc_reset(b2j_ctx *ctx) {
+    CK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(Ctrl), ctx->stream));
+    // descriptors actually reachable for this image: bounded by its worst-case entropy bytes
+    size_t nd = std::min(ctx->ndesc, ((size_t)ctx->g.nblocks * 208) / STUFF_CHUNK + 4);
+    CK(cudaMemsetAsync(ctx->d_desc, 0, nd * 8, ctx->stream));
+    return B2J_OK;
+}
+
+static inline void tick(b2j_ctx *ctx, int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], ctx->stream); }
+
+int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows) {
+    if (!ctx || !d_bgr) return B2J_EINVAL;
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    rc = set_strip_geom(ctx, width, rows); if (rc) return rc;
+    rc = enc_reset(ctx); if (rc) return rc;
+    tick(ctx, 1);
+    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_coef, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_coef, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, 0, ctx->stream));
+    ctx->launches += 2;
+    tick(ctx, 2);
+    return B2J_OK;
+}
+
+int b2j_strip_phase1b(b2j_ctx *ctx) {
+    if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
+    CK(launch_dc_edge_hist(ctx->d_coef, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, ctx->p.optimize, ctx->stream));
+    ctx->launches += 1;
+    tick(ctx, 3);
+    return B2J_OK;
+}
+
+int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
+    if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
+    // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
+    CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, ctx->stream));
+    tick(ctx, 4);
+    CK(launch_pack(ctx->d_coef, ctx->g, ctx->d_huff, ctx->d_pred_in, ctx->d_slots, ctx->d_tile_bits, ctx->stream));
+    tick(ctx, 5);
+    CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->stream));
+    ctx->launches += 3;
+    tick(ctx, 6);
+    return B2J_OK;
+}
+
+__global__ void k_set_hdr_len(HuffDev *h, uint32_t v) { h->hdr_len = v; }
+
+int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
+    if (!ctx || !ctx->enc_ready || skip_bits < 0 || skip_bits > 7) return B2J_EINVAL;
+    if (!(flags & 1)) { k_set_hdr_len<<<1, 1, 0, ctx->stream>>>(ctx->d_huff, 0); ctx->launches++; }
+    StuffArgs a;
+    a.slots = ctx->d_slots; a.tile_bits = ctx->d_tile_bits; a.tile_off = ctx->d_tile_off; a.ntiles = ctx->g.ntiles;
+    a.skip = skip_bits; a.ext = ext_byte & 0xFF; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
+    a.out = ctx->d_out; a.cap = ctx->out_cap; a.desc = ctx->d_desc; a.ticket = &ctx->d_ctrl->ticket;
+    a.out_len = &ctx->d_ctrl->out_len; a.err = &ctx->d_ctrl->err;
+    CK(launch_stuff(a, 148 * 6, ctx->stream));
+    ctx->launches += 1;
+    tick(ctx, 7);
+    return B2J_OK;
+}
+
+int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st) {
+    if (!ctx || !st) return B2J_EINVAL;
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    st->d_hist = ctx->d_ctrl->hist; st->d_last_dc = ctx->d_ctrl->last_dc; st->d_pred_in = ctx->d_pred_in;
+    st->d_strip_bits = ctx->d_ctrl->strip_bits; st->d_out_len = &ctx->d_ctrl->out_len; st->d_out = ctx->d_out;
+    return B2J_OK;
+}
+
+// ------------------------------------------------------------------------------------------ whole-image encode
+static int enc_tail(b2j_ctx *ctx, int width, int height) {
+    int rc = b2j_strip_phase1b(ctx); if (rc) return rc;
+    rc = b2j_strip_phase2(ctx, width, height); if (rc) return rc;
+    return b2j_strip_phase3(ctx, 0, 0xFF, 3);
+}
+
+int b2j_encode_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int height, const uint8_t **d_out,
+                      const uint64_t **d_len) {
+    if (!ctx || !d_bgr || step < (size_t)width * 3) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    rc = set_strip_geom(ctx, width, height); if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_pred_in, 0, 16, ctx->stream));
+    tick(ctx, 0);
+    rc = enc_reset(ctx); if (rc) return rc;
+    tick(ctx, 1);
+    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_coef, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, ctx->stream));
+    ctx->launches += 1;
+    tick(ctx, 2);
+    rc = enc_tail(ctx, width, height); if (rc) return rc;
+    if (d_out) *d_out = ctx->d_out;
+    if (d_len) *d_len = &ctx->d_ctrl->out_len;
+    return B2J_OK;
+}
+
+static int fetch_ret(b2j_ctx *ctx) {
+    CK(cudaMemcpyAsync(&ctx->h_ret->out_len, &ctx->d_ctrl->out_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->h_ret->strip_bits, &ctx->d_ctrl->strip_bits, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->h_ret->err, &ctx->d_ctrl->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->h_ret->huff_err, &ctx->d_huff->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ret->err || ctx->h_ret->huff_err) {
+        snprintf(ctx->err, sizeof(ctx->err), "device check failed: stuff err=%u tables err=%u", ctx->h_ret->err, ctx->h_ret->huff_err);
+        return ctx->h_ret->err == 3 ? B2J_ECAPACITY : B2J_EINTERNAL;
+    }
+    return B2J_OK;
+}
+
+static void collect_timings(b2j_ctx *ctx) {
+    if (!ctx->timing) return;
+    float *dst[7] = {&ctx->tm.h2d, &ctx->tm.fdct, &ctx->tm.hist_edge, &ctx->tm.tables, &ctx->tm.pack, &ctx->tm.scan, &ctx->tm.stuff};
+    for (int i = 0; i < 7; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) { ms = -1; cudaGetLastError(); } *dst[i] = ms; }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[7]) != cudaSuccess) { ms = -1; cudaGetLastError(); }
+    ctx->tm.total = ms;
+}
+
+int b2j_encode_finish(b2j_ctx *ctx, size_t *len) {
+    if (!ctx) return B2J_EINVAL;
+    int rc = fetch_ret(ctx); if (rc) return rc;
+    collect_timings(ctx);
+    if (len) *len = (size_t)ctx->h_ret->out_len;
+    return B2J_OK;
+}
+
+static int ensure_img(b2j_ctx *ctx, size_t bytes) {
+    if (ctx->d_img_bytes >= bytes) return B2J_OK;
+    cudaFree(ctx->d_img); ctx->d_img = nullptr; ctx->d_img_bytes = 0;
+    CK(cudaMalloc(&ctx->d_img, bytes));
+    ctx->d_img_bytes = bytes;
+    return B2J_OK;
+}
+
+int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
+    if (!ctx || !bgr || !out || !len || step < (size_t)width * 3) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    rc = set_strip_geom(ctx, width, height); if (rc) return rc;
+    const Geom &g = ctx->g;
+    const size_t dstep = ((size_t)width * 3 + 15) & ~(size_t)15;  // 16-byte pitch keeps the TMA path for any width
+    rc = ensure_img(ctx, dstep * height); if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_pred_in, 0, 16, ctx->stream));
+    tick(ctx, 0);
+    rc = enc_reset(ctx); if (rc) return rc;
+    // upload in MCU-row groups on the copy stream; the fdct of a group starts as soon as its rows have landed
+    const int ngroups = std::max(1, std::min(32, g.mcuy / 64));
+    const int rows_per = (g.mcuy + ngroups - 1) / ngroups;
+    CK(cudaEventRecord(ctx->ev_copy[63], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[63], 0));
+    const int mcu_h = 8 * g.vs;
+    tick(ctx, 1);
+    for (int gi = 0, my0 = 0; my0 < g.mcuy; gi++, my0 += rows_per) {
+        const int nr = std::min(rows_per, g.mcuy - my0);
+        const int y0 = my0 * mcu_h, y1 = std::min(height, (my0 + nr) * mcu_h);
+        CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copy[gi], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[gi], 0));
+        CK(launch_fdct(ctx->d_img, dstep, g, ctx->d_quant, ctx->d_coef, ctx->d_ctrl->hist, ctx->p.optimize, my0, nr, ctx->stream));
+        ctx->launches += 1;
+    }
+    tick(ctx, 2);
+    rc = enc_tail(ctx, width, height); if (rc) return rc;
+    rc = fetch_ret(ctx); if (rc) return rc;
+    collect_timings(ctx);
+    const size_t n = (size_t)ctx->h_ret->out_len;
+    if (n > cap) { snprintf(ctx->err, sizeof(ctx->err), "output needs %zu bytes, buffer has %zu", n, cap); return B2J_ECAPACITY; }
+    CK(cudaMemcpyAsync(out, ctx->d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *len = n;
+    return B2J_OK;
+}
+
+int b2j_last_timings(b2j_ctx *ctx, b2j_timings *t) { if (!ctx || !t) return B2J_EINVAL; *t = ctx->tm; return B2J_OK; }
+
+// ------------------------------------------------------------------------------------------ decode
+static int dec_ensure(b2j_ctx *ctx) {
+    if (ctx->dec) return B2J_OK;
+    ctx->dec = dec_create(ctx->cap_g.nblocks, ctx->err, sizeof(ctx->err));
+    return ctx->dec ? B2J_OK : B2J_ECUDA;
+}
+
+int b2j_peek(const uint8_t *jpg, size_t len, int *width, int *height, int *css) {
+    JpegInfo info;
+    int rc = parse_jpeg(jpg, len, &info);
+    if (rc) return rc;
+    if (width) *width = info.W;
+    if (height) *height = info.H;
+    if (css) *css = info.css;
+    return B2J_OK;
+}
+
+int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_bgr, size_t step, int *width, int *height) {
+    if (!ctx || !jpg) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    JpegInfo info;
+    int rc = parse_jpeg(jpg, len, &info);
+    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "unsupported or corrupt JPEG (parse rc=%d)", rc); return B2J_EFORMAT; }
+    if (width) *width = info.W;
+    if (height) *height = info.H;
+    if (!d_bgr) return B2J_OK;
+    if (step < (size_t)info.W * 3) return B2J_EINVAL;
+    rc = dec_ensure(ctx); if (rc) return rc;
+    Geom g; rc = make_geom(info.W, info.H, info.css, &g); if (rc) return rc;
+    rc = dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches);
+    return rc;
+}
+
+int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *width, int *height) {
+    if (!ctx || !jpg) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    JpegInfo info;
+    int rc = parse_jpeg(jpg, len, &info);
+    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "unsupported or corrupt JPEG (parse rc=%d)", rc); return B2J_EFORMAT; }
+    if (width) *width = info.W;
+    if (height) *height = info.H;
+    if (!bgr) return B2J_OK;
+    if (step < (size_t)info.W * 3) return B2J_EINVAL;
+    const size_t dstep = ((size_t)info.W * 3 + 15) & ~(size_t)15;
+    if (ctx->d_recon_bytes < dstep * info.H) {
+        cudaFree(ctx->d_recon); ctx->d_recon = nullptr; ctx->d_recon_bytes = 0;
+        CK(cudaMalloc(&ctx->d_recon, dstep * info.H));
+        ctx->d_recon_bytes = dstep * info.H;
+    }
+    rc = b2j_decode_device(ctx, jpg, len, ctx->d_recon, dstep, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(bgr, step, ctx->d_recon, dstep, (size_t)info.W * 3, info.H, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ diff / PSNR / secondary
+int b2j_diff_psnr_device(b2j_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t n, int mode, uint8_t *d_out,
+                         const uint64_t **d_ssd) {
+    if (!ctx || !d_a || !d_b || (mode != 0 && mode != 1)) return B2J_EINVAL;
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    CK(cudaMemsetAsync(&ctx->d_ctrl->ssd, 0, 8, ctx->stream));
+    CK(launch_diff_psnr(d_a, d_b, n, mode, d_out, &ctx->d_ctrl->ssd, ctx->stream));
+    ctx->launches += 1;
+    if (d_ssd) *d_ssd = &ctx->d_ctrl->ssd;
+    return B2J_OK;
+}
+
+static double psnr_from_ssd(uint64_t ssd, size_t n) {
+    const double diff = sqrt((double)ssd / (double)n);
+    return 20.0 * log10(255.0 / (diff + 2.220446049250313e-16));  // cv::PSNR
+}
+
+static int diff_psnr_host(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int mode, uint8_t *out, double *psnr, uint64_t *ssd) {
+    if (!ctx || !a || !b || n == 0) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    CK(cudaMalloc(&d, 3 * ((n + 15) & ~(size_t)15)));
+    const size_t pitch = (n + 15) & ~(size_t)15;
+    int rc = B2J_OK;
+    do {
+        if (cudaMemcpyAsync(d, a, n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d + pitch, b, n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = B2J_ECUDA; break; }
+        rc = b2j_diff_psnr_device(ctx, d, d + pitch, n, mode, out ? d + 2 * pitch : nullptr, nullptr);
+        if (rc) break;
+        if (out && cudaMemcpyAsync(out, d + 2 * pitch, n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = B2J_ECUDA; break; }
+        if (cudaMemcpyAsync(&ctx->h_ret->ssd, &ctx->d_ctrl->ssd, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = B2J_ECUDA; break; }
+        if (ssd) *ssd = ctx->h_ret->ssd;
+        if (psnr) *psnr = psnr_from_ssd(ctx->h_ret->ssd, n);
+    } while (0);
+    cudaFree(d);
+    if (rc == B2J_ECUDA) snprintf(ctx->err, sizeof(ctx->err), "%s in diff/psnr", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+int b2j_diff(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int mode, uint8_t *out) {
+    if (!out || (mode != 0 && mode != 1)) return B2J_EINVAL;
+    return diff_psnr_host(ctx, a, b, n, mode, out, nullptr, nullptr);
+}
+
+int b2j_psnr(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, double *psnr, uint64_t *ssd) {
+    return diff_psnr_host(ctx, a, b, n, 0, nullptr, psnr, ssd);
+}
+
+int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, int diff_mode, uint8_t *jpg1,
+                  size_t cap1, size_t *len1, uint8_t *jpg2, size_t cap2, size_t *len2, uint8_t *recon, size_t recon_step,
+                  double *psnr) {
+    if (!ctx || !bgr || step < (size_t)width * 3 || (diff_mode != 0 && diff_mode != 1)) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    // 1. encode (keeps the uploaded image in d_img and the JPEG in d_out)
+    std::vector<uint8_t> tmp;
+    uint8_t *o1 = jpg1; size_t c1 = cap1;
+    if (!o1) { tmp.resize(b2j_encode_bound(ctx) < ((size_t)width * height * 3 + 4096) ? b2j_encode_bound(ctx) : (size_t)width * height * 3 + 4096); o1 = tmp.data(); c1 = tmp.size(); }
+    size_t n1 = 0;
+    int rc = b2j_encode(ctx, bgr, step, width, height, o1, c1, &n1); if (rc) return rc;
+    if (len1) *len1 = n1;
+    // 2. reconstruct on the device from the host JPEG bytes (the decoder parses headers on the host)
+    const size_t dstep = ((size_t)width * 3 + 15) & ~(size_t)15;
+    const size_t bytes = dstep * height;
+    if (ctx->d_recon_bytes < bytes) {
+        cudaFree(ctx->d_recon); ctx->d_recon = nullptr; ctx->d_recon_bytes = 0;
+        CK(cudaMalloc(&ctx->d_recon, bytes)); ctx->d_recon_bytes = bytes;
+    }
+    cudaFree(ctx->d_diff); ctx->d_diff = nullptr;
+    CK(cudaMalloc(&ctx->d_diff, bytes));
+    rc = b2j_decode_device(ctx, o1, n1, ctx->d_recon, dstep, nullptr, nullptr); if (rc) return rc;
+    // 3. difference map + SSD; the pitch padding of both device images is zero-filled so it adds nothing
+    if (dstep != (size_t)width * 3) {
+        CK(cudaMemset2DAsync(ctx->d_img + (size_t)width * 3, dstep, 0, dstep - (size_t)width * 3, height, ctx->stream));
+        CK(cudaMemset2DAsync(ctx->d_recon + (size_t)width * 3, dstep, 0, dstep - (size_t)width * 3, height, ctx->stream));
+    }
+    rc = b2j_diff_psnr_device(ctx, ctx->d_img, ctx->d_recon, bytes, diff_mode, ctx->d_diff, nullptr); if (rc) return rc;
+    CK(cudaMemcpyAsync(&ctx->h_ret->ssd, &ctx->d_ctrl->ssd, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (recon) CK(cudaMemcpy2DAsync(recon, recon_step, ctx->d_recon, dstep, (size_t)width * 3, height, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err)); if (rc) return rc;
+    if (psnr) *psnr = psnr_from_ssd(ctx->h_ret->ssd, (size_t)width * height * 3);
+    // 4. encode the difference image with the same parameters (second encoder state, same stream)
+    if (jpg2 || len2) {
+        if (!ctx->second) {
+            b2j_params p2 = ctx->p; p2.flags = 0; p2.device = ctx->device;
+            rc = b2j_create(&p2, &ctx->second); if (rc) return rc;
+        }
+        b2j_set_stream(ctx->second, ctx->stream);
+        const uint8_t *dj; const uint64_t *dl;
+        rc = b2j_encode_device(ctx->second, ctx->d_diff, dstep, width, height, &dj, &dl);
+        size_t n2 = 0;
+        if (!rc) rc = b2j_encode_finish(ctx->second, &n2);
+        if (rc) { snprintf(ctx->err, sizeof(ctx->err), "secondary encode: %s", ctx->second->err); return rc; }
+        if (len2) *len2 = n2;
+        if (jpg2) {
+            if (n2 > cap2) return B2J_ECAPACITY;
+            CK(cudaMemcpyAsync(jpg2, dj, n2, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return B2J_OK;
+}
+
+// ------------------------------------------------------------------------------------------ introspection
+int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len) {
+    if (!ctx || !dst) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const void *src = nullptr; size_t n = 0;
+    switch (what) {
+    case B2J_DBG_COEF: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_coef; n = (size_t)ctx->g.nblocks * 128; break;
+    case B2J_DBG_HIST: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_ctrl->hist; n = 4 * 257 * 4; break;
+    case B2J_DBG_TABLES: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_huff; n = sizeof(HuffDev); break;
+    case B2J_DBG_TILE_BITS: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_tile_bits; n = (size_t)ctx->g.ntiles * 4; break;
+    case B2J_DBG_DEC_COEF: if (!ctx->dec) return B2J_EINVAL; src = dec_coef_ptr(ctx->dec, &n); break;
+    default: return B2J_EINVAL;
+    }
+    if (len) *len = n;
+    if (n > cap) return B2J_ECAPACITY;
+    CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost));
+    return B2J_OK;
+}
+
+}  // extern "C"

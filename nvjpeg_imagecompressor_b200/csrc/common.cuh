@@ -1,0 +1,139 @@
+// common.cuh -- shared device/host declarations of the B200 JPEG engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2j {
+
+// ---- geometry of one image / MCU-row strip (libjpeg jcmaster.c per_scan_setup) -------------------------
+struct Geom {
+    int W, H;          // pixels
+    int hs, vs;        // luma sampling factors; chroma is 1x1
+    int mcux, mcuy;    // MCU grid
+    int bpm;           // blocks per MCU = hs*vs + 2
+    int wib[3], hib[3];// real blocks per component (width/height in blocks)
+    int dh[3];         // true downsampled height in samples
+    int dw[3];         // true downsampled width in samples
+    int tm;            // MCUs per fdct tile (even)
+    int tiles_x;       // fdct tiles per MCU row
+    int nblocks;       // mcux*mcuy*bpm, scan order
+    int ntiles;        // pack tiles = ceil(nblocks / PACK_BLOCKS)
+};
+
+constexpr int PACK_BLOCKS = 256;               // blocks (= threads) per pack tile
+constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
+constexpr int STUFF_THREADS = 256;
+constexpr int STUFF_CHUNK = STUFF_THREADS * 16; // unstuffed bytes per stuff chunk
+
+// ---- zig-zag ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int zigzag_nat(int k) {
+    constexpr int z[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return z[k];
+}
+
+// ---- device-side tables -------------------------------------------------------------------------------
+struct QuantDev {          // forward: q = umulhi(|c| + half, recip), natural order; [0] luma, [1] chroma
+    uint32_t recip[2][64];
+    uint32_t half[2][64];
+    uint16_t q[2][64];     // natural order quant values (dequantisation + DQT marker)
+};
+
+struct HuffDev {           // produced by k_tables
+    uint32_t enc[4][256];  // (code << 8) | length, index: DC0, AC0, DC1, AC1
+    uint8_t bits[4][17];
+    uint8_t vals[4][256];
+    uint32_t nsym[4];
+    uint32_t hdr_len;      // bytes of SOI..SOS written at the start of the output buffer
+    uint32_t err;
+};
+
+// look-back descriptor: [63:62] status, [61:0] value
+constexpr uint64_t LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+
+// ---- small device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    uint32_t ok;
+    uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_na_v4(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Decoupled look-back over 64-bit descriptors; executed by ONE full warp. Chunk ids must be handed out in
+// launch order (atomic ticket) so every predecessor is resident or finished. Returns the exclusive prefix.
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, int id, uint64_t local, uint32_t *err) {
+    const int lane = threadIdx.x & 31;
+    if (id == 0) {
+        if (lane == 0) st_volatile_u64(&desc[0], LB_INC | local);
+        return 0;
+    }
+    if (lane == 0) st_volatile_u64(&desc[id], LB_AGG | local);
+    uint64_t prefix = 0;
+    int j = id - 1;
+    for (;;) {
+        int idx = j - lane;
+        uint64_t d = LB_INC;
+        if (idx >= 0) {
+            unsigned spins = 0;
+            d = ld_volatile_u64(&desc[idx]);
+            while ((d >> 62) == 0) {
+                __nanosleep(20);
+                d = ld_volatile_u64(&desc[idx]);
+                if (++spins > (1u << 22)) { *err = 1; d = LB_INC; break; }  // never hang the GPU
+            }
+        }
+        unsigned inc = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+        int first = inc ? (__ffs(inc) - 1) : 32;
+        uint64_t v = (lane <= first) ? (d & LB_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prefix += v;
+        if (inc) break;
+        j -= 32;
+    }
+    if (lane == 0) st_volatile_u64(&desc[id], LB_INC | ((prefix + local) & LB_MASK));
+    return prefix;
+}
+
+}  // namespace b2j

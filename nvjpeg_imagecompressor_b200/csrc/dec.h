@@ -1,0 +1,31 @@
+// dec.h -- decoder interface internal to libb2jpeg.so (host parser + device pipeline)
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b2jpeg.h"
+#include "common.cuh"
+
+namespace b2j {
+
+struct JpegInfo {
+    int W, H, css, hs, vs;
+    int restart_interval;
+    size_t scan_offset, scan_len;  // entropy-coded segment (stuffed bytes, up to the terminating marker)
+    uint16_t qt[2][64];            // natural order: luma, chroma
+    uint8_t bits[4][17];           // DC0, AC0, DC1, AC1 as used by Y / (Cb,Cr)
+    uint8_t vals[4][256];
+};
+
+// jdmarker.c subset: baseline SOF0, 3 components, chroma 1x1, luma in {1x1,2x1,1x2,2x2,4x1}, one interleaved scan.
+int parse_jpeg(const uint8_t *jpg, size_t len, JpegInfo *info);
+
+struct Decoder;
+Decoder *dec_create(int nblocks_cap, char *err, size_t errlen);
+void dec_destroy(Decoder *d);
+int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
+            cudaStream_t s, b2j_timings *tm, uint64_t *launches);
+int dec_check(Decoder *d, char *err, size_t errlen);
+const void *dec_coef_ptr(Decoder *d, size_t *bytes);
+
+}  // namespace b2j

@@ -1,0 +1,410 @@
+// enc_fdct.cu -- K1: BGR -> YCbCr -> chroma downsample -> islow FDCT -> quantise -> zig-zag int16 coefficients
+// in scan order, with the AC / in-tile DC symbol histograms fused in (optimized-Huffman pass 1).
+//
+// Replaces the first half of nvjpegEncodeImage (reference call site ImageCompressorImpl.cu:280; nvJPEG kernels
+// format_to_ycbcr_kernel / subsample_chroma_kernel / forwardDct32x8Kernel). Arithmetic follows
+// libjpeg-turbo (jccolor.c, jcsample.c, jfdctint.c, jcdctmgr.c) as restated in SURVEY.md Appendix A.2-A.6,
+// bit-exactly (tests/ compare every stage with the CPU checker).
+//
+// One CTA = one tile of up to TM_MAX MCUs inside one MCU row:
+//   TMA bulk copies (cp.async.bulk, one per pixel row) stage the raw BGR rows in shared memory   [interior tiles]
+//   stage A: every thread converts 8 pixels x VS rows -> Y / Cb / Cr sample planes in shared memory
+//   stage B: one thread per 8x8 block: 64 samples in registers, both FDCT passes, reciprocal quantisation,
+//            zig-zag, symbol statistics, 8 x STS.128 into a 16-byte-chunk-swizzled staging area
+//   copy-out: coalesced 16-byte stores of the tile's blocks (contiguous in scan order)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2j {
+
+template <int HS, int VS>
+struct K1 {
+    static constexpr int HV = HS * VS;
+    static constexpr int BPM = HV + 2;
+    static constexpr int TM_MAX = (256 / BPM) & ~1;  // 444: 84, 422/440: 64, 420/411: 42
+    static constexpr int MCU_W = 8 * HS, MCU_H = 8 * VS;
+    static constexpr int TILE_PX = TM_MAX * MCU_W;
+    static constexpr int RAW_STRIDE = TILE_PX * 3;  // multiple of 16 for all five modes
+    static constexpr int RAW_BYTES = RAW_STRIDE * MCU_H;
+    static constexpr int STAGE_BYTES = 256 * 128;
+    static constexpr int Y_STRIDE = TILE_PX;
+    static constexpr int Y_BYTES = Y_STRIDE * MCU_H;
+    static constexpr int C_STRIDE = TM_MAX * 8;
+    static constexpr int C_BYTES = C_STRIDE * 8;
+    static constexpr int OFF_Y = STAGE_BYTES;  // raw aliases the staging area
+    static constexpr int OFF_CB = OFF_Y + Y_BYTES;
+    static constexpr int OFF_CR = OFF_CB + C_BYTES;
+    static constexpr int OFF_Q = OFF_CR + C_BYTES;       // uint2[2][64]
+    static constexpr int OFF_HIST = OFF_Q + 1024;        // uint32[4][256]
+    static constexpr int OFF_BAR = OFF_HIST + 4096;      // mbarrier
+    static constexpr int SMEM = OFF_BAR + 16;
+    static_assert(RAW_BYTES <= STAGE_BYTES, "raw tile must fit in the staging area");
+    static_assert(RAW_STRIDE % 16 == 0, "row stride must allow 16-byte bulk copies");
+};
+
+// ---- libjpeg jfdctint.c constants (CONST_BITS = 13) ----
+#define FIX_0_298631336 2446
+#define FIX_0_390180644 3196
+#define FIX_0_541196100 4433
+#define FIX_0_765366865 6270
+#define FIX_0_899976223 7373
+#define FIX_1_175875602 9633
+#define FIX_1_501321110 12299
+#define FIX_1_847759065 15137
+#define FIX_1_961570560 16069
+#define FIX_2_053119869 16819
+#define FIX_2_562915447 20995
+#define FIX_3_072711026 25172
+
+template <bool PASS2>
+__device__ __forceinline__ void fdct8(int &d0, int &d1, int &d2, int &d3, int &d4, int &d5, int &d6, int &d7) {
+    constexpr int SH = PASS2 ? 15 : 11;
+    constexpr int RND = 1 << (SH - 1);
+    int t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6, t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
+    int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    if (!PASS2) {
+        d0 = (t10 + t11) << 2;
+        d4 = (t10 - t11) << 2;
+    } else {
+        d0 = (t10 + t11 + 2) >> 2;
+        d4 = (t10 - t11 + 2) >> 2;
+    }
+    int z1 = (t12 + t13) * FIX_0_541196100;
+    d2 = (z1 + t13 * FIX_0_765366865 + RND) >> SH;
+    d6 = (z1 - t12 * FIX_1_847759065 + RND) >> SH;
+    z1 = t4 + t7;
+    int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+    int z5 = (z3 + z4) * FIX_1_175875602;
+    t4 *= FIX_0_298631336;
+    t5 *= FIX_2_053119869;
+    t6 *= FIX_3_072711026;
+    t7 *= FIX_1_501321110;
+    z1 *= -FIX_0_899976223;
+    z2 *= -FIX_2_562915447;
+    z3 = z3 * (-FIX_1_961570560) + z5;
+    z4 = z4 * (-FIX_0_390180644) + z5;
+    d7 = (t4 + z1 + z3 + RND) >> SH;
+    d5 = (t5 + z2 + z4 + RND) >> SH;
+    d3 = (t6 + z2 + z3 + RND) >> SH;
+    d1 = (t7 + z1 + z4 + RND) >> SH;
+}
+
+// jccolor.c rgb_ycc_convert, 16-bit fixed point
+__device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &cr) {
+    y = (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
+    cb = (-11059 * r - 21709 * g + 32768 * b + ((128 << 16) + 32767)) >> 16;
+    cr = (32768 * r - 27439 * g - 5329 * b + ((128 << 16) + 32767)) >> 16;
+}
+
+__device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : v); }
+
+template <int HS, int VS>
+__global__ void __launch_bounds__(256, 2)
+k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__restrict__ qd,
+       int16_t *__restrict__ coef, uint32_t *__restrict__ ghist, int do_hist, int bulk_ok, int my0) {
+    using C = K1<HS, VS>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *raw = smem;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem);
+    uint8_t *Yp = smem + C::OFF_Y, *Cbp = smem + C::OFF_CB, *Crp = smem + C::OFF_CR;
+    uint2 *qs = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
+    uint32_t *hs = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+
+    const int tid = threadIdx.x;
+    const int my = blockIdx.y + my0;
+    const int mx0 = blockIdx.x * g.tm;
+    const int nmcu = min(g.tm, g.mcux - mx0);
+    const int nblk = nmcu * C::BPM;
+    const int x0 = mx0 * C::MCU_W, y0 = my * C::MCU_H;
+    const int tile_px = nmcu * C::MCU_W;
+    const bool interior = (x0 + tile_px <= g.W) && (y0 + C::MCU_H <= g.H);
+
+    // quantisation constants + histogram init
+    if (tid < 128) qs[tid] = make_uint2(qd->recip[tid >> 6][tid & 63], qd->half[tid >> 6][tid & 63]);
+    if (do_hist)
+        for (int i = tid; i < 1024; i += 256) hs[i] = 0;
+
+    if (interior) {
+        const unsigned row_bytes = (unsigned)tile_px * 3;
+        const uint8_t *src = img + (size_t)y0 * step + (size_t)x0 * 3;
+        if (bulk_ok) {
+            if (tid == 0) {
+                mbar_init(bar, 1);
+                mbar_fence_init();
+            }
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(bar, row_bytes * C::MCU_H);
+#pragma unroll
+                for (int r = 0; r < C::MCU_H; r++) bulk_g2s(raw + r * C::RAW_STRIDE, src + (size_t)r * step, row_bytes, bar);
+            }
+            mbar_wait(bar, 0);
+        } else {
+            for (int r = 0; r < C::MCU_H; r++)
+                for (int i = tid; i < (int)row_bytes; i += 256) raw[r * C::RAW_STRIDE + i] = src[(size_t)r * step + i];
+            __syncthreads();
+        }
+        // ---- stage A (fast): 8 pixels x VS rows per item
+        const int ngx = nmcu * HS;
+        for (int it = tid; it < ngx * 8; it += 256) {
+            const int rg = it / ngx, gx = it - rg * ngx;
+            int cbv[VS][8], crv[VS][8];
+#pragma unroll
+            for (int v = 0; v < VS; v++) {
+                const int r = rg * VS + v;
+                const uint2 *p = reinterpret_cast<const uint2 *>(raw + r * C::RAW_STRIDE + gx * 24);
+                uint2 a = p[0], b = p[1], c = p[2];
+                uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                uint32_t yw[2] = {0, 0};
+#pragma unroll
+                for (int px = 0; px < 8; px++) {
+                    int bb = (w[(3 * px) >> 2] >> (((3 * px) & 3) * 8)) & 0xFF;
+                    int gg = (w[(3 * px + 1) >> 2] >> (((3 * px + 1) & 3) * 8)) & 0xFF;
+                    int rr = (w[(3 * px + 2) >> 2] >> (((3 * px + 2) & 3) * 8)) & 0xFF;
+                    int y, cb, cr;
+                    ycc(bb, gg, rr, y, cb, cr);
+                    yw[px >> 2] |= (uint32_t)y << ((px & 3) * 8);
+                    cbv[v][px] = cb;
+                    crv[v][px] = cr;
+                }
+                *reinterpret_cast<uint2 *>(Yp + r * C::Y_STRIDE + gx * 8) = make_uint2(yw[0], yw[1]);
+            }
+            // jcsample.c: fullsize / h2v1 (bias 0,1) / h2v2 (bias 1,2) / int_downsample (h1v2, h4v1)
+            uint32_t ob[2] = {0, 0}, orr[2] = {0, 0};
+#pragma unroll
+            for (int j = 0; j < 8 / HS; j++) {
+                int sb = 0, sr = 0;
+#pragma unroll
+                for (int v = 0; v < VS; v++)
+#pragma unroll
+                    for (int h = 0; h < HS; h++) {
+                        sb += cbv[v][j * HS + h];
+                        sr += crv[v][j * HS + h];
+                    }
+                int ocb, ocr;
+                if (HS == 1 && VS == 1) { ocb = sb; ocr = sr; }
+                else if (HS == 2 && VS == 1) { ocb = (sb + (j & 1)) >> 1; ocr = (sr + (j & 1)) >> 1; }
+                else if (HS == 2 && VS == 2) { ocb = (sb + 1 + (j & 1)) >> 2; ocr = (sr + 1 + (j & 1)) >> 2; }
+                else if (HS == 1 && VS == 2) { ocb = (sb + 1) >> 1; ocr = (sr + 1) >> 1; }
+                else { ocb = (sb + 2) >> 2; ocr = (sr + 2) >> 2; }
+                ob[j >> 2] |= (uint32_t)ocb << ((j & 3) * 8);
+                orr[j >> 2] |= (uint32_t)ocr << ((j & 3) * 8);
+            }
+            uint8_t *dcb = Cbp + rg * C::C_STRIDE + gx * (8 / HS), *dcr = Crp + rg * C::C_STRIDE + gx * (8 / HS);
+            if (HS == 1) {
+                *reinterpret_cast<uint2 *>(dcb) = make_uint2(ob[0], ob[1]);
+                *reinterpret_cast<uint2 *>(dcr) = make_uint2(orr[0], orr[1]);
+            } else if (HS == 2) {
+                *reinterpret_cast<uint32_t *>(dcb) = ob[0];
+                *reinterpret_cast<uint32_t *>(dcr) = orr[0];
+            } else {
+                *reinterpret_cast<uint16_t *>(dcb) = (uint16_t)ob[0];
+                *reinterpret_cast<uint16_t *>(dcr) = (uint16_t)orr[0];
+            }
+        }
+    } else {
+        // ---- stage A (edge tiles): per-sample with libjpeg's padding rules (jcprepct.c / jcsample.c expand_right_edge)
+        for (int i = tid; i < C::MCU_H * tile_px; i += 256) {
+            const int r = i / tile_px, x = i - r * tile_px;
+            const int yy = min(y0 + r, g.H - 1), xx = min(x0 + x, g.W - 1);
+            const uint8_t *p = img + (size_t)yy * step + (size_t)xx * 3;
+            int y, cb, cr;
+            ycc(p[0], p[1], p[2], y, cb, cr);
+            Yp[r * C::Y_STRIDE + x] = (uint8_t)y;
+        }
+        const int cw = nmcu * 8;
+        for (int i = tid; i < 8 * cw; i += 256) {
+            const int rd = i / cw, j = i - rd * cw;
+            const int rs = min(my * 8 + rd, g.dh[1] - 1);  // replicate the last DOWNSAMPLED row
+            const int jg = mx0 * 8 + j;
+            int sb = 0, sr = 0;
+            for (int v = 0; v < VS; v++) {
+                const int yy = min(rs * VS + v, g.H - 1);   // replicate the last pixel row
+                for (int h = 0; h < HS; h++) {
+                    const int xx = min(jg * HS + h, g.W - 1);
+                    const uint8_t *p = img + (size_t)yy * step + (size_t)xx * 3;
+                    int y, cb, cr;
+                    ycc(p[0], p[1], p[2], y, cb, cr);
+                    sb += cb;
+                    sr += cr;
+                }
+            }
+            int ocb, ocr;
+            if (HS == 1 && VS == 1) { ocb = sb; ocr = sr; }
+            else if (HS == 2 && VS == 1) { ocb = (sb + (jg & 1)) >> 1; ocr = (sr + (jg & 1)) >> 1; }
+            else if (HS == 2 && VS == 2) { ocb = (sb + 1 + (jg & 1)) >> 2; ocr = (sr + 1 + (jg & 1)) >> 2; }
+            else if (HS == 1 && VS == 2) { ocb = (sb + 1) >> 1; ocr = (sr + 1) >> 1; }
+            else { ocb = (sb + 2) >> 2; ocr = (sr + 2) >> 2; }
+            Cbp[rd * C::C_STRIDE + j] = (uint8_t)ocb;
+            Crp[rd * C::C_STRIDE + j] = (uint8_t)ocr;
+        }
+    }
+    __syncthreads();  // planes complete; raw is dead, staging may be written
+
+    // ---- stage B: one thread per block
+    const int blk = tid;
+    const bool active = blk < nblk;
+    const int m = blk / C::BPM, bn = blk - m * C::BPM;
+    const bool isY = bn < C::HV;
+    const int by = isY ? bn / HS : 0, bx = isY ? bn - by * HS : 0;
+    const int tbl = isY ? 0 : 1;
+    bool real = true;
+    if (isY) real = ((mx0 + m) * HS + bx < g.wib[0]) && (my * VS + by < g.hib[0]);
+    if (active) {
+        const uint8_t *src;
+        int stride;
+        if (isY) { src = Yp + (by * 8) * C::Y_STRIDE + (m * HS + bx) * 8; stride = C::Y_STRIDE; }
+        else { src = (bn == C::HV ? Cbp : Crp) + m * 8; stride = C::C_STRIDE; }
+        int v[64];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint2 w = *reinterpret_cast<const uint2 *>(src + r * stride);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                v[r * 8 + c] = (w.x >> (8 * c)) & 0xFF;       // level shift folded into the DC term below
+                v[r * 8 + 4 + c] = (w.y >> (8 * c)) & 0xFF;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            fdct8<false>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            fdct8<true>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+        v[0] -= 8192;  // 64 samples x 128: the only output the -128 level shift changes (exact: multiple of 4)
+
+        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply
+        uint32_t pk[32];
+        int run = 0;
+        uint32_t *hac = hs + (tbl * 2 + 1) * 256;
+        const uint2 *qt = qs + tbl * 64;
+#pragma unroll
+        for (int k = 0; k < 64; k++) {
+            const int n = zigzag_nat(k);
+            const int x = v[n];
+            const uint2 rq = qt[n];
+            const int s = x >> 31;
+            const uint32_t a = (uint32_t)((x ^ s) - s) + rq.y;
+            const int qa = (int)__umulhi(a, rq.x);
+            const int z = (qa ^ s) - s;
+            if (k & 1) pk[k >> 1] |= (uint32_t)z << 16;
+            else pk[k >> 1] = (uint32_t)z & 0xFFFFu;
+            if (do_hist && real && k > 0) {  // jchuff.c htest_one_block, AC part
+                if (z != 0) {
+                    if (run > 15) { atomicAdd(&hac[0xF0], (uint32_t)(run >> 4)); run &= 15; }
+                    atomicAdd(&hac[(run << 4) + (32 - __clz(qa))], 1u);
+                    run = 0;
+                } else run++;
+            }
+        }
+        if (do_hist && real && run > 0) atomicAdd(&hac[0], 1u);
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
+    __syncthreads();
+
+    // ---- dummy blocks (jccoefct.c compress_data): zero AC, DC of the last real block before them in the MCU
+    if (active && !real) {
+        const int nrx = min(HS, g.wib[0] - (mx0 + m) * HS), nry = min(VS, g.hib[0] - my * VS);
+        const int sby = min(by, nry - 1);
+        const int sblk = m * C::BPM + sby * HS + (nrx - 1);
+        const uint32_t dc = stage[sblk * 8 + (0 ^ (sblk & 7))].x & 0xFFFFu;
+#pragma unroll
+        for (int c = 0; c < 8; c++) stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(c == 0 ? dc : 0u, 0u, 0u, 0u);
+        if (do_hist) atomicAdd(&hs[1 * 256 + 0], 1u);  // one EOB
+    }
+    if (HS * VS > 1) __syncthreads();  // only luma with several blocks per MCU can have dummies
+
+    // ---- DC symbols whose predecessor lies inside this tile (the tile-leading ones: k_dc_edge_hist)
+    if (do_hist && active) {
+        int pb = -1;
+        if (isY) pb = bn > 0 ? blk - 1 : (m > 0 ? blk - C::BPM + C::HV - 1 : -1);
+        else pb = m > 0 ? blk - C::BPM : -1;
+        if (pb >= 0) {
+            const int dc = (int)(int16_t)(stage[blk * 8 + (blk & 7)].x & 0xFFFFu);
+            const int pd = (int)(int16_t)(stage[pb * 8 + (pb & 7)].x & 0xFFFFu);
+            atomicAdd(&hs[(tbl * 2) * 256 + nbits_of(dc - pd)], 1u);
+        }
+    }
+
+    // ---- copy-out: the tile's blocks are contiguous in scan order
+    uint4 *dst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM) * 64);
+    for (int i = tid; i < nblk * 8; i += 256) {
+        const int b = i >> 3, c = i & 7;
+        dst[i] = stage[b * 8 + (c ^ (b & 7))];
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (int i = tid; i < 1024; i += 256) {
+            const uint32_t n = hs[i];
+            if (n) atomicAdd(&ghist[(i >> 8) * 257 + (i & 255)], n);
+        }
+    }
+}
+
+// DC-difference symbols of each fdct tile's first MCU (their predecessor block lives in the previous tile), plus
+// the strip's very first MCU (predecessor = pred_in) and the strip's last DCs for the next strip.
+__global__ void k_dc_edge_hist(const int16_t *__restrict__ coef, Geom g, const int16_t *__restrict__ pred_in,
+                               uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist) {
+    const int hv = g.hs * g.vs;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ntile = g.tiles_x * g.mcuy;
+    if (t < ntile * 3 && do_hist) {
+        const int tile = t / 3, c = t - tile * 3;
+        const int my = tile / g.tiles_x, tx = tile - my * g.tiles_x;
+        const long long M0 = (long long)my * g.mcux + (long long)tx * g.tm;
+        const int off = c == 0 ? 0 : hv + c - 1;
+        const int poff = c == 0 ? hv - 1 : hv + c - 1;
+        const int dc = coef[(M0 * g.bpm + off) * 64];
+        const int pd = M0 > 0 ? coef[((M0 - 1) * g.bpm + poff) * 64] : pred_in[c];
+        atomicAdd(&ghist[(c ? 2 : 0) * 257 + nbits_of(dc - pd)], 1u);
+    }
+    if (t < 3) {
+        const long long ML = (long long)g.mcux * g.mcuy - 1;
+        last_dc[t] = coef[(ML * g.bpm + (t == 0 ? hv - 1 : hv + t - 1)) * 64];
+    }
+}
+
+template <int HS, int VS>
+static cudaError_t launch_one(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, int16_t *coef,
+                              uint32_t *hist, int do_hist, int my0, int nrows, cudaStream_t s) {
+    using C = K1<HS, VS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_fdct<HS, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    // TMA bulk copies need 16-byte aligned global addresses and sizes for every row of every interior tile
+    const int row_unit = g.tm * C::MCU_W * 3;  // byte offset between tiles in a row
+    int bulk_ok = ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (step % 16 == 0) && (row_unit % 16 == 0);
+    // the last tile of a row may hold fewer MCUs: its byte count must be a multiple of 16 as well
+    const int last_n = g.mcux - (g.tiles_x - 1) * g.tm;
+    if ((last_n * C::MCU_W * 3) % 16 != 0 && (long long)g.mcux * C::MCU_W <= g.W) bulk_ok = 0;
+    dim3 grid(g.tiles_x, nrows);
+    k_fdct<HS, VS><<<grid, 256, C::SMEM, s>>>(img, step, g, qd, coef, hist, do_hist, bulk_ok, my0);
+    return cudaGetLastError();
+}
+
+int fdct_tm_max(int hs, int vs) { return (256 / (hs * vs + 2)) & ~1; }
+
+cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, int16_t *coef, uint32_t *hist,
+                        int do_hist, int my0, int nrows, cudaStream_t s) {
+    if (g.hs == 1 && g.vs == 1) return launch_one<1, 1>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
+    if (g.hs == 2 && g.vs == 1) return launch_one<2, 1>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
+    if (g.hs == 1 && g.vs == 2) return launch_one<1, 2>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
+    if (g.hs == 2 && g.vs == 2) return launch_one<2, 2>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
+    if (g.hs == 4 && g.vs == 1) return launch_one<4, 1>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_dc_edge_hist(const int16_t *coef, const Geom &g, const int16_t *pred_in, uint32_t *hist,
+                                int16_t *last_dc, int do_hist, cudaStream_t s) {
+    const int n = max(3, g.tiles_x * g.mcuy * 3);
+    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(coef, g, pred_in, hist, last_dc, do_hist);
+    return cudaGetLastError();
+}
+
+}  // namespace b2j

@@ -1,0 +1,559 @@
+// enc_huff.cu -- optimized-Huffman table generation, entropy coding (pack), tile scan and byte stuffing.
+//
+// Replaces the second half of nvjpegEncodeImage (reference call site ImageCompressorImpl.cu:280; nvJPEG kernels
+// GenerateOptimizeHuffmanTableKernel / BlockLengthKernel / SumBlocksKernel / BlockAssembleKernel /
+// ByteStuffingKernel) and nvjpegEncodeRetrieveBitstream's header writing (:285-287).
+// Algorithms follow libjpeg-turbo jchuff.c (jpeg_gen_optimal_table, encode_one_block) and jcmarker.c as
+// restated in SURVEY.md Appendix A.6-A.8, bit-exactly (checked by tests/ against the CPU checker).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2j {
+
+// ------------------------------------------------------------------------------------------------------
+// Annex K.3-K.6 standard tables (jcparam.c std_huff_tables)
+__constant__ uint8_t c_std_bits[4][17] = {
+    {0, 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0},
+    {0, 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d},
+    {0, 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+    {0, 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77}};
+__constant__ uint8_t c_std_dc_val[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+__constant__ uint8_t c_std_ac_val[2][162] = {
+    {0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71,
+     0x14, 0x32, 0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72,
+     0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37,
+     0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59,
+     0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83,
+     0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3,
+     0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3,
+     0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2,
+     0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa},
+    {0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22,
+     0x32, 0x81, 0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1,
+     0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36,
+     0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58,
+     0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a,
+     0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a,
+     0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba,
+     0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda,
+     0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa}};
+
+// ------------------------------------------------------------------------------------------------------
+// k_tables: one CTA, warp t builds table t (DC0, AC0, DC1, AC1), then the JFIF headers are written.
+//
+// jpeg_gen_optimal_table, warp-parallel: lane l owns symbols l, l+32, ... (9 per lane, symbol 256 = the reserved
+// all-ones code point). Each merge step finds c1 = least non-zero frequency with ties to the LARGER index, c2 = next
+// least, by two warp reductions each (min of frequency, then max of index among the minima); tree membership is a
+// group id per symbol so "increment codesize along the others chain" becomes "increment every member".
+__global__ void __launch_bounds__(128)
+k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ huff, const QuantDev *__restrict__ qd,
+         int full_w, int full_h, int hs, int vs, uint8_t *__restrict__ out, int emit_header) {
+    __shared__ uint8_t s_bits[4][17];
+    __shared__ uint8_t s_vals[4][256];
+    __shared__ uint32_t s_enc[4][256];
+    __shared__ int s_cs[4][257];
+    __shared__ int s_cnt[4][33];
+    __shared__ uint32_t s_nsym[4];
+    __shared__ uint32_t s_err;
+    __shared__ uint8_t s_hdr[1024];
+    __shared__ uint32_t s_hdr_len;
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    if (threadIdx.x == 0) s_err = 0;
+    for (int i = lane; i < 256; i += 32) { s_vals[t][i] = 0; s_enc[t][i] = 0; }
+    __syncthreads();
+
+    if (!optimize) {
+        if (lane < 17) s_bits[t][lane] = c_std_bits[t][lane];
+        const int ns = (t & 1) ? 162 : 12;
+        for (int i = lane; i < ns; i += 32) s_vals[t][i] = (t & 1) ? c_std_ac_val[t >> 1][i] : c_std_dc_val[i];
+        if (lane == 0) s_nsym[t] = ns;
+    } else {
+        uint32_t f[9];
+        int cs[9], grp[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int i = lane + 32 * j;
+            f[j] = i < 256 ? hist[t * 257 + i] : (i == 256 ? 1u : 0u);
+            cs[j] = 0;
+            grp[j] = i;
+        }
+        for (int iter = 0; iter < 300; iter++) {
+            // c1
+            uint32_t bf = 0xffffffffu;
+            int bi = -1;
+#pragma unroll
+            for (int j = 0; j < 9; j++)
+                if (f[j] != 0 && f[j] <= 1000000000u && f[j] <= bf) { bf = f[j]; bi = lane + 32 * j; }
+            const uint32_t m1 = __reduce_min_sync(FULL, bf);
+            if (m1 == 0xffffffffu) break;
+            const int c1 = __reduce_max_sync(FULL, bf == m1 ? bi : -1);
+            // c2
+            bf = 0xffffffffu;
+            bi = -1;
+#pragma unroll
+            for (int j = 0; j < 9; j++)
+                if (f[j] != 0 && f[j] <= 1000000000u && f[j] <= bf && (lane + 32 * j) != c1) { bf = f[j]; bi = lane + 32 * j; }
+            const uint32_t m2 = __reduce_min_sync(FULL, bf);
+            if (m2 == 0xffffffffu) break;
+            const int c2 = __reduce_max_sync(FULL, bf == m2 ? bi : -1);
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+                const int i = lane + 32 * j;
+                if (i == c1) f[j] = m1 + m2;
+                if (i == c2) f[j] = 0;
+                if (i <= 256 && (grp[j] == c1 || grp[j] == c2) && (cs[j] > 0 || i == c1 || i == c2)) {
+                    cs[j]++;
+                    grp[j] = c1;
+                }
+            }
+        }
+        for (int l = lane; l < 33; l += 32) s_cnt[t][l] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int i = lane + 32 * j;
+            if (i <= 256) {
+                s_cs[t][i] = cs[j];
+                if (cs[j] > 32) s_err = 2;
+                else if (cs[j] > 0) atomicAdd(&s_cnt[t][cs[j]], 1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int *bits = s_cnt[t];
+            for (int i = 32; i > 16; i--)
+                while (bits[i] > 0) {
+                    int j = i - 2;
+                    while (bits[j] == 0) j--;
+                    bits[i] -= 2;
+                    bits[i - 1]++;
+                    bits[j + 1] += 2;
+                    bits[j]--;
+                }
+            int i = 16;
+            while (bits[i] == 0) i--;
+            bits[i]--;
+            s_bits[t][0] = 0;
+            for (int l = 1; l <= 16; l++) s_bits[t][l] = (uint8_t)bits[l];
+        }
+        // huffval: symbols 0..255 sorted by (natural codesize, symbol)
+        int p = 0;
+        for (int len = 1; len <= 32; len++)
+            for (int c = 0; c < 8; c++) {
+                const int sym = c * 32 + lane;
+                const bool hit = s_cs[t][sym] == len;
+                const unsigned bal = __ballot_sync(FULL, hit);
+                if (hit) s_vals[t][p + __popc(bal & ((1u << lane) - 1))] = (uint8_t)sym;
+                p += __popc(bal);
+            }
+        if (lane == 0) s_nsym[t] = p;
+    }
+    __syncwarp();
+    // Annex C code assignment
+    if (lane == 0) {
+        int p = 0;
+        uint32_t code = 0;
+        for (int l = 1; l <= 16; l++) {
+            const int n = s_bits[t][l];
+            for (int i = 0; i < n; i++, p++, code++) s_enc[t][s_vals[t][p]] = (code << 8) | (uint32_t)l;
+            code <<= 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- headers (jcmarker.c): SOI, JFIF APP0, 2 x DQT, SOF0, 4 x DHT, SOS
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (emit_header) {
+            uint8_t *h = s_hdr;
+            const uint8_t app0[] = {0xFF, 0xD8, 0xFF, 0xE0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};
+            for (int i = 0; i < 20; i++) h[n++] = app0[i];
+            for (int q = 0; q < 2; q++) {
+                h[n++] = 0xFF; h[n++] = 0xDB; h[n++] = 0; h[n++] = 67; h[n++] = (uint8_t)q;
+                for (int k = 0; k < 64; k++) h[n++] = (uint8_t)qd->q[q][zigzag_nat(k)];
+            }
+            h[n++] = 0xFF; h[n++] = 0xC0; h[n++] = 0; h[n++] = 17; h[n++] = 8;
+            h[n++] = (uint8_t)(full_h >> 8); h[n++] = (uint8_t)full_h; h[n++] = (uint8_t)(full_w >> 8); h[n++] = (uint8_t)full_w;
+            h[n++] = 3;
+            h[n++] = 1; h[n++] = (uint8_t)((hs << 4) | vs); h[n++] = 0;
+            h[n++] = 2; h[n++] = 0x11; h[n++] = 1;
+            h[n++] = 3; h[n++] = 0x11; h[n++] = 1;
+            const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
+            for (int q = 0; q < 4; q++) {
+                const int ns = (int)s_nsym[q];
+                h[n++] = 0xFF; h[n++] = 0xC4; h[n++] = (uint8_t)((19 + ns) >> 8); h[n++] = (uint8_t)(19 + ns); h[n++] = tcth[q];
+                for (int l = 1; l <= 16; l++) h[n++] = s_bits[q][l];
+                for (int i = 0; i < ns; i++) h[n++] = s_vals[q][i];
+            }
+            const uint8_t sos[] = {0xFF, 0xDA, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
+            for (int i = 0; i < 14; i++) h[n++] = sos[i];
+        }
+        s_hdr_len = (uint32_t)n;
+        huff->hdr_len = (uint32_t)n;
+        huff->err = s_err;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)s_hdr_len; i += 128) out[i] = s_hdr[i];
+    for (int i = threadIdx.x; i < 1024; i += 128) {
+        huff->enc[i >> 8][i & 255] = s_enc[i >> 8][i & 255];
+        huff->vals[i >> 8][i & 255] = s_vals[i >> 8][i & 255];
+    }
+    if (threadIdx.x < 68) huff->bits[threadIdx.x / 17][threadIdx.x % 17] = s_bits[threadIdx.x / 17][threadIdx.x % 17];
+    if (threadIdx.x < 4) huff->nsym[threadIdx.x] = s_nsym[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_pack: one CTA = 256 consecutive blocks of the scan; one thread per block (jchuff.c encode_one_block).
+//   1. coalesced 16-byte loads stage the tile's coefficients in swizzled shared memory
+//   2. each thread pulls its 64 coefficients into 32 registers, fetches its DC predictor
+//   3. length pass (registers only) -> CTA exclusive scan -> bit offset of every block inside the tile
+//   4. emit pass: codes are appended to a 64-bit accumulator and flushed as 32-bit words straight to the block's
+//      final position in the (re-used) shared buffer; only the first/last word of a block is shared with its
+//      neighbours (atomicOr), interior words are plain stores
+//   5. the tile's words are copied to its fixed-size slot in global memory (tile t at t*SLOT_WORDS)
+// Tiles whose bit string exceeds the 32 KB shared window run steps 4-5 once per window.
+constexpr int WIN_WORDS = 8192;
+
+struct Emitter {
+    uint64_t acc;
+    int cnt;
+    int wpos;        // absolute word index inside the tile
+    int wbase;       // first word of the current window
+    bool first;
+    uint32_t *buf;
+    __device__ __forceinline__ void flush(uint32_t w, bool shared_word) {
+        const unsigned wi = (unsigned)(wpos - wbase);
+        if (wi < (unsigned)WIN_WORDS) {
+            if (shared_word) atomicOr(&buf[wi], w);
+            else buf[wi] = w;
+        }
+        wpos++;
+    }
+    __device__ __forceinline__ void put(uint32_t bits, int n) {
+        acc = (acc << n) | bits;
+        cnt += n;
+        if (cnt >= 32) {
+            cnt -= 32;
+            flush((uint32_t)(acc >> cnt), first);
+            first = false;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (cnt > 0) flush((uint32_t)(acc << (32 - cnt)), true);
+    }
+};
+
+__global__ void __launch_bounds__(PACK_BLOCKS, 2)
+k_pack(const int16_t *__restrict__ coef, Geom g, const HuffDev *__restrict__ huff, const int16_t *__restrict__ pred_in,
+       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
+    __shared__ __align__(16) uint32_t s_buf[WIN_WORDS];  // coefficients first, bit buffer afterwards
+    __shared__ uint32_t s_enc[4][256];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t = blockIdx.x;
+    const int b0 = t * PACK_BLOCKS;
+    const int nb = min(PACK_BLOCKS, g.nblocks - b0);
+    uint4 *cb = reinterpret_cast<uint4 *>(s_buf);
+
+    for (int i = tid; i < nb * 8; i += PACK_BLOCKS) {
+        const int b = i >> 3, c = i & 7;
+        cb[b * 8 + (c ^ (b & 7))] = ld_nc_v4(reinterpret_cast<const uint4 *>(coef) + (size_t)b0 * 8 + i);
+    }
+    for (int i = tid; i < 1024; i += PACK_BLOCKS) s_enc[i >> 8][i & 255] = huff->enc[i >> 8][i & 255];
+    __syncthreads();
+
+    const bool active = tid < nb;
+    const int b = b0 + tid;
+    const int hv = g.bpm - 2;
+    const int bn = b % g.bpm;
+    const int comp = bn < hv ? 0 : bn - hv + 1;
+    const uint32_t *edc = s_enc[comp ? 2 : 0], *eac = s_enc[comp ? 3 : 1];
+    uint32_t c[32];
+    int pred = 0;
+    if (active) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            const uint4 q = cb[tid * 8 + (ch ^ (tid & 7))];
+            c[4 * ch] = q.x; c[4 * ch + 1] = q.y; c[4 * ch + 2] = q.z; c[4 * ch + 3] = q.w;
+        }
+        const int pb = comp == 0 ? (bn > 0 ? b - 1 : b - g.bpm + hv - 1) : b - g.bpm;
+        if (pb < 0) pred = pred_in[comp];
+        else if (pb >= b0) pred = (int)(int16_t)(s_buf[((pb - b0) * 8 + ((pb - b0) & 7)) * 4] & 0xFFFFu);
+        else pred = coef[(size_t)pb * 64];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) c[i] = 0;
+    }
+    const int dcv = (int)(int16_t)(c[0] & 0xFFFFu);
+    const int diff = dcv - pred;
+    const int dnb = 32 - __clz(diff < 0 ? -diff : diff);
+    const uint32_t zrl = eac[0xF0], eob = eac[0];
+
+    // ---- length pass
+    uint32_t len = 0;
+    if (active) {
+        len = (edc[dnb] & 31u) + dnb;
+        int run = 0;
+#pragma unroll
+        for (int k = 1; k < 64; k++) {
+            const int v = (k & 1) ? ((int)c[k >> 1] >> 16) : (int)(int16_t)(c[k >> 1] & 0xFFFFu);
+            if (v != 0) {
+                if (run > 15) { len += (run >> 4) * (zrl & 31u); run &= 15; }
+                const int n = 32 - __clz(v < 0 ? -v : v);
+                len += (eac[(run << 4) + n] & 31u) + n;
+                run = 0;
+            } else run++;
+        }
+        if (run > 0) len += eob & 31u;
+    }
+    // ---- CTA exclusive scan
+    uint32_t inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    __syncthreads();  // everyone holds its coefficients in registers: s_buf is free; s_warp writable
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t x = s_warp[w]; s_warp[w] = s; s += x; }
+        s_total = s;
+        tile_bits[t] = s;
+    }
+    __syncthreads();
+    const uint32_t off = s_warp[wid] + inc - len;
+    const uint32_t total = s_total;
+    const int nwords = (int)((total + 31) >> 5);
+    uint32_t *slot = slots + (size_t)t * SLOT_WORDS;
+
+    for (int wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
+        const int wn = min(WIN_WORDS, nwords - wbase);
+        for (int i = tid; i < wn; i += PACK_BLOCKS) s_buf[i] = 0;
+        __syncthreads();
+        if (active) {
+            Emitter e;
+            e.acc = 0; e.cnt = (int)(off & 31u); e.wpos = (int)(off >> 5); e.wbase = wbase; e.first = true; e.buf = s_buf;
+            {   // DC
+                const uint32_t ed = edc[dnb];
+                const uint32_t vb = (uint32_t)(diff + (diff >> 31)) & ((1u << dnb) - 1u);
+                e.put(((ed >> 8) << dnb) | vb, (int)(ed & 31u) + dnb);
+            }
+            int run = 0;
+#pragma unroll
+            for (int k = 1; k < 64; k++) {
+                const int v = (k & 1) ? ((int)c[k >> 1] >> 16) : (int)(int16_t)(c[k >> 1] & 0xFFFFu);
+                if (v != 0) {
+                    while (run > 15) { e.put(zrl >> 8, (int)(zrl & 31u)); run -= 16; }
+                    const int n = 32 - __clz(v < 0 ? -v : v);
+                    const uint32_t ea = eac[(run << 4) + n];
+                    const uint32_t vb = (uint32_t)(v + (v >> 31)) & ((1u << n) - 1u);
+                    e.put(((ea >> 8) << n) | vb, (int)(ea & 31u) + n);
+                    run = 0;
+                } else run++;
+            }
+            if (run > 0) e.put(eob >> 8, (int)(eob & 31u));
+            e.finish();
+        }
+        __syncthreads();
+        for (int i = tid; i < wn; i += PACK_BLOCKS) slot[wbase + i] = s_buf[i];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_scan_tiles: exclusive scan of the per-tile bit counts (one CTA; ntiles ~ 4e4 for the headline image)
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__restrict__ tile_off,
+             const uint32_t *__restrict__ slots, uint64_t *__restrict__ strip_bits) {
+    __shared__ uint64_t s_part[1024];
+    const int tid = threadIdx.x;
+    const int per = (ntiles + 1023) / 1024;
+    const int lo = min(ntiles, tid * per), hi = min(ntiles, lo + per);
+    uint64_t s = 0;
+    for (int i = lo; i < hi; i++) s += tile_bits[i];
+    s_part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const uint64_t y = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += y;
+        __syncthreads();
+    }
+    uint64_t run = s_part[tid] - s;
+    for (int i = lo; i < hi; i++) { tile_off[i] = run; run += tile_bits[i]; }
+    if (tid == 1023) {
+        tile_off[ntiles] = s_part[1023];
+        strip_bits[0] = s_part[1023];
+        strip_bits[1] = ntiles > 0 ? slots[0] : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_stuff: the strip's bit string (tile slots, concatenated virtually) -> shifted to the global bit phase ->
+// bytes -> 0xFF00 stuffing -> final position. Persistent CTAs take 4 KB chunks of unstuffed bytes in ticket order;
+// a decoupled look-back over the stuffed byte counts gives each chunk its output offset in the same pass.
+// Byte j of the strip = local bits [skip + 8j, skip + 8j + 8); bits past the strip's end come from `ext`
+// (the next strip's first bits) followed by 1-bits (jchuff.c flush_bits padding).
+__global__ void __launch_bounds__(STUFF_THREADS)
+k_stuff(StuffArgs a) {
+    constexpr int TWIN = 72;
+    __shared__ uint64_t s_toff[TWIN];
+    __shared__ uint32_t s_tbits[TWIN];
+    __shared__ int s_chunk, s_tau0;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint64_t s_goff;
+    __shared__ __align__(16) uint8_t s_out[2 * STUFF_CHUNK + 16];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t T = a.tile_off[a.ntiles];
+    const uint64_t NB = T > (uint64_t)a.skip ? (T - a.skip + 7) >> 3 : 0;
+    const int nchunks = (int)max((uint64_t)1, (NB + STUFF_CHUNK - 1) / STUFF_CHUNK);
+    const uint32_t hdr = a.huff->hdr_len;
+
+    for (;;) {
+        if (tid == 0) s_chunk = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int ch = s_chunk;
+        if (ch >= nchunks) break;
+        const uint64_t j0c = (uint64_t)ch * STUFF_CHUNK;
+        const uint64_t p0c = (uint64_t)a.skip + 8 * j0c;
+        if (tid == 0) {  // tile containing the chunk's first bit
+            int lo = 0, hi = a.ntiles;  // find largest tau with tile_off[tau] <= p0c
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (a.tile_off[mid] <= p0c) lo = mid; else hi = mid;
+            }
+            s_tau0 = lo;
+        }
+        __syncthreads();
+        const int tau0 = s_tau0;
+        for (int i = tid; i < TWIN; i += STUFF_THREADS) {
+            const int ti = min(tau0 + i, a.ntiles);
+            s_toff[i] = a.tile_off[ti];
+            s_tbits[i] = ti < a.ntiles ? a.tile_bits[ti] : 0;
+        }
+        __syncthreads();
+        // tile offsets / sizes: shared window first, global memory beyond it (only flat images get there)
+        auto TOFF = [&](int ti) -> uint64_t { const int r = ti - tau0; return r < TWIN ? s_toff[r] : a.tile_off[min(ti, a.ntiles)]; };
+        auto TBITS = [&](int ti) -> uint32_t { const int r = ti - tau0; return r < TWIN ? s_tbits[r] : a.tile_bits[ti]; };
+
+        // ---- 16 bytes per thread
+        const uint64_t j0 = j0c + (uint64_t)tid * 16;
+        const int nvalid = j0 >= NB ? 0 : (int)min((uint64_t)16, NB - j0);
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (nvalid > 0) {
+            uint64_t p = (uint64_t)a.skip + 8 * j0;
+            int tau = tau0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t res = 0;
+                int got = 0;
+                while (got < 32) {
+                    if (p >= T) {
+                        const uint64_t e = p - T;
+                        uint32_t x = 0xffffffffu;
+                        if (e < 32) {
+                            x = ((uint32_t)a.ext << 24) | 0x00ffffffu;
+                            if (e) x = (x << e) | ((1u << e) - 1u);
+                        }
+                        res |= x >> got;
+                        p += 32 - got;
+                        got = 32;
+                        break;
+                    }
+                    while (TOFF(tau + 1) <= p) tau++;
+                    const uint32_t tb = TBITS(tau);
+                    const uint32_t qb = (uint32_t)(p - TOFF(tau));
+                    const uint32_t rem = tb - qb;
+                    const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS;
+                    const uint32_t wi = qb >> 5, sh = qb & 31u;
+                    const uint32_t nw = (tb + 31u) >> 5;
+                    const uint32_t w0 = slot[wi];
+                    const uint32_t w1 = (sh && wi + 1 < nw) ? slot[wi + 1] : 0u;
+                    uint32_t x = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;
+                    const int take = min(32 - got, (int)min(rem, 32u));
+                    if (take < 32) x &= ~(0xffffffffu >> take);
+                    res |= x >> got;
+                    got += take;
+                    p += take;
+                }
+                w[q] = res;
+            }
+        }
+        // bytes in stream order: w[q] big-endian
+        int nff = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
+            if (i < nvalid && byte == 0xFFu) nff++;
+        }
+        const uint32_t cnt = (uint32_t)(nvalid + nff);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t x = s_warp[i];
+            if (i < wid) wbase += x;
+            total += x;
+        }
+        uint32_t o = wbase + inc - cnt;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
+            if (i < nvalid) {
+                s_out[o++] = (uint8_t)byte;
+                if (byte == 0xFFu) s_out[o++] = 0;
+            }
+        }
+        if (wid == 0) {
+            const uint64_t pre = lookback_exclusive(a.desc, ch, total, a.err);
+            if (lane == 0) s_goff = pre;
+        }
+        __syncthreads();
+        const uint64_t goff = (uint64_t)hdr + s_goff;
+        const bool last = ch == nchunks - 1;
+        const uint64_t end = goff + total + ((last && a.append_eoi) ? 2 : 0);
+        if (end > a.cap) {
+            if (tid == 0) *a.err = 3;
+        } else {
+            uint8_t *dst = a.out + goff;
+            for (uint32_t i = tid; i < total; i += STUFF_THREADS) dst[i] = s_out[i];
+            if (last && a.append_eoi && tid == 0) { dst[total] = 0xFF; dst[total + 1] = 0xD9; }
+        }
+        if (last && tid == 0) *a.out_len = end;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
+                          int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s) {
+    k_tables<<<1, 128, 0, s>>>(hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack(const int16_t *coef, const Geom &g, const HuffDev *huff, const int16_t *pred_in, uint32_t *slots,
+                        uint32_t *tile_bits, cudaStream_t s) {
+    k_pack<<<g.ntiles, PACK_BLOCKS, 0, s>>>(coef, g, huff, pred_in, slots, tile_bits);
+    return cudaGetLastError();
+}
+cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
+                              uint64_t *strip_bits, cudaStream_t s) {
+    k_scan_tiles<<<1, 1024, 0, s>>>(tile_bits, ntiles, tile_off, slots, strip_bits);
+    return cudaGetLastError();
+}
+cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s) {
+    k_stuff<<<grid, STUFF_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace b2j

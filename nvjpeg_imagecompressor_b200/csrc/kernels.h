@@ -1,0 +1,44 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to libb2jpeg.so)
+#pragma once
+#include "common.cuh"
+
+namespace b2j {
+
+// encode
+int fdct_tm_max(int hs, int vs);
+// MCU rows [my0, my0+nrows) of the image `img` (img points at pixel row 0)
+cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, int16_t *coef, uint32_t *hist,
+                        int do_hist, int my0, int nrows, cudaStream_t s);
+cudaError_t launch_dc_edge_hist(const int16_t *coef, const Geom &g, const int16_t *pred_in, uint32_t *hist,
+                                int16_t *last_dc, int do_hist, cudaStream_t s);
+cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
+                          int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s);
+cudaError_t launch_pack(const int16_t *coef, const Geom &g, const HuffDev *huff, const int16_t *pred_in, uint32_t *slots,
+                        uint32_t *tile_bits, cudaStream_t s);
+cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
+                              uint64_t *strip_bits, cudaStream_t s);
+struct StuffArgs {
+    const uint32_t *slots;
+    const uint32_t *tile_bits;
+    const uint64_t *tile_off;   // [ntiles+1]
+    int ntiles;
+    int skip;                   // leading bits owned by the previous strip's last byte
+    int ext;                    // next strip's first 8 bits (0xFF: pad with ones)
+    int append_eoi;
+    const HuffDev *huff;        // hdr_len
+    uint8_t *out;
+    size_t cap;
+    uint64_t *desc;             // look-back descriptors (zeroed)
+    uint32_t *ticket;           // zeroed
+    uint64_t *out_len;
+    uint32_t *err;
+};
+cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s);
+
+// decode
+struct DecArgs;
+// metrics
+cudaError_t launch_diff_psnr(const uint8_t *a, const uint8_t *b, size_t n, int mode, uint8_t *out, uint64_t *ssd,
+                             cudaStream_t s);
+
+}  // namespace b2j

@@ -1,0 +1,181 @@
+"""Engine: thin Python owner of one b2j_ctx (one encoder/decoder state on one GPU)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class B2JError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"b2jpeg error {rc} ({N.ERRORS.get(rc, '?')}): {msg}")
+        self.rc = rc
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """width/height: the largest image this context will see (buffers are sized once, like the reference's
+    initCompressEnv, ImageCompressorImpl.cu:33-37)."""
+
+    def __init__(self, width=8320, height=40000, quality=95, optimize=True, css="422", device=-1, flags=0):
+        self._L = N.lib()
+        p = N.Params(int(width), int(height), int(quality), int(bool(optimize)),
+                     N.CSS[css] if isinstance(css, str) else int(css), int(device), int(flags))
+        self.params = p
+        h = C.c_void_p()
+        rc = self._L.b2j_create(C.byref(p), C.byref(h))
+        if rc:
+            raise B2JError(rc, "b2j_create failed (is a CUDA device visible? there is no CPU fallback)")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2j_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise B2JError(rc, self._L.b2j_last_error(self._h).decode())
+
+    # ---------------------------------------------------------------- host API
+    def encode(self, img, out=None):
+        img = np.asarray(img)
+        assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3 and img.strides[2] == 1 and img.strides[1] == 3
+        H, W = img.shape[:2]
+        if out is None:
+            out = np.empty(min(self._L.b2j_encode_bound(self._h), W * H * 3 * 2 + 65536), np.uint8)
+        n = C.c_size_t(0)
+        self._ck(self._L.b2j_encode(self._h, _ptr(img), img.strides[0], W, H, _ptr(out), out.size, C.byref(n)))
+        return out[: n.value]
+
+    def encode_ptr(self, ptr, step, W, H, out_ptr, cap):
+        n = C.c_size_t(0)
+        self._ck(self._L.b2j_encode(self._h, C.c_void_p(ptr), step, W, H, C.c_void_p(out_ptr), cap, C.byref(n)))
+        return n.value
+
+    def decode(self, jpg):
+        jpg = np.ascontiguousarray(jpg, np.uint8)
+        W, H = C.c_int(0), C.c_int(0)
+        self._ck(self._L.b2j_decode(self._h, _ptr(jpg), jpg.size, None, 0, C.byref(W), C.byref(H)))
+        out = np.empty((H.value, W.value, 3), np.uint8)
+        self._ck(self._L.b2j_decode(self._h, _ptr(jpg), jpg.size, _ptr(out), W.value * 3, C.byref(W), C.byref(H)))
+        return out
+
+    def decode_ptr(self, jpg, out_ptr, step):
+        W, H = C.c_int(0), C.c_int(0)
+        self._ck(self._L.b2j_decode(self._h, _ptr(jpg), jpg.size, C.c_void_p(out_ptr), step, C.byref(W), C.byref(H)))
+        return W.value, H.value
+
+    @staticmethod
+    def peek(jpg):
+        jpg = np.ascontiguousarray(jpg, np.uint8)
+        W, H, css = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = N.lib().b2j_peek(_ptr(jpg), jpg.size, C.byref(W), C.byref(H), C.byref(css))
+        if rc:
+            raise B2JError(rc, "b2j_peek")
+        return W.value, H.value, css.value
+
+    def diff(self, a, b, mode=0):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        out = np.empty_like(a)
+        self._ck(self._L.b2j_diff(self._h, _ptr(a), _ptr(b), a.size, int(mode), _ptr(out)))
+        return out
+
+    def psnr(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        ps, ssd = C.c_double(0), C.c_uint64(0)
+        self._ck(self._L.b2j_psnr(self._h, _ptr(a), _ptr(b), a.size, C.byref(ps), C.byref(ssd)))
+        return ps.value, ssd.value
+
+    def secondary(self, img, diff_mode=1, want_recon=True):
+        img = np.asarray(img)
+        H, W = img.shape[:2]
+        cap = W * H * 3 * 2 + 65536
+        j1, j2 = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+        n1, n2, ps = C.c_size_t(0), C.c_size_t(0), C.c_double(0)
+        recon = np.empty((H, W, 3), np.uint8) if want_recon else None
+        self._ck(self._L.b2j_secondary(self._h, _ptr(img), img.strides[0], W, H, int(diff_mode), _ptr(j1), cap,
+                                       C.byref(n1), _ptr(j2), cap, C.byref(n2),
+                                       _ptr(recon) if want_recon else None, W * 3, C.byref(ps)))
+        return j1[: n1.value], j2[: n2.value], recon, ps.value
+
+    # ---------------------------------------------------------------- device API (pointers from torch tensors)
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.b2j_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def encode_device(self, d_ptr, step, W, H):
+        """Asynchronous; returns (device pointer of the JPEG, device pointer of its uint64 length)."""
+        o, l = C.c_void_p(), C.c_void_p()
+        self._ck(self._L.b2j_encode_device(self._h, C.c_void_p(d_ptr), step, W, H, C.byref(o), C.byref(l)))
+        return o.value, l.value
+
+    def encode_finish(self):
+        n = C.c_size_t(0)
+        self._ck(self._L.b2j_encode_finish(self._h, C.byref(n)))
+        return n.value
+
+    def decode_device(self, jpg, d_ptr, step):
+        jpg = np.ascontiguousarray(jpg, np.uint8)
+        W, H = C.c_int(0), C.c_int(0)
+        self._ck(self._L.b2j_decode_device(self._h, _ptr(jpg), jpg.size, C.c_void_p(d_ptr), step, C.byref(W), C.byref(H)))
+        return W.value, H.value
+
+    def diff_psnr_device(self, a_ptr, b_ptr, n, mode, out_ptr):
+        s = C.c_void_p()
+        self._ck(self._L.b2j_diff_psnr_device(self._h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), n, mode,
+                                              C.c_void_p(out_ptr) if out_ptr else None, C.byref(s)))
+        return s.value
+
+    # staged strip interface
+    def strip_state(self):
+        st = N.StripState()
+        self._ck(self._L.b2j_strip_state_get(self._h, C.byref(st)))
+        return st
+
+    def strip_phase1(self, d_ptr, step, W, rows):
+        self._ck(self._L.b2j_strip_phase1(self._h, C.c_void_p(d_ptr), step, W, rows))
+
+    def strip_phase1b(self):
+        self._ck(self._L.b2j_strip_phase1b(self._h))
+
+    def strip_phase2(self, full_w, full_h):
+        self._ck(self._L.b2j_strip_phase2(self._h, full_w, full_h))
+
+    def strip_phase3(self, skip_bits, ext_byte, flags):
+        self._ck(self._L.b2j_strip_phase3(self._h, skip_bits, ext_byte, flags))
+
+    # introspection
+    def debug_read(self, what, dtype, count_hint=None):
+        n = C.c_size_t(0)
+        rc = self._L.b2j_debug_read(self._h, what, C.c_void_p(C.addressof(C.c_char())), 0, C.byref(n))
+        if rc not in (0, -4):
+            self._ck(rc)
+        buf = np.empty(max(1, n.value), np.uint8)
+        self._ck(self._L.b2j_debug_read(self._h, what, _ptr(buf), buf.size, C.byref(n)))
+        return buf[: n.value].view(dtype)
+
+    def tables(self):
+        raw = self.debug_read(N.DBG_TABLES, np.uint8)
+        return N.HuffDev.from_buffer_copy(raw.tobytes())
+
+    def enable_timing(self, on=True):
+        self._ck(self._L.b2j_enable_timing(self._h, int(on)))
+
+    def timings(self):
+        t = N.Timings()
+        self._ck(self._L.b2j_last_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in N.Timings._fields_}
+
+    def launch_count(self):
+        return int(self._L.b2j_launch_count(self._h))
