@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on B200: encode Mpix/s of one synthetic 8320x40000 BGR image,
+quality 95, 4:2:2, optimized Huffman (config 2), bit-exact with libjpeg-turbo.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N=1 : the whole image on one GPU.  N>1 (torchrun, one rank per GPU): the image is cut into MCU-row strips, one per
+      GPU, stitched with three small NCCL collectives (strong scaling: total work is fixed).
+One "step" = one complete encode of the image (device-resident input -> complete JPEG bytes in HBM).
+Prints ONE JSON line (rank 0). `value` is device-resident throughput, `e2e` is the same metric through the C-ABI with
+pinned HOST buffers (H2D of the pixels and D2H of the JPEG inside the timed region).
+
+--impl reference: the reference's nvJPEG path (baseline/ref_nvjpeg.cu = its exact call sequence, see that file) on
+      the same GPU, else -- if nvJPEG cannot run -- libjpeg-turbo (cv2.imencode) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, QUALITY, CSS, OPT = 8320, 40000, 95, "422", 1
+WORKLOAD = "8320x40000 BGR synth(seed=0,amp=8), q95, 4:2:2, optimized Huffman (BASELINE.json configs[1])"
+PEAKS_FALLBACK_GBS = 6650.0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return PEAKS_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for i, n in enumerate(names):
+                    if r[3 + i].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def _cv_worker(args):
+    import cv2
+    cv2.setNumThreads(1)
+    arr, y0, y1, css, q, opt, reps = args
+    sf = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+          "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+          "411": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}[css]
+    n = 0
+    for _ in range(reps):
+        ok, b = cv2.imencode(".jpg", arr[y0:y1], [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_OPTIMIZE, opt,
+                                                  cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf])
+        n += b.size
+    return n
+
+
+_SHARED = {}
+
+
+def _cv_worker_shared(args):
+    y0, y1, css, q, opt, reps = args
+    return _cv_worker((_SHARED["img"], y0, y1, css, q, opt, reps))
+
+
+def cpu_baseline(sample_rows=8000, reps=1):
+    """libjpeg-turbo 3.1.2 (cv2.imencode, the north-star's bit-exactness oracle) on all host cores: the first
+    `sample_rows` rows of the workload cut into one MCU-row-aligned strip per core, one process per core."""
+    import multiprocessing as mp
+    import oracle as O
+    cores = os.cpu_count() or 1
+    rows = min(H, sample_rows)
+    img = O.synth(W, H, 0, 8, y0=0, rows=rows)
+    _SHARED["img"] = img
+    per = max(8, (rows // cores) // 8 * 8)
+    jobs = [(y, min(rows, y + per), CSS, QUALITY, OPT, reps) for y in range(0, rows, per)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cv_worker_shared, [(0, 8, CSS, QUALITY, OPT, 1)] * cores)  # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cv_worker_shared, jobs)
+        dt = time.perf_counter() - t0
+    mpix = W * rows * reps / 1e6
+    return {"value": round(mpix / dt, 2), "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": f"cv2.imencode (libjpeg-turbo 3.1.2, the bit-exactness oracle itself) on the first {rows} rows of the "
+                      f"workload, {len(jobs)} MCU-row strips, one process per core, {dt:.2f} s"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    import oracle as O
+    line = {"impl": "reference", "metric": "encode_mpix_per_s", "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": {"workload": WORKLOAD}}
+    lib = os.path.join(ROOT, "baseline", "_ref", "libref_nvjpeg.so")
+    err = None
+    if args.ref_kind in ("auto", "nvjpeg") and os.path.exists(lib):
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device")
+            L = C.CDLL(lib)
+            h = C.c_void_p()
+            assert L.ref_create(W, H, QUALITY, OPT, 1, int(args.ref_progressive), C.byref(h)) == 0
+            if L.ref_build_compress_env(h) != 0:
+                raise RuntimeError("nvJPEG env setup failed")
+            img = np.empty((H, W, 3), np.uint8)
+            for y0 in range(0, H, 2000):
+                img[y0:y0 + 2000] = O.synth(W, H, 0, 8, y0=y0, rows=2000)
+            out = np.empty(W * H * 3, np.uint8)
+            n = C.c_size_t(0)
+            gpu_ms, e2e_ms = [], []
+            tt = [C.c_float(0) for _ in range(4)]
+            for i in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                rc = L.ref_compress(h, C.c_void_p(img.ctypes.data), C.c_size_t(W * 3), C.c_void_p(out.ctypes.data),
+                                    C.c_size_t(out.size), C.byref(n))
+                dt = (time.perf_counter() - t0) * 1e3
+                if rc != 0:
+                    raise RuntimeError(f"ref_compress rc={rc}")
+                L.ref_last_times(h, *[C.byref(t) for t in tt])
+                if i >= args.warmup:
+                    e2e_ms.append(dt)
+            # device-resident bracket (planes already uploaded): ImageCompressorImpl.cu:279-281 + size query
+            for i in range(args.warmup + args.steps):
+                ms = C.c_float(0)
+                if L.ref_encode_resident(h, C.byref(ms), C.byref(n)) != 0:
+                    raise RuntimeError("ref_encode_resident failed")
+                if i >= args.warmup:
+                    gpu_ms.append(ms.value)
+            L.ref_destroy(h)
+            ms = float(np.mean(gpu_ms))
+            e2e = float(np.mean(e2e_ms))
+            line.update({"value": round(W * H / ms / 1e3, 1), "ms_per_step": round(ms, 3), "gpu_launches": None,
+                         "e2e": {"value": round(W * H / e2e / 1e3, 1), "unit": "Mpix/s", "ms_per_step": round(e2e, 2),
+                                 "h2d_bytes_per_step": W * H * 3, "d2h_bytes_per_step": int(n.value),
+                                 "split_ms": round(tt[1].value, 1), "h2d_ms": round(tt[2].value, 1)},
+                         "reference_kind": "nvjpeg call sequence of ImageCompressorImpl.cu:19-45,269-294 "
+                                           f"({'progressive as shipped' if args.ref_progressive else 'baseline sequential'}, "
+                                           "4:2:2, q95, optimized Huffman) on this GPU; n_gpus ignored (single-GPU library)",
+                         "jpeg_bytes": int(n.value)})
+            line["cpu_baseline"] = cpu_baseline()
+            return line
+        except Exception as e:  # fall through to the CPU arm
+            err = f"{type(e).__name__}: {e}"
+    cb = cpu_baseline(sample_rows=8000, reps=max(1, args.steps // 4))
+    line.update({"value": cb["value"], "ms_per_step": round(W * H / 1e3 / cb["value"], 2), "cpu_baseline": cb,
+                 "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "reference_kind": "libjpeg-turbo on host cores (nvJPEG harness unavailable: %s)" % err})
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import nvjpeg_imagecompressor_b200 as P
+    from nvjpeg_imagecompressor_b200.strips import StripEncoder, strip_rows
+    from nvjpeg_imagecompressor_b200.synth import synth_rows
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    P.lib()
+    css_i = P.CSS[CSS]
+    rows = strip_rows(H, css_i, world)
+    y0, y1 = rows[rank]
+    nrows = y1 - y0
+    img = torch.empty((nrows, W, 3), dtype=torch.uint8, device=dev)
+    for r0 in range(0, nrows, 500):
+        n = min(500, nrows - r0)
+        img[r0:r0 + n] = synth_rows(W, H, y0 + r0, n, 0, 8, dev)
+    stream = torch.cuda.Stream(device=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stage_acc, launches0 = {}, 0
+    if world == 1:
+        eng = P.Engine(W, H, QUALITY, bool(OPT), CSS, device=local_rank)
+        eng.set_stream(stream.cuda_stream)
+        eng.enable_timing(True)
+
+        def step():
+            eng.encode_device(img.data_ptr(), W * 3, W, H)
+            return eng.encode_finish()
+    else:
+        enc = StripEncoder(W, H, QUALITY, bool(OPT), CSS, device=local_rank)
+        eng = enc.b.eng
+        eng.set_stream(stream.cuda_stream)
+        eng.enable_timing(True)
+
+        def step():
+            enc.encode_strip(img.data_ptr(), W * 3)
+            return 0
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            nbytes = step()
+        barrier()
+        if sampler:
+            sampler.start()
+        launches0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            nbytes = step()
+            if world == 1:
+                for k, v in eng.timings().items():
+                    stage_acc[k] = stage_acc.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = eng.launch_count() - launches0
+        if world > 1:
+            t = torch.tensor([ms_total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+            lens = enc.gather_lengths()
+            nbytes = int(lens.sum())
+            lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+            dist.all_reduce(lt)
+            launches = int(lt.item())
+    ms = ms_total / args.steps
+    clocks = sampler.finish() if sampler else None
+
+    # ---- end to end through the C-ABI with pinned host buffers (N=1: b2j_encode; N>1: per-rank upload + strip encode
+    #      + per-rank download of its strip's bytes)
+    e2e = None
+    k2 = max(2, min(args.steps, 5))
+    h_img = torch.empty((nrows, W, 3), dtype=torch.uint8, pin_memory=True)
+    h_img.copy_(img)
+    h_out = torch.empty(int(nbytes) + (1 << 20), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    if world == 1:
+        def e2e_step():
+            return eng.encode_ptr(h_img.data_ptr(), W * 3, W, H, h_out.data_ptr(), h_out.numel())
+    else:
+        def e2e_step():
+            with torch.cuda.stream(stream):
+                img.copy_(h_img, non_blocking=True)
+                ol = enc.encode_strip(img.data_ptr(), W * 3)
+                n = int(ol.item())
+                h_out[:n].copy_(enc.b.out_view(n), non_blocking=True)
+                stream.synchronize()
+            return n
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        n2 = e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / k2
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": round(W * H / dt / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dt * 1e3, 2),
+           "h2d_bytes_per_step": W * H * 3, "d2h_bytes_per_step": int(nbytes),
+           "api": "b2j_encode (host BGR -> host JPEG), pinned buffers" if world == 1 else
+                  "per rank: pinned H2D of its strip + b2j_strip_phase1..3 + pinned D2H of its bytes"}
+    if rank != 0:
+        return None
+
+    peak, which = measured_peak()
+    line = {"metric": "encode_mpix_per_s", "value": round(W * H / ms / 1e3, 1), "unit": "Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "jpeg_bytes": int(nbytes), "l2": "inputs (998 MB image, 1.33 GB coefficients) "
+                       "exceed the 126 MB L2; no flush between steps", "parallelism": "single GPU" if world == 1 else
+                       f"{world} MCU-row strips, 1 all_reduce + 2 all_gather per image"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if world == 1:
+        st = {k: v / args.steps for k, v in stage_acc.items()}
+        g_blocks = (W // 16) * (H // 8) * 4
+        coef_bytes = g_blocks * 128
+        algo = {"fdct": W * H * 3 + coef_bytes, "pack": coef_bytes + int(nbytes), "stuff": 2 * int(nbytes)}
+        top = max(("fdct", "pack", "stuff"), key=lambda k: st.get(k, 0))
+        ach = algo[top] / (st[top] * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": {"fdct": "k_fdct<2,1>", "pack": "k_pack", "stuff": "k_stuff"}[top],
+                            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                            "traffic": None, "peak_source": which,
+                            "algorithmic_bytes_per_launch": int(algo[top]), "kernel_ms": round(st[top], 4),
+                            "whole_encode": {"algorithmic_bytes": W * H * 3 + int(nbytes),
+                                             "achieved": round((W * H * 3 + int(nbytes)) / (ms * 1e-3) / 1e9, 1),
+                                             "frac": round((W * H * 3 + int(nbytes)) / (ms * 1e-3) / 1e9 / peak, 4)}}
+        line["stages_ms"] = {k: round(v, 4) for k, v in st.items() if k in ("fdct", "hist_edge", "tables", "pack", "scan", "stuff", "total")}
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "nvjpeg", "cpu"])
+    ap.add_argument("--ref-progressive", type=int, default=0,
+                    help="1 = nvJPEG progressive encoding as the reference ships it (ImageCompressorImpl.cu:28); default is "
+                         "baseline sequential, the stream type this engine and the north-star target")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else max(1, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_b200(args, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+"""Multi-GPU encode of ONE image as MCU-row strips, one process (rank) per GPU, torch.distributed for the plumbing.
+
+Not in the reference (single GPU, no communication: SURVEY.md 2a); this is BASELINE.json's multi-GPU design
+(SURVEY.md 8e). Per image every rank runs the staged C-ABI on its strip and the ranks exchange three small things:
+
+  1. all_gather  last DC of each strip (3 x int16)        -> DC predictors at the next strip's start
+  2. all_reduce  4 x 257 symbol counts (optimized Huffman) -> identical tables on every rank
+  3. all_gather  (strip bit count, first 32 bits)          -> global bit phase of each strip and the bits that
+                                                              complete the previous strip's last byte
+
+Strip k then byte-stuffs its own bits shifted to phase G_k mod 8; it owns every output byte whose FIRST bit it holds,
+so the concatenation [headers | strip 0 | ... | strip N-1 | EOI] is the single-GPU stream, byte for byte.
+
+`backend` abstracts the device: EngineBackend drives libb2jpeg.so on a GPU; the CPU tests plug a checker-backed
+backend into the same host logic over gloo.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+_HS = {0: 1, 1: 2, 2: 1, 3: 2, 4: 4}
+_VS = {0: 1, 1: 1, 2: 2, 3: 2, 4: 1}
+
+
+def strip_rows(H, css, world):
+    """Pixel-row range [y0, y1) of every rank: contiguous MCU rows, as even as possible."""
+    mcu_h = 8 * _VS[css]
+    mcuy = (H + mcu_h - 1) // mcu_h
+    base, rem = divmod(mcuy, world)
+    out, m0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((min(H, m0 * mcu_h), min(H, (m0 + n) * mcu_h)))
+        m0 += n
+    return out
+
+
+def seam_params(strip_bits, first_words):
+    """strip_bits[k], first_words[k] (top-aligned first 32 bits) -> per strip (skip_bits, ext_byte)."""
+    n = len(strip_bits)
+    out, G = [], 0
+    for k in range(n):
+        skip = (8 - G % 8) % 8
+        ext = 0xFF if k == n - 1 else (int(first_words[k + 1]) >> 24) & 0xFF
+        out.append((skip, ext))
+        G += int(strip_bits[k])
+    return out
+
+
+class _CudaView:
+    """Zero-copy torch view of device memory owned by the C library (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def _view(ptr, shape, typestr, device):
+    return torch.as_tensor(_CudaView(ptr, shape, typestr), device=device)
+
+
+class EngineBackend:
+    """Strip phases on one GPU through the C-ABI (b2j_strip_*)."""
+
+    def __init__(self, W, rows_max, quality, optimize, css, device):
+        from .engine import Engine
+        self.device = torch.device("cuda", device)
+        self.eng = Engine(W, rows_max, quality, optimize, css, device=device)
+        st = self.eng.strip_state()
+        self.hist = _view(st.d_hist, (4 * 257,), "<i4", self.device)
+        self.last_dc = _view(st.d_last_dc, (4,), "<i2", self.device)
+        self.pred_in = _view(st.d_pred_in, (4,), "<i2", self.device)
+        self.strip_bits = _view(st.d_strip_bits, (2,), "<i8", self.device)
+        self.out_len = _view(st.d_out_len, (1,), "<i8", self.device)
+        self._d_out = st.d_out
+
+    def set_stream(self, s):
+        self.eng.set_stream(s)
+
+    def phase1(self, d_ptr, step, W, rows):
+        self.eng.strip_phase1(d_ptr, step, W, rows)
+
+    def phase1b(self):
+        self.eng.strip_phase1b()
+
+    def phase2(self, W, H):
+        self.eng.strip_phase2(W, H)
+
+    def phase3(self, skip, ext, flags):
+        self.eng.strip_phase3(skip, ext, flags)
+
+    def out_view(self, n):
+        return _view(self._d_out, (int(n),), "|u1", self.device)
+
+
+class StripEncoder:
+    def __init__(self, W, H, quality=95, optimize=True, css="422", rank=None, world=None, backend=None, device=None,
+                 group=None):
+        self.W, self.H = W, H
+        self.css = N.CSS[css] if isinstance(css, str) else int(css)
+        self.optimize = bool(optimize)
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.rows = strip_rows(H, self.css, self.world)
+        self.y0, self.y1 = self.rows[self.rank]
+        if backend is None:
+            dev = torch.cuda.current_device() if device is None else device
+            backend = EngineBackend(W, max(y1 - y0 for y0, y1 in self.rows), quality, optimize, self.css, dev)
+        self.b = backend
+        dev = self.b.last_dc.device
+        self._dc_all = torch.zeros((self.world, 4), dtype=torch.int16, device=dev)
+        self._bits_all = torch.zeros((self.world, 2), dtype=torch.int64, device=dev)
+        self._len_all = torch.zeros((self.world, 1), dtype=torch.int64, device=dev)
+
+    def encode_strip(self, d_ptr, step):
+        """d_ptr: this rank's strip (rows [y0, y1) of the image). Returns (stuffed byte count, all ranks' counts)."""
+        b, w, r = self.b, self.world, self.rank
+        b.phase1(d_ptr, step, self.W, self.y1 - self.y0)
+        if w > 1:
+            dist.all_gather_into_tensor(self._dc_all.view(torch.uint8).view(-1), b.last_dc.view(torch.uint8), group=self.group)
+            if r > 0:
+                b.pred_in.copy_(self._dc_all[r - 1])
+            else:
+                b.pred_in.zero_()
+        else:
+            b.pred_in.zero_()
+        b.phase1b()
+        if w > 1 and self.optimize:
+            dist.all_reduce(b.hist, op=dist.ReduceOp.SUM, group=self.group)
+        b.phase2(self.W, self.H)
+        if w > 1:
+            dist.all_gather_into_tensor(self._bits_all.view(-1), b.strip_bits, group=self.group)
+            bits = self._bits_all.cpu().numpy()  # the one host sync of the pipeline: phase 3 takes host scalars
+            skip, ext = seam_params(bits[:, 0], bits[:, 1].astype(np.uint64) & 0xFFFFFFFF)[r]
+        else:
+            skip, ext = 0, 0xFF
+        b.phase3(skip, ext, (1 if r == 0 else 0) | (2 if r == w - 1 else 0))
+        return b.out_len
+
+    def gather_lengths(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._len_all.view(-1), self.b.out_len, group=self.group)
+            return self._len_all.cpu().numpy()[:, 0]
+        return self.b.out_len.cpu().numpy()
+
+    def gather_jpeg(self, dst=0):
+        """Concatenate the strips' bytes on rank `dst` (device tensor there, None elsewhere)."""
+        lens = self.gather_lengths()
+        mine = self.b.out_view(int(lens[self.rank]))
+        if self.world == 1:
+            return mine.clone()
+        if self.rank == dst:
+            total = torch.empty(int(lens.sum()), dtype=torch.uint8, device=mine.device)
+            off = 0
+            reqs = []
+            for k in range(self.world):
+                part = total[off:off + int(lens[k])]
+                if k == dst:
+                    part.copy_(mine)
+                else:
+                    reqs.append(dist.irecv(part, src=k, group=self.group))
+                off += int(lens[k])
+            for q in reqs:
+                q.wait()
+            return total
+        dist.send(mine.contiguous(), dst=dst, group=self.group)
+        return None
