@@ -1,0 +1,194 @@
+// dec.cu -- host side of the decoder: buffers, stage sequencing, the synchronisation loop.
+// Mirrors NvjpegCompressRunnerImpl::DecodeWorker (reference ImageCompressorImpl.cu:311-385) with nvJPEG replaced by
+// this library's kernels; output planes are never materialised as three B/G/R planes (the reference's
+// getCVImageOnCPU :184-232 step disappears into k_upcolor's interleaved store).
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "dec.h"
+#include "dec_kernels.h"
+
+namespace b2j {
+
+struct DecCtrl {
+    uint64_t u_len;
+    uint32_t ticket[8];  // 0 destuff, 1 nblk scan, 2..4 dc scan
+    uint32_t err;
+    uint32_t changed;
+};
+
+struct Decoder {
+    int nblocks_cap = 0;
+    // entropy segment
+    uint8_t *d_scan = nullptr, *d_u = nullptr;
+    size_t scan_cap = 0;
+    uint64_t *d_desc = nullptr;
+    size_t desc_cap = 0;       // entries per descriptor array (5 arrays)
+    uint64_t *d_st_in = nullptr, *d_st_out = nullptr;
+    uint32_t *d_nblk = nullptr, *d_blk_start = nullptr;
+    size_t nsub_cap = 0;
+    DecCtrl *d_ctrl = nullptr;
+    void *d_tb = nullptr;
+    void *h_tb = nullptr;      // pinned
+    uint32_t *h_flag = nullptr;  // pinned: [0] changed, [1] err
+    int16_t *d_coef = nullptr;
+    uint8_t *d_planes = nullptr;
+    size_t planes_cap = 0;
+    cudaEvent_t ev[8];
+    int last_rounds = 0;
+    char *err;
+    size_t errlen;
+    cudaStream_t last_stream = nullptr;
+};
+
+#define DCK(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t _e = (call);                                                                                   \
+        if (_e != cudaSuccess) {                                                                                   \
+            snprintf(d->err, d->errlen, "%s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+            return B2J_ECUDA;                                                                                      \
+        }                                                                                                          \
+    } while (0)
+
+Decoder *dec_create(int nblocks_cap, char *err, size_t errlen) {
+    Decoder *d = new Decoder();
+    d->nblocks_cap = nblocks_cap;
+    d->err = err;
+    d->errlen = errlen;
+    bool ok = cudaMalloc(&d->d_ctrl, sizeof(DecCtrl)) == cudaSuccess && cudaMalloc(&d->d_tb, dec_tables_size()) == cudaSuccess &&
+              cudaHostAlloc(&d->h_tb, dec_tables_size(), cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc(&d->h_flag, 16, cudaHostAllocDefault) == cudaSuccess &&
+              cudaMalloc(&d->d_coef, (size_t)nblocks_cap * 128) == cudaSuccess;
+    for (auto &e : d->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    if (!ok) {
+        snprintf(err, errlen, "decoder allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        dec_destroy(d);
+        return nullptr;
+    }
+    return d;
+}
+
+void dec_destroy(Decoder *d) {
+    if (!d) return;
+    cudaFree(d->d_scan); cudaFree(d->d_u); cudaFree(d->d_desc); cudaFree(d->d_st_in); cudaFree(d->d_st_out);
+    cudaFree(d->d_nblk); cudaFree(d->d_blk_start); cudaFree(d->d_ctrl); cudaFree(d->d_tb); cudaFree(d->d_coef);
+    cudaFree(d->d_planes);
+    if (d->h_tb) cudaFreeHost(d->h_tb);
+    if (d->h_flag) cudaFreeHost(d->h_flag);
+    for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+    delete d;
+}
+
+const void *dec_coef_ptr(Decoder *d, size_t *bytes) { *bytes = (size_t)d->nblocks_cap * 128; return d->d_coef; }
+
+static int ensure(Decoder *d, size_t scan_len, const Geom &g) {
+    if (scan_len + 256 > d->scan_cap) {
+        cudaFree(d->d_scan); cudaFree(d->d_u); d->d_scan = d->d_u = nullptr; d->scan_cap = 0;
+        const size_t cap = scan_len + scan_len / 4 + 4096;
+        DCK(cudaMalloc(&d->d_scan, cap));
+        DCK(cudaMalloc(&d->d_u, cap));
+        d->scan_cap = cap;
+    }
+    const size_t nsub = (scan_len * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS + 256;
+    if (nsub > d->nsub_cap) {
+        cudaFree(d->d_st_in); cudaFree(d->d_st_out); cudaFree(d->d_nblk); cudaFree(d->d_blk_start);
+        d->d_st_in = d->d_st_out = nullptr; d->d_nblk = d->d_blk_start = nullptr; d->nsub_cap = 0;
+        const size_t cap = nsub + nsub / 4;
+        DCK(cudaMalloc(&d->d_st_in, cap * 8));
+        DCK(cudaMalloc(&d->d_st_out, cap * 8));
+        DCK(cudaMalloc(&d->d_nblk, (cap + 1) * 4));
+        DCK(cudaMalloc(&d->d_blk_start, (cap + 1) * 4));
+        d->nsub_cap = cap;
+    }
+    // descriptor arrays: destuff chunks (4 KB), nblk scan chunks (2048), dc scan chunks (1024 blocks) x 3
+    const size_t nd = std::max(std::max(scan_len / 4096, d->nsub_cap / 2048), (size_t)g.nblocks / 1024) + 8;
+    if (nd > d->desc_cap) {
+        cudaFree(d->d_desc); d->d_desc = nullptr; d->desc_cap = 0;
+        DCK(cudaMalloc(&d->d_desc, nd * 5 * 8));
+        d->desc_cap = nd;
+    }
+    const size_t pl = (size_t)g.mcux * 8 * g.hs * g.mcuy * 8 * g.vs + 2 * (size_t)g.mcux * 8 * g.mcuy * 8 + 256;
+    if (pl > d->planes_cap) {
+        cudaFree(d->d_planes); d->d_planes = nullptr; d->planes_cap = 0;
+        DCK(cudaMalloc(&d->d_planes, pl));
+        d->planes_cap = pl;
+    }
+    return B2J_OK;
+}
+
+int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
+            cudaStream_t s, b2j_timings *tm, uint64_t *launches) {
+    if (info.restart_interval != 0) { snprintf(d->err, d->errlen, "restart markers (DRI=%d) are not supported yet", info.restart_interval); return B2J_EFORMAT; }
+    if (g.nblocks > d->nblocks_cap) { snprintf(d->err, d->errlen, "image exceeds the context's size"); return B2J_ESIZE; }
+    if (info.scan_offset + info.scan_len > len || info.scan_len == 0) return B2J_EFORMAT;
+    int rc = ensure(d, info.scan_len, g);
+    if (rc) return rc;
+    d->last_stream = s;
+    const size_t n = info.scan_len;
+    const size_t nsub_max = (n * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
+    const int hv = g.bpm - 2;
+    if (tm) cudaEventRecord(d->ev[0], s);
+    dec_build_tables(info, d->h_tb);
+    DCK(cudaMemcpyAsync(d->d_tb, d->h_tb, dec_tables_size(), cudaMemcpyHostToDevice, s));
+    DCK(cudaMemcpyAsync(d->d_scan, jpg + info.scan_offset, n, cudaMemcpyHostToDevice, s));
+    DCK(cudaMemsetAsync(d->d_ctrl, 0, sizeof(DecCtrl), s));
+    DCK(cudaMemsetAsync(d->d_desc, 0, d->desc_cap * 5 * 8, s));
+    DCK(cudaMemsetAsync(d->d_nblk, 0, (nsub_max + 1) * 4, s));
+    DCK(cudaMemsetAsync(d->d_coef, 0, (size_t)g.nblocks * 128, s));
+    if (tm) cudaEventRecord(d->ev[1], s);
+    DCK(launch_destuff(d->d_scan, n, d->d_u, d->d_desc, &d->d_ctrl->ticket[0], &d->d_ctrl->u_len, &d->d_ctrl->err, s));
+    if (launches) (*launches)++;
+    // ---- self-synchronisation: launches of 8 in-CTA rounds until no end state moves
+    int rounds = 0;
+    for (;; rounds++) {
+        if (rounds >= 256) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
+        DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
+        DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, rounds == 0,
+                            &d->d_ctrl->changed, nsub_max, s));
+        if (launches) (*launches)++;
+        if (rounds == 0) continue;  // the first launch always moves states
+        DCK(cudaMemcpyAsync(d->h_flag, &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
+        DCK(cudaStreamSynchronize(s));
+        if (d->h_flag[0] == 0) break;
+    }
+    d->last_rounds = rounds + 1;
+    if (tm) cudaEventRecord(d->ev[2], s);
+    DCK(launch_scan_u32(d->d_nblk, d->d_blk_start, nsub_max, d->d_desc + d->desc_cap, &d->d_ctrl->ticket[1], &d->d_ctrl->err, s));
+    DCK(launch_dec_write(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_out, d->d_blk_start, g.bpm, hv, d->d_coef, (uint32_t)g.nblocks,
+                         &d->d_ctrl->err, nsub_max, s));
+    DCK(launch_dc_scan(d->d_coef, g, d->d_desc + 2 * d->desc_cap, &d->d_ctrl->ticket[2], d->desc_cap, &d->d_ctrl->err, s));
+    if (tm) cudaEventRecord(d->ev[3], s);
+    uint8_t *py = d->d_planes;
+    uint8_t *pcb = py + (((size_t)g.mcux * 8 * g.hs * g.mcuy * 8 * g.vs + 63) & ~(size_t)63);
+    uint8_t *pcr = pcb + (((size_t)g.mcux * 8 * g.mcuy * 8 + 63) & ~(size_t)63);
+    DCK(launch_idct(d->d_coef, g, d->d_tb, py, pcb, pcr, s));
+    if (tm) cudaEventRecord(d->ev[4], s);
+    DCK(launch_upcolor(py, pcb, pcr, g, d_bgr, step, s));
+    if (tm) cudaEventRecord(d->ev[5], s);
+    if (launches) (*launches) += 5;
+    if (tm) {
+        DCK(cudaStreamSynchronize(s));
+        cudaEventElapsedTime(&tm->dec_parse, d->ev[0], d->ev[1]);
+        cudaEventElapsedTime(&tm->dec_sync, d->ev[1], d->ev[2]);
+        cudaEventElapsedTime(&tm->dec_write, d->ev[2], d->ev[3]);
+        cudaEventElapsedTime(&tm->dec_idct, d->ev[3], d->ev[4]);
+        cudaEventElapsedTime(&tm->dec_color, d->ev[4], d->ev[5]);
+        cudaEventElapsedTime(&tm->total, d->ev[0], d->ev[5]);
+    }
+    return B2J_OK;
+}
+
+int dec_check(Decoder *d, char *err, size_t errlen) {
+    if (!d) return B2J_OK;
+    if (cudaMemcpyAsync(&d->h_flag[1], &d->d_ctrl->err, 4, cudaMemcpyDeviceToHost, d->last_stream) != cudaSuccess ||
+        cudaStreamSynchronize(d->last_stream) != cudaSuccess) {
+        snprintf(err, errlen, "%s in dec_check", cudaGetErrorString(cudaGetLastError()));
+        return B2J_ECUDA;
+    }
+    if (d->h_flag[1]) { snprintf(err, errlen, "decoder consistency check failed (err=%u)", d->h_flag[1]); return B2J_EINTERNAL; }
+    return B2J_OK;
+}
+
+}  // namespace b2j

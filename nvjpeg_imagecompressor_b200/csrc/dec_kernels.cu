@@ -1,0 +1,641 @@
+// dec_kernels.cu -- the decode path: de-stuff, self-synchronising parallel Huffman decode, DC prefix sums,
+// islow IDCT, fancy upsampling + YCbCr->BGR with an interleaved store.
+//
+// Replaces nvjpegDecodeJpegHost / TransferToDevice / Device (reference call sites ImageCompressorImpl.cu:364-366)
+// and the planar->interleaved CPU loop getCVImageOnCPU (:184-232; the dead combineChannels kernel :171-182).
+// Arithmetic follows libjpeg-turbo jdhuff.c / jidctint.c / jdsample.c / jdcolor.c as restated in SURVEY.md
+// Appendix A.9, pixel-exactly. The stream has no restart markers, so the Huffman stage is the self-synchronising
+// scheme of Weissenberger & Schmidt (ICPP'18): every thread decodes a fixed 1024-bit subsequence from a guessed
+// state, then re-decodes from its predecessor's end state until the states stop changing.
+#include "common.cuh"
+#include "dec.h"
+#include "dec_kernels.h"
+
+namespace b2j {
+
+// ------------------------------------------------------------------------------------------------------
+// k_destuff: drop the 0x00 that follows every 0xFF. 16 bytes per thread, 4 KB per chunk, persistent CTAs with
+// ticketed chunks and a decoupled look-back over the kept-byte counts. Output is padded with 0xFF bytes (1-bits).
+__global__ void __launch_bounds__(256)
+k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint64_t *__restrict__ desc,
+          uint32_t *__restrict__ ticket, uint64_t *__restrict__ out_len, uint32_t *__restrict__ err) {
+    __shared__ int s_chunk;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint64_t s_goff;
+    __shared__ uint8_t s_out[4096];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nchunks = (int)((n + 4095) / 4096);
+    for (;;) {
+        if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int ch = s_chunk;
+        if (ch >= nchunks) break;
+        const size_t base = (size_t)ch * 4096 + (size_t)tid * 16;
+        uint8_t b[17];
+        b[0] = base > 0 && base <= n ? in[base - 1] : 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) b[i + 1] = base + i < n ? in[base + i] : 0;
+        uint32_t keep = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (base + i < n && !(b[i + 1] == 0 && b[i] == 0xFF)) keep |= 1u << i;
+        const uint32_t cnt = __popc(keep);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t x = s_warp[i];
+            if (i < wid) wbase += x;
+            total += x;
+        }
+        uint32_t o = wbase + inc - cnt;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (keep & (1u << i)) s_out[o++] = b[i + 1];
+        if (wid == 0) {
+            const uint64_t pre = lookback_exclusive(desc, ch, total, err);
+            if (lane == 0) s_goff = pre;
+        }
+        __syncthreads();
+        uint8_t *dst = out + s_goff;
+        for (uint32_t i = tid; i < total; i += 256) dst[i] = s_out[i];
+        if (ch == nchunks - 1) {
+            if (tid < 64) dst[total + tid] = 0xFF;  // padding the bit reader may peek into
+            if (tid == 0) *out_len = s_goff + total;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Huffman decoding of one symbol from the top 16 bits of a window (jdhuff.c jpeg_huff_decode, table-driven)
+struct DecTables {                 // device copy, one per decode
+    uint16_t lut[4][1 << DEC_LUT_BITS];  // (len << 8) | symbol for codes of length <= DEC_LUT_BITS, else 0
+    int32_t maxcode[4][18];        // maxcode[l] = largest code of length l, -1 if none; [17] = sentinel
+    int32_t valoff[4][17];         // valptr[l] - mincode[l]
+    uint8_t vals[4][256];
+    uint16_t q[2][64];             // dequantisation table, natural order
+};
+
+__device__ __forceinline__ uint32_t huff_sym(const uint16_t *lut, const int32_t *maxcode, const int32_t *valoff,
+                                             const uint8_t *vals, uint32_t top16, int &len) {
+    const uint32_t e = lut[top16 >> (16 - DEC_LUT_BITS)];
+    if (e) {
+        len = (int)(e >> 8);
+        return e & 0xFFu;
+    }
+#pragma unroll 1
+    for (int l = DEC_LUT_BITS + 1; l <= 16; l++) {
+        const int code = (int)(top16 >> (16 - l));
+        if (code <= maxcode[l]) {
+            len = l;
+            return vals[(valoff[l] + code) & 255];
+        }
+    }
+    len = 1;  // invalid code (only reached while unsynchronised): skip one bit and keep going
+    return 0x100u;
+}
+
+constexpr int SUB_BITS = 1024;                 // subsequence length
+constexpr int SUB_WORDS = SUB_BITS / 32;
+constexpr int DEC_THREADS = 256;               // subsequences per CTA
+constexpr int DEC_SMEM_WORDS = SUB_WORDS * (DEC_THREADS + 1);
+
+struct DecShared {
+    uint32_t words[DEC_SMEM_WORDS];            // [word-in-subsequence][subsequence(+1 overflow column)]
+    uint16_t lut[4][1 << DEC_LUT_BITS];
+    int32_t maxcode[4][18];
+    int32_t valoff[4][17];
+    uint8_t vals[4][256];
+    uint64_t state[DEC_THREADS + 1];
+};
+
+// state word: bit position << 16 | block-in-MCU << 8 | zig-zag index
+__device__ __forceinline__ uint64_t pack_state(uint64_t p, int c, int k) { return (p << 16) | ((uint64_t)c << 8) | (uint64_t)k; }
+
+template <bool WRITE>
+__device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t chunk_bit0, uint64_t start_state,
+                                                 uint64_t end_bit, uint64_t total_bits, int bpm, int hv,
+                                                 uint32_t &nblk_out, int16_t *__restrict__ coef, uint32_t blk_base,
+                                                 uint32_t nblocks) {
+    uint64_t p = start_state >> 16;
+    int c = (int)((start_state >> 8) & 0xFF), k = (int)(start_state & 0xFF);
+    uint32_t nblk = 0;
+    const uint64_t stop = end_bit < total_bits ? end_bit : total_bits;
+    while (p < stop) {
+        const uint32_t q = (uint32_t)(p - chunk_bit0);
+        const uint32_t g = q >> 5, o = q & 31u;
+        const uint32_t w0 = sh.words[(g & 31u) * (DEC_THREADS + 1) + (g >> 5)];
+        const uint32_t g1 = g + 1;
+        const uint32_t w1 = sh.words[(g1 & 31u) * (DEC_THREADS + 1) + (g1 >> 5)];
+        const uint32_t win = __funnelshift_l(w1, w0, o);  // 32 bits starting at p
+        const int t = (c < hv ? 0 : 2) + (k ? 1 : 0);
+        int len;
+        const uint32_t sym = huff_sym(sh.lut[t], sh.maxcode[t], sh.valoff[t], sh.vals[t], win >> 16, len);
+        if (sym > 0xFFu) { p += 1; continue; }
+        const int s = (int)(sym & 15u);
+        if (p + len + s > total_bits) { p = total_bits; break; }  // padding bits at the very end
+        int val = 0;
+        if (s) {
+            const uint32_t v = (win << len) >> (32 - s);
+            val = v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v;  // jdhuff.c HUFF_EXTEND
+        }
+        p += len + s;
+        bool done = false;
+        if (k == 0) {
+            if (WRITE) { const uint32_t b = blk_base + nblk; if (b < nblocks && val) coef[(size_t)b * 64] = (int16_t)val; }
+            k = 1;
+        } else {
+            const int r = (int)(sym >> 4);
+            if (s == 0) {
+                if (r == 15) k += 16; else done = true;
+            } else {
+                k += r;
+                if (WRITE) { const uint32_t b = blk_base + nblk; if (k < 64 && b < nblocks) coef[(size_t)b * 64 + k] = (int16_t)val; }
+                k++;
+            }
+            if (k > 63) done = true;
+        }
+        if (done) { k = 0; c = c + 1 == bpm ? 0 : c + 1; nblk++; }
+    }
+    nblk_out = nblk;
+    return pack_state(p, c, k);
+}
+
+__device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__restrict__ u, uint64_t nbytes_padded,
+                                               size_t cta, const DecTables *__restrict__ tb) {
+    const int tid = threadIdx.x;
+    const uint32_t *uw = reinterpret_cast<const uint32_t *>(u);
+    const size_t w0 = cta * (size_t)(SUB_WORDS * DEC_THREADS);
+    const size_t nwords = (size_t)(nbytes_padded >> 2);
+    for (int i = tid; i < SUB_WORDS * DEC_THREADS + 2; i += DEC_THREADS) {
+        const size_t gw = w0 + i;
+        const uint32_t w = gw < nwords ? uw[gw] : 0xFFFFFFFFu;
+        sh.words[(i & 31) * (DEC_THREADS + 1) + (i >> 5)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
+    }
+    for (int i = tid; i < 4 * (1 << DEC_LUT_BITS); i += DEC_THREADS) (&sh.lut[0][0])[i] = (&tb->lut[0][0])[i];
+    for (int i = tid; i < 4 * 18; i += DEC_THREADS) (&sh.maxcode[0][0])[i] = (&tb->maxcode[0][0])[i];
+    for (int i = tid; i < 4 * 17; i += DEC_THREADS) (&sh.valoff[0][0])[i] = (&tb->valoff[0][0])[i];
+    for (int i = tid; i < 4 * 256; i += DEC_THREADS) (&sh.vals[0][0])[i] = (&tb->vals[0][0])[i];
+}
+
+// One synchronisation launch: every CTA iterates up to `inner` rounds over its 256 subsequences (states in shared
+// memory), then publishes the end states. st_out[i] = state after subsequence i; st_in[i] = the start state that
+// produced it. `changed` is raised when a CTA did not converge or its last end state moved.
+__global__ void __launch_bounds__(DEC_THREADS)
+k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
+           uint64_t *__restrict__ st_in, uint64_t *__restrict__ st_out, uint32_t *__restrict__ nblk, int bpm, int hv,
+           int inner, int first_launch, uint32_t *__restrict__ changed) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint64_t nbytes = *u_len;
+    const uint64_t total_bits = nbytes * 8;
+    const size_t cta = blockIdx.x;
+    const uint64_t chunk_bit0 = (uint64_t)cta * SUB_BITS * DEC_THREADS;
+    if (chunk_bit0 >= total_bits) return;
+    dec_load_chunk(sh, u, (nbytes + 64) & ~(uint64_t)3, cta, tb);
+    const size_t i = cta * DEC_THREADS + tid;
+    const uint64_t my_bit0 = chunk_bit0 + (uint64_t)tid * SUB_BITS;
+    const uint64_t my_end = my_bit0 + SUB_BITS;
+    const bool live = my_bit0 < total_bits;
+    // incoming state of the CTA's first subsequence; initial guess = "a block starts exactly at my first bit"
+    if (tid == 0) sh.state[0] = cta == 0 ? pack_state(0, 0, 0) : (first_launch ? pack_state(chunk_bit0, 0, 0) : st_out[i - 1]);
+    uint64_t used = first_launch ? ~0ull : st_in[i];
+    uint64_t mine = first_launch ? pack_state(my_end, 0, 0) : st_out[i];
+    const uint64_t before = mine;
+    uint32_t my_nblk = first_launch ? 0 : nblk[i];
+    sh.state[tid + 1] = mine;
+    __syncthreads();
+    int any = 1;
+    for (int round = 0; round < inner && any; round++) {
+        const uint64_t in = sh.state[tid];
+        int ch = 0;
+        uint64_t outst = mine;
+        if (live && in != used) {
+            outst = decode_range<false>(sh, chunk_bit0, in, my_end, total_bits, bpm, hv, my_nblk, nullptr, 0, 0);
+            used = in;
+            ch = outst != mine;
+            mine = outst;
+        }
+        __syncthreads();
+        sh.state[tid + 1] = mine;
+        any = __syncthreads_or(ch);
+    }
+    if (live) {
+        st_in[i] = used;
+        st_out[i] = mine;
+        nblk[i] = my_nblk;
+    }
+    // not converged inside the CTA, or the state handed to the next CTA moved
+    const bool last_live = tid == DEC_THREADS - 1 || my_end >= total_bits;
+    if (any || (live && last_live && mine != before) || (live && sh.state[tid] != used)) atomicOr(changed, 1u);
+}
+
+// Final pass: decode every subsequence from its synchronised start state and scatter the non-zero coefficients
+// (zig-zag order, DC still differential) into the zero-filled coefficient array.
+__global__ void __launch_bounds__(DEC_THREADS)
+k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
+            const uint64_t *__restrict__ st_out, const uint32_t *__restrict__ blk_start, int bpm, int hv,
+            int16_t *__restrict__ coef, uint32_t nblocks, uint32_t *__restrict__ err) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint64_t nbytes = *u_len;
+    const uint64_t total_bits = nbytes * 8;
+    const size_t cta = blockIdx.x;
+    const uint64_t chunk_bit0 = (uint64_t)cta * SUB_BITS * DEC_THREADS;
+    if (chunk_bit0 >= total_bits) return;
+    dec_load_chunk(sh, u, (nbytes + 64) & ~(uint64_t)3, cta, tb);
+    __syncthreads();
+    const size_t i = cta * DEC_THREADS + tid;
+    const uint64_t my_bit0 = chunk_bit0 + (uint64_t)tid * SUB_BITS;
+    if (my_bit0 >= total_bits) return;
+    const uint64_t in = i == 0 ? pack_state(0, 0, 0) : st_out[i - 1];
+    uint32_t n = 0;
+    const uint64_t o = decode_range<true>(sh, chunk_bit0, in, my_bit0 + SUB_BITS, total_bits, bpm, hv, n, coef, blk_start[i], nblocks);
+    if (o != st_out[i]) atomicOr(err, 4u);  // the states were not a fixed point
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Generic exclusive scan of uint32 (chunked, look-back). out[n] receives the total.
+__global__ void __launch_bounds__(256)
+k_scan_u32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n, uint64_t *__restrict__ desc,
+           uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
+    constexpr int ITEMS = 8, CH = 256 * ITEMS;
+    __shared__ int s_chunk;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint64_t s_goff;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nchunks = (int)((n + CH - 1) / CH);
+    for (;;) {
+        if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int ch = s_chunk;
+        if (ch >= nchunks) break;
+        const size_t base = (size_t)ch * CH + (size_t)tid * ITEMS;
+        uint32_t v[ITEMS], sum = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) { v[j] = base + j < n ? in[base + j] : 0; sum += v[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const uint32_t x = s_warp[j]; if (j < wid) wbase += x; total += x; }
+        if (wid == 0) {
+            const uint64_t pre = lookback_exclusive(desc, ch, total, err);
+            if (lane == 0) s_goff = pre;
+        }
+        __syncthreads();
+        uint32_t run = (uint32_t)s_goff + wbase + inc - sum;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) { if (base + j < n) out[base + j] = run; run += v[j]; }
+        if (ch == nchunks - 1 && tid == 255) out[n] = (uint32_t)s_goff + total;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// DC un-differencing: inclusive prefix sum of the DC differences of one component over its blocks in scan order
+// (jdhuff.c decode_mcu: s += last_dc_val). blockIdx.y = component; chunked look-back per component.
+__global__ void __launch_bounds__(256)
+k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__restrict__ desc_all,
+          uint32_t *__restrict__ ticket_all, size_t desc_stride, uint32_t *__restrict__ err) {
+    constexpr int ITEMS = 4, CH = 256 * ITEMS;
+    __shared__ int s_chunk;
+    __shared__ int s_warp[8];
+    __shared__ uint64_t s_goff;
+    const int comp = blockIdx.y;
+    uint64_t *desc = desc_all + (size_t)comp * desc_stride;
+    uint32_t *ticket = ticket_all + comp;
+    const int per = comp == 0 ? hv : 1;
+    const size_t n = nmcu * per;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nchunks = (int)((n + CH - 1) / CH);
+    for (;;) {
+        if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int ch = s_chunk;
+        if (ch >= nchunks) break;
+        const size_t base = (size_t)ch * CH + (size_t)tid * ITEMS;
+        int v[ITEMS], sum = 0;
+        size_t idx[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const size_t e = base + j;
+            const size_t m = comp == 0 ? e / hv : e;
+            const int sub = comp == 0 ? (int)(e - m * hv) : hv + comp - 1;
+            idx[j] = (m * bpm + sub) * 64;
+            v[j] = e < n ? (int)coef[idx[j]] : 0;
+            sum += v[j];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const int x = s_warp[j]; if (j < wid) wbase += x; total += x; }
+        if (wid == 0) {
+            const uint64_t pre = lookback_exclusive(desc, ch, (uint64_t)(int64_t)total & LB_MASK, err);
+            if (lane == 0) s_goff = pre;
+        }
+        __syncthreads();
+        int run = (int)(uint32_t)s_goff + wbase + inc - sum;  // low 32 bits of the modular sum are exact
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            run += v[j];
+            if (base + j < n) coef[idx[j]] = (int16_t)run;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_idct: de-quantise + jidctint.c jpeg_idct_islow, one thread per block, samples to per-component planes.
+#define FIX_0_298631336 2446
+#define FIX_0_390180644 3196
+#define FIX_0_541196100 4433
+#define FIX_0_765366865 6270
+#define FIX_0_899976223 7373
+#define FIX_1_175875602 9633
+#define FIX_1_501321110 12299
+#define FIX_1_847759065 15137
+#define FIX_1_961570560 16069
+#define FIX_2_053119869 16819
+#define FIX_2_562915447 20995
+#define FIX_3_072711026 25172
+
+template <int SH>
+__device__ __forceinline__ void idct8(int &i0, int &i1, int &i2, int &i3, int &i4, int &i5, int &i6, int &i7) {
+    constexpr int RND = 1 << (SH - 1);
+    int z1 = (i2 + i6) * FIX_0_541196100;
+    const int t2 = z1 - i6 * FIX_1_847759065, t3 = z1 + i2 * FIX_0_765366865;
+    const int t0 = (i0 + i4) << 13, t1 = (i0 - i4) << 13;
+    const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    int a0 = i7, a1 = i5, a2 = i3, a3 = i1;
+    z1 = a0 + a3;
+    int z2 = a1 + a2, z3 = a0 + a2, z4 = a1 + a3;
+    const int z5 = (z3 + z4) * FIX_1_175875602;
+    a0 *= FIX_0_298631336; a1 *= FIX_2_053119869; a2 *= FIX_3_072711026; a3 *= FIX_1_501321110;
+    z1 *= -FIX_0_899976223; z2 *= -FIX_2_562915447;
+    z3 = z3 * (-FIX_1_961570560) + z5;
+    z4 = z4 * (-FIX_0_390180644) + z5;
+    a0 += z1 + z3; a1 += z2 + z4; a2 += z2 + z3; a3 += z1 + z4;
+    i0 = (t10 + a3 + RND) >> SH; i7 = (t10 - a3 + RND) >> SH;
+    i1 = (t11 + a2 + RND) >> SH; i6 = (t11 - a2 + RND) >> SH;
+    i2 = (t12 + a1 + RND) >> SH; i5 = (t12 - a1 + RND) >> SH;
+    i3 = (t13 + a0 + RND) >> SH; i4 = (t13 - a0 + RND) >> SH;
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_idct(const int16_t *__restrict__ coef, Geom g, const DecTables *__restrict__ tb, uint8_t *__restrict__ py,
+       uint8_t *__restrict__ pcb, uint8_t *__restrict__ pcr) {
+    __shared__ __align__(16) uint4 s_c[256 * 8];
+    __shared__ uint16_t s_q[2][64];
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * 256;
+    const int nb = min(256, g.nblocks - b0);
+    for (int i = tid; i < nb * 8; i += 256) {
+        const int b = i >> 3, c = i & 7;
+        s_c[b * 8 + (c ^ (b & 7))] = ld_nc_v4(reinterpret_cast<const uint4 *>(coef) + (size_t)b0 * 8 + i);
+    }
+    if (tid < 128) s_q[tid >> 6][tid & 63] = tb->q[tid >> 6][tid & 63];
+    __syncthreads();
+    if (tid >= nb) return;
+    const int b = b0 + tid;
+    const int hv = g.bpm - 2;
+    const int m = b / g.bpm, bn = b - m * g.bpm;
+    const int my = m / g.mcux, mx = m - my * g.mcux;
+    const bool isY = bn < hv;
+    const uint16_t *q = s_q[isY ? 0 : 1];
+    int v[64];
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) {
+        const uint4 w = s_c[tid * 8 + (ch ^ (tid & 7))];
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = ch * 8 + j;
+            const int n = zigzag_nat(k);
+            const int cv = (j & 1) ? ((int)ww[j >> 1] >> 16) : (int)(int16_t)(ww[j >> 1] & 0xFFFFu);
+            v[n] = cv * (int)q[n];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) idct8<11>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+    uint8_t *dst;
+    size_t stride;
+    if (isY) {
+        const int by = bn / g.hs, bx = bn - by * g.hs;
+        stride = (size_t)g.mcux * 8 * g.hs;
+        dst = py + ((size_t)(my * g.vs + by) * 8) * stride + (size_t)(mx * g.hs + bx) * 8;
+    } else {
+        stride = (size_t)g.mcux * 8;
+        dst = (bn == hv ? pcb : pcr) + ((size_t)my * 8) * stride + (size_t)mx * 8;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        idct8<18>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            lo |= (uint32_t)min(255, max(0, v[r * 8 + c] + 128)) << (8 * c);
+            hi |= (uint32_t)min(255, max(0, v[r * 8 + 4 + c] + 128)) << (8 * c);
+        }
+        *reinterpret_cast<uint2 *>(dst + r * stride) = make_uint2(lo, hi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_upcolor: jdsample.c fancy upsampling (h2v1 / h2v2 / h1v2 triangle filters, h4v1 replication) on the TRUE
+// downsampled size + jdcolor.c YCbCr->RGB, 8 pixels per thread, stored interleaved B,G,R (cv::Mat CV_8UC3).
+template <int HS, int VS>
+__device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, size_t stride, int dw, int dh, int x, int y) {
+    if (HS == 1 && VS == 1) return p[(size_t)y * stride + x];
+    if (HS == 4) return p[(size_t)y * stride + (x >> 2)];
+    if (HS == 2 && VS == 1) {
+        const uint8_t *row = p + (size_t)y * stride;
+        const int i = x >> 1;
+        if (dw <= 2) return row[i];
+        if (x & 1) return i < dw - 1 ? (3 * row[i] + row[i + 1] + 2) >> 2 : row[dw - 1];
+        return i > 0 ? (3 * row[i] + row[i - 1] + 1) >> 2 : row[0];
+    }
+    if (HS == 1 && VS == 2) {
+        const int r = y >> 1;
+        const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+        return (3 * p[(size_t)r * stride + x] + p[(size_t)rn * stride + x] + ((y & 1) ? 2 : 1)) >> 2;
+    }
+    // h2v2
+    const int r = y >> 1, i = x >> 1;
+    if (dw <= 2) return p[(size_t)r * stride + i];
+    const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+    const uint8_t *r0 = p + (size_t)r * stride, *r1 = p + (size_t)rn * stride;
+    const int s = 3 * r0[i] + r1[i];
+    if (x & 1) return i < dw - 1 ? (3 * s + 3 * r0[i + 1] + r1[i + 1] + 7) >> 4 : (4 * s + 7) >> 4;
+    return i > 0 ? (3 * s + 3 * r0[i - 1] + r1[i - 1] + 8) >> 4 : (4 * s + 8) >> 4;
+}
+
+template <int HS, int VS>
+__global__ void __launch_bounds__(256)
+k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const uint8_t *__restrict__ pcr, Geom g,
+          uint8_t *__restrict__ bgr, size_t step) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 pixels
+    const int y = blockIdx.y;
+    const int x0 = gx * 8;
+    if (x0 >= g.W) return;
+    const size_t ys = (size_t)g.mcux * 8 * HS, cs = (size_t)g.mcux * 8;
+    const int dw = g.dw[1], dh = g.dh[1];
+    uint8_t o[24];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int x = min(x0 + i, g.W - 1);
+        const int Y = py[(size_t)y * ys + x];
+        const int cb = chroma_at<HS, VS>(pcb, cs, dw, dh, x, y) - 128;
+        const int cr = chroma_at<HS, VS>(pcr, cs, dw, dh, x, y) - 128;
+        const int r = Y + ((91881 * cr + 32768) >> 16);
+        const int b = Y + ((116130 * cb + 32768) >> 16);
+        const int gg = Y + ((-22554 * cb - 46802 * cr + 32768) >> 16);
+        o[3 * i] = (uint8_t)min(255, max(0, b));
+        o[3 * i + 1] = (uint8_t)min(255, max(0, gg));
+        o[3 * i + 2] = (uint8_t)min(255, max(0, r));
+    }
+    uint8_t *dst = bgr + (size_t)y * step + (size_t)x0 * 3;
+    const int nv = min(8, g.W - x0);
+    if (nv == 8 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) { lo |= (uint32_t)o[8 * j + c] << (8 * c); hi |= (uint32_t)o[8 * j + 4 + c] << (8 * c); }
+            d2[j] = make_uint2(lo, hi);
+        }
+    } else {
+        for (int j = 0; j < nv * 3; j++) dst[j] = o[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+size_t dec_sync_smem() { return sizeof(DecShared); }
+
+cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, uint64_t *out_len,
+                           uint32_t *err, cudaStream_t s) {
+    k_destuff<<<148 * 6, 256, 0, s>>>(in, n, out, desc, ticket, out_len, err);
+    return cudaGetLastError();
+}
+
+static cudaError_t dec_attr() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    if (e != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
+                            uint32_t *nblk, int bpm, int hv, int inner, int first, uint32_t *changed, size_t nsub_max,
+                            cudaStream_t s) {
+    cudaError_t e = dec_attr();
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((nsub_max + DEC_THREADS - 1) / DEC_THREADS);
+    k_dec_sync<<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv, inner,
+                                                            first, changed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
+                             const uint32_t *blk_start, int bpm, int hv, int16_t *coef, uint32_t nblocks, uint32_t *err,
+                             size_t nsub_max, cudaStream_t s) {
+    cudaError_t e = dec_attr();
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((nsub_max + DEC_THREADS - 1) / DEC_THREADS);
+    k_dec_write<<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm, hv, coef,
+                                                             nblocks, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint64_t *desc, uint32_t *ticket, uint32_t *err,
+                            cudaStream_t s) {
+    k_scan_u32<<<148 * 4, 256, 0, s>>>(in, out, n, desc, ticket, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_t *ticket, size_t desc_stride, uint32_t *err,
+                           cudaStream_t s) {
+    dim3 grid(148 * 2, 3);
+    k_dc_scan<<<grid, 256, 0, s>>>(coef, g.bpm, g.bpm - 2, (size_t)g.mcux * g.mcuy, desc, ticket, desc_stride, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_idct(const int16_t *coef, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb, uint8_t *pcr,
+                        cudaStream_t s) {
+    k_idct<<<g.ntiles, 256, 0, s>>>(coef, g, (const DecTables *)tb, py, pcb, pcr);
+    return cudaGetLastError();
+}
+
+template <int HS, int VS>
+static cudaError_t upcolor_one(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr,
+                               size_t step, cudaStream_t s) {
+    dim3 grid(((g.W + 7) / 8 + 255) / 256, g.H);
+    k_upcolor<HS, VS><<<grid, 256, 0, s>>>(py, pcb, pcr, g, bgr, step);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr, size_t step,
+                           cudaStream_t s) {
+    if (g.hs == 1 && g.vs == 1) return upcolor_one<1, 1>(py, pcb, pcr, g, bgr, step, s);
+    if (g.hs == 2 && g.vs == 1) return upcolor_one<2, 1>(py, pcb, pcr, g, bgr, step, s);
+    if (g.hs == 1 && g.vs == 2) return upcolor_one<1, 2>(py, pcb, pcr, g, bgr, step, s);
+    if (g.hs == 2 && g.vs == 2) return upcolor_one<2, 2>(py, pcb, pcr, g, bgr, step, s);
+    if (g.hs == 4 && g.vs == 1) return upcolor_one<4, 1>(py, pcb, pcr, g, bgr, step, s);
+    return cudaErrorInvalidValue;
+}
+
+size_t dec_tables_size() { return sizeof(DecTables); }
+
+// host-side construction of the decode tables (jdhuff.c jpeg_make_d_derived_tbl)
+void dec_build_tables(const JpegInfo &info, void *dst) {
+    DecTables *t = (DecTables *)dst;
+    memset(t, 0, sizeof(*t));
+    for (int ti = 0; ti < 4; ti++) {
+        int code = 0, p = 0;
+        for (int l = 1; l <= 16; l++) {
+            const int n = info.bits[ti][l];
+            t->valoff[ti][l] = p - code;
+            for (int i = 0; i < n; i++, p++, code++) {
+                if (l <= DEC_LUT_BITS) {
+                    const int lo = code << (DEC_LUT_BITS - l), cnt = 1 << (DEC_LUT_BITS - l);
+                    for (int j = 0; j < cnt; j++) t->lut[ti][lo + j] = (uint16_t)((l << 8) | info.vals[ti][p]);
+                }
+            }
+            t->maxcode[ti][l] = n ? code - 1 : -1;
+            code <<= 1;
+        }
+        t->maxcode[ti][17] = 0x7fffffff;
+        memcpy(t->vals[ti], info.vals[ti], 256);
+    }
+    memcpy(t->q, info.qt, sizeof(t->q));
+}
+
+}  // namespace b2j

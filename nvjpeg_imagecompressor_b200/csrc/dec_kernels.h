@@ -1,0 +1,31 @@
+// dec_kernels.h -- launchers of the decode kernels (internal)
+#pragma once
+#include "common.cuh"
+#include "dec.h"
+
+namespace b2j {
+
+constexpr int DEC_LUT_BITS = 10;
+constexpr int DEC_SUB_BITS = 1024;
+
+size_t dec_tables_size();
+void dec_build_tables(const JpegInfo &info, void *dst_host);
+
+cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, uint64_t *out_len,
+                           uint32_t *err, cudaStream_t s);
+cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
+                            uint32_t *nblk, int bpm, int hv, int inner, int first, uint32_t *changed, size_t nsub_max,
+                            cudaStream_t s);
+cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
+                             const uint32_t *blk_start, int bpm, int hv, int16_t *coef, uint32_t nblocks, uint32_t *err,
+                             size_t nsub_max, cudaStream_t s);
+cudaError_t launch_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint64_t *desc, uint32_t *ticket, uint32_t *err,
+                            cudaStream_t s);
+cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_t *ticket, size_t desc_stride, uint32_t *err,
+                           cudaStream_t s);
+cudaError_t launch_idct(const int16_t *coef, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb, uint8_t *pcr,
+                        cudaStream_t s);
+cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr, size_t step,
+                           cudaStream_t s);
+
+}  // namespace b2j

@@ -1,0 +1,167 @@
+"""GPU parity: the CUDA decoder (through the C-ABI) against the CPU oracle / libjpeg-turbo digests, plus the
+difference-map, PSNR and secondary-compression entry points."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def P():
+    import nvjpeg_imagecompressor_b200 as P
+    P.lib()
+    return P
+
+
+def _check(P, O, eng, jpg, tag):
+    from nvjpeg_imagecompressor_b200 import _native as N
+    out = eng.decode(jpg)
+    want = O.decode(jpg)
+    if not np.array_equal(out, want):
+        coef = eng.debug_read(N.DBG_DEC_COEF, np.int16).reshape(-1, 64)
+        ref, info = O.decode_coefs(jpg)
+        coef = coef[: ref.shape[0]]
+        bad = np.nonzero((coef != ref).any(axis=1))[0]
+        d = np.abs(out.astype(int) - want.astype(int))
+        raise AssertionError(f"{tag}: pixels differ (max {d.max()}, {np.count_nonzero(d)} values); coefficient blocks differing: "
+                             f"{bad.size} first {bad[:6]}")
+
+
+def test_golden_files(P, oracle, golden):
+    eng = P.Engine(256, 256, 95, True, "422")
+    for f in golden["files"]:
+        jpg = np.fromfile(os.path.join(HERE, "golden", f["file"]), np.uint8)
+        assert P.Engine.peek(jpg) == (f["W"], f["H"], f["css"])
+        out = eng.decode(jpg)
+        assert sha(out) == f["decoded_sha256"], f
+    eng.close()
+
+
+def test_small_sizes_all_modes(P, oracle):
+    rng = np.random.default_rng(6)
+    sizes = [(64, 96), (48, 64), (50, 70), (17, 33), (135, 121), (8, 8), (1, 1), (257, 63), (33, 17), (2, 2), (3, 5), (5, 3), (4, 4)]
+    eng = P.Engine(320, 160, 95, True, "444")
+    for css in range(5):
+        for q, opt in ((95, 1), (95, 0), (75, 1), (100, 0)):
+            for (W, H) in sizes:
+                img = oracle.synth(W, H, W * 31 + H, 8)
+                _check(P, oracle, eng, oracle.encode(img, css, q, opt), f"synth {W}x{H} css{css} q{q} opt{opt}")
+            img = rng.integers(0, 256, (77, 130, 3), dtype=np.uint8)
+            _check(P, oracle, eng, oracle.encode(img, css, q, opt), f"random css{css} q{q} opt{opt}")
+    eng.close()
+
+
+def test_golden_case_digests(P, oracle, golden):
+    """decoded pixels == cv2.imdecode digests for streams made by the oracle encoder (== cv2.imencode bytes)."""
+    eng = P.Engine(1920, 1088, 95, True, "444")
+    for c in golden["cases"]:
+        if c["quality"] != 95:
+            continue
+        img = oracle.synth(c["W"], c["H"], c["seed"], c["amp"])
+        jpg = oracle.encode(img, c["css"], c["quality"], c["optimize"])
+        assert sha(jpg) == c["jpeg_sha256"]
+        assert sha(eng.decode(jpg)) == c["decoded_sha256"], c
+    eng.close()
+
+
+def test_degenerate_streams(P, oracle):
+    """Flat image (2-4 bit blocks: hundreds of blocks per 1024-bit subsequence), saturated noise (long codes,
+    blocks longer than a subsequence), checkerboard."""
+    rng = np.random.default_rng(10)
+    imgs = {"flat": np.full((512, 768, 3), 128, np.uint8), "noise": rng.integers(0, 256, (256, 384, 3), dtype=np.uint8),
+            "checker": (np.indices((128, 192)).sum(0) % 2 * 255).astype(np.uint8)[:, :, None].repeat(3, 2)}
+    eng = P.Engine(768, 512, 95, True, "444")
+    for css in (0, 1, 3, 4):
+        for q, opt in ((100, 1), (95, 0), (40, 1)):
+            for name, img in imgs.items():
+                _check(P, oracle, eng, oracle.encode(np.ascontiguousarray(img), css, q, opt), f"{name} css{css} q{q} opt{opt}")
+    eng.close()
+
+
+def test_roundtrip_own_encoder_and_metrics(P, oracle):
+    img = oracle.synth(640, 360, 3, 8)
+    eng = P.Engine(640, 360, 95, True, "422")
+    jpg = eng.encode(img)
+    rec = eng.decode(jpg)
+    assert np.array_equal(rec, oracle.decode(jpg))
+    for mode in (0, 1):
+        assert np.array_equal(eng.diff(img, rec, mode), oracle.diff(img, rec, mode))
+    ps, ssd = eng.psnr(img, rec)
+    assert ssd == oracle.ssd(img, rec)
+    assert abs(ps - oracle.psnr(img, rec)) < 1e-12
+    # odd lengths / unaligned views through the scalar tail
+    a = img.reshape(-1)[3:100003]
+    b = rec.reshape(-1)[5:100005]
+    assert np.array_equal(eng.diff(a, b, 1), oracle.diff(a, b, 1))
+    assert eng.psnr(a, b)[1] == oracle.ssd(a, b)
+    eng.close()
+
+
+def test_secondary_compression(P, oracle):
+    """encode -> reconstruct -> difference map -> encode(diff) + PSNR, each step == oracle."""
+    img = oracle.synth(333, 222, 8, 8)
+    for css, mode in ((1, 1), (3, 0)):
+        eng = P.Engine(333, 222, 90, True, css)
+        j1, j2, recon, ps = eng.secondary(img, diff_mode=mode)
+        w1 = oracle.encode(img, css, 90, 1)
+        assert np.array_equal(j1, w1)
+        wrec = oracle.decode(w1)
+        assert np.array_equal(recon, wrec)
+        wdiff = oracle.diff(img, wrec, mode)
+        assert np.array_equal(j2, oracle.encode(wdiff, css, 90, 1))
+        assert abs(ps - oracle.psnr(img, wrec)) < 1e-12
+        eng.close()
+
+
+def test_runner_facade_demo_sequence(P, oracle, tmp_path):
+    """The reference demo's call order (src/ImageCompressor/main.cpp:24-78) through the Python facade."""
+    r = P.NvjpegCompressRunner(640, 360, 95, True, verbose=False)
+    r.buildCompressEnv()
+    img1, img2 = oracle.synth(640, 360, 1, 8), oracle.synth(640, 360, 2, 8)
+    b1, s1 = r.compress(img1)
+    b2, s2 = r.compress(img2)
+    assert s1 == 1 and s2 == 1
+    r.deleteCompressEnv()
+    r.buildDecodeEnv()
+    p1, p2 = str(tmp_path / "a.jpeg"), str(tmp_path / "b.jpeg")
+    r.save(p1, b1)
+    r.save(p2, b2)
+    d1, t1 = r.decode(p1)
+    d2, t2 = r.decode(p2)
+    assert t1 == 1 and t2 == 1
+    assert np.array_equal(d1, oracle.decode(oracle.encode(img1, 1, 95, 1)))
+    assert np.array_equal(d2, oracle.decode(oracle.encode(img2, 1, 95, 1)))
+    bad, st = r.decode(str(tmp_path / "missing.jpeg"))
+    assert st == 0 and bad.size == 0
+    r.deleteDecodeEnv()
+
+
+def test_rejects_unsupported(P, oracle):
+    cv2 = pytest.importorskip("cv2")
+    img = oracle.synth(64, 64, 1, 8)
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    eng = P.Engine(64, 64)
+    with pytest.raises(P.B2JError) as ei:
+        eng.decode(prog.ravel())
+    assert ei.value.rc == -5
+    with pytest.raises(P.B2JError):
+        eng.decode(np.zeros(1000, np.uint8))
+    eng.close()
+
+
+def test_slab_8320x2000(P, oracle, golden):
+    img = oracle.synth(8320, 2000, 0, 8)
+    eng = P.Engine(8320, 2000, 95, True, "444")
+    for c in golden["slab"]:
+        jpg = oracle.encode(img, c["css"], c["quality"], c["optimize"])
+        assert sha(jpg) == c["jpeg_sha256"]
+        assert sha(eng.decode(jpg)) == c["decoded_sha256"], c
+    eng.close()
