@@ -165,3 +165,20 @@ def test_slab_8320x2000(P, oracle, golden):
         assert sha(jpg) == c["jpeg_sha256"]
         assert sha(eng.decode(jpg)) == c["decoded_sha256"], c
     eng.close()
+
+
+def test_headline_full_image_decode_digest(P, golden, oracle):
+    """8320x40000: encode on the GPU (bytes == cv2.imencode, checked in test_gpu_encode), decode on the GPU, pixels ==
+    cv2.imdecode (decoded-BGR SHA-256 from SURVEY.md App. B) and PSNR == the survey's figure."""
+    h = golden["headline"]
+    W, H = h["image"]["W"], h["image"]["H"]
+    img = np.empty((H, W, 3), np.uint8)
+    for y0 in range(0, H, 2000):
+        img[y0:y0 + 2000] = oracle.synth(W, H, 0, 8, y0=y0, rows=2000)
+    for e in h["encodes"][:2]:
+        eng = P.Engine(W, H, e["quality"], bool(e["optimize"]), e["css"])
+        jpg = eng.encode(img)
+        assert sha(jpg)[:32] == e["jpeg_sha256_128"]
+        rec = eng.decode(jpg)
+        assert sha(rec)[:32] == e["decoded_sha256_128"], e
+        eng.close()
