@@ -1,0 +1,66 @@
+// ImageCompressor.h -- drop-in C++ facade with the reference's public interface
+// (OroChippw/Nvjpeg-ImageCompressor src/ImageCompressorDll/ImageCompressor.h:22-42): same class name, constructor
+// defaults, method names, argument meaning and failure convention (empty result + *run_state = 0). The body
+// (facade/ImageCompressor.cpp) forwards to the extern "C" engine in libb2jpeg.so instead of nvJPEG.
+//
+// Differences a maintainer should know (all additive):
+//   * the sampling factor the reference hard-codes (ImageCompressorImpl.cu:31) is a defaulted 5th constructor argument
+//     (README default 4:2:2) and the stream is baseline sequential, not progressive (ImageCompressorImpl.cu:28)
+//   * CUDA failures never exit(1) (ImageCompressorImpl.cuh:16-34); they produce the documented failure signal
+//   * reconstruct / differenceMap / psnr / secondaryCompress implement the README's feature bullet (README.md:8)
+#ifndef IMAGECOMPRESSOR_H_
+#define IMAGECOMPRESSOR_H_
+
+#include <iostream>
+#include <string>
+#include <vector>
+
+#if defined(B2J_USE_CV_SHIM) || !__has_include(<opencv2/core.hpp>)
+#include "cv_shim.h"
+#else
+#include <opencv2/core.hpp>
+#endif
+
+#if defined(_WIN32)
+#ifdef NVJPEG_COMPRESS_RUNNER_EXPORTS
+#define NVJPEG_COMPRESS_RUNNER_API __declspec(dllexport)
+#else
+#define NVJPEG_COMPRESS_RUNNER_API __declspec(dllimport)
+#endif
+#else
+#define NVJPEG_COMPRESS_RUNNER_API __attribute__((visibility("default")))
+#endif
+
+class NvjpegCompressRunnerImpl;
+
+class NVJPEG_COMPRESS_RUNNER_API NvjpegCompressRunner {
+private:
+    NvjpegCompressRunnerImpl *compressor;
+
+public:
+    // sampling: 444, 422, 440, 420 or 411
+    NvjpegCompressRunner(int width = 8320, int height = 40000, int quality = 95, bool optimize = true, int sampling = 422);
+    ~NvjpegCompressRunner();
+
+    NvjpegCompressRunner(const NvjpegCompressRunner &) = delete;
+    NvjpegCompressRunner &operator=(const NvjpegCompressRunner &) = delete;
+
+    std::vector<unsigned char> compress(cv::Mat image, int *run_state);
+    cv::Mat decode(std::string image_path, int *run_state);
+    void save(std::string save_path, std::vector<unsigned char> obuffer);
+
+    void buildCompressEnv();
+    void buildDecodeEnv();
+    void deleteCompressEnv();
+    void deleteDecodeEnv();
+
+    // README.md:8 -- reconstruction, difference map, secondary compression, PSNR
+    cv::Mat reconstruct(const std::vector<unsigned char> &obuffer, int *run_state);
+    cv::Mat differenceMap(cv::Mat a, cv::Mat b, bool offset128, int *run_state);
+    double psnr(cv::Mat a, cv::Mat b, int *run_state);
+    // returns the JPEG of `image`; diff_jpeg receives the JPEG of the difference map (orig vs reconstruction)
+    std::vector<unsigned char> secondaryCompress(cv::Mat image, std::vector<unsigned char> *diff_jpeg, cv::Mat *reconstruction,
+                                                 double *psnr_db, bool offset128, int *run_state);
+};
+
+#endif  // IMAGECOMPRESSOR_H_

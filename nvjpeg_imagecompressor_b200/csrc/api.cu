@@ -424,30 +424,35 @@ int b2j_peek(const uint8_t *jpg, size_t len, int *width, int *height, int *css) 
     return B2J_OK;
 }
 
+static int decode_parsed(b2j_ctx *ctx, const uint8_t *jpg, size_t len, const JpegInfo &info, uint8_t *d_bgr, size_t step) {
+    if (step < (size_t)info.W * 3) return B2J_EINVAL;
+    int rc = dec_ensure(ctx); if (rc) return rc;
+    Geom g; rc = make_geom(info.W, info.H, info.css, &g); if (rc) return rc;
+    return dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches);
+}
+
+static int parse_for(b2j_ctx *ctx, const uint8_t *jpg, size_t len, JpegInfo *info, int *width, int *height) {
+    int rc = parse_jpeg(jpg, len, info);
+    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "unsupported or corrupt JPEG (parse rc=%d)", rc); return B2J_EFORMAT; }
+    if (width) *width = info->W;
+    if (height) *height = info->H;
+    return B2J_OK;
+}
+
 int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_bgr, size_t step, int *width, int *height) {
     if (!ctx || !jpg) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
     JpegInfo info;
-    int rc = parse_jpeg(jpg, len, &info);
-    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "unsupported or corrupt JPEG (parse rc=%d)", rc); return B2J_EFORMAT; }
-    if (width) *width = info.W;
-    if (height) *height = info.H;
+    int rc = parse_for(ctx, jpg, len, &info, width, height); if (rc) return rc;
     if (!d_bgr) return B2J_OK;
-    if (step < (size_t)info.W * 3) return B2J_EINVAL;
-    rc = dec_ensure(ctx); if (rc) return rc;
-    Geom g; rc = make_geom(info.W, info.H, info.css, &g); if (rc) return rc;
-    rc = dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches);
-    return rc;
+    return decode_parsed(ctx, jpg, len, info, d_bgr, step);
 }
 
 int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *width, int *height) {
     if (!ctx || !jpg) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
     JpegInfo info;
-    int rc = parse_jpeg(jpg, len, &info);
-    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "unsupported or corrupt JPEG (parse rc=%d)", rc); return B2J_EFORMAT; }
-    if (width) *width = info.W;
-    if (height) *height = info.H;
+    int rc = parse_for(ctx, jpg, len, &info, width, height); if (rc) return rc;
     if (!bgr) return B2J_OK;
     if (step < (size_t)info.W * 3) return B2J_EINVAL;
     const size_t dstep = ((size_t)info.W * 3 + 15) & ~(size_t)15;
@@ -456,7 +461,7 @@ int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_
         CK(cudaMalloc(&ctx->d_recon, dstep * info.H));
         ctx->d_recon_bytes = dstep * info.H;
     }
-    rc = b2j_decode_device(ctx, jpg, len, ctx->d_recon, dstep, nullptr, nullptr);
+    rc = decode_parsed(ctx, jpg, len, info, ctx->d_recon, dstep);
     if (rc) return rc;
     CK(cudaMemcpy2DAsync(bgr, step, ctx->d_recon, dstep, (size_t)info.W * 3, info.H, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -90,18 +90,23 @@ int parse_jpeg(const uint8_t *jpg, size_t len, JpegInfo *info) {
             memcpy(info->bits[2], hb[0][td[1]], 17); memcpy(info->vals[2], hv[0][td[1]], 256);
             memcpy(info->bits[3], hb[1][ta[1]], 17); memcpy(info->vals[3], hv[1][ta[1]], 256);
             info->scan_offset = p + L;
-            // the entropy-coded segment ends at the first marker that is neither a stuffed zero nor RSTn
+            // the entropy-coded segment ends at the first marker that is neither a stuffed zero nor RSTn. Fast path for
+            // the files this engine and libjpeg write (one scan, EOI as the last two bytes): no 0xFF search at all.
             size_t e = info->scan_offset;
-            const uint8_t *f;
-            while (e < len && (f = (const uint8_t *)memchr(jpg + e, 0xFF, len - e)) != nullptr) {
-                e = (size_t)(f - jpg);
-                if (e + 1 >= len) { e = len; break; }
-                const uint8_t nx = jpg[e + 1];
-                if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7)) { e += 2; continue; }
-                if (nx == 0xFF) { e += 1; continue; }
-                break;
+            if (len >= e + 2 && jpg[len - 2] == 0xFF && jpg[len - 1] == 0xD9) {
+                e = len - 2;
+            } else {
+                const uint8_t *f = nullptr;
+                while (e < len && (f = (const uint8_t *)memchr(jpg + e, 0xFF, len - e)) != nullptr) {
+                    e = (size_t)(f - jpg);
+                    if (e + 1 >= len) { e = len; break; }
+                    const uint8_t nx = jpg[e + 1];
+                    if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7)) { e += 2; continue; }
+                    if (nx == 0xFF) { e += 1; continue; }
+                    break;
+                }
+                if (e > len || f == nullptr) e = len;
             }
-            if (e > len || f == nullptr) e = len;
             info->scan_len = e - info->scan_offset;
             return B2J_OK;
         }

@@ -1,0 +1,63 @@
+"""The staged strip C-ABI on a real GPU: N strips of one image encoded by N contexts on ONE device (the collectives
+replaced by explicit copies, as B200_PROFILING.md recommends when there are fewer GPUs than ranks); the stitched
+stream must equal the single-context stream and the oracle. The torch.distributed plumbing itself is covered by
+tests/test_strips_gloo.py (CPU) and exercised on real GPUs by `bench.py --gpus N`."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def encode_strips_one_gpu(img, css, q, opt, nstrips):
+    from nvjpeg_imagecompressor_b200.strips import EngineBackend, seam_params, strip_rows
+    H, W = img.shape[:2]
+    d = torch.from_numpy(img).cuda()
+    rows = strip_rows(H, css, nstrips)
+    bs = [EngineBackend(W, max(b - a for a, b in rows), q, bool(opt), css, 0) for _ in rows]
+    for b, (y0, y1) in zip(bs, rows):
+        b.phase1(d[y0:y1].data_ptr(), W * 3, W, y1 - y0)
+    torch.cuda.synchronize()
+    for k, b in enumerate(bs):
+        if k:
+            b.pred_in.copy_(bs[k - 1].last_dc)
+        else:
+            b.pred_in.zero_()
+    torch.cuda.synchronize()
+    for b in bs:
+        b.phase1b()
+    torch.cuda.synchronize()
+    if opt:
+        tot = torch.stack([b.hist for b in bs]).sum(0).to(torch.int32)
+        for b in bs:
+            b.hist.copy_(tot)
+    torch.cuda.synchronize()
+    for b in bs:
+        b.phase2(W, H)
+    torch.cuda.synchronize()
+    sb = np.stack([b.strip_bits.cpu().numpy() for b in bs])
+    sp = seam_params(sb[:, 0], sb[:, 1].astype(np.uint64) & 0xFFFFFFFF)
+    for k, b in enumerate(bs):
+        b.phase3(sp[k][0], sp[k][1], (1 if k == 0 else 0) | (2 if k == nstrips - 1 else 0))
+    torch.cuda.synchronize()
+    parts = [b.out_view(int(b.out_len.item())).cpu().numpy() for b in bs]
+    for b in bs:
+        b.eng.close()
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("W,H,css,q,opt,n", [(256, 320, 1, 95, 1, 2), (256, 320, 1, 95, 1, 8), (200, 333, 3, 90, 1, 4),
+                                           (129, 200, 0, 75, 0, 3), (96, 250, 2, 95, 1, 5), (160, 64, 4, 100, 1, 8)])
+def test_strips_equal_single_stream(oracle, W, H, css, q, opt, n):
+    img = oracle.synth(W, H, 7, 8)
+    out = encode_strips_one_gpu(img, css, q, opt, n)
+    want = oracle.encode(img, css, q, opt)
+    assert out.size == want.size and np.array_equal(out, want)
+
+
+def test_strips_headline_slab(oracle, golden):
+    import hashlib
+    img = oracle.synth(8320, 2000, 0, 8)
+    c = golden["slab"][0]
+    out = encode_strips_one_gpu(img, c["css"], c["quality"], c["optimize"], 8)
+    assert out.size == c["jpeg_len"] and hashlib.sha256(out.tobytes()).hexdigest() == c["jpeg_sha256"]
