@@ -46,6 +46,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.t_lo, self.t_hi = 0.0, float("inf")
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -54,7 +55,7 @@ class ClockSampler(threading.Thread):
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
                 if self.stop_flag:
                     break
         except Exception:
@@ -71,15 +72,17 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
+                mx = max(mx, float(r[2]))
+                if not (self.t_lo <= r[0] <= self.t_hi):
+                    continue
+                sm.append(float(r[1]))
                 for i, n in enumerate(names):
-                    if r[3 + i].lower().startswith("active"):
+                    if r[4 + i].lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "timed device-resident steps + timed end-to-end steps (GPU busy throughout)"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -106,7 +109,7 @@ def _cv_worker_shared(args):
     return _cv_worker((_SHARED["img"], y0, y1, css, q, opt, reps))
 
 
-def cpu_baseline(sample_rows=8000, reps=1):
+def cpu_baseline(sample_rows=8000, reps=10):
     """libjpeg-turbo 3.1.2 (cv2.imencode, the north-star's bit-exactness oracle) on all host cores: the first
     `sample_rows` rows of the workload cut into one MCU-row-aligned strip per core, one process per core."""
     import multiprocessing as mp
@@ -243,12 +246,14 @@ def run_b200(args, rank, world, local_rank):
             enc.encode_strip(img.data_ptr(), W * 3)
             return 0
 
+    if sampler:
+        sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             nbytes = step()
         barrier()
         if sampler:
-            sampler.start()
+            sampler.t_lo = time.time()
         launches0 = eng.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -271,12 +276,11 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(lt)
             launches = int(lt.item())
     ms = ms_total / args.steps
-    clocks = sampler.finish() if sampler else None
 
     # ---- end to end through the C-ABI with pinned host buffers (N=1: b2j_encode; N>1: per-rank upload + strip encode
     #      + per-rank download of its strip's bytes)
     e2e = None
-    k2 = max(2, min(args.steps, 5))
+    k2 = max(3, min(args.steps, 10))
     h_img = torch.empty((nrows, W, 3), dtype=torch.uint8, pin_memory=True)
     h_img.copy_(img)
     h_out = torch.empty(int(nbytes) + (1 << 20), dtype=torch.uint8, pin_memory=True)
@@ -308,6 +312,9 @@ def run_b200(args, rank, world, local_rank):
            "h2d_bytes_per_step": W * H * 3, "d2h_bytes_per_step": int(nbytes),
            "api": "b2j_encode (host BGR -> host JPEG), pinned buffers" if world == 1 else
                   "per rank: pinned H2D of its strip + b2j_strip_phase1..3 + pinned D2H of its bytes"}
+    if sampler:
+        sampler.t_hi = time.time()
+    clocks = sampler.finish() if sampler else None
     if rank != 0:
         return None
 
