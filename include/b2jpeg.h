@@ -149,6 +149,9 @@ B2J_API int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flag
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
 enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4 };
 B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len);
+/* flags bit0 (B2J_DEBUG_COEF): the next encodes also store the quantised coefficients for B2J_DBG_COEF */
+enum { B2J_DEBUG_COEF = 1 };
+B2J_API int b2j_set_debug(b2j_ctx *ctx, int flags);
 
 /* per-stage device times (ms) of the last encode/decode, measured with CUDA events on the context stream */
 typedef struct b2j_timings {

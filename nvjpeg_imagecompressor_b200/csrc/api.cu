@@ -22,6 +22,8 @@ struct Ctrl {  // zeroed before every encode with one memset
     uint32_t hist[4 * 257];
     uint32_t ticket;
     uint32_t err;
+    uint32_t pool_count;
+    uint32_t pad0;
     uint64_t out_len;
     uint64_t strip_bits[2];
     uint64_t ssd;
@@ -49,7 +51,12 @@ struct b2j_ctx {
     bool enc_ready;
     uint8_t *d_img;
     size_t d_img_bytes;
-    int16_t *d_coef;
+    int16_t *d_coef;      // only with B2J_DEBUG_COEF
+    uint32_t *d_pool;     // token pool, 64 tokens per block worst case
+    TileRec *d_recs;
+    int tiles_cap;
+    size_t slot_words_cap;
+    int debug;
     uint32_t *d_slots, *d_tile_bits;
     uint64_t *d_tile_off, *d_desc;
     size_t ndesc;
@@ -99,7 +106,6 @@ static int make_geom(int W, int H, int css, Geom *g) {
     const long long nb = (long long)g->mcux * g->mcuy * g->bpm;
     if (nb > 0x7fffffffLL / 64) return B2J_EINVAL;
     g->nblocks = (int)nb;
-    g->ntiles = (g->nblocks + PACK_BLOCKS - 1) / PACK_BLOCKS;
     // fdct tiles: as even as possible, an even MCU count per tile (16-byte alignment of the bulk copies)
     const int tmax = fdct_tm_max(g->hs, g->vs);
     g->tiles_x = (g->mcux + tmax - 1) / tmax;
@@ -108,6 +114,7 @@ static int make_geom(int W, int H, int css, Geom *g) {
     if (tm > tmax) tm = tmax;
     g->tm = tm;
     g->tiles_x = (g->mcux + tm - 1) / tm;
+    g->ntiles = g->tiles_x * g->mcuy;
     return B2J_OK;
 }
 
@@ -144,13 +151,24 @@ const char *b2j_version(void) { return "b2jpeg 0.1 (sm_100a)"; }
 
 const char *b2j_last_error(const b2j_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 
+static int ensure_tiles(b2j_ctx *ctx, const Geom &g) {
+    if (g.ntiles <= ctx->tiles_cap) return B2J_OK;
+    cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits); cudaFree(ctx->d_tile_off); cudaFree(ctx->d_recs);
+    ctx->d_slots = nullptr; ctx->d_tile_bits = nullptr; ctx->d_tile_off = nullptr; ctx->d_recs = nullptr; ctx->tiles_cap = 0;
+    const int n = g.ntiles + g.ntiles / 8 + 16;
+    CK(cudaMalloc(&ctx->d_slots, (size_t)n * SLOT_WORDS * 4));
+    CK(cudaMalloc(&ctx->d_tile_bits, (size_t)(n + 1) * 4));
+    CK(cudaMalloc(&ctx->d_tile_off, (size_t)(n + 2) * 8));
+    CK(cudaMalloc(&ctx->d_recs, (size_t)(n + 1) * sizeof(TileRec)));
+    ctx->tiles_cap = n;
+    return B2J_OK;
+}
+
 static int enc_alloc(b2j_ctx *ctx) {
     if (ctx->enc_ready) return B2J_OK;
     const Geom &g = ctx->cap_g;
-    CK(cudaMalloc(&ctx->d_coef, (size_t)g.nblocks * 128));
-    CK(cudaMalloc(&ctx->d_slots, (size_t)g.ntiles * SLOT_WORDS * 4));
-    CK(cudaMalloc(&ctx->d_tile_bits, (size_t)(g.ntiles + 1) * 4));
-    CK(cudaMalloc(&ctx->d_tile_off, (size_t)(g.ntiles + 2) * 8));
+    CK(cudaMalloc(&ctx->d_pool, (size_t)g.nblocks * 64 * 4));
+    int rc = ensure_tiles(ctx, g); if (rc) return rc;
     ctx->out_cap = (size_t)g.nblocks * 208 + 4096;
     CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
     ctx->ndesc = ctx->out_cap / STUFF_CHUNK + 4;
@@ -162,6 +180,11 @@ static int enc_alloc(b2j_ctx *ctx) {
     CK(cudaMalloc(&ctx->d_quant, sizeof(QuantDev)));
     CK(cudaMemcpy(ctx->d_quant, &ctx->hq, sizeof(QuantDev), cudaMemcpyHostToDevice));
     ctx->enc_ready = true;
+    return B2J_OK;
+}
+
+static int ensure_debug(b2j_ctx *ctx) {
+    if ((ctx->debug & 1) && !ctx->d_coef) CK(cudaMalloc(&ctx->d_coef, (size_t)ctx->cap_g.nblocks * 128));
     return B2J_OK;
 }
 
@@ -199,7 +222,7 @@ void b2j_destroy(b2j_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->second) b2j_destroy(ctx->second);
     if (ctx->dec) dec_destroy(ctx->dec);
-    cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
+    cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_pool); cudaFree(ctx->d_recs); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
     cudaFree(ctx->d_tile_off); cudaFree(ctx->d_desc); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_pred_in);
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
     if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
@@ -218,6 +241,7 @@ int b2j_set_stream(b2j_ctx *ctx, void *s) {
 
 size_t b2j_encode_bound(const b2j_ctx *ctx) { return ctx ? (size_t)ctx->cap_g.nblocks * 208 + 4096 : 0; }
 uint64_t b2j_launch_count(const b2j_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int b2j_set_debug(b2j_ctx *ctx, int flags) { if (!ctx) return B2J_EINVAL; ctx->debug = flags; return B2J_OK; }
 int b2j_enable_timing(b2j_ctx *ctx, int on) { if (!ctx) return B2J_EINVAL; ctx->timing = on != 0; return B2J_OK; }
 
 void *b2j_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
@@ -230,7 +254,8 @@ static int set_strip_geom(b2j_ctx *ctx, int width, int rows) {
     if (rc) return rc;
     if (g.nblocks > ctx->cap_g.nblocks) { snprintf(ctx->err, sizeof(ctx->err), "image %dx%d exceeds the context's %dx%d", width, rows, ctx->p.width, ctx->p.height); return B2J_ESIZE; }
     ctx->g = g;
-    return B2J_OK;
+    rc = ensure_tiles(ctx, g); if (rc) return rc;
+    return ensure_debug(ctx);
 }
 
 static int enc_reset(b2j_ctx *ctx) {
@@ -249,8 +274,8 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
     rc = set_strip_geom(ctx, width, rows); if (rc) return rc;
     rc = enc_reset(ctx); if (rc) return rc;
     tick(ctx, 1);
-    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_coef, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, ctx->stream));
-    CK(launch_dc_edge_hist(ctx->d_coef, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, 0, ctx->stream));
+    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, 0, ctx->stream));
     ctx->launches += 2;
     tick(ctx, 2);
     return B2J_OK;
@@ -258,7 +283,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
 
 int b2j_strip_phase1b(b2j_ctx *ctx) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
-    CK(launch_dc_edge_hist(ctx->d_coef, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, ctx->p.optimize, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, ctx->p.optimize, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 3);
     return B2J_OK;
@@ -269,7 +294,7 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
     CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, ctx->stream));
     tick(ctx, 4);
-    CK(launch_pack(ctx->d_coef, ctx->g, ctx->d_huff, ctx->d_pred_in, ctx->d_slots, ctx->d_tile_bits, ctx->stream));
+    CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_pred_in, ctx->d_slots, ctx->d_tile_bits, ctx->stream));
     tick(ctx, 5);
     CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->stream));
     ctx->launches += 3;
@@ -318,7 +343,7 @@ int b2j_encode_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width
     tick(ctx, 0);
     rc = enc_reset(ctx); if (rc) return rc;
     tick(ctx, 1);
-    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_coef, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, ctx->stream));
+    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 2);
     rc = enc_tail(ctx, width, height); if (rc) return rc;
@@ -390,7 +415,7 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
                              cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->ev_copy[gi], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[gi], 0));
-        CK(launch_fdct(ctx->d_img, dstep, g, ctx->d_quant, ctx->d_coef, ctx->d_ctrl->hist, ctx->p.optimize, my0, nr, ctx->stream));
+        CK(launch_fdct(ctx->d_img, dstep, g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, my0, nr, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
         ctx->launches += 1;
     }
     tick(ctx, 2);
@@ -580,7 +605,7 @@ int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len) {
     CK(cudaStreamSynchronize(ctx->stream));
     const void *src = nullptr; size_t n = 0;
     switch (what) {
-    case B2J_DBG_COEF: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_coef; n = (size_t)ctx->g.nblocks * 128; break;
+    case B2J_DBG_COEF: if (!ctx->enc_ready || !ctx->d_coef) return B2J_EINVAL; src = ctx->d_coef; n = (size_t)ctx->g.nblocks * 128; break;
     case B2J_DBG_HIST: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_ctrl->hist; n = 4 * 257 * 4; break;
     case B2J_DBG_TABLES: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_huff; n = sizeof(HuffDev); break;
     case B2J_DBG_TILE_BITS: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_tile_bits; n = (size_t)ctx->g.ntiles * 4; break;

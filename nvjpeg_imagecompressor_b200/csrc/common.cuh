@@ -17,10 +17,20 @@ struct Geom {
     int tm;            // MCUs per fdct tile (even)
     int tiles_x;       // fdct tiles per MCU row
     int nblocks;       // mcux*mcuy*bpm, scan order
-    int ntiles;        // pack tiles = ceil(nblocks / PACK_BLOCKS)
+    int ntiles;        // fdct/pack tiles = tiles_x * mcuy
 };
 
-constexpr int PACK_BLOCKS = 256;               // blocks (= threads) per pack tile
+// One token per Huffman symbol: [25:24] table (0 DC0, 1 AC0, 2 DC1, 3 AC1), [23:16] symbol (run<<4 | size),
+// [15:0] value bits (already masked to `size` bits). TOK_RAWDC: DC of a block whose predecessor lives in the
+// previous tile; [17:16] = component, [15:0] = the quantised DC itself (the entropy coder forms the difference).
+constexpr uint32_t TOK_RAWDC = 1u << 26;
+struct TileRec {                               // one per fdct tile (<= 256 blocks, one MCU-row segment)
+    uint32_t base, count;                      // token run in the pool
+    int16_t first_dc[3], last_dc[3];           // DCs of the tile's first / last MCU (last Y block, Cb, Cr)
+    uint32_t pad;
+};
+
+constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)
 constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
 constexpr int STUFF_THREADS = 256;
 constexpr int STUFF_CHUNK = STUFF_THREADS * 16; // unstuffed bytes per stuff chunk

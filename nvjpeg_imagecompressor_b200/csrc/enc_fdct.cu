@@ -1,5 +1,5 @@
-// enc_fdct.cu -- K1: BGR -> YCbCr -> chroma downsample -> islow FDCT -> quantise -> zig-zag int16 coefficients
-// in scan order, with the AC / in-tile DC symbol histograms fused in (optimized-Huffman pass 1).
+// enc_fdct.cu -- K1: BGR -> YCbCr -> chroma downsample -> islow FDCT -> quantise -> run-length TOKENS in scan order,
+// with the symbol histograms (optimized-Huffman pass 1) taken from the compacted tokens.
 //
 // Replaces the first half of nvjpegEncodeImage (reference call site ImageCompressorImpl.cu:280; nvJPEG kernels
 // format_to_ycbcr_kernel / subsample_chroma_kernel / forwardDct32x8Kernel). Arithmetic follows
@@ -10,8 +10,12 @@
 //   TMA bulk copies (cp.async.bulk, one per pixel row) stage the raw BGR rows in shared memory   [interior tiles]
 //   stage A: every thread converts 8 pixels x VS rows -> Y / Cb / Cr sample planes in shared memory
 //   stage B: one thread per 8x8 block: 64 samples in registers, both FDCT passes, reciprocal quantisation,
-//            zig-zag, symbol statistics, 8 x STS.128 into a 16-byte-chunk-swizzled staging area
-//   copy-out: coalesced 16-byte stores of the tile's blocks (contiguous in scan order)
+//            zig-zag, and the jchuff.c run-length walk emitting one 32-bit token per Huffman symbol
+//            (table | run/size symbol | value bits) into a per-thread list in shared memory
+//   stage C: per warp, the 32 lists are transposed into one compact block-ordered token run with full-warp
+//            coalesced stores (head-flag bitmap + popcount ranks), counting symbols with full-warp shared atomics
+// The entropy coder (enc_huff.cu k_pack) then works token-parallel: uniform work per lane instead of a divergent
+// per-coefficient branch. With DUMP the quantised coefficients are also written (parity tests only).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,19 +30,26 @@ struct K1 {
     static constexpr int TILE_PX = TM_MAX * MCU_W;
     static constexpr int RAW_STRIDE = TILE_PX * 3;  // multiple of 16 for all five modes
     static constexpr int RAW_BYTES = RAW_STRIDE * MCU_H;
-    static constexpr int STAGE_BYTES = 256 * 128;
+    static constexpr int TOK_STRIDE = 257;                 // tokens of one thread: tok[j * 257 + tid] (bank = j + tid)
+    static constexpr int TOK_BYTES = 64 * TOK_STRIDE * 4;   // <= 64 tokens per block
+    static constexpr int STAGE_BYTES = 256 * 128;           // DUMP only
     static constexpr int Y_STRIDE = TILE_PX;
     static constexpr int Y_BYTES = Y_STRIDE * MCU_H;
     static constexpr int C_STRIDE = TM_MAX * 8;
     static constexpr int C_BYTES = C_STRIDE * 8;
-    static constexpr int OFF_Y = STAGE_BYTES;  // raw aliases the staging area
+    static constexpr int OFF_Y = TOK_BYTES;  // raw aliases the token area
     static constexpr int OFF_CB = OFF_Y + Y_BYTES;
     static constexpr int OFF_CR = OFF_CB + C_BYTES;
     static constexpr int OFF_Q = OFF_CR + C_BYTES;       // uint2[2][64]
     static constexpr int OFF_HIST = OFF_Q + 1024;        // uint32[4][256]
-    static constexpr int OFF_BAR = OFF_HIST + 4096;      // mbarrier
-    static constexpr int SMEM = OFF_BAR + 16;
-    static_assert(RAW_BYTES <= STAGE_BYTES, "raw tile must fit in the staging area");
+    static constexpr int OFF_DC = OFF_HIST + 4096;       // int16[256]
+    static constexpr int OFF_BM = OFF_DC + 512;          // per warp: head bitmap[64], word ranks[64], offsets[32]
+    static constexpr int OFF_MISC = OFF_BM + 8 * 160 * 4;  // warp totals[8], pool base
+    static constexpr int OFF_BAR = OFF_MISC + 64;        // mbarrier
+    static constexpr int OFF_STAGE = OFF_BAR + 16;       // DUMP only
+    static constexpr int SMEM = OFF_STAGE;
+    static constexpr int SMEM_DUMP = OFF_STAGE + STAGE_BYTES;
+    static_assert(RAW_BYTES <= TOK_BYTES, "raw tile must fit in the token area");
     static_assert(RAW_STRIDE % 16 == 0, "row stride must allow 16-byte bulk copies");
 };
 
@@ -98,20 +109,24 @@ __device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &c
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : v); }
 
-template <int HS, int VS>
+template <int HS, int VS, bool DUMP>
 __global__ void __launch_bounds__(256, 2)
 k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__restrict__ qd,
-       int16_t *__restrict__ coef, uint32_t *__restrict__ ghist, int do_hist, int bulk_ok, int my0) {
+       uint32_t *__restrict__ pool, uint32_t *__restrict__ pool_count, TileRec *__restrict__ recs,
+       uint32_t *__restrict__ ghist, int do_hist, int bulk_ok, int my0, int16_t *__restrict__ coef) {
     using C = K1<HS, VS>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *raw = smem;
-    uint4 *stage = reinterpret_cast<uint4 *>(smem);
+    uint32_t *tok = reinterpret_cast<uint32_t *>(smem);
     uint8_t *Yp = smem + C::OFF_Y, *Cbp = smem + C::OFF_CB, *Crp = smem + C::OFF_CR;
     uint2 *qs = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
     uint32_t *hs = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
+    int16_t *dcs = reinterpret_cast<int16_t *>(smem + C::OFF_DC);
+    uint32_t *misc = reinterpret_cast<uint32_t *>(smem + C::OFF_MISC);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    uint4 *stage = reinterpret_cast<uint4 *>(smem + C::OFF_STAGE);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int my = blockIdx.y + my0;
     const int mx0 = blockIdx.x * g.tm;
     const int nmcu = min(g.tm, g.mcux - mx0);
@@ -119,6 +134,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     const int x0 = mx0 * C::MCU_W, y0 = my * C::MCU_H;
     const int tile_px = nmcu * C::MCU_W;
     const bool interior = (x0 + tile_px <= g.W) && (y0 + C::MCU_H <= g.H);
+    const int tile = my * g.tiles_x + blockIdx.x;
 
     // quantisation constants + histogram init
     if (tid < 128) qs[tid] = make_uint2(qd->recip[tid >> 6][tid & 63], qd->half[tid >> 6][tid & 63]);
@@ -145,10 +161,10 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
                 for (int i = tid; i < (int)row_bytes; i += 256) raw[r * C::RAW_STRIDE + i] = src[(size_t)r * step + i];
             __syncthreads();
         }
-        // ---- stage A (fast): 8 pixels x VS rows per item
+        // ---- stage A (fast): one warp per row group (VS pixel rows), 8 pixels per lane and step
         const int ngx = nmcu * HS;
-        for (int it = tid; it < ngx * 8; it += 256) {
-            const int rg = it / ngx, gx = it - rg * ngx;
+        const int rg = wid;
+        for (int gx = lane; gx < ngx; gx += 32) {
             int cbv[VS][8], crv[VS][8];
 #pragma unroll
             for (int v = 0; v < VS; v++) {
@@ -240,7 +256,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             Crp[rd * C::C_STRIDE + j] = (uint8_t)ocr;
         }
     }
-    __syncthreads();  // planes complete; raw is dead, staging may be written
+    __syncthreads();  // planes complete; raw is dead, the token area may be written
 
     // ---- stage B: one thread per block
     const int blk = tid;
@@ -249,8 +265,11 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     const bool isY = bn < C::HV;
     const int by = isY ? bn / HS : 0, bx = isY ? bn - by * HS : 0;
     const int tbl = isY ? 0 : 1;
+    const int comp = isY ? 0 : bn - C::HV + 1;
     bool real = true;
     if (isY) real = ((mx0 + m) * HS + bx < g.wib[0]) && (my * VS + by < g.hib[0]);
+    int ntok = 0;
+    int mydc = 0;
     if (active) {
         const uint8_t *src;
         int stride;
@@ -274,11 +293,13 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             fdct8<true>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
         v[0] -= 8192;  // 64 samples x 128: the only output the -128 level shift changes (exact: multiple of 4)
 
-        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply
-        uint32_t pk[32];
-        int run = 0;
-        uint32_t *hac = hs + (tbl * 2 + 1) * 256;
+        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply;
+        // walk the zig-zag sequence exactly like jchuff.c encode_one_block, one token per Huffman symbol
+        uint32_t pk[DUMP ? 32 : 1];
+        int run = 0, j = 1;  // slot 0 is the DC token
+        const uint32_t acsel = (uint32_t)(tbl * 2 + 1) << 24;
         const uint2 *qt = qs + tbl * 64;
+        uint32_t *mytok = tok + tid;
 #pragma unroll
         for (int k = 0; k < 64; k++) {
             const int n = zigzag_nat(k);
@@ -287,53 +308,132 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             const int s = x >> 31;
             const uint32_t a = (uint32_t)((x ^ s) - s) + rq.y;
             const int qa = (int)__umulhi(a, rq.x);
-            const int z = (qa ^ s) - s;
-            if (k & 1) pk[k >> 1] |= (uint32_t)z << 16;
-            else pk[k >> 1] = (uint32_t)z & 0xFFFFu;
-            if (do_hist && real && k > 0) {  // jchuff.c htest_one_block, AC part
+            int z = (qa ^ s) - s;
+            if (k == 0) mydc = z;
+            if (C::HV > 1 && !real && k > 0) z = 0;
+            if constexpr (DUMP) {
+                if (k & 1) pk[k >> 1] |= (uint32_t)z << 16;
+                else pk[k >> 1] = (uint32_t)z & 0xFFFFu;
+            }
+            if (k > 0) {
                 if (z != 0) {
-                    if (run > 15) { atomicAdd(&hac[0xF0], (uint32_t)(run >> 4)); run &= 15; }
-                    atomicAdd(&hac[(run << 4) + (32 - __clz(qa))], 1u);
+                    while (run > 15) { mytok[j * C::TOK_STRIDE] = acsel | (0xF0u << 16); j++; run -= 16; }
+                    const int nb = 32 - __clz(z < 0 ? -z : z);
+                    const uint32_t vb = (uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u);
+                    mytok[j * C::TOK_STRIDE] = acsel | ((uint32_t)((run << 4) + nb) << 16) | vb;
+                    j++;
                     run = 0;
                 } else run++;
             }
         }
-        if (do_hist && real && run > 0) atomicAdd(&hac[0], 1u);
+        if (run > 0) { mytok[j * C::TOK_STRIDE] = acsel; j++; }  // EOB
+        ntok = j;
+        if constexpr (DUMP) {
 #pragma unroll
-        for (int c = 0; c < 8; c++)
-            stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            for (int c = 0; c < 8; c++)
+                stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        if (real) dcs[blk] = (int16_t)mydc;
     }
     __syncthreads();
 
     // ---- dummy blocks (jccoefct.c compress_data): zero AC, DC of the last real block before them in the MCU
-    if (active && !real) {
-        const int nrx = min(HS, g.wib[0] - (mx0 + m) * HS), nry = min(VS, g.hib[0] - my * VS);
-        const int sby = min(by, nry - 1);
-        const int sblk = m * C::BPM + sby * HS + (nrx - 1);
-        const uint32_t dc = stage[sblk * 8 + (0 ^ (sblk & 7))].x & 0xFFFFu;
+    if (C::HV > 1) {
+        if (active && !real) {
+            const int nrx = min(HS, g.wib[0] - (mx0 + m) * HS), nry = min(VS, g.hib[0] - my * VS);
+            const int sby = min(by, nry - 1);
+            const int sblk = m * C::BPM + sby * HS + (nrx - 1);
+            mydc = dcs[sblk];
+        }
+        __syncthreads();
+        if (active && !real) {
+            dcs[blk] = (int16_t)mydc;
+            if constexpr (DUMP) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(c == 0 ? dc : 0u, 0u, 0u, 0u);
-        if (do_hist) atomicAdd(&hs[1 * 256 + 0], 1u);  // one EOB
+                for (int c = 0; c < 8; c++) stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(c == 0 ? ((uint32_t)mydc & 0xFFFFu) : 0u, 0u, 0u, 0u);
+            }
+        }
+        __syncthreads();
     }
-    if (HS * VS > 1) __syncthreads();  // only luma with several blocks per MCU can have dummies
 
-    // ---- DC symbols whose predecessor lies inside this tile (the tile-leading ones: k_dc_edge_hist)
-    if (do_hist && active) {
+    // ---- DC token: difference to the previous block of the same component; predecessors outside the tile are
+    //      resolved by the entropy coder from TileRec.last_dc (token carries the raw DC)
+    if (active) {
         int pb = -1;
         if (isY) pb = bn > 0 ? blk - 1 : (m > 0 ? blk - C::BPM + C::HV - 1 : -1);
         else pb = m > 0 ? blk - C::BPM : -1;
+        uint32_t t0;
         if (pb >= 0) {
-            const int dc = (int)(int16_t)(stage[blk * 8 + (blk & 7)].x & 0xFFFFu);
-            const int pd = (int)(int16_t)(stage[pb * 8 + (pb & 7)].x & 0xFFFFu);
-            atomicAdd(&hs[(tbl * 2) * 256 + nbits_of(dc - pd)], 1u);
+            const int diff = mydc - (int)dcs[pb];
+            const int nb = 32 - __clz(diff < 0 ? -diff : diff);
+            t0 = ((uint32_t)(tbl * 2) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+        } else {
+            t0 = TOK_RAWDC | ((uint32_t)(tbl * 2) << 24) | ((uint32_t)comp << 16) | ((uint32_t)mydc & 0xFFFFu);
+        }
+        tok[tid] = t0;
+    }
+
+    // ---- stage C: per-warp transposition of the 32 token lists into one block-ordered run
+    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + C::OFF_BM) + wid * 160;  // [0,64) heads, [64,128) ranks, [128,160) offsets
+    uint32_t inc = (uint32_t)ntok;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    const uint32_t off = inc - (uint32_t)ntok;
+    const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+    bm[lane] = 0; bm[lane + 32] = 0;
+    bm[128 + lane] = off;
+    if (lane == 31) misc[wid] = wtot;
+    __syncthreads();  // also orders the DC tokens / bitmap zeroing before their use below
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t x = misc[w]; if (w < wid) wbase += x; total += x; }
+    if (tid == 0) {
+        const uint32_t base = atomicAdd(pool_count, total);
+        misc[8] = base;
+        TileRec r;
+        r.base = base; r.count = total; r.pad = 0;
+        r.first_dc[0] = dcs[0]; r.first_dc[1] = dcs[C::HV]; r.first_dc[2] = dcs[C::HV + 1];
+        r.last_dc[0] = dcs[nblk - 3]; r.last_dc[1] = dcs[nblk - 2]; r.last_dc[2] = dcs[nblk - 1];
+        recs[tile] = r;
+    }
+    if (ntok > 0) atomicOr(&bm[off >> 5], 1u << (off & 31));
+    __syncthreads();
+    {
+        const uint32_t c0 = __popc(bm[2 * lane]), c1 = __popc(bm[2 * lane + 1]);
+        uint32_t pc = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, pc, o);
+            if (lane >= o) pc += y;
+        }
+        bm[64 + 2 * lane] = pc - c0 - c1;
+        bm[64 + 2 * lane + 1] = pc - c1;
+    }
+    __syncwarp();
+    uint32_t *dst = pool + (size_t)misc[8] + wbase;
+    const uint32_t *wtok = tok + wid * 32;
+    for (uint32_t i0 = 0; i0 < wtot; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        if (i < wtot) {
+            const uint32_t w = i0 >> 5;
+            const uint32_t heads = bm[w] & (0xffffffffu >> (31 - lane));
+            const uint32_t t = bm[64 + w] + __popc(heads) - 1;   // owning lane (block) of output position i
+            const uint32_t jj = i - bm[128 + t];
+            const uint32_t tk = wtok[jj * C::TOK_STRIDE + t];
+            dst[i] = tk;
+            if (do_hist && !(tk & TOK_RAWDC)) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
         }
     }
 
-    // ---- copy-out: the tile's blocks are contiguous in scan order
-    uint4 *dst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM) * 64);
-    for (int i = tid; i < nblk * 8; i += 256) {
-        const int b = i >> 3, c = i & 7;
-        dst[i] = stage[b * 8 + (c ^ (b & 7))];
+    if constexpr (DUMP) {  // quantised coefficients, scan order (parity tests)
+        uint4 *cdst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM) * 64);
+        for (int i = tid; i < nblk * 8; i += 256) {
+            const int b = i >> 3, c = i & 7;
+            cdst[i] = stage[b * 8 + (c ^ (b & 7))];
+        }
     }
     if (do_hist) {
         __syncthreads();
@@ -346,34 +446,28 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 
 // DC-difference symbols of each fdct tile's first MCU (their predecessor block lives in the previous tile), plus
 // the strip's very first MCU (predecessor = pred_in) and the strip's last DCs for the next strip.
-__global__ void k_dc_edge_hist(const int16_t *__restrict__ coef, Geom g, const int16_t *__restrict__ pred_in,
+__global__ void k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restrict__ pred_in,
                                uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist) {
-    const int hv = g.hs * g.vs;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ntile = g.tiles_x * g.mcuy;
     if (t < ntile * 3 && do_hist) {
         const int tile = t / 3, c = t - tile * 3;
-        const int my = tile / g.tiles_x, tx = tile - my * g.tiles_x;
-        const long long M0 = (long long)my * g.mcux + (long long)tx * g.tm;
-        const int off = c == 0 ? 0 : hv + c - 1;
-        const int poff = c == 0 ? hv - 1 : hv + c - 1;
-        const int dc = coef[(M0 * g.bpm + off) * 64];
-        const int pd = M0 > 0 ? coef[((M0 - 1) * g.bpm + poff) * 64] : pred_in[c];
+        const int dc = recs[tile].first_dc[c];
+        const int pd = tile > 0 ? recs[tile - 1].last_dc[c] : pred_in[c];
         atomicAdd(&ghist[(c ? 2 : 0) * 257 + nbits_of(dc - pd)], 1u);
     }
-    if (t < 3) {
-        const long long ML = (long long)g.mcux * g.mcuy - 1;
-        last_dc[t] = coef[(ML * g.bpm + (t == 0 ? hv - 1 : hv + t - 1)) * 64];
-    }
+    if (t < 3) last_dc[t] = recs[ntile - 1].last_dc[t];
 }
 
-template <int HS, int VS>
-static cudaError_t launch_one(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, int16_t *coef,
-                              uint32_t *hist, int do_hist, int my0, int nrows, cudaStream_t s) {
+template <int HS, int VS, bool DUMP>
+static cudaError_t launch_one2(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, uint32_t *pool,
+                               uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
+                               int16_t *coef, cudaStream_t s) {
     using C = K1<HS, VS>;
+    constexpr int SM = DUMP ? C::SMEM_DUMP : C::SMEM;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_fdct<HS, VS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_fdct<HS, VS, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -384,26 +478,37 @@ static cudaError_t launch_one(const uint8_t *img, size_t step, const Geom &g, co
     const int last_n = g.mcux - (g.tiles_x - 1) * g.tm;
     if ((last_n * C::MCU_W * 3) % 16 != 0 && (long long)g.mcux * C::MCU_W <= g.W) bulk_ok = 0;
     dim3 grid(g.tiles_x, nrows);
-    k_fdct<HS, VS><<<grid, 256, C::SMEM, s>>>(img, step, g, qd, coef, hist, do_hist, bulk_ok, my0);
+    k_fdct<HS, VS, DUMP><<<grid, 256, SM, s>>>(img, step, g, qd, pool, pool_count, recs, hist, do_hist, bulk_ok, my0, coef);
     return cudaGetLastError();
+}
+
+template <int HS, int VS>
+static cudaError_t launch_one(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, uint32_t *pool,
+                              uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
+                              int16_t *coef, cudaStream_t s) {
+    return coef ? launch_one2<HS, VS, true>(img, step, g, qd, pool, pool_count, recs, hist, do_hist, my0, nrows, coef, s)
+                : launch_one2<HS, VS, false>(img, step, g, qd, pool, pool_count, recs, hist, do_hist, my0, nrows, coef, s);
 }
 
 int fdct_tm_max(int hs, int vs) { return (256 / (hs * vs + 2)) & ~1; }
 
-cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, int16_t *coef, uint32_t *hist,
-                        int do_hist, int my0, int nrows, cudaStream_t s) {
-    if (g.hs == 1 && g.vs == 1) return launch_one<1, 1>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
-    if (g.hs == 2 && g.vs == 1) return launch_one<2, 1>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
-    if (g.hs == 1 && g.vs == 2) return launch_one<1, 2>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
-    if (g.hs == 2 && g.vs == 2) return launch_one<2, 2>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
-    if (g.hs == 4 && g.vs == 1) return launch_one<4, 1>(img, step, g, qd, coef, hist, do_hist, my0, nrows, s);
+cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, uint32_t *pool,
+                        uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
+                        int16_t *coef_dump, cudaStream_t s) {
+#define B2J_ARGS img, step, g, qd, pool, pool_count, recs, hist, do_hist, my0, nrows, coef_dump, s
+    if (g.hs == 1 && g.vs == 1) return launch_one<1, 1>(B2J_ARGS);
+    if (g.hs == 2 && g.vs == 1) return launch_one<2, 1>(B2J_ARGS);
+    if (g.hs == 1 && g.vs == 2) return launch_one<1, 2>(B2J_ARGS);
+    if (g.hs == 2 && g.vs == 2) return launch_one<2, 2>(B2J_ARGS);
+    if (g.hs == 4 && g.vs == 1) return launch_one<4, 1>(B2J_ARGS);
+#undef B2J_ARGS
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_dc_edge_hist(const int16_t *coef, const Geom &g, const int16_t *pred_in, uint32_t *hist,
+cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
                                 int16_t *last_dc, int do_hist, cudaStream_t s) {
     const int n = max(3, g.tiles_x * g.mcuy * 3);
-    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(coef, g, pred_in, hist, last_dc, do_hist);
+    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(recs, g, pred_in, hist, last_dc, do_hist);
     return cudaGetLastError();
 }
 

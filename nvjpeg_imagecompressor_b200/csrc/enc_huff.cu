@@ -204,15 +204,14 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_pack: one CTA = 256 consecutive blocks of the scan; one thread per block (jchuff.c encode_one_block).
-//   1. coalesced 16-byte loads stage the tile's coefficients in swizzled shared memory
-//   2. each thread pulls its 64 coefficients into 32 registers, fetches its DC predictor
-//   3. length pass (registers only) -> CTA exclusive scan -> bit offset of every block inside the tile
-//   4. emit pass: codes are appended to a 64-bit accumulator and flushed as 32-bit words straight to the block's
-//      final position in the (re-used) shared buffer; only the first/last word of a block is shared with its
-//      neighbours (atomicOr), interior words are plain stores
-//   5. the tile's words are copied to its fixed-size slot in global memory (tile t at t*SLOT_WORDS)
-// Tiles whose bit string exceeds the 32 KB shared window run steps 4-5 once per window.
+// k_pack: token-parallel entropy coding (jchuff.c encode_one_block's emit_bits, without its run-length walk: that
+// happened once, in k_fdct). One CTA = one fdct tile's token run; every thread takes an equal, contiguous share:
+//   1. length pass: sum of (code length + value bits) over the share      (one table lookup per token)
+//   2. CTA exclusive scan -> the share's bit offset inside the tile
+//   3. emit pass: codes are appended to a 64-bit accumulator and flushed as 32-bit words straight to their final
+//      position in a shared bit buffer; only the first/last word of a share is shared with its neighbours (atomicOr)
+//   4. the tile's words are copied to its fixed-size slot in global memory (tile t at t*SLOT_WORDS)
+// Work per lane is uniform (no per-coefficient branch). Tiles whose bit string exceeds the 32 KB window repeat 3-4.
 constexpr int WIN_WORDS = 8192;
 
 struct Emitter {
@@ -244,78 +243,46 @@ struct Emitter {
     }
 };
 
-__global__ void __launch_bounds__(PACK_BLOCKS, 2)
-k_pack(const int16_t *__restrict__ coef, Geom g, const HuffDev *__restrict__ huff, const int16_t *__restrict__ pred_in,
-       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
-    __shared__ __align__(16) uint32_t s_buf[WIN_WORDS];  // coefficients first, bit buffer afterwards
-    __shared__ uint32_t s_enc[4][256];
+// raw-DC tokens (first MCU of a tile): form the difference against the previous tile's last DC
+__device__ __forceinline__ uint32_t resolve_token(uint32_t t, const int16_t *pd) {
+    if (!(t & TOK_RAWDC)) return t;
+    const int comp = (int)((t >> 16) & 3u);
+    const int diff = (int)(int16_t)(t & 0xFFFFu) - (int)pd[comp];
+    const int nb = 32 - __clz(diff < 0 ? -diff : diff);
+    return (t & (3u << 24)) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+}
+
+__global__ void __launch_bounds__(PACK_BLOCKS, 4)
+k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const HuffDev *__restrict__ huff,
+       const int16_t *__restrict__ pred_in, uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
+    __shared__ __align__(16) uint32_t s_buf[WIN_WORDS];
+    __shared__ uint32_t s_enc[1024];
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_total;
+    __shared__ int16_t s_pd[4];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int t = blockIdx.x;
-    const int b0 = t * PACK_BLOCKS;
-    const int nb = min(PACK_BLOCKS, g.nblocks - b0);
-    uint4 *cb = reinterpret_cast<uint4 *>(s_buf);
-
-    for (int i = tid; i < nb * 8; i += PACK_BLOCKS) {
-        const int b = i >> 3, c = i & 7;
-        cb[b * 8 + (c ^ (b & 7))] = ld_nc_v4(reinterpret_cast<const uint4 *>(coef) + (size_t)b0 * 8 + i);
-    }
-    for (int i = tid; i < 1024; i += PACK_BLOCKS) s_enc[i >> 8][i & 255] = huff->enc[i >> 8][i & 255];
+    const TileRec rec = recs[t];
+    const uint32_t ntok = rec.count;
+    const uint32_t *tk = pool + rec.base;
+    for (int i = tid; i < 1024; i += PACK_BLOCKS) s_enc[i] = huff->enc[i >> 8][i & 255];
+    if (tid < 3) s_pd[tid] = t > 0 ? recs[t - 1].last_dc[tid] : pred_in[tid];
     __syncthreads();
-
-    const bool active = tid < nb;
-    const int b = b0 + tid;
-    const int hv = g.bpm - 2;
-    const int bn = b % g.bpm;
-    const int comp = bn < hv ? 0 : bn - hv + 1;
-    const uint32_t *edc = s_enc[comp ? 2 : 0], *eac = s_enc[comp ? 3 : 1];
-    uint32_t c[32];
-    int pred = 0;
-    if (active) {
-#pragma unroll
-        for (int ch = 0; ch < 8; ch++) {
-            const uint4 q = cb[tid * 8 + (ch ^ (tid & 7))];
-            c[4 * ch] = q.x; c[4 * ch + 1] = q.y; c[4 * ch + 2] = q.z; c[4 * ch + 3] = q.w;
-        }
-        const int pb = comp == 0 ? (bn > 0 ? b - 1 : b - g.bpm + hv - 1) : b - g.bpm;
-        if (pb < 0) pred = pred_in[comp];
-        else if (pb >= b0) pred = (int)(int16_t)(s_buf[((pb - b0) * 8 + ((pb - b0) & 7)) * 4] & 0xFFFFu);
-        else pred = coef[(size_t)pb * 64];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; i++) c[i] = 0;
-    }
-    const int dcv = (int)(int16_t)(c[0] & 0xFFFFu);
-    const int diff = dcv - pred;
-    const int dnb = 32 - __clz(diff < 0 ? -diff : diff);
-    const uint32_t zrl = eac[0xF0], eob = eac[0];
+    const uint32_t per = (ntok + PACK_BLOCKS - 1) / PACK_BLOCKS;
+    const uint32_t lo = min(ntok, (uint32_t)tid * per), hi = min(ntok, lo + per);
 
     // ---- length pass
     uint32_t len = 0;
-    if (active) {
-        len = (edc[dnb] & 31u) + dnb;
-        int run = 0;
-#pragma unroll
-        for (int k = 1; k < 64; k++) {
-            const int v = (k & 1) ? ((int)c[k >> 1] >> 16) : (int)(int16_t)(c[k >> 1] & 0xFFFFu);
-            if (v != 0) {
-                if (run > 15) { len += (run >> 4) * (zrl & 31u); run &= 15; }
-                const int n = 32 - __clz(v < 0 ? -v : v);
-                len += (eac[(run << 4) + n] & 31u) + n;
-                run = 0;
-            } else run++;
-        }
-        if (run > 0) len += eob & 31u;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t tkn = resolve_token(__ldg(tk + i), s_pd);
+        len += (s_enc[(tkn >> 16) & 0x3FFu] & 31u) + ((tkn >> 16) & 15u);
     }
-    // ---- CTA exclusive scan
     uint32_t inc = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += y;
     }
-    __syncthreads();  // everyone holds its coefficients in registers: s_buf is free; s_warp writable
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (tid == 0) {
@@ -334,28 +301,15 @@ k_pack(const int16_t *__restrict__ coef, Geom g, const HuffDev *__restrict__ huf
         const int wn = min(WIN_WORDS, nwords - wbase);
         for (int i = tid; i < wn; i += PACK_BLOCKS) s_buf[i] = 0;
         __syncthreads();
-        if (active) {
+        if (lo < hi) {
             Emitter e;
             e.acc = 0; e.cnt = (int)(off & 31u); e.wpos = (int)(off >> 5); e.wbase = wbase; e.first = true; e.buf = s_buf;
-            {   // DC
-                const uint32_t ed = edc[dnb];
-                const uint32_t vb = (uint32_t)(diff + (diff >> 31)) & ((1u << dnb) - 1u);
-                e.put(((ed >> 8) << dnb) | vb, (int)(ed & 31u) + dnb);
+            for (uint32_t i = lo; i < hi; i++) {
+                const uint32_t tkn = resolve_token(__ldg(tk + i), s_pd);
+                const uint32_t en = s_enc[(tkn >> 16) & 0x3FFu];
+                const uint32_t nb = (tkn >> 16) & 15u;
+                e.put(((en >> 8) << nb) | (tkn & 0xFFFFu), (int)((en & 31u) + nb));
             }
-            int run = 0;
-#pragma unroll
-            for (int k = 1; k < 64; k++) {
-                const int v = (k & 1) ? ((int)c[k >> 1] >> 16) : (int)(int16_t)(c[k >> 1] & 0xFFFFu);
-                if (v != 0) {
-                    while (run > 15) { e.put(zrl >> 8, (int)(zrl & 31u)); run -= 16; }
-                    const int n = 32 - __clz(v < 0 ? -v : v);
-                    const uint32_t ea = eac[(run << 4) + n];
-                    const uint32_t vb = (uint32_t)(v + (v >> 31)) & ((1u << n) - 1u);
-                    e.put(((ea >> 8) << n) | vb, (int)(ea & 31u) + n);
-                    run = 0;
-                } else run++;
-            }
-            if (run > 0) e.put(eob >> 8, (int)(eob & 31u));
             e.finish();
         }
         __syncthreads();
@@ -541,9 +495,9 @@ cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, con
     k_tables<<<1, 128, 0, s>>>(hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header);
     return cudaGetLastError();
 }
-cudaError_t launch_pack(const int16_t *coef, const Geom &g, const HuffDev *huff, const int16_t *pred_in, uint32_t *slots,
-                        uint32_t *tile_bits, cudaStream_t s) {
-    k_pack<<<g.ntiles, PACK_BLOCKS, 0, s>>>(coef, g, huff, pred_in, slots, tile_bits);
+cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff, const int16_t *pred_in,
+                        uint32_t *slots, uint32_t *tile_bits, cudaStream_t s) {
+    k_pack<<<g.ntiles, PACK_BLOCKS, 0, s>>>(pool, recs, huff, pred_in, slots, tile_bits);
     return cudaGetLastError();
 }
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,

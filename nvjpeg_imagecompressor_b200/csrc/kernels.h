@@ -6,15 +6,16 @@ namespace b2j {
 
 // encode
 int fdct_tm_max(int hs, int vs);
-// MCU rows [my0, my0+nrows) of the image `img` (img points at pixel row 0)
-cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, int16_t *coef, uint32_t *hist,
-                        int do_hist, int my0, int nrows, cudaStream_t s);
-cudaError_t launch_dc_edge_hist(const int16_t *coef, const Geom &g, const int16_t *pred_in, uint32_t *hist,
+// MCU rows [my0, my0+nrows) of the image `img` (img points at pixel row 0); coef_dump != NULL also writes coefficients
+cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, uint32_t *pool,
+                        uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
+                        int16_t *coef_dump, cudaStream_t s);
+cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
                                 int16_t *last_dc, int do_hist, cudaStream_t s);
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
                           int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s);
-cudaError_t launch_pack(const int16_t *coef, const Geom &g, const HuffDev *huff, const int16_t *pred_in, uint32_t *slots,
-                        uint32_t *tile_bits, cudaStream_t s);
+cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff, const int16_t *pred_in,
+                        uint32_t *slots, uint32_t *tile_bits, cudaStream_t s);
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
                               uint64_t *strip_bits, cudaStream_t s);
 struct StuffArgs {

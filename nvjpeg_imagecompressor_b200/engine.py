@@ -165,6 +165,9 @@ class Engine:
         self._ck(self._L.b2j_debug_read(self._h, what, _ptr(buf), buf.size, C.byref(n)))
         return buf[: n.value].view(dtype)
 
+    def set_debug(self, flags=1):
+        self._ck(self._L.b2j_set_debug(self._h, int(flags)))
+
     def tables(self):
         raw = self.debug_read(N.DBG_TABLES, np.uint8)
         return N.HuffDev.from_buffer_copy(raw.tobytes())

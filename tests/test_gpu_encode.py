@@ -21,6 +21,7 @@ def P():
 def _stage_check(P, O, eng, img, css, q, opt, tag):
     from nvjpeg_imagecompressor_b200 import _native as N
     H, W = img.shape[:2]
+    eng.set_debug(1)
     jpg = eng.encode(img)
     g = O.geometry(W, H, css)
     coef = eng.debug_read(N.DBG_COEF, np.int16).reshape(-1, 64)
