@@ -296,10 +296,10 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply;
         // walk the zig-zag sequence exactly like jchuff.c encode_one_block, one token per Huffman symbol
         uint32_t pk[DUMP ? 32 : 1];
-        int run = 0, j = 1;  // slot 0 is the DC token
+        int lastk = 0;
         const uint32_t acsel = (uint32_t)(tbl * 2 + 1) << 24;
         const uint2 *qt = qs + tbl * 64;
-        uint32_t *mytok = tok + tid;
+        uint32_t *mytok = tok + tid + C::TOK_STRIDE;  // slot 0 is the DC token
 #pragma unroll
         for (int k = 0; k < 64; k++) {
             const int n = zigzag_nat(k);
@@ -315,18 +315,18 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
                 if (k & 1) pk[k >> 1] |= (uint32_t)z << 16;
                 else pk[k >> 1] = (uint32_t)z & 0xFFFFu;
             }
-            if (k > 0) {
-                if (z != 0) {
-                    while (run > 15) { mytok[j * C::TOK_STRIDE] = acsel | (0xF0u << 16); j++; run -= 16; }
-                    const int nb = 32 - __clz(z < 0 ? -z : z);
-                    const uint32_t vb = (uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u);
-                    mytok[j * C::TOK_STRIDE] = acsel | ((uint32_t)((run << 4) + nb) << 16) | vb;
-                    j++;
-                    run = 0;
-                } else run++;
+            if (k > 0 && z != 0) {
+                // divergent region kept minimal: a raw entry (zero run | value); size and value bits are derived in
+                // stage C with full warps
+                int gap = k - 1 - lastk;
+                while (gap > 15) { *mytok = acsel | (0xF0u << 16); mytok += C::TOK_STRIDE; gap -= 16; }
+                *mytok = TOK_RAWAC | ((uint32_t)gap << 16) | ((uint32_t)z & 0xFFFFu);
+                mytok += C::TOK_STRIDE;
+                lastk = k;
             }
         }
-        if (run > 0) { mytok[j * C::TOK_STRIDE] = acsel; j++; }  // EOB
+        if (lastk != 63) { *mytok = acsel; mytok += C::TOK_STRIDE; }  // EOB
+        const int j = (int)((mytok - (tok + tid)) / C::TOK_STRIDE);
         ntok = j;
         if constexpr (DUMP) {
 #pragma unroll
@@ -422,7 +422,13 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             const uint32_t heads = bm[w] & (0xffffffffu >> (31 - lane));
             const uint32_t t = bm[64 + w] + __popc(heads) - 1;   // owning lane (block) of output position i
             const uint32_t jj = i - bm[128 + t];
-            const uint32_t tk = wtok[jj * C::TOK_STRIDE + t];
+            uint32_t tk = wtok[jj * C::TOK_STRIDE + t];
+            if (tk & TOK_RAWAC) {  // (zero run | value) -> (table | run/size symbol | value bits)
+                const int z = (int)(int16_t)(tk & 0xFFFFu);
+                const int nb = 32 - __clz(z < 0 ? -z : z);
+                const uint32_t isy = (uint32_t)((wid * 32 + t) % C::BPM) < (uint32_t)C::HV ? 1u : 3u;
+                tk = (isy << 24) | ((((tk >> 16) & 15u) << 4 | (uint32_t)nb) << 16) | ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
+            }
             dst[i] = tk;
             if (do_hist && !(tk & TOK_RAWDC)) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
         }

@@ -212,7 +212,7 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
 //      position in a shared bit buffer; only the first/last word of a share is shared with its neighbours (atomicOr)
 //   4. the tile's words are copied to its fixed-size slot in global memory (tile t at t*SLOT_WORDS)
 // Work per lane is uniform (no per-coefficient branch). Tiles whose bit string exceeds the 32 KB window repeat 3-4.
-constexpr int WIN_WORDS = 8192;
+constexpr int WIN_WORDS = 2048;   // 64 kbit bit-buffer window (a typical tile is ~30 kbit)
 
 struct Emitter {
     uint64_t acc;
@@ -252,9 +252,12 @@ __device__ __forceinline__ uint32_t resolve_token(uint32_t t, const int16_t *pd)
     return (t & (3u << 24)) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
 }
 
+constexpr int TOK_CAP = 8192;   // tokens staged in shared memory (32 per block); denser tiles read the pool directly
+
 __global__ void __launch_bounds__(PACK_BLOCKS, 4)
 k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const HuffDev *__restrict__ huff,
        const int16_t *__restrict__ pred_in, uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
+    __shared__ __align__(16) uint32_t s_tok[TOK_CAP];
     __shared__ __align__(16) uint32_t s_buf[WIN_WORDS];
     __shared__ uint32_t s_enc[1024];
     __shared__ uint32_t s_warp[8];
@@ -265,16 +268,23 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, cons
     const TileRec rec = recs[t];
     const uint32_t ntok = rec.count;
     const uint32_t *tk = pool + rec.base;
-    for (int i = tid; i < 1024; i += PACK_BLOCKS) s_enc[i] = huff->enc[i >> 8][i & 255];
+    const bool staged = ntok <= TOK_CAP;
     if (tid < 3) s_pd[tid] = t > 0 ? recs[t - 1].last_dc[tid] : pred_in[tid];
+    for (int i = tid; i < 1024; i += PACK_BLOCKS) s_enc[i] = huff->enc[i >> 8][i & 255];
     __syncthreads();
-    const uint32_t per = (ntok + PACK_BLOCKS - 1) / PACK_BLOCKS;
+    if (staged)
+        for (uint32_t i = tid; i < ntok; i += PACK_BLOCKS) s_tok[i] = resolve_token(__ldg(tk + i), s_pd);
+    __syncthreads();
+    // equal contiguous shares; an odd share length keeps the strided shared-memory reads conflict-free
+    uint32_t per = (ntok + PACK_BLOCKS - 1) / PACK_BLOCKS;
+    per |= 1u;
     const uint32_t lo = min(ntok, (uint32_t)tid * per), hi = min(ntok, lo + per);
+    auto TOKEN = [&](uint32_t i) -> uint32_t { return staged ? s_tok[i] : resolve_token(__ldg(tk + i), s_pd); };
 
     // ---- length pass
     uint32_t len = 0;
     for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t tkn = resolve_token(__ldg(tk + i), s_pd);
+        const uint32_t tkn = TOKEN(i);
         len += (s_enc[(tkn >> 16) & 0x3FFu] & 31u) + ((tkn >> 16) & 15u);
     }
     uint32_t inc = len;
@@ -305,7 +315,7 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, cons
             Emitter e;
             e.acc = 0; e.cnt = (int)(off & 31u); e.wpos = (int)(off >> 5); e.wbase = wbase; e.first = true; e.buf = s_buf;
             for (uint32_t i = lo; i < hi; i++) {
-                const uint32_t tkn = resolve_token(__ldg(tk + i), s_pd);
+                const uint32_t tkn = TOKEN(i);
                 const uint32_t en = s_enc[(tkn >> 16) & 0x3FFu];
                 const uint32_t nb = (tkn >> 16) & 15u;
                 e.put(((en >> 8) << nb) | (tkn & 0xFFFFu), (int)((en & 31u) + nb));
