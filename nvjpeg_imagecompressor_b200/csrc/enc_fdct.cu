@@ -296,10 +296,11 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply;
         // walk the zig-zag sequence exactly like jchuff.c encode_one_block, one token per Huffman symbol
         uint32_t pk[DUMP ? 32 : 1];
-        int lastk = 0;
         const uint32_t acsel = (uint32_t)(tbl * 2 + 1) << 24;
         const uint2 *qt = qs + tbl * 64;
-        uint32_t *mytok = tok + tid + C::TOK_STRIDE;  // slot 0 is the DC token
+        const uint32_t sa0 = smem_u32(tok + tid);
+        uint32_t sa = sa0 + C::TOK_STRIDE * 4;  // slot 0 is the DC token
+        int zlast = 0;
 #pragma unroll
         for (int k = 0; k < 64; k++) {
             const int n = zigzag_nat(k);
@@ -311,22 +312,23 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             int z = (qa ^ s) - s;
             if (k == 0) mydc = z;
             if (C::HV > 1 && !real && k > 0) z = 0;
+            if (k == 63) zlast = z;
             if constexpr (DUMP) {
                 if (k & 1) pk[k >> 1] |= (uint32_t)z << 16;
                 else pk[k >> 1] = (uint32_t)z & 0xFFFFu;
             }
             if (k > 0 && z != 0) {
-                // divergent region kept minimal: a raw entry (zero run | value); size and value bits are derived in
-                // stage C with full warps
-                int gap = k - 1 - lastk;
-                while (gap > 15) { *mytok = acsel | (0xF0u << 16); mytok += C::TOK_STRIDE; gap -= 16; }
-                *mytok = TOK_RAWAC | ((uint32_t)gap << 16) | ((uint32_t)z & 0xFFFFu);
-                mytok += C::TOK_STRIDE;
-                lastk = k;
+                // the divergent region is three instructions: store (position | value); zero runs, ZRLs, sizes and
+                // value bits are derived in stage C with full warps
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(TOK_RAWAC | ((uint32_t)k << 16) | ((uint32_t)z & 0xFFFFu)) : "memory");
+                sa += C::TOK_STRIDE * 4;
             }
         }
-        if (lastk != 63) { *mytok = acsel; mytok += C::TOK_STRIDE; }  // EOB
-        const int j = (int)((mytok - (tok + tid)) / C::TOK_STRIDE);
+        if (zlast == 0) {  // EOB iff the last coefficient is zero (jchuff.c: r > 0 after the loop)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(acsel) : "memory");
+            sa += C::TOK_STRIDE * 4;
+        }
+        const int j = (int)((sa - sa0) / (C::TOK_STRIDE * 4));
         ntok = j;
         if constexpr (DUMP) {
 #pragma unroll
@@ -423,11 +425,16 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             const uint32_t t = bm[64 + w] + __popc(heads) - 1;   // owning lane (block) of output position i
             const uint32_t jj = i - bm[128 + t];
             uint32_t tk = wtok[jj * C::TOK_STRIDE + t];
-            if (tk & TOK_RAWAC) {  // (zero run | value) -> (table | run/size symbol | value bits)
+            if (tk & TOK_RAWAC) {  // (position | value) -> (ZRL count | table | run/size symbol | value bits)
+                const int kprev = jj > 1 ? (int)((wtok[(jj - 1) * C::TOK_STRIDE + t] >> 16) & 63u) : 0;
+                const int gap = (int)((tk >> 16) & 63u) - kprev - 1;
                 const int z = (int)(int16_t)(tk & 0xFFFFu);
                 const int nb = 32 - __clz(z < 0 ? -z : z);
-                const uint32_t isy = (uint32_t)((wid * 32 + t) % C::BPM) < (uint32_t)C::HV ? 1u : 3u;
-                tk = (isy << 24) | ((((tk >> 16) & 15u) << 4 | (uint32_t)nb) << 16) | ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
+                const uint32_t actb = (uint32_t)((wid * 32 + t) % C::BPM) < (uint32_t)C::HV ? 1u : 3u;
+                const uint32_t nz = (uint32_t)gap >> 4;
+                tk = (nz << 28) | (actb << 24) | ((uint32_t)(((gap & 15) << 4) | nb) << 16) |
+                     ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
+                if (do_hist && nz) atomicAdd(&hs[(actb << 8) | 0xF0u], nz);
             }
             dst[i] = tk;
             if (do_hist && !(tk & TOK_RAWDC)) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);

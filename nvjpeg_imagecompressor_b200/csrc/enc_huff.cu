@@ -286,6 +286,7 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, cons
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t tkn = TOKEN(i);
         len += (s_enc[(tkn >> 16) & 0x3FFu] & 31u) + ((tkn >> 16) & 15u);
+        if (tkn >> 28) len += (tkn >> 28) * (s_enc[((tkn >> 16) & 0x300u) | 0xF0u] & 31u);  // ZRLs (rare)
     }
     uint32_t inc = len;
 #pragma unroll
@@ -318,6 +319,10 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, cons
                 const uint32_t tkn = TOKEN(i);
                 const uint32_t en = s_enc[(tkn >> 16) & 0x3FFu];
                 const uint32_t nb = (tkn >> 16) & 15u;
+                if (tkn >> 28) {
+                    const uint32_t zr = s_enc[((tkn >> 16) & 0x300u) | 0xF0u];
+                    for (uint32_t q = tkn >> 28; q; q--) e.put(zr >> 8, (int)(zr & 31u));
+                }
                 e.put(((en >> 8) << nb) | (tkn & 0xFFFFu), (int)((en & 31u) + nb));
             }
             e.finish();
