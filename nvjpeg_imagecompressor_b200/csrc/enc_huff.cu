@@ -254,39 +254,31 @@ __device__ __forceinline__ uint32_t resolve_token(uint32_t t, const int16_t *pd)
 
 constexpr int TOK_CAP = 8192;   // tokens staged in shared memory (32 per block); denser tiles read the pool directly
 
-__global__ void __launch_bounds__(PACK_BLOCKS, 4)
-k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const HuffDev *__restrict__ huff,
-       const int16_t *__restrict__ pred_in, uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
-    __shared__ __align__(16) uint32_t s_tok[TOK_CAP];
-    __shared__ __align__(16) uint32_t s_buf[WIN_WORDS];
-    __shared__ uint32_t s_enc[1024];
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_total;
-    __shared__ int16_t s_pd[4];
+struct PackShared {
+    uint32_t tok[TOK_CAP];
+    uint32_t buf[WIN_WORDS];
+    uint32_t enc[1024];
+    uint32_t warp[8];
+    uint32_t total;
+    int16_t pd[4];
+};
+
+template <bool STAGED>
+__device__ __forceinline__ void pack_tile(PackShared &sh, const uint32_t *__restrict__ tk, uint32_t ntok, int t,
+                                          uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int t = blockIdx.x;
-    const TileRec rec = recs[t];
-    const uint32_t ntok = rec.count;
-    const uint32_t *tk = pool + rec.base;
-    const bool staged = ntok <= TOK_CAP;
-    if (tid < 3) s_pd[tid] = t > 0 ? recs[t - 1].last_dc[tid] : pred_in[tid];
-    for (int i = tid; i < 1024; i += PACK_BLOCKS) s_enc[i] = huff->enc[i >> 8][i & 255];
-    __syncthreads();
-    if (staged)
-        for (uint32_t i = tid; i < ntok; i += PACK_BLOCKS) s_tok[i] = resolve_token(__ldg(tk + i), s_pd);
-    __syncthreads();
     // equal contiguous shares; an odd share length keeps the strided shared-memory reads conflict-free
     uint32_t per = (ntok + PACK_BLOCKS - 1) / PACK_BLOCKS;
     per |= 1u;
     const uint32_t lo = min(ntok, (uint32_t)tid * per), hi = min(ntok, lo + per);
-    auto TOKEN = [&](uint32_t i) -> uint32_t { return staged ? s_tok[i] : resolve_token(__ldg(tk + i), s_pd); };
+    auto TOKEN = [&](uint32_t i) -> uint32_t { return STAGED ? sh.tok[i] : resolve_token(__ldg(tk + i), sh.pd); };
+    const uint32_t zl_y = sh.enc[0x1F0] & 31u, zl_c = sh.enc[0x3F0] & 31u;
 
     // ---- length pass
     uint32_t len = 0;
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t tkn = TOKEN(i);
-        len += (s_enc[(tkn >> 16) & 0x3FFu] & 31u) + ((tkn >> 16) & 15u);
-        if (tkn >> 28) len += (tkn >> 28) * (s_enc[((tkn >> 16) & 0x300u) | 0xF0u] & 31u);  // ZRLs (rare)
+        len += (sh.enc[(tkn >> 16) & 0x3FFu] & 31u) + ((tkn >> 16) & 15u) + (tkn >> 28) * ((tkn & (2u << 24)) ? zl_c : zl_y);
     }
     uint32_t inc = len;
 #pragma unroll
@@ -294,33 +286,34 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, cons
         const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += y;
     }
-    if (lane == 31) s_warp[wid] = inc;
+    if (lane == 31) sh.warp[wid] = inc;
     __syncthreads();
     if (tid == 0) {
         uint32_t s = 0;
-        for (int w = 0; w < 8; w++) { const uint32_t x = s_warp[w]; s_warp[w] = s; s += x; }
-        s_total = s;
+        for (int w = 0; w < 8; w++) { const uint32_t x = sh.warp[w]; sh.warp[w] = s; s += x; }
+        sh.total = s;
         tile_bits[t] = s;
     }
     __syncthreads();
-    const uint32_t off = s_warp[wid] + inc - len;
-    const uint32_t total = s_total;
+    const uint32_t off = sh.warp[wid] + inc - len;
+    const uint32_t total = sh.total;
     const int nwords = (int)((total + 31) >> 5);
     uint32_t *slot = slots + (size_t)t * SLOT_WORDS;
 
     for (int wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
         const int wn = min(WIN_WORDS, nwords - wbase);
-        for (int i = tid; i < wn; i += PACK_BLOCKS) s_buf[i] = 0;
+        for (int i = tid; i < wn; i += PACK_BLOCKS) sh.buf[i] = 0;
         __syncthreads();
         if (lo < hi) {
             Emitter e;
-            e.acc = 0; e.cnt = (int)(off & 31u); e.wpos = (int)(off >> 5); e.wbase = wbase; e.first = true; e.buf = s_buf;
+            e.acc = 0; e.cnt = (int)(off & 31u); e.wpos = (int)(off >> 5); e.wbase = wbase; e.first = true; e.buf = sh.buf;
             for (uint32_t i = lo; i < hi; i++) {
                 const uint32_t tkn = TOKEN(i);
-                const uint32_t en = s_enc[(tkn >> 16) & 0x3FFu];
+                const uint32_t en = sh.enc[(tkn >> 16) & 0x3FFu];
                 const uint32_t nb = (tkn >> 16) & 15u;
-                if (tkn >> 28) {
-                    const uint32_t zr = s_enc[((tkn >> 16) & 0x300u) | 0xF0u];
+                if (tkn >> 28) {  // ZRL symbols ahead of this coefficient
+                    const uint32_t zr = sh.enc[((tkn >> 16) & 0x300u) | 0xF0u];
+#pragma unroll 1
                     for (uint32_t q = tkn >> 28; q; q--) e.put(zr >> 8, (int)(zr & 31u));
                 }
                 e.put(((en >> 8) << nb) | (tkn & 0xFFFFu), (int)((en & 31u) + nb));
@@ -328,8 +321,32 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, cons
             e.finish();
         }
         __syncthreads();
-        for (int i = tid; i < wn; i += PACK_BLOCKS) slot[wbase + i] = s_buf[i];
+        for (int i = tid; i < wn; i += PACK_BLOCKS) slot[wbase + i] = sh.buf[i];
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PACK_BLOCKS, 4)
+k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const HuffDev *__restrict__ huff,
+       const int16_t *__restrict__ pred_in, uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
+    __shared__ __align__(16) PackShared sh;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    const TileRec rec = recs[t];
+    const uint32_t ntok = rec.count;
+    const uint32_t *tk = pool + rec.base;
+    if (tid < 3) sh.pd[tid] = t > 0 ? recs[t - 1].last_dc[tid] : pred_in[tid];
+    for (int i = tid; i < 1024; i += PACK_BLOCKS) sh.enc[i] = huff->enc[i >> 8][i & 255];
+    if (ntok <= TOK_CAP) {
+        __syncthreads();
+        // coalesced loads of the tile's token run; the (at most three) raw-DC tokens are resolved on the way in
+#pragma unroll 4
+        for (uint32_t i = tid; i < ntok; i += PACK_BLOCKS) sh.tok[i] = resolve_token(__ldg(tk + i), sh.pd);
+        __syncthreads();
+        pack_tile<true>(sh, tk, ntok, t, slots, tile_bits);
+    } else {
+        __syncthreads();
+        pack_tile<false>(sh, tk, ntok, t, slots, tile_bits);
     }
 }
 
@@ -375,7 +392,7 @@ k_stuff(StuffArgs a) {
     __shared__ int s_chunk, s_tau0;
     __shared__ uint32_t s_warp[8];
     __shared__ uint64_t s_goff;
-    __shared__ __align__(16) uint8_t s_out[2 * STUFF_CHUNK + 16];
+    __shared__ __align__(16) uint8_t s_out[2 * STUFF_CHUNK + 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t T = a.tile_off[a.ntiles];
     const uint64_t NB = T > (uint64_t)a.skip ? (T - a.skip + 7) >> 3 : 0;
@@ -389,8 +406,8 @@ k_stuff(StuffArgs a) {
         if (ch >= nchunks) break;
         const uint64_t j0c = (uint64_t)ch * STUFF_CHUNK;
         const uint64_t p0c = (uint64_t)a.skip + 8 * j0c;
-        if (tid == 0) {  // tile containing the chunk's first bit
-            int lo = 0, hi = a.ntiles;  // find largest tau with tile_off[tau] <= p0c
+        if (tid == 0) {  // tile containing the chunk's first bit: largest tau with tile_off[tau] <= p0c
+            int lo = 0, hi = a.ntiles;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (a.tile_off[mid] <= p0c) lo = mid; else hi = mid;
@@ -409,55 +426,78 @@ k_stuff(StuffArgs a) {
         auto TOFF = [&](int ti) -> uint64_t { const int r = ti - tau0; return r < TWIN ? s_toff[r] : a.tile_off[min(ti, a.ntiles)]; };
         auto TBITS = [&](int ti) -> uint32_t { const int r = ti - tau0; return r < TWIN ? s_tbits[r] : a.tile_bits[ti]; };
 
-        // ---- 16 bytes per thread
+        // ---- 16 bytes per thread: w[q] = stream bits [p + 32q, p + 32q + 32), MSB first
         const uint64_t j0 = j0c + (uint64_t)tid * 16;
         const int nvalid = j0 >= NB ? 0 : (int)min((uint64_t)16, NB - j0);
         uint32_t w[4] = {0, 0, 0, 0};
         if (nvalid > 0) {
             uint64_t p = (uint64_t)a.skip + 8 * j0;
             int tau = tau0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t res = 0;
-                int got = 0;
-                while (got < 32) {
-                    if (p >= T) {
-                        const uint64_t e = p - T;
-                        uint32_t x = 0xffffffffu;
-                        if (e < 32) {
-                            x = ((uint32_t)a.ext << 24) | 0x00ffffffu;
-                            if (e) x = (x << e) | ((1u << e) - 1u);
+            while (TOFF(tau + 1) <= p) tau++;
+            const uint64_t tend = TOFF(tau + 1);
+            if (p + 128 <= tend) {  // fast path: all 128 bits inside one tile
+                const uint32_t qb = (uint32_t)(p - TOFF(tau));
+                const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS + (qb >> 5);
+                const uint32_t sh = qb & 31u;
+                const uint32_t nleft = ((TBITS(tau) + 31u) >> 5) - (qb >> 5);  // words available from slot[0]
+                const uint32_t x0 = slot[0], x1 = slot[1], x2 = slot[2], x3 = slot[3];
+                const uint32_t x4 = (sh && nleft > 4) ? slot[4] : 0u;
+                w[0] = __funnelshift_l(x1, x0, sh);
+                w[1] = __funnelshift_l(x2, x1, sh);
+                w[2] = __funnelshift_l(x3, x2, sh);
+                w[3] = __funnelshift_l(x4, x3, sh);
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < 4; q++) {
+                    uint32_t res = 0;
+                    int got = 0;
+                    while (got < 32) {
+                        if (p >= T) {
+                            const uint64_t e = p - T;
+                            uint32_t x = 0xffffffffu;
+                            if (e < 32) {
+                                x = ((uint32_t)a.ext << 24) | 0x00ffffffu;
+                                if (e) x = (x << e) | ((1u << e) - 1u);
+                            }
+                            res |= x >> got;
+                            p += 32 - got;
+                            got = 32;
+                            break;
                         }
+                        while (TOFF(tau + 1) <= p) tau++;
+                        const uint32_t tb = TBITS(tau);
+                        const uint32_t qb = (uint32_t)(p - TOFF(tau));
+                        const uint32_t rem = tb - qb;
+                        const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS;
+                        const uint32_t wi = qb >> 5, sh = qb & 31u;
+                        const uint32_t nw = (tb + 31u) >> 5;
+                        const uint32_t w0 = slot[wi];
+                        const uint32_t w1 = (sh && wi + 1 < nw) ? slot[wi + 1] : 0u;
+                        uint32_t x = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;
+                        const int take = min(32 - got, (int)min(rem, 32u));
+                        if (take < 32) x &= ~(0xffffffffu >> take);
                         res |= x >> got;
-                        p += 32 - got;
-                        got = 32;
-                        break;
+                        got += take;
+                        p += take;
                     }
-                    while (TOFF(tau + 1) <= p) tau++;
-                    const uint32_t tb = TBITS(tau);
-                    const uint32_t qb = (uint32_t)(p - TOFF(tau));
-                    const uint32_t rem = tb - qb;
-                    const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS;
-                    const uint32_t wi = qb >> 5, sh = qb & 31u;
-                    const uint32_t nw = (tb + 31u) >> 5;
-                    const uint32_t w0 = slot[wi];
-                    const uint32_t w1 = (sh && wi + 1 < nw) ? slot[wi + 1] : 0u;
-                    uint32_t x = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;
-                    const int take = min(32 - got, (int)min(rem, 32u));
-                    if (take < 32) x &= ~(0xffffffffu >> take);
-                    res |= x >> got;
-                    got += take;
-                    p += take;
+                    if (q == 0) w[0] = res; else if (q == 1) w[1] = res; else if (q == 2) w[2] = res; else w[3] = res;
                 }
-                w[q] = res;
             }
         }
-        // bytes in stream order: w[q] big-endian
+        // 0xFF bytes (per word: a byte is 0xFF iff all eight bits survive the and-fold)
         int nff = 0;
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
-            if (i < nvalid && byte == 0xFFu) nff++;
+        for (int q = 0; q < 4; q++) {
+            uint32_t m = w[q] & (w[q] >> 4) & 0x0F0F0F0Fu;
+            m &= m >> 2;
+            m &= m >> 1;
+            m &= 0x01010101u;
+            if (nvalid < 16) {  // tail thread: ignore bytes past the end
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4 * q + b >= nvalid) m &= ~(1u << (24 - 8 * b));
+            }
+            nff += __popc(m);
         }
         const uint32_t cnt = (uint32_t)(nvalid + nff);
         uint32_t inc = cnt;
@@ -475,29 +515,61 @@ k_stuff(StuffArgs a) {
             if (i < wid) wbase += x;
             total += x;
         }
-        uint32_t o = wbase + inc - cnt;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
-            if (i < nvalid) {
-                s_out[o++] = (uint8_t)byte;
-                if (byte == 0xFFu) s_out[o++] = 0;
-            }
-        }
         if (wid == 0) {
             const uint64_t pre = lookback_exclusive(a.desc, ch, total, a.err);
             if (lane == 0) s_goff = pre;
         }
         __syncthreads();
         const uint64_t goff = (uint64_t)hdr + s_goff;
+        // shared staging is laid out so that s_out[k] <-> out[goff - pad + k] with (goff - pad) 16-byte aligned
+        const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + goff) & 15u);
+        uint32_t o = pad + wbase + inc - cnt;
+        if (nff == 0 && nvalid == 16) {
+            // little-endian words of the 16 stream bytes
+            const uint32_t l0 = __byte_perm(w[0], 0, 0x0123), l1 = __byte_perm(w[1], 0, 0x0123),
+                           l2 = __byte_perm(w[2], 0, 0x0123), l3 = __byte_perm(w[3], 0, 0x0123);
+            const uint32_t al = o & 3u;
+            if (al == 0) {
+                uint32_t *d = reinterpret_cast<uint32_t *>(s_out + o);
+                d[0] = l0; d[1] = l1; d[2] = l2; d[3] = l3;
+            } else {
+                const uint32_t sh8 = al * 8;
+                // head bytes up to the next word boundary, three whole words, tail bytes
+                for (uint32_t b = 0; b < 4 - al; b++) s_out[o + b] = (uint8_t)(l0 >> (8 * b));
+                uint32_t *d = reinterpret_cast<uint32_t *>(s_out + o + (4 - al));
+                const uint32_t r = 32 - sh8;
+                d[0] = __funnelshift_r(l0, l1, r);
+                d[1] = __funnelshift_r(l1, l2, r);
+                d[2] = __funnelshift_r(l2, l3, r);
+                for (uint32_t b = 0; b < al; b++) s_out[o + 16 - al + b] = (uint8_t)(l3 >> (r + 8 * b));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
+                if (i < nvalid) {
+                    s_out[o++] = (uint8_t)byte;
+                    if (byte == 0xFFu) s_out[o++] = 0;
+                }
+            }
+        }
+        __syncthreads();
         const bool last = ch == nchunks - 1;
         const uint64_t end = goff + total + ((last && a.append_eoi) ? 2 : 0);
         if (end > a.cap) {
             if (tid == 0) *a.err = 3;
         } else {
-            uint8_t *dst = a.out + goff;
-            for (uint32_t i = tid; i < total; i += STUFF_THREADS) dst[i] = s_out[i];
-            if (last && a.append_eoi && tid == 0) { dst[total] = 0xFF; dst[total + 1] = 0xD9; }
+            uint8_t *base = a.out + goff - pad;  // 16-byte aligned
+            const uint32_t lim = pad + total;
+            for (uint32_t v = tid; v * 16 < lim; v += STUFF_THREADS) {
+                const uint32_t k0 = v * 16;
+                if (k0 >= pad && k0 + 16 <= lim) {
+                    *reinterpret_cast<uint4 *>(base + k0) = *reinterpret_cast<const uint4 *>(s_out + k0);
+                } else {
+                    for (uint32_t k = max(k0, pad); k < min(k0 + 16, lim); k++) base[k] = s_out[k];
+                }
+            }
+            if (last && a.append_eoi && tid == 0) { a.out[goff + total] = 0xFF; a.out[goff + total + 1] = 0xD9; }
         }
         if (last && tid == 0) *a.out_len = end;
         __syncthreads();
