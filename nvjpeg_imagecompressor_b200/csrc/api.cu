@@ -312,7 +312,7 @@ int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
     a.skip = skip_bits; a.ext = ext_byte & 0xFF; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
     a.out = ctx->d_out; a.cap = ctx->out_cap; a.desc = ctx->d_desc; a.ticket = &ctx->d_ctrl->ticket;
     a.out_len = &ctx->d_ctrl->out_len; a.err = &ctx->d_ctrl->err;
-    CK(launch_stuff(a, 148 * 6, ctx->stream));
+    CK(launch_stuff(a, 148 * 8, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 7);
     return B2J_OK;

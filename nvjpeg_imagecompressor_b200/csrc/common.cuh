@@ -34,7 +34,8 @@ struct TileRec {                               // one per fdct tile (<= 256 bloc
 constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)
 constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
 constexpr int STUFF_THREADS = 256;
-constexpr int STUFF_CHUNK = STUFF_THREADS * 16; // unstuffed bytes per stuff chunk
+constexpr int STUFF_BPT = 32;                   // unstuffed bytes per thread and chunk
+constexpr int STUFF_CHUNK = STUFF_THREADS * STUFF_BPT; // unstuffed bytes per stuff chunk
 
 // ---- zig-zag ------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int zigzag_nat(int k) {

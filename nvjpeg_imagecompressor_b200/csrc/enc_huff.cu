@@ -406,13 +406,21 @@ k_stuff(StuffArgs a) {
         if (ch >= nchunks) break;
         const uint64_t j0c = (uint64_t)ch * STUFF_CHUNK;
         const uint64_t p0c = (uint64_t)a.skip + 8 * j0c;
-        if (tid == 0) {  // tile containing the chunk's first bit: largest tau with tile_off[tau] <= p0c
-            int lo = 0, hi = a.ntiles;
+        if (wid == 0) {  // tile containing the chunk's first bit: largest tau with tile_off[tau] <= p0c (32-ary search)
+            int lo = 0, hi = a.ntiles;  // invariant: tile_off[lo] <= p0c < tile_off[hi]
             while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (a.tile_off[mid] <= p0c) lo = mid; else hi = mid;
+                const int span = hi - lo;
+                const int stepw = (span + 31) >> 5;
+                const int probe = min(hi, lo + (lane + 1) * stepw);
+                const bool le = probe < hi && a.tile_off[probe] <= p0c;
+                const unsigned m = __ballot_sync(0xffffffffu, le);
+                const int nle = __popc(m);  // probes are monotone: the first nle lanes are <=
+                const int nlo = lo + nle * stepw;
+                const int nhi = min(hi, lo + (nle + 1) * stepw);
+                lo = min(nlo, hi - 1);
+                hi = max(nhi, lo + 1);
             }
-            s_tau0 = lo;
+            if (lane == 0) s_tau0 = lo;
         }
         __syncthreads();
         const int tau0 = s_tau0;
@@ -426,29 +434,31 @@ k_stuff(StuffArgs a) {
         auto TOFF = [&](int ti) -> uint64_t { const int r = ti - tau0; return r < TWIN ? s_toff[r] : a.tile_off[min(ti, a.ntiles)]; };
         auto TBITS = [&](int ti) -> uint32_t { const int r = ti - tau0; return r < TWIN ? s_tbits[r] : a.tile_bits[ti]; };
 
-        // ---- 16 bytes per thread: w[q] = stream bits [p + 32q, p + 32q + 32), MSB first
-        const uint64_t j0 = j0c + (uint64_t)tid * 16;
-        const int nvalid = j0 >= NB ? 0 : (int)min((uint64_t)16, NB - j0);
-        uint32_t w[4] = {0, 0, 0, 0};
+        // ---- STUFF_BPT bytes per thread: w[q] = stream bits [p + 32q, p + 32q + 32), MSB first
+        constexpr int NW = STUFF_BPT / 4;
+        const uint64_t j0 = j0c + (uint64_t)tid * STUFF_BPT;
+        const int nvalid = j0 >= NB ? 0 : (int)min((uint64_t)STUFF_BPT, NB - j0);
+        uint32_t w[NW];
+#pragma unroll
+        for (int q = 0; q < NW; q++) w[q] = 0;
         if (nvalid > 0) {
             uint64_t p = (uint64_t)a.skip + 8 * j0;
             int tau = tau0;
             while (TOFF(tau + 1) <= p) tau++;
             const uint64_t tend = TOFF(tau + 1);
-            if (p + 128 <= tend) {  // fast path: all 128 bits inside one tile
+            if (p + 32 * NW <= tend) {  // fast path: all bits inside one tile
                 const uint32_t qb = (uint32_t)(p - TOFF(tau));
                 const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS + (qb >> 5);
                 const uint32_t sh = qb & 31u;
-                const uint32_t nleft = ((TBITS(tau) + 31u) >> 5) - (qb >> 5);  // words available from slot[0]
-                const uint32_t x0 = slot[0], x1 = slot[1], x2 = slot[2], x3 = slot[3];
-                const uint32_t x4 = (sh && nleft > 4) ? slot[4] : 0u;
-                w[0] = __funnelshift_l(x1, x0, sh);
-                w[1] = __funnelshift_l(x2, x1, sh);
-                w[2] = __funnelshift_l(x3, x2, sh);
-                w[3] = __funnelshift_l(x4, x3, sh);
+                uint32_t x[NW + 1];
+#pragma unroll
+                for (int q = 0; q < NW; q++) x[q] = slot[q];
+                x[NW] = sh ? slot[NW] : 0u;
+#pragma unroll
+                for (int q = 0; q < NW; q++) w[q] = __funnelshift_l(x[q + 1], x[q], sh);
             } else {
 #pragma unroll 1
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < NW; q++) {
                     uint32_t res = 0;
                     int got = 0;
                     while (got < 32) {
@@ -480,19 +490,20 @@ k_stuff(StuffArgs a) {
                         got += take;
                         p += take;
                     }
-                    if (q == 0) w[0] = res; else if (q == 1) w[1] = res; else if (q == 2) w[2] = res; else w[3] = res;
+#pragma unroll
+                    for (int qq = 0; qq < NW; qq++) if (qq == q) w[qq] = res;
                 }
             }
         }
         // 0xFF bytes (per word: a byte is 0xFF iff all eight bits survive the and-fold)
         int nff = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NW; q++) {
             uint32_t m = w[q] & (w[q] >> 4) & 0x0F0F0F0Fu;
             m &= m >> 2;
             m &= m >> 1;
             m &= 0x01010101u;
-            if (nvalid < 16) {  // tail thread: ignore bytes past the end
+            if (nvalid < STUFF_BPT) {  // tail thread: ignore bytes past the end
 #pragma unroll
                 for (int b = 0; b < 4; b++)
                     if (4 * q + b >= nvalid) m &= ~(1u << (24 - 8 * b));
@@ -524,28 +535,28 @@ k_stuff(StuffArgs a) {
         // shared staging is laid out so that s_out[k] <-> out[goff - pad + k] with (goff - pad) 16-byte aligned
         const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + goff) & 15u);
         uint32_t o = pad + wbase + inc - cnt;
-        if (nff == 0 && nvalid == 16) {
-            // little-endian words of the 16 stream bytes
-            const uint32_t l0 = __byte_perm(w[0], 0, 0x0123), l1 = __byte_perm(w[1], 0, 0x0123),
-                           l2 = __byte_perm(w[2], 0, 0x0123), l3 = __byte_perm(w[3], 0, 0x0123);
+        if (nff == 0 && nvalid == STUFF_BPT) {
+            // little-endian words of the stream bytes, written at byte offset o: head bytes to the next word boundary,
+            // NW-1 whole words built with funnel shifts, tail bytes
+            uint32_t l[NW];
+#pragma unroll
+            for (int q = 0; q < NW; q++) l[q] = __byte_perm(w[q], 0, 0x0123);
             const uint32_t al = o & 3u;
             if (al == 0) {
                 uint32_t *d = reinterpret_cast<uint32_t *>(s_out + o);
-                d[0] = l0; d[1] = l1; d[2] = l2; d[3] = l3;
+#pragma unroll
+                for (int q = 0; q < NW; q++) d[q] = l[q];
             } else {
-                const uint32_t sh8 = al * 8;
-                // head bytes up to the next word boundary, three whole words, tail bytes
-                for (uint32_t b = 0; b < 4 - al; b++) s_out[o + b] = (uint8_t)(l0 >> (8 * b));
+                const uint32_t r = 32 - al * 8;
+                for (uint32_t b = 0; b < 4 - al; b++) s_out[o + b] = (uint8_t)(l[0] >> (8 * b));
                 uint32_t *d = reinterpret_cast<uint32_t *>(s_out + o + (4 - al));
-                const uint32_t r = 32 - sh8;
-                d[0] = __funnelshift_r(l0, l1, r);
-                d[1] = __funnelshift_r(l1, l2, r);
-                d[2] = __funnelshift_r(l2, l3, r);
-                for (uint32_t b = 0; b < al; b++) s_out[o + 16 - al + b] = (uint8_t)(l3 >> (r + 8 * b));
+#pragma unroll
+                for (int q = 0; q < NW - 1; q++) d[q] = __funnelshift_r(l[q], l[q + 1], r);
+                for (uint32_t b = 0; b < al; b++) s_out[o + STUFF_BPT - al + b] = (uint8_t)(l[NW - 1] >> (r + 8 * b));
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < STUFF_BPT; i++) {
                 const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
                 if (i < nvalid) {
                     s_out[o++] = (uint8_t)byte;
