@@ -37,18 +37,23 @@ struct K1 {
     static constexpr int Y_BYTES = Y_STRIDE * MCU_H;
     static constexpr int C_STRIDE = TM_MAX * 8;
     static constexpr int C_BYTES = C_STRIDE * 8;
-    static constexpr int OFF_Y = TOK_BYTES;  // raw aliases the token area
+    // the raw pixel tile and the sample planes both live inside the token area: they are dead before the first token
+    // is stored (a barrier separates the sample loads of stage B from its token stores)
+    static constexpr int OFF_Y = (RAW_BYTES + 15) & ~15;
     static constexpr int OFF_CB = OFF_Y + Y_BYTES;
     static constexpr int OFF_CR = OFF_CB + C_BYTES;
-    static constexpr int OFF_Q = OFF_CR + C_BYTES;       // uint2[2][64]
+    static constexpr int OFF_Q = TOK_BYTES;              // uint2[2][64]
     static constexpr int OFF_HIST = OFF_Q + 1024;        // uint32[4][256]
     static constexpr int OFF_DC = OFF_HIST + 4096;       // int16[256]
-    static constexpr int OFF_BM = OFF_DC + 512;          // per warp: head bitmap[64], word ranks[64], offsets[32]
-    static constexpr int OFF_MISC = OFF_BM + 8 * 160 * 4;  // warp totals[8], pool base
+    static constexpr int BM_BYTES = 256 + 64 + 64;       // per warp: head bitmap u32[64], word ranks u8[64], offsets u16[32]
+    static constexpr int OFF_BM = OFF_DC + 512;
+    static constexpr int OFF_MISC = OFF_BM + 8 * BM_BYTES;  // warp totals[8], pool base
     static constexpr int OFF_BAR = OFF_MISC + 64;        // mbarrier
     static constexpr int OFF_STAGE = OFF_BAR + 16;       // DUMP only
     static constexpr int SMEM = OFF_STAGE;
     static constexpr int SMEM_DUMP = OFF_STAGE + STAGE_BYTES;
+    static_assert(OFF_CR + C_BYTES <= TOK_BYTES, "planes must fit inside the token area");
+    static_assert(SMEM <= 75 * 1024, "three CTAs per SM");
     static_assert(RAW_BYTES <= TOK_BYTES, "raw tile must fit in the token area");
     static_assert(RAW_STRIDE % 16 == 0, "row stride must allow 16-byte bulk copies");
 };
@@ -110,7 +115,7 @@ __device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &c
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : v); }
 
 template <int HS, int VS, bool DUMP>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__restrict__ qd,
        uint32_t *__restrict__ pool, uint32_t *__restrict__ pool_count, TileRec *__restrict__ recs,
        uint32_t *__restrict__ ghist, int do_hist, int bulk_ok, int my0, int16_t *__restrict__ coef) {
@@ -270,12 +275,12 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     if (isY) real = ((mx0 + m) * HS + bx < g.wib[0]) && (my * VS + by < g.hib[0]);
     int ntok = 0;
     int mydc = 0;
+    int v[64];
     if (active) {
         const uint8_t *src;
         int stride;
         if (isY) { src = Yp + (by * 8) * C::Y_STRIDE + (m * HS + bx) * 8; stride = C::Y_STRIDE; }
         else { src = (bn == C::HV ? Cbp : Crp) + m * 8; stride = C::C_STRIDE; }
-        int v[64];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             uint2 w = *reinterpret_cast<const uint2 *>(src + r * stride);
@@ -285,6 +290,9 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
                 v[r * 8 + 4 + c] = (w.y >> (8 * c)) & 0xFF;
             }
         }
+    }
+    __syncthreads();  // every sample is in registers: the planes are dead, the token area may be written
+    if (active) {
 #pragma unroll
         for (int r = 0; r < 8; r++)
             fdct8<false>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
@@ -376,7 +384,9 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     }
 
     // ---- stage C: per-warp transposition of the 32 token lists into one block-ordered run
-    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + C::OFF_BM) + wid * 160;  // [0,64) heads, [64,128) ranks, [128,160) offsets
+    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + C::OFF_BM + wid * C::BM_BYTES);  // head flags of the warp's run
+    uint8_t *rk = reinterpret_cast<uint8_t *>(bm + 64);                                 // heads before each bitmap word
+    uint16_t *ofs = reinterpret_cast<uint16_t *>(rk + 64);                              // first output index per lane
     uint32_t inc = (uint32_t)ntok;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -386,7 +396,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     const uint32_t off = inc - (uint32_t)ntok;
     const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
     bm[lane] = 0; bm[lane + 32] = 0;
-    bm[128 + lane] = off;
+    ofs[lane] = (uint16_t)off;
     if (lane == 31) misc[wid] = wtot;
     __syncthreads();  // also orders the DC tokens / bitmap zeroing before their use below
     uint32_t wbase = 0, total = 0;
@@ -411,8 +421,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             const uint32_t y = __shfl_up_sync(0xffffffffu, pc, o);
             if (lane >= o) pc += y;
         }
-        bm[64 + 2 * lane] = pc - c0 - c1;
-        bm[64 + 2 * lane + 1] = pc - c1;
+        rk[2 * lane] = (uint8_t)(pc - c0 - c1);
+        rk[2 * lane + 1] = (uint8_t)(pc - c1);
     }
     __syncwarp();
     uint32_t *dst = pool + (size_t)misc[8] + wbase;
@@ -422,8 +432,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         if (i < wtot) {
             const uint32_t w = i0 >> 5;
             const uint32_t heads = bm[w] & (0xffffffffu >> (31 - lane));
-            const uint32_t t = bm[64 + w] + __popc(heads) - 1;   // owning lane (block) of output position i
-            const uint32_t jj = i - bm[128 + t];
+            const uint32_t t = rk[w] + __popc(heads) - 1;   // owning lane (block) of output position i
+            const uint32_t jj = i - ofs[t];
             uint32_t tk = wtok[jj * C::TOK_STRIDE + t];
             if (tk & TOK_RAWAC) {  // (position | value) -> (ZRL count | table | run/size symbol | value bits)
                 const int kprev = jj > 1 ? (int)((wtok[(jj - 1) * C::TOK_STRIDE + t] >> 16) & 63u) : 0;
