@@ -145,6 +145,9 @@ B2J_API int b2j_strip_phase2(b2j_ctx *ctx, int full_width, int full_height);
 /* shift to the global bit phase, byte-stuff. skip_bits = (8 - global_start_bit%8)%8, ext_byte = next strip's
  * first 8 bits (0xFF for the last strip). flags: bit0 = emit headers first, bit1 = append EOI. */
 B2J_API int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags);
+/* Same, with the seam derived on the device (no host synchronisation in the multi-GPU step): d_bits_all is the
+ * all-gathered table [world][2] of int64 {d_strip_bits[0], d_strip_bits[1]} of every strip, in strip order. */
+B2J_API int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int world, int flags);
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
 enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4 };

@@ -23,11 +23,12 @@ struct Ctrl {  // zeroed before every encode with one memset
     uint32_t ticket;
     uint32_t err;
     uint32_t pool_count;
-    uint32_t pad0;
+    uint32_t scan_ticket;
     uint64_t out_len;
     uint64_t strip_bits[2];
     uint64_t ssd;
     int16_t last_dc[4];
+    int seam[2];
 };
 
 struct HostRet {  // pinned
@@ -58,8 +59,8 @@ struct b2j_ctx {
     size_t slot_words_cap;
     int debug;
     uint32_t *d_slots, *d_tile_bits;
-    uint64_t *d_tile_off, *d_desc;
-    size_t ndesc;
+    uint64_t *d_tile_off, *d_desc, *d_sdesc;   // look-back descriptors: byte stuffing, tile scan
+    size_t ndesc, nsdesc;
     Ctrl *d_ctrl;
     int16_t *d_pred_in;
     HuffDev *d_huff;
@@ -167,12 +168,14 @@ static int ensure_tiles(b2j_ctx *ctx, const Geom &g) {
 static int enc_alloc(b2j_ctx *ctx) {
     if (ctx->enc_ready) return B2J_OK;
     const Geom &g = ctx->cap_g;
-    CK(cudaMalloc(&ctx->d_pool, (size_t)g.nblocks * 64 * 4));
+    CK(cudaMalloc(&ctx->d_pool, (size_t)g.nblocks * 64 * 4 + 64));  // +64: k_pack reads whole 16-byte groups
     int rc = ensure_tiles(ctx, g); if (rc) return rc;
     ctx->out_cap = (size_t)g.nblocks * 208 + 4096;
     CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
     ctx->ndesc = ctx->out_cap / STUFF_CHUNK + 4;
     CK(cudaMalloc(&ctx->d_desc, ctx->ndesc * 8));
+    ctx->nsdesc = (size_t)scan_desc_count(g.ntiles) + 64;
+    CK(cudaMalloc(&ctx->d_sdesc, ctx->nsdesc * 8));
     CK(cudaMalloc(&ctx->d_ctrl, sizeof(Ctrl)));
     CK(cudaMalloc(&ctx->d_pred_in, 16));
     CK(cudaMemset(ctx->d_pred_in, 0, 16));
@@ -223,7 +226,7 @@ void b2j_destroy(b2j_ctx *ctx) {
     if (ctx->second) b2j_destroy(ctx->second);
     if (ctx->dec) dec_destroy(ctx->dec);
     cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_pool); cudaFree(ctx->d_recs); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
-    cudaFree(ctx->d_tile_off); cudaFree(ctx->d_desc); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_pred_in);
+    cudaFree(ctx->d_tile_off); cudaFree(ctx->d_desc); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_pred_in);
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
     if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -263,6 +266,12 @@ static int enc_reset(b2j_ctx *ctx) {
     // descriptors actually reachable for this image: bounded by its worst-case entropy bytes
     size_t nd = std::min(ctx->ndesc, ((size_t)ctx->g.nblocks * 208) / STUFF_CHUNK + 4);
     CK(cudaMemsetAsync(ctx->d_desc, 0, nd * 8, ctx->stream));
+    if ((size_t)scan_desc_count(ctx->g.ntiles) > ctx->nsdesc) {   // strips with more (smaller) tiles than the configured image
+        cudaFree(ctx->d_sdesc); ctx->d_sdesc = nullptr;
+        ctx->nsdesc = (size_t)scan_desc_count(ctx->g.ntiles) + 64;
+        CK(cudaMalloc(&ctx->d_sdesc, ctx->nsdesc * 8));
+    }
+    CK(cudaMemsetAsync(ctx->d_sdesc, 0, (size_t)scan_desc_count(ctx->g.ntiles) * 8, ctx->stream));
     return B2J_OK;
 }
 
@@ -275,7 +284,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
     rc = enc_reset(ctx); if (rc) return rc;
     tick(ctx, 1);
     CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, 0, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, 0, ctx->d_pool, 0, ctx->stream));
     ctx->launches += 2;
     tick(ctx, 2);
     return B2J_OK;
@@ -283,7 +292,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
 
 int b2j_strip_phase1b(b2j_ctx *ctx) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, ctx->p.optimize, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, ctx->p.optimize, ctx->d_pool, 1, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 3);
     return B2J_OK;
@@ -294,9 +303,10 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
     CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, ctx->stream));
     tick(ctx, 4);
-    CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_pred_in, ctx->d_slots, ctx->d_tile_bits, ctx->stream));
+    CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_slots, ctx->d_tile_bits, ctx->stream));
     tick(ctx, 5);
-    CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->stream));
+    CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->d_sdesc,
+                         &ctx->d_ctrl->scan_ticket, &ctx->d_ctrl->err, ctx->stream));
     ctx->launches += 3;
     tick(ctx, 6);
     return B2J_OK;
@@ -304,18 +314,31 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
 
 __global__ void k_set_hdr_len(HuffDev *h, uint32_t v) { h->hdr_len = v; }
 
-int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
-    if (!ctx || !ctx->enc_ready || skip_bits < 0 || skip_bits > 7) return B2J_EINVAL;
+static int phase3_launch(b2j_ctx *ctx, int flags) {
     if (!(flags & 1)) { k_set_hdr_len<<<1, 1, 0, ctx->stream>>>(ctx->d_huff, 0); ctx->launches++; }
     StuffArgs a;
     a.slots = ctx->d_slots; a.tile_bits = ctx->d_tile_bits; a.tile_off = ctx->d_tile_off; a.ntiles = ctx->g.ntiles;
-    a.skip = skip_bits; a.ext = ext_byte & 0xFF; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
+    a.seam = ctx->d_ctrl->seam; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
     a.out = ctx->d_out; a.cap = ctx->out_cap; a.desc = ctx->d_desc; a.ticket = &ctx->d_ctrl->ticket;
     a.out_len = &ctx->d_ctrl->out_len; a.err = &ctx->d_ctrl->err;
     CK(launch_stuff(a, 148 * 8, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 7);
     return B2J_OK;
+}
+
+int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
+    if (!ctx || !ctx->enc_ready || skip_bits < 0 || skip_bits > 7) return B2J_EINVAL;
+    CK(launch_set_seam(ctx->d_ctrl->seam, skip_bits, ext_byte & 0xFF, ctx->stream));
+    ctx->launches += 1;
+    return phase3_launch(ctx, flags);
+}
+
+int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int world, int flags) {
+    if (!ctx || !ctx->enc_ready || !d_bits_all || rank < 0 || rank >= world) return B2J_EINVAL;
+    CK(launch_seam_from_bits(ctx->d_ctrl->seam, d_bits_all, rank, world, ctx->stream));
+    ctx->launches += 1;
+    return phase3_launch(ctx, flags);
 }
 
 int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st) {

@@ -22,13 +22,13 @@ struct Geom {
 
 // One token per coded coefficient / EOB: [29:28] number of ZRL (0xF0) symbols that precede it, [25:24] table (0 DC0,
 // 1 AC0, 2 DC1, 3 AC1), [23:16] symbol (run<<4 | size), [15:0] value bits (already masked to `size` bits). TOK_RAWDC: DC of a block whose predecessor lives in the
-// previous tile; [17:16] = component, [15:0] = the quantised DC itself (the entropy coder forms the difference).
+// previous tile; [17:16] = component, [15:0] = the quantised DC itself (k_dc_edge_hist rewrites it as a difference token).
 constexpr uint32_t TOK_RAWDC = 1u << 26;
 constexpr uint32_t TOK_RAWAC = 1u << 27;   // k_fdct-internal: [21:16] zig-zag position, [15:0] coefficient; never leaves the kernel
 struct TileRec {                               // one per fdct tile (<= 256 blocks, one MCU-row segment)
     uint32_t base, count;                      // token run in the pool
     int16_t first_dc[3], last_dc[3];           // DCs of the tile's first / last MCU (last Y block, Cb, Cr)
-    uint32_t pad;
+    uint16_t pos_cb, pos_cr;                   // run offsets of the first MCU's Cb / Cr DC tokens (Y: offset 0)
 };
 
 constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)

@@ -398,6 +398,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     bm[lane] = 0; bm[lane + 32] = 0;
     ofs[lane] = (uint16_t)off;
     if (lane == 31) misc[wid] = wtot;
+    if (tid == C::HV) misc[9] = off;        // run offsets of the first MCU's chroma DC tokens (warp 0: no warp base)
+    if (tid == C::HV + 1) misc[10] = off;
     __syncthreads();  // also orders the DC tokens / bitmap zeroing before their use below
     uint32_t wbase = 0, total = 0;
 #pragma unroll
@@ -406,7 +408,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         const uint32_t base = atomicAdd(pool_count, total);
         misc[8] = base;
         TileRec r;
-        r.base = base; r.count = total; r.pad = 0;
+        r.base = base; r.count = total; r.pos_cb = (uint16_t)misc[9]; r.pos_cr = (uint16_t)misc[10];
         r.first_dc[0] = dcs[0]; r.first_dc[1] = dcs[C::HV]; r.first_dc[2] = dcs[C::HV + 1];
         r.last_dc[0] = dcs[nblk - 3]; r.last_dc[1] = dcs[nblk - 2]; r.last_dc[2] = dcs[nblk - 1];
         recs[tile] = r;
@@ -467,19 +469,38 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     }
 }
 
-// DC-difference symbols of each fdct tile's first MCU (their predecessor block lives in the previous tile), plus
-// the strip's very first MCU (predecessor = pred_in) and the strip's last DCs for the next strip.
-__global__ void k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restrict__ pred_in,
-                               uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist) {
+// DC-difference symbols of each fdct tile's first MCU (their predecessor block lives in the previous tile; the
+// strip's very first MCU takes pred_in), plus the strip's last DCs for the next strip. With `resolve` the three
+// raw-DC tokens of every tile are rewritten in the pool as final difference tokens, so the entropy coder sees one
+// uniform token format.
+__global__ void __launch_bounds__(256)
+k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restrict__ pred_in,
+               uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist,
+               uint32_t *__restrict__ pool, int resolve) {
+    __shared__ uint32_t s_h[2][16];   // DC categories 0..11 of the two DC tables, aggregated per CTA
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ntile = g.tiles_x * g.mcuy;
-    if (t < ntile * 3 && do_hist) {
+    if (threadIdx.x < 32) s_h[threadIdx.x >> 4][threadIdx.x & 15] = 0;
+    __syncthreads();
+    if (t < ntile * 3 && (do_hist || resolve)) {
         const int tile = t / 3, c = t - tile * 3;
-        const int dc = recs[tile].first_dc[c];
+        const TileRec r = recs[tile];
+        const int dc = r.first_dc[c];
         const int pd = tile > 0 ? recs[tile - 1].last_dc[c] : pred_in[c];
-        atomicAdd(&ghist[(c ? 2 : 0) * 257 + nbits_of(dc - pd)], 1u);
+        const int diff = dc - pd;
+        const int nb = nbits_of(diff);
+        if (do_hist) atomicAdd(&s_h[c ? 1 : 0][nb & 15], 1u);
+        if (resolve) {
+            const uint32_t p = c == 0 ? 0u : (c == 1 ? r.pos_cb : r.pos_cr);
+            pool[r.base + p] = ((uint32_t)(c ? 2 : 0) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+        }
     }
     if (t < 3) last_dc[t] = recs[ntile - 1].last_dc[t];
+    __syncthreads();
+    if (do_hist && threadIdx.x < 32) {
+        const uint32_t n = s_h[threadIdx.x >> 4][threadIdx.x & 15];
+        if (n) atomicAdd(&ghist[(threadIdx.x >> 4) * 2 * 257 + (threadIdx.x & 15)], n);
+    }
 }
 
 template <int HS, int VS, bool DUMP>
@@ -529,9 +550,9 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 }
 
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, cudaStream_t s) {
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, cudaStream_t s) {
     const int n = max(3, g.tiles_x * g.mcuy * 3);
-    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(recs, g, pred_in, hist, last_dc, do_hist);
+    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(recs, g, pred_in, hist, last_dc, do_hist, pool, resolve);
     return cudaGetLastError();
 }
 

@@ -205,175 +205,289 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
 
 // ------------------------------------------------------------------------------------------------------
 // k_pack: token-parallel entropy coding (jchuff.c encode_one_block's emit_bits, without its run-length walk: that
-// happened once, in k_fdct). One CTA = one fdct tile's token run; every thread takes an equal, contiguous share:
-//   1. length pass: sum of (code length + value bits) over the share      (one table lookup per token)
-//   2. CTA exclusive scan -> the share's bit offset inside the tile
-//   3. emit pass: codes are appended to a 64-bit accumulator and flushed as 32-bit words straight to their final
-//      position in a shared bit buffer; only the first/last word of a share is shared with its neighbours (atomicOr)
-//   4. the tile's words are copied to its fixed-size slot in global memory (tile t at t*SLOT_WORDS)
-// Work per lane is uniform (no per-coefficient branch). Tiles whose bit string exceeds the 32 KB window repeat 3-4.
-constexpr int WIN_WORDS = 2048;   // 64 kbit bit-buffer window (a typical tile is ~30 kbit)
+// happened once, in k_fdct). Persistent CTAs of PACK_WARPS warps walk the fdct tiles; all the work is convergent:
+//   1. length pass: warp w takes a contiguous share of the tile's token run; every lane loads PACK_K consecutive
+//      tokens per step (16-byte loads) and sums (code length + value bits); the warp totals give each warp its bit
+//      offset inside the tile and the tile's size                                     [the only CTA barrier per tile]
+//   2. scatter pass: the same walk; a warp scan of the lanes' bit counts gives every lane its bit position; the
+//      lane appends its PACK_K codes to a 64-bit accumulator and ORs every completed 32-bit word into the tile's
+//      bit buffer (predicated shared-memory reductions: the words at a lane's ends are shared with its neighbours)
+//   3. every warp copies the words that lie wholly inside its own bit range to the tile's fixed-size slot in
+//      global memory (tile t at t*SLOT_WORDS); the few words shared by two warps are copied after the NEXT tile's
+//      barrier, which is why the bit buffer is double-buffered
+// Tiles whose bit string exceeds the 64 kbit buffer take a fully synchronised path, one window at a time.
+// Raw-DC tokens were resolved by k_dc_edge_hist; ZRL prefixes (token bits 29:28) are emitted in a side branch.
+constexpr int WIN_WORDS = 2048;                  // 64 kbit bit-buffer window (a typical tile is ~30 kbit)
+constexpr int PACK_THREADS = 128;                // one CTA per tile at a time, PACK_WARPS contiguous shares
+constexpr int PACK_WARPS = PACK_THREADS / 32;
+constexpr int PACK_CTAS = 8;                     // resident CTAs per SM (register budget)
+constexpr int PACK_K = 8;                        // consecutive tokens per lane and step
+constexpr int PACK_STEP = 32 * PACK_K;           // tokens per warp and step
+constexpr uint32_t TOK_NULL = 0x00100000u;       // DC0 symbol 0x10 does not exist: code length 0, no value bits
 
-struct Emitter {
+struct PackShared {
+    uint32_t buf[2][WIN_WORDS];
+    uint32_t enc[1024];
+    uint32_t wlen[3][PACK_WARPS];                // bit counts of the warps' shares, three tiles deep
+};
+
+// One lane's contiguous piece of the bit string: bits are appended to a 64-bit accumulator and every completed
+// 32-bit word is OR-ed into the window. `cnt` = valid low bits of acc that are not flushed yet (< 32 between calls).
+// Fast variant: predicated red.shared (no branch); windowed variant: words outside the window are skipped.
+template <bool WINDOWED>
+struct LaneEmitter {
     uint64_t acc;
-    int cnt;
-    int wpos;        // absolute word index inside the tile
-    int wbase;       // first word of the current window
-    bool first;
+    uint32_t cnt;
+    uint32_t addr;   // fast: shared byte address of the current word
+    int wi;          // windowed: word index relative to the window
     uint32_t *buf;
-    __device__ __forceinline__ void flush(uint32_t w, bool shared_word) {
-        const unsigned wi = (unsigned)(wpos - wbase);
-        if (wi < (unsigned)WIN_WORDS) {
-            if (shared_word) atomicOr(&buf[wi], w);
-            else buf[wi] = w;
-        }
-        wpos++;
+    __device__ __forceinline__ void start(uint32_t *b, int pos) {
+        buf = b; acc = 0; cnt = (uint32_t)pos & 31u; wi = pos >> 5;
+        addr = smem_u32(b) + (uint32_t)(pos >> 5) * 4u;
     }
-    __device__ __forceinline__ void put(uint32_t bits, int n) {
+    __device__ __forceinline__ void put(uint32_t bits, uint32_t n) {   // n <= 32
         acc = (acc << n) | bits;
         cnt += n;
-        if (cnt >= 32) {
-            cnt -= 32;
-            flush((uint32_t)(acc >> cnt), first);
-            first = false;
+        if (WINDOWED) {
+            if (cnt >= 32u) {
+                cnt -= 32u;
+                if ((uint32_t)wi < (uint32_t)WIN_WORDS) atomicOr(&buf[wi], (uint32_t)(acc >> cnt));
+                wi++;
+            }
+        } else {
+            const uint32_t wv = __funnelshift_r((uint32_t)acc, (uint32_t)(acc >> 32), cnt);   // acc >> (cnt - 32) if cnt >= 32
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, 32;\n\t@p red.shared.or.b32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t@p sub.u32 %1, %1, 32;\n\t}"
+                         : "+r"(addr), "+r"(cnt) : "r"(wv) : "memory");
         }
     }
     __device__ __forceinline__ void finish() {
-        if (cnt > 0) flush((uint32_t)(acc << (32 - cnt)), true);
+        if (cnt) {
+            const uint32_t wv = (uint32_t)acc << (32u - cnt);
+            if (WINDOWED) { if ((uint32_t)wi < (uint32_t)WIN_WORDS) atomicOr(&buf[wi], wv); }
+            else asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(wv) : "memory");
+        }
     }
 };
 
-// raw-DC tokens (first MCU of a tile): form the difference against the previous tile's last DC
-__device__ __forceinline__ uint32_t resolve_token(uint32_t t, const int16_t *pd) {
-    if (!(t & TOK_RAWDC)) return t;
-    const int comp = (int)((t >> 16) & 3u);
-    const int diff = (int)(int16_t)(t & 0xFFFFu) - (int)pd[comp];
-    const int nb = 32 - __clz(diff < 0 ? -diff : diff);
-    return (t & (3u << 24)) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+// PACK_K tokens of one lane: virtual indices [v0, v0 + PACK_K) of the walk that starts at the 16-byte boundary
+// below the tile's run; indices outside [a, hi) become TOK_NULL
+__device__ __forceinline__ void load_tokens(const uint4 *tk4, uint32_t v0, uint32_t a, uint32_t hi, uint32_t (&w)[PACK_K]) {
+#pragma unroll
+    for (int q = 0; q < PACK_K / 4; q++) {
+        const uint4 x = __ldg(tk4 + (v0 >> 2) + q);
+        w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
+    }
+    if (v0 < a || v0 + PACK_K > hi) {
+#pragma unroll
+        for (int k = 0; k < PACK_K; k++)
+            if (v0 + k < a || v0 + k >= hi) w[k] = TOK_NULL;
+    }
 }
 
-constexpr int TOK_CAP = 8192;   // tokens staged in shared memory (32 per block); denser tiles read the pool directly
-
-struct PackShared {
-    uint32_t tok[TOK_CAP];
-    uint32_t buf[WIN_WORDS];
-    uint32_t enc[1024];
-    uint32_t warp[8];
-    uint32_t total;
-    int16_t pd[4];
-};
-
-template <bool STAGED>
-__device__ __forceinline__ void pack_tile(PackShared &sh, const uint32_t *__restrict__ tk, uint32_t ntok, int t,
-                                          uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // equal contiguous shares; an odd share length keeps the strided shared-memory reads conflict-free
-    uint32_t per = (ntok + PACK_BLOCKS - 1) / PACK_BLOCKS;
-    per |= 1u;
-    const uint32_t lo = min(ntok, (uint32_t)tid * per), hi = min(ntok, lo + per);
-    auto TOKEN = [&](uint32_t i) -> uint32_t { return STAGED ? sh.tok[i] : resolve_token(__ldg(tk + i), sh.pd); };
-    const uint32_t zl_y = sh.enc[0x1F0] & 31u, zl_c = sh.enc[0x3F0] & 31u;
-
-    // ---- length pass
-    uint32_t len = 0;
-    for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t tkn = TOKEN(i);
-        len += (sh.enc[(tkn >> 16) & 0x3FFu] & 31u) + ((tkn >> 16) & 15u) + (tkn >> 28) * ((tkn & (2u << 24)) ? zl_c : zl_y);
+template <bool WINDOWED>
+__device__ __forceinline__ void pack_scatter(const uint32_t *enc, uint32_t *buf, const uint4 *tk4, uint32_t a, uint32_t lo,
+                                             uint32_t hi, int run, int lane, uint32_t zr_y, uint32_t zr_c) {
+    const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
+    for (uint32_t s0 = lo; s0 < hi; s0 += PACK_STEP) {
+        const uint32_t v0 = s0 + lane * PACK_K;
+        uint32_t w[PACK_K], L[PACK_K], bits[PACK_K];
+        uint32_t Lt = 0;
+        if (v0 < hi) load_tokens(tk4, v0, a, hi, w);
+        else {
+#pragma unroll
+            for (int k = 0; k < PACK_K; k++) w[k] = TOK_NULL;
+        }
+#pragma unroll
+        for (int k = 0; k < PACK_K; k++) {
+            const uint32_t en = enc[(w[k] >> 16) & 0x3FFu];
+            const uint32_t nb = (w[k] >> 16) & 15u;
+            L[k] = (en & 31u) + nb;
+            bits[k] = ((en >> 8) << nb) | (w[k] & 0xFFFFu);
+            Lt += L[k] + (w[k] >> 28) * ((w[k] & (2u << 24)) ? zl_c : zl_y);
+        }
+        uint32_t inc = Lt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        LaneEmitter<WINDOWED> e;
+        e.start(buf, run + (int)(inc - Lt));
+        run += (int)__shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int k = 0; k < PACK_K; k++) {
+            const uint32_t nz = w[k] >> 28;
+            if (nz) {   // ZRL symbols ahead of this coefficient (about one token in sixty)
+                const uint32_t zr = (w[k] & (2u << 24)) ? zr_c : zr_y;
+                e.put(zr >> 8, zr & 31u);
+                if (nz > 1u) {
+                    e.put(zr >> 8, zr & 31u);
+                    if (nz > 2u) e.put(zr >> 8, zr & 31u);
+                }
+            }
+            e.put(bits[k], L[k]);
+        }
+        e.finish();
     }
-    uint32_t inc = len;
+}
+
+// words of the previous tile that two warps share (and its last, partial word): copy to the slot, clear
+__device__ __forceinline__ void pack_flush_shared_words(uint32_t *buf, const uint32_t *wlen, uint32_t *slot) {
+    uint32_t pos = 0, last = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < PACK_WARPS; w++) {
+        pos += wlen[w];   // end of warp w = start of warp w + 1 (or the tile's end)
+        const uint32_t wi = pos >> 5;
+        if ((pos & 31u) && wi != last) { slot[wi] = buf[wi]; buf[wi] = 0; last = wi; }
+    }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
+k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int ntiles, const HuffDev *__restrict__ huff,
+       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
+    __shared__ __align__(16) PackShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 1024; i += PACK_THREADS) sh.enc[i] = huff->enc[i >> 8][i & 255];
+    for (int i = tid; i < 2 * WIN_WORDS; i += PACK_THREADS) sh.buf[0][i] = 0;
+    __syncthreads();
+    const uint32_t zr_y = sh.enc[0x1F0], zr_c = sh.enc[0x3F0];   // ZRL (0xF0) codes of the two AC tables
+    const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
+
+    bool pend = false;      // the previous tile's shared words are still in its buffer
+    uint32_t *pslot = nullptr;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        const int cur = it & 1, l3 = it % 3, pl3 = (it + 2) % 3;
+        const TileRec rec = recs[t];
+        // the walk starts at the 16-byte boundary below the run: virtual index v = token index + a
+        const uint32_t a = rec.base & 3u;
+        const uint32_t vend = a + rec.count;
+        const uint4 *tk4 = reinterpret_cast<const uint4 *>(pool + (rec.base - a));
+        // warp shares: contiguous, a multiple of PACK_STEP tokens; every lane owns PACK_K consecutive tokens per step
+        const uint32_t per = (((vend + PACK_WARPS - 1u) / PACK_WARPS) + PACK_STEP - 1u) & ~(uint32_t)(PACK_STEP - 1);
+        const uint32_t lo = min(vend, (uint32_t)wid * per), hi = min(vend, lo + per);
+
+        // the next tile's token run on its way into L2 while this one is coded
+        if (t + (int)gridDim.x < ntiles) {
+            const TileRec nx = recs[t + gridDim.x];
+            const char *p0 = reinterpret_cast<const char *>(pool + (nx.base & ~31u));
+            const uint32_t nbytes = ((nx.base & 31u) + nx.count) * 4u;
+            for (uint32_t o = tid * 128u; o < nbytes; o += PACK_THREADS * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+        }
+
+        // ---- 1. length pass (loads run one step ahead of the table lookups)
+        uint32_t len = 0;
+        {
+            uint32_t v0 = lo + lane * PACK_K;
+            uint32_t w[PACK_K], wn[PACK_K];
+            if (v0 < hi) load_tokens(tk4, v0, a, hi, w);
+            while (v0 < hi) {
+                const uint32_t v1 = v0 + PACK_STEP;
+                if (v1 < hi) load_tokens(tk4, v1, a, hi, wn);
+#pragma unroll
+                for (int k = 0; k < PACK_K; k++)
+                    len += (sh.enc[(w[k] >> 16) & 0x3FFu] & 31u) + ((w[k] >> 16) & 15u) + (w[k] >> 28) * ((w[k] & (2u << 24)) ? zl_c : zl_y);
+#pragma unroll
+                for (int k = 0; k < PACK_K; k++) w[k] = wn[k];
+                v0 = v1;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+        if (lane == 0) sh.wlen[l3][wid] = len;
+        __syncthreads();   // also: every warp is done with the previous tile's buffer
+        if (pend && tid == 0) pack_flush_shared_words(sh.buf[cur ^ 1], sh.wlen[pl3], pslot);
+        uint32_t base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < PACK_WARPS; w++) { const uint32_t x = sh.wlen[l3][w]; if (w < wid) base += x; total += x; }
+        if (tid == 0) tile_bits[t] = total;
+        const uint32_t nwords = (total + 31u) >> 5;
+        uint32_t *slot = slots + (size_t)t * SLOT_WORDS;
+        uint32_t *buf = sh.buf[cur];
+
+        if (nwords <= (uint32_t)WIN_WORDS) {
+            // ---- 2. scatter pass (the buffer is all zero here)
+            pack_scatter<false>(sh.enc, buf, tk4, a, lo, hi, (int)base, lane, zr_y, zr_c);
+            __syncwarp();
+            // ---- 3. words wholly inside this warp's bit range: copy out and clear
+            const uint32_t fw = (base + 31u) >> 5, lw = (base + len) >> 5;
+            for (uint32_t i = fw + lane; i < lw; i += 32) { slot[i] = buf[i]; buf[i] = 0; }
+            pend = true;
+            pslot = slot;
+        } else {
+            for (uint32_t wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
+                pack_scatter<true>(sh.enc, buf, tk4, a, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
+                __syncthreads();
+                const uint32_t wn = min((uint32_t)WIN_WORDS, nwords - wbase);
+                for (uint32_t i = tid; i < wn; i += PACK_THREADS) { slot[wbase + i] = buf[i]; buf[i] = 0; }
+                __syncthreads();
+            }
+            pend = false;
+        }
+    }
+    __syncthreads();
+    if (pend && tid == 0) pack_flush_shared_words(sh.buf[(it + 1) & 1], sh.wlen[(it + 2) % 3], pslot);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_scan_tiles: exclusive scan of the per-tile bit counts (ntiles ~ 4e4 for the headline image). One CTA per chunk
+// of 4096 counts (16-byte coalesced loads, 4 counts per thread, warp shuffles), chunks chained by a decoupled
+// look-back over `desc` (zeroed per encode; chunk ids come from a ticket so predecessors are always running).
+constexpr int SCAN_CHUNK = 4096;
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__restrict__ tile_off,
+             const uint32_t *__restrict__ slots, uint64_t *__restrict__ strip_bits, uint64_t *__restrict__ desc,
+             uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint64_t s_carry;
+    __shared__ int s_chunk;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int ch = s_chunk;
+    const int i0 = ch * SCAN_CHUNK + tid * 4;
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (i0 + 3 < ntiles) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(tile_bits + i0);   // tile_bits is 16-byte aligned, i0 % 4 == 0
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k < ntiles) v[k] = tile_bits[i0 + k];
+    }
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];   // < 2^32: a chunk holds at most 4096 * 425984 bits
+    uint32_t inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += y;
     }
-    if (lane == 31) sh.warp[wid] = inc;
+    if (lane == 31) s_w[wid] = inc;
     __syncthreads();
-    if (tid == 0) {
-        uint32_t s = 0;
-        for (int w = 0; w < 8; w++) { const uint32_t x = sh.warp[w]; sh.warp[w] = s; s += x; }
-        sh.total = s;
-        tile_bits[t] = s;
+    uint32_t wv = s_w[lane], winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += y;
+    }
+    const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wv, wid);
+    const uint32_t ctotal = __shfl_sync(0xffffffffu, winc, 31);
+    if (wid == 0) {
+        const uint64_t pre = lookback_exclusive(desc, ch, ctotal, err);
+        if (lane == 0) s_carry = pre;
     }
     __syncthreads();
-    const uint32_t off = sh.warp[wid] + inc - len;
-    const uint32_t total = sh.total;
-    const int nwords = (int)((total + 31) >> 5);
-    uint32_t *slot = slots + (size_t)t * SLOT_WORDS;
-
-    for (int wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
-        const int wn = min(WIN_WORDS, nwords - wbase);
-        for (int i = tid; i < wn; i += PACK_BLOCKS) sh.buf[i] = 0;
-        __syncthreads();
-        if (lo < hi) {
-            Emitter e;
-            e.acc = 0; e.cnt = (int)(off & 31u); e.wpos = (int)(off >> 5); e.wbase = wbase; e.first = true; e.buf = sh.buf;
-            for (uint32_t i = lo; i < hi; i++) {
-                const uint32_t tkn = TOKEN(i);
-                const uint32_t en = sh.enc[(tkn >> 16) & 0x3FFu];
-                const uint32_t nb = (tkn >> 16) & 15u;
-                if (tkn >> 28) {  // ZRL symbols ahead of this coefficient
-                    const uint32_t zr = sh.enc[((tkn >> 16) & 0x300u) | 0xF0u];
-#pragma unroll 1
-                    for (uint32_t q = tkn >> 28; q; q--) e.put(zr >> 8, (int)(zr & 31u));
-                }
-                e.put(((en >> 8) << nb) | (tkn & 0xFFFFu), (int)((en & 31u) + nb));
-            }
-            e.finish();
-        }
-        __syncthreads();
-        for (int i = tid; i < wn; i += PACK_BLOCKS) slot[wbase + i] = sh.buf[i];
-        __syncthreads();
+    const uint64_t carry = s_carry;
+    uint64_t run = carry + wbase + (inc - mine);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i0 + k < ntiles) tile_off[i0 + k] = run;
+        run += v[k];
     }
-}
-
-__global__ void __launch_bounds__(PACK_BLOCKS, 4)
-k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const HuffDev *__restrict__ huff,
-       const int16_t *__restrict__ pred_in, uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
-    __shared__ __align__(16) PackShared sh;
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x;
-    const TileRec rec = recs[t];
-    const uint32_t ntok = rec.count;
-    const uint32_t *tk = pool + rec.base;
-    if (tid < 3) sh.pd[tid] = t > 0 ? recs[t - 1].last_dc[tid] : pred_in[tid];
-    for (int i = tid; i < 1024; i += PACK_BLOCKS) sh.enc[i] = huff->enc[i >> 8][i & 255];
-    if (ntok <= TOK_CAP) {
-        __syncthreads();
-        // coalesced loads of the tile's token run; the (at most three) raw-DC tokens are resolved on the way in
-#pragma unroll 4
-        for (uint32_t i = tid; i < ntok; i += PACK_BLOCKS) sh.tok[i] = resolve_token(__ldg(tk + i), sh.pd);
-        __syncthreads();
-        pack_tile<true>(sh, tk, ntok, t, slots, tile_bits);
-    } else {
-        __syncthreads();
-        pack_tile<false>(sh, tk, ntok, t, slots, tile_bits);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// k_scan_tiles: exclusive scan of the per-tile bit counts (one CTA; ntiles ~ 4e4 for the headline image)
-__global__ void __launch_bounds__(1024)
-k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__restrict__ tile_off,
-             const uint32_t *__restrict__ slots, uint64_t *__restrict__ strip_bits) {
-    __shared__ uint64_t s_part[1024];
-    const int tid = threadIdx.x;
-    const int per = (ntiles + 1023) / 1024;
-    const int lo = min(ntiles, tid * per), hi = min(ntiles, lo + per);
-    uint64_t s = 0;
-    for (int i = lo; i < hi; i++) s += tile_bits[i];
-    s_part[tid] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const uint64_t y = tid >= o ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += y;
-        __syncthreads();
-    }
-    uint64_t run = s_part[tid] - s;
-    for (int i = lo; i < hi; i++) { tile_off[i] = run; run += tile_bits[i]; }
-    if (tid == 1023) {
-        tile_off[ntiles] = s_part[1023];
-        strip_bits[0] = s_part[1023];
+    if (ch == (int)gridDim.x - 1 && tid == 0) {
+        const uint64_t T = carry + ctotal;
+        tile_off[ntiles] = T;
+        strip_bits[0] = T;
         strip_bits[1] = ntiles > 0 ? slots[0] : 0;
     }
 }
@@ -395,7 +509,8 @@ k_stuff(StuffArgs a) {
     __shared__ __align__(16) uint8_t s_out[2 * STUFF_CHUNK + 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t T = a.tile_off[a.ntiles];
-    const uint64_t NB = T > (uint64_t)a.skip ? (T - a.skip + 7) >> 3 : 0;
+    const int a_skip = a.seam[0], a_ext = a.seam[1];
+    const uint64_t NB = T > (uint64_t)a_skip ? (T - a_skip + 7) >> 3 : 0;
     const int nchunks = (int)max((uint64_t)1, (NB + STUFF_CHUNK - 1) / STUFF_CHUNK);
     const uint32_t hdr = a.huff->hdr_len;
 
@@ -405,7 +520,7 @@ k_stuff(StuffArgs a) {
         const int ch = s_chunk;
         if (ch >= nchunks) break;
         const uint64_t j0c = (uint64_t)ch * STUFF_CHUNK;
-        const uint64_t p0c = (uint64_t)a.skip + 8 * j0c;
+        const uint64_t p0c = (uint64_t)a_skip + 8 * j0c;
         if (wid == 0) {  // tile containing the chunk's first bit: largest tau with tile_off[tau] <= p0c (32-ary search)
             int lo = 0, hi = a.ntiles;  // invariant: tile_off[lo] <= p0c < tile_off[hi]
             while (hi - lo > 1) {
@@ -442,7 +557,7 @@ k_stuff(StuffArgs a) {
 #pragma unroll
         for (int q = 0; q < NW; q++) w[q] = 0;
         if (nvalid > 0) {
-            uint64_t p = (uint64_t)a.skip + 8 * j0;
+            uint64_t p = (uint64_t)a_skip + 8 * j0;
             int tau = tau0;
             while (TOFF(tau + 1) <= p) tau++;
             const uint64_t tend = TOFF(tau + 1);
@@ -466,7 +581,7 @@ k_stuff(StuffArgs a) {
                             const uint64_t e = p - T;
                             uint32_t x = 0xffffffffu;
                             if (e < 32) {
-                                x = ((uint32_t)a.ext << 24) | 0x00ffffffu;
+                                x = ((uint32_t)a_ext << 24) | 0x00ffffffu;
                                 if (e) x = (x << e) | ((1u << e) - 1u);
                             }
                             res |= x >> got;
@@ -554,6 +669,28 @@ k_stuff(StuffArgs a) {
                 for (int q = 0; q < NW - 1; q++) d[q] = __funnelshift_r(l[q], l[q + 1], r);
                 for (uint32_t b = 0; b < al; b++) s_out[o + STUFF_BPT - al + b] = (uint8_t)(l[NW - 1] >> (r + 8 * b));
             }
+        } else if (nvalid == STUFF_BPT) {
+            // some 0xFF in these 32 bytes (one thread in eight): whole words without one go out as four byte stores,
+            // only the word that holds it is walked byte by byte
+#pragma unroll
+            for (int q = 0; q < NW; q++) {
+                uint32_t m = w[q] & (w[q] >> 4) & 0x0F0F0F0Fu;
+                m &= m >> 2;
+                m &= m >> 1;
+                m &= 0x01010101u;
+                if (m == 0u) {
+                    s_out[o] = (uint8_t)(w[q] >> 24); s_out[o + 1] = (uint8_t)(w[q] >> 16);
+                    s_out[o + 2] = (uint8_t)(w[q] >> 8); s_out[o + 3] = (uint8_t)w[q];
+                    o += 4;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t byte = (w[q] >> (24 - 8 * b)) & 0xFFu;
+                        s_out[o++] = (uint8_t)byte;
+                        if (byte == 0xFFu) s_out[o++] = 0;
+                    }
+                }
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < STUFF_BPT; i++) {
@@ -593,14 +730,37 @@ cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, con
     k_tables<<<1, 128, 0, s>>>(hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header);
     return cudaGetLastError();
 }
-cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff, const int16_t *pred_in,
+cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, cudaStream_t s) {
-    k_pack<<<g.ntiles, PACK_BLOCKS, 0, s>>>(pool, recs, huff, pred_in, slots, tile_bits);
+    const int grid = min(g.ntiles, 148 * PACK_CTAS);
+    k_pack<<<grid, PACK_THREADS, 0, s>>>(pool, recs, g.ntiles, huff, slots, tile_bits);
     return cudaGetLastError();
 }
+int scan_desc_count(int ntiles) { return (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
-                              uint64_t *strip_bits, cudaStream_t s) {
-    k_scan_tiles<<<1, 1024, 0, s>>>(tile_bits, ntiles, tile_off, slots, strip_bits);
+                              uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *err, cudaStream_t s) {
+    const int grid = max(1, (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    k_scan_tiles<<<grid, 1024, 0, s>>>(tile_bits, ntiles, tile_off, slots, strip_bits, desc, ticket, err);
+    return cudaGetLastError();
+}
+__global__ void k_set_seam(int *seam, int skip, int ext) { seam[0] = skip; seam[1] = ext; }
+
+// bits_all[k] = {entropy bits of strip k, its first 32 bits (top-aligned)}: strip `rank` starts at global bit G =
+// sum of the bit counts before it; it skips the (8 - G % 8) % 8 bits that complete the previous strip's last byte and
+// borrows the next strip's first byte for its own last one (1-bits after the last strip).
+__global__ void k_seam_from_bits(int *seam, const int64_t *__restrict__ bits_all, int rank, int world) {
+    uint64_t G = 0;
+    for (int k = 0; k < rank; k++) G += (uint64_t)bits_all[2 * k];
+    seam[0] = (int)((8u - (uint32_t)(G & 7u)) & 7u);
+    seam[1] = rank == world - 1 ? 0xFF : (int)(((uint64_t)bits_all[2 * (rank + 1) + 1] >> 24) & 0xFFu);
+}
+
+cudaError_t launch_set_seam(int *seam, int skip, int ext, cudaStream_t s) {
+    k_set_seam<<<1, 1, 0, s>>>(seam, skip, ext);
+    return cudaGetLastError();
+}
+cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, int world, cudaStream_t s) {
+    k_seam_from_bits<<<1, 1, 0, s>>>(seam, bits_all, rank, world);
     return cudaGetLastError();
 }
 cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s) {

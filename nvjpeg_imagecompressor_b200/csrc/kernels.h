@@ -10,21 +10,24 @@ int fdct_tm_max(int hs, int vs);
 cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, uint32_t *pool,
                         uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
                         int16_t *coef_dump, cudaStream_t s);
+// resolve != 0: also rewrite each tile's three raw-DC tokens in `pool` as final DC-difference tokens
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, cudaStream_t s);
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, cudaStream_t s);
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
                           int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s);
-cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff, const int16_t *pred_in,
+cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, cudaStream_t s);
+// desc: scan_desc_count(ntiles) zeroed look-back descriptors; ticket: zeroed
+int scan_desc_count(int ntiles);
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
-                              uint64_t *strip_bits, cudaStream_t s);
+                              uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *err, cudaStream_t s);
 struct StuffArgs {
     const uint32_t *slots;
     const uint32_t *tile_bits;
     const uint64_t *tile_off;   // [ntiles+1]
     int ntiles;
-    int skip;                   // leading bits owned by the previous strip's last byte
-    int ext;                    // next strip's first 8 bits (0xFF: pad with ones)
+    const int *seam;            // device: [0] skip = leading bits owned by the previous strip's last byte,
+                                //         [1] ext = next strip's first 8 bits (0xFF: pad with ones)
     int append_eoi;
     const HuffDev *huff;        // hdr_len
     uint8_t *out;
@@ -35,6 +38,9 @@ struct StuffArgs {
     uint32_t *err;
 };
 cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s);
+// seam[0..1] from host scalars, or from the all-gathered per-strip (bit count, first 32 bits) table on the device
+cudaError_t launch_set_seam(int *seam, int skip, int ext, cudaStream_t s);
+cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, int world, cudaStream_t s);
 
 // decode
 struct DecArgs;

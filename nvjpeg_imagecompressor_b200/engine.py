@@ -155,6 +155,9 @@ class Engine:
     def strip_phase3(self, skip_bits, ext_byte, flags):
         self._ck(self._L.b2j_strip_phase3(self._h, skip_bits, ext_byte, flags))
 
+    def strip_phase3_dev(self, d_bits_all, rank, world, flags):
+        self._ck(self._L.b2j_strip_phase3_dev(self._h, C.c_void_p(d_bits_all), rank, world, flags))
+
     # introspection
     def debug_read(self, what, dtype, count_hint=None):
         n = C.c_size_t(0)

@@ -90,6 +90,10 @@ class EngineBackend:
     def phase3(self, skip, ext, flags):
         self.eng.strip_phase3(skip, ext, flags)
 
+    def phase3_dev(self, bits_all, rank, world, flags):
+        """bits_all: device int64 [world][2] (all-gathered strip_bits); the seam is derived on the device."""
+        self.eng.strip_phase3_dev(bits_all.data_ptr(), rank, world, flags)
+
     def out_view(self, n):
         return _view(self._d_out, (int(n),), "|u1", self.device)
 
@@ -130,13 +134,17 @@ class StripEncoder:
         if w > 1 and self.optimize:
             dist.all_reduce(b.hist, op=dist.ReduceOp.SUM, group=self.group)
         b.phase2(self.W, self.H)
+        flags = (1 if r == 0 else 0) | (2 if r == w - 1 else 0)
         if w > 1:
             dist.all_gather_into_tensor(self._bits_all.view(-1), b.strip_bits, group=self.group)
-            bits = self._bits_all.cpu().numpy()  # the one host sync of the pipeline: phase 3 takes host scalars
+            if hasattr(b, "phase3_dev"):   # GPU backend: seam parameters derived on the device, no host sync
+                b.phase3_dev(self._bits_all, r, w, flags)
+                return b.out_len
+            bits = self._bits_all.cpu().numpy()
             skip, ext = seam_params(bits[:, 0], bits[:, 1].astype(np.uint64) & 0xFFFFFFFF)[r]
         else:
             skip, ext = 0, 0xFF
-        b.phase3(skip, ext, (1 if r == 0 else 0) | (2 if r == w - 1 else 0))
+        b.phase3(skip, ext, flags)
         return b.out_len
 
     def gather_lengths(self):

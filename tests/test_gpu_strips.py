@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def encode_strips_one_gpu(img, css, q, opt, nstrips):
+def encode_strips_one_gpu(img, css, q, opt, nstrips, dev_seam=False):
     from nvjpeg_imagecompressor_b200.strips import EngineBackend, seam_params, strip_rows
     H, W = img.shape[:2]
     d = torch.from_numpy(img).cuda()
@@ -35,10 +35,15 @@ def encode_strips_one_gpu(img, css, q, opt, nstrips):
     for b in bs:
         b.phase2(W, H)
     torch.cuda.synchronize()
-    sb = np.stack([b.strip_bits.cpu().numpy() for b in bs])
-    sp = seam_params(sb[:, 0], sb[:, 1].astype(np.uint64) & 0xFFFFFFFF)
-    for k, b in enumerate(bs):
-        b.phase3(sp[k][0], sp[k][1], (1 if k == 0 else 0) | (2 if k == nstrips - 1 else 0))
+    if dev_seam:   # what the NCCL path does: all-gathered (bits, first word) table stays on the device
+        bits_all = torch.stack([b.strip_bits for b in bs]).contiguous()
+        for k, b in enumerate(bs):
+            b.phase3_dev(bits_all, k, nstrips, (1 if k == 0 else 0) | (2 if k == nstrips - 1 else 0))
+    else:
+        sb = np.stack([b.strip_bits.cpu().numpy() for b in bs])
+        sp = seam_params(sb[:, 0], sb[:, 1].astype(np.uint64) & 0xFFFFFFFF)
+        for k, b in enumerate(bs):
+            b.phase3(sp[k][0], sp[k][1], (1 if k == 0 else 0) | (2 if k == nstrips - 1 else 0))
     torch.cuda.synchronize()
     parts = [b.out_view(int(b.out_len.item())).cpu().numpy() for b in bs]
     for b in bs:
@@ -50,14 +55,15 @@ def encode_strips_one_gpu(img, css, q, opt, nstrips):
                                            (129, 200, 0, 75, 0, 3), (96, 250, 2, 95, 1, 5), (160, 64, 4, 100, 1, 8)])
 def test_strips_equal_single_stream(oracle, W, H, css, q, opt, n):
     img = oracle.synth(W, H, 7, 8)
-    out = encode_strips_one_gpu(img, css, q, opt, n)
     want = oracle.encode(img, css, q, opt)
-    assert out.size == want.size and np.array_equal(out, want)
+    for dev_seam in (False, True):
+        out = encode_strips_one_gpu(img, css, q, opt, n, dev_seam)
+        assert out.size == want.size and np.array_equal(out, want), f"dev_seam={dev_seam}"
 
 
 def test_strips_headline_slab(oracle, golden):
     import hashlib
     img = oracle.synth(8320, 2000, 0, 8)
     c = golden["slab"][0]
-    out = encode_strips_one_gpu(img, c["css"], c["quality"], c["optimize"], 8)
+    out = encode_strips_one_gpu(img, c["css"], c["quality"], c["optimize"], 8, dev_seam=True)
     assert out.size == c["jpeg_len"] and hashlib.sha256(out.tobytes()).hexdigest() == c["jpeg_sha256"]
