@@ -9,11 +9,12 @@
 // One CTA = one tile of up to TM_MAX MCUs inside one MCU row:
 //   TMA bulk copies (cp.async.bulk, one per pixel row) stage the raw BGR rows in shared memory   [interior tiles]
 //   stage A: every thread converts 8 pixels x VS rows -> Y / Cb / Cr sample planes in shared memory
-//   stage B: one thread per 8x8 block: 64 samples in registers, both FDCT passes, reciprocal quantisation,
-//            zig-zag, and the jchuff.c run-length walk emitting one 32-bit token per Huffman symbol
-//            (table | run/size symbol | value bits) into a per-thread list in shared memory
-//   stage C: per warp, the 32 lists are transposed into one compact block-ordered token run with full-warp
-//            coalesced stores (head-flag bitmap + popcount ranks), counting symbols with full-warp shared atomics
+//   stage B: one thread per 8x8 block: 64 samples in registers, both FDCT passes, reciprocal quantisation in place,
+//            branch-free count of the non-zero coefficients; a CTA scan of the counts gives every block its place
+//            in the tile's token run, then the jchuff.c run-length walk stores one (run | value) entry per non-zero
+//            coefficient straight to its final slot of the run in shared memory (two-instruction divergent body)
+//   stage C: the whole CTA walks the run in output order: entry -> (ZRL count | table | run/size symbol | value
+//            bits), symbol statistics with full-warp shared atomics, coalesced stores to the token pool
 // The entropy coder (enc_huff.cu k_pack) then works token-parallel: uniform work per lane instead of a divergent
 // per-coefficient branch. With DUMP the quantised coefficients are also written (parity tests only).
 #include "common.cuh"
@@ -30,8 +31,7 @@ struct K1 {
     static constexpr int TILE_PX = TM_MAX * MCU_W;
     static constexpr int RAW_STRIDE = TILE_PX * 3;  // multiple of 16 for all five modes
     static constexpr int RAW_BYTES = RAW_STRIDE * MCU_H;
-    static constexpr int TOK_STRIDE = 257;                 // tokens of one thread: tok[j * 257 + tid] (bank = j + tid)
-    static constexpr int TOK_BYTES = 64 * TOK_STRIDE * 4;   // <= 64 tokens per block
+    static constexpr int TOK_BYTES = 64 * 256 * 4 + 256;    // the tile's token run: <= 64 tokens per block
     static constexpr int STAGE_BYTES = 256 * 128;           // DUMP only
     static constexpr int Y_STRIDE = TILE_PX;
     static constexpr int Y_BYTES = Y_STRIDE * MCU_H;
@@ -45,9 +45,7 @@ struct K1 {
     static constexpr int OFF_Q = TOK_BYTES;              // uint2[2][64]
     static constexpr int OFF_HIST = OFF_Q + 1024;        // uint32[4][256]
     static constexpr int OFF_DC = OFF_HIST + 4096;       // int16[256]
-    static constexpr int BM_BYTES = 256 + 64 + 64;       // per warp: head bitmap u32[64], word ranks u8[64], offsets u16[32]
-    static constexpr int OFF_BM = OFF_DC + 512;
-    static constexpr int OFF_MISC = OFF_BM + 8 * BM_BYTES;  // warp totals[8], pool base
+    static constexpr int OFF_MISC = OFF_DC + 512;        // warp totals[8], pool base, chroma DC token offsets
     static constexpr int OFF_BAR = OFF_MISC + 64;        // mbarrier
     static constexpr int OFF_STAGE = OFF_BAR + 16;       // DUMP only
     static constexpr int SMEM = OFF_STAGE;
@@ -275,6 +273,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     if (isY) real = ((mx0 + m) * HS + bx < g.wib[0]) && (my * VS + by < g.hib[0]);
     int ntok = 0;
     int mydc = 0;
+    uint32_t pk[32];   // quantised coefficients, zig-zag order, two per word
     int v[64];
     if (active) {
         const uint8_t *src;
@@ -301,14 +300,11 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             fdct8<true>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
         v[0] -= 8192;  // 64 samples x 128: the only output the -128 level shift changes (exact: multiple of 4)
 
-        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply;
-        // walk the zig-zag sequence exactly like jchuff.c encode_one_block, one token per Huffman symbol
-        uint32_t pk[DUMP ? 32 : 1];
-        const uint32_t acsel = (uint32_t)(tbl * 2 + 1) << 24;
+        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply; the
+        // results are kept as 16-bit pairs in zig-zag order (they live across the CTA scan below); the non-zero AC
+        // coefficients are counted on the way (one token each)
         const uint2 *qt = qs + tbl * 64;
-        const uint32_t sa0 = smem_u32(tok + tid);
-        uint32_t sa = sa0 + C::TOK_STRIDE * 4;  // slot 0 is the DC token
-        int zlast = 0;
+        int nnz = 0, zprev = 0;
 #pragma unroll
         for (int k = 0; k < 64; k++) {
             const int n = zigzag_nat(k);
@@ -320,24 +316,11 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             int z = (qa ^ s) - s;
             if (k == 0) mydc = z;
             if (C::HV > 1 && !real && k > 0) z = 0;
-            if (k == 63) zlast = z;
-            if constexpr (DUMP) {
-                if (k & 1) pk[k >> 1] |= (uint32_t)z << 16;
-                else pk[k >> 1] = (uint32_t)z & 0xFFFFu;
-            }
-            if (k > 0 && z != 0) {
-                // the divergent region is three instructions: store (position | value); zero runs, ZRLs, sizes and
-                // value bits are derived in stage C with full warps
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(TOK_RAWAC | ((uint32_t)k << 16) | ((uint32_t)z & 0xFFFFu)) : "memory");
-                sa += C::TOK_STRIDE * 4;
-            }
+            if (k > 0) nnz += (z != 0);
+            if (k & 1) pk[k >> 1] = __byte_perm((uint32_t)zprev, (uint32_t)z, 0x5410);
+            else zprev = z;
         }
-        if (zlast == 0) {  // EOB iff the last coefficient is zero (jchuff.c: r > 0 after the loop)
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(acsel) : "memory");
-            sa += C::TOK_STRIDE * 4;
-        }
-        const int j = (int)((sa - sa0) / (C::TOK_STRIDE * 4));
-        ntok = j;
+        ntok = 1 + nnz + ((pk[31] >> 16) == 0u ? 1 : 0);   // DC, one per non-zero AC, EOB iff the last coefficient is zero
         if constexpr (DUMP) {
 #pragma unroll
             for (int c = 0; c < 8; c++)
@@ -367,12 +350,12 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     }
 
     // ---- DC token: difference to the previous block of the same component; predecessors outside the tile are
-    //      resolved by the entropy coder from TileRec.last_dc (token carries the raw DC)
+    //      resolved later by k_dc_edge_hist from TileRec.last_dc (the token carries the raw DC until then)
+    uint32_t t0 = 0;
     if (active) {
         int pb = -1;
         if (isY) pb = bn > 0 ? blk - 1 : (m > 0 ? blk - C::BPM + C::HV - 1 : -1);
         else pb = m > 0 ? blk - C::BPM : -1;
-        uint32_t t0;
         if (pb >= 0) {
             const int diff = mydc - (int)dcs[pb];
             const int nb = 32 - __clz(diff < 0 ? -diff : diff);
@@ -380,30 +363,47 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         } else {
             t0 = TOK_RAWDC | ((uint32_t)(tbl * 2) << 24) | ((uint32_t)comp << 16) | ((uint32_t)mydc & 0xFFFFu);
         }
-        tok[tid] = t0;
     }
 
-    // ---- stage C: per-warp transposition of the 32 token lists into one block-ordered run
-    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + C::OFF_BM + wid * C::BM_BYTES);  // head flags of the warp's run
-    uint8_t *rk = reinterpret_cast<uint8_t *>(bm + 64);                                 // heads before each bitmap word
-    uint16_t *ofs = reinterpret_cast<uint16_t *>(rk + 64);                              // first output index per lane
+    // ---- place of every block in the tile's token run: CTA scan of the token counts
     uint32_t inc = (uint32_t)ntok;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += y;
     }
-    const uint32_t off = inc - (uint32_t)ntok;
-    const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
-    bm[lane] = 0; bm[lane + 32] = 0;
-    ofs[lane] = (uint16_t)off;
-    if (lane == 31) misc[wid] = wtot;
-    if (tid == C::HV) misc[9] = off;        // run offsets of the first MCU's chroma DC tokens (warp 0: no warp base)
-    if (tid == C::HV + 1) misc[10] = off;
-    __syncthreads();  // also orders the DC tokens / bitmap zeroing before their use below
-    uint32_t wbase = 0, total = 0;
+    if (lane == 31) misc[wid] = inc;
+    __syncthreads();
+    uint32_t off = inc - (uint32_t)ntok, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const uint32_t x = misc[w]; if (w < wid) wbase += x; total += x; }
+    for (int w = 0; w < 8; w++) { const uint32_t x = misc[w]; if (w < wid) off += x; total += x; }
+    if (tid == C::HV) misc[9] = off;        // run offsets of the first MCU's chroma DC tokens
+    if (tid == C::HV + 1) misc[10] = off;
+
+    // ---- run-length walk (jchuff.c encode_one_block): one entry per non-zero AC coefficient, straight to its slot:
+    //      TOK_RAWAC | chroma << 24 | zero run << 16 | coefficient. The divergent region is the store and the reset
+    //      of the run counter; sizes, value bits and ZRL counts are derived in stage C with full warps.
+    if (active) {
+        uint32_t sa = smem_u32(tok + off);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(t0) : "memory");
+        sa += 4;
+        const uint32_t rbase = TOK_RAWAC | ((uint32_t)tbl << 24);
+        uint32_t r = rbase;
+#pragma unroll
+        for (int k = 1; k < 64; k++) {
+            const uint32_t p2 = pk[k >> 1];
+            const bool nzk = (k & 1) ? (p2 >= 0x10000u) : ((p2 & 0xFFFFu) != 0u);
+            if (nzk) {
+                const uint32_t e = (k & 1) ? __byte_perm(p2, r, 0x7632) : ((p2 & 0xFFFFu) | r);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(e) : "memory");
+                sa += 4;
+                r = rbase - 0x10000u;
+            }
+            r += 0x10000u;
+        }
+        if (pk[31] < 0x10000u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"((uint32_t)(tbl * 2 + 1) << 24) : "memory");
+    }
+    __syncthreads();
     if (tid == 0) {
         const uint32_t base = atomicAdd(pool_count, total);
         misc[8] = base;
@@ -413,38 +413,20 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         r.last_dc[0] = dcs[nblk - 3]; r.last_dc[1] = dcs[nblk - 2]; r.last_dc[2] = dcs[nblk - 1];
         recs[tile] = r;
     }
-    if (ntok > 0) atomicOr(&bm[off >> 5], 1u << (off & 31));
     __syncthreads();
+
+    // ---- stage C: the run in output order -> final tokens, symbol statistics, coalesced stores
     {
-        const uint32_t c0 = __popc(bm[2 * lane]), c1 = __popc(bm[2 * lane + 1]);
-        uint32_t pc = c0 + c1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, pc, o);
-            if (lane >= o) pc += y;
-        }
-        rk[2 * lane] = (uint8_t)(pc - c0 - c1);
-        rk[2 * lane + 1] = (uint8_t)(pc - c1);
-    }
-    __syncwarp();
-    uint32_t *dst = pool + (size_t)misc[8] + wbase;
-    const uint32_t *wtok = tok + wid * 32;
-    for (uint32_t i0 = 0; i0 < wtot; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        if (i < wtot) {
-            const uint32_t w = i0 >> 5;
-            const uint32_t heads = bm[w] & (0xffffffffu >> (31 - lane));
-            const uint32_t t = rk[w] + __popc(heads) - 1;   // owning lane (block) of output position i
-            const uint32_t jj = i - ofs[t];
-            uint32_t tk = wtok[jj * C::TOK_STRIDE + t];
-            if (tk & TOK_RAWAC) {  // (position | value) -> (ZRL count | table | run/size symbol | value bits)
-                const int kprev = jj > 1 ? (int)((wtok[(jj - 1) * C::TOK_STRIDE + t] >> 16) & 63u) : 0;
-                const int gap = (int)((tk >> 16) & 63u) - kprev - 1;
+        uint32_t *dst = pool + (size_t)misc[8];
+        for (uint32_t i = tid; i < total; i += 256) {
+            uint32_t tk = tok[i];
+            if (tk & TOK_RAWAC) {  // (chroma | run | value) -> (ZRL count | table | run/size symbol | value bits)
+                const uint32_t run = (tk >> 16) & 63u;
                 const int z = (int)(int16_t)(tk & 0xFFFFu);
                 const int nb = 32 - __clz(z < 0 ? -z : z);
-                const uint32_t actb = (uint32_t)((wid * 32 + t) % C::BPM) < (uint32_t)C::HV ? 1u : 3u;
-                const uint32_t nz = (uint32_t)gap >> 4;
-                tk = (nz << 28) | (actb << 24) | ((uint32_t)(((gap & 15) << 4) | nb) << 16) |
+                const uint32_t actb = 1u + ((tk >> 23) & 2u);
+                const uint32_t nz = run >> 4;
+                tk = (nz << 28) | (actb << 24) | ((((run & 15u) << 4) | (uint32_t)nb) << 16) |
                      ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
                 if (do_hist && nz) atomicAdd(&hs[(actb << 8) | 0xF0u], nz);
             }
