@@ -42,8 +42,8 @@ struct K1 {
     static constexpr int OFF_Y = (RAW_BYTES + 15) & ~15;
     static constexpr int OFF_CB = OFF_Y + Y_BYTES;
     static constexpr int OFF_CR = OFF_CB + C_BYTES;
-    static constexpr int OFF_Q = TOK_BYTES;              // uint2[2][64]
-    static constexpr int OFF_HIST = OFF_Q + 1024;        // uint32[4][256]
+    static constexpr int OFF_Q = TOK_BYTES;              // uint2[3][64]: luma, chroma, all-zero (dummy blocks)
+    static constexpr int OFF_HIST = OFF_Q + 1536;        // uint32[4][256]
     static constexpr int OFF_DC = OFF_HIST + 4096;       // int16[256]
     static constexpr int OFF_MISC = OFF_DC + 512;        // warp totals[8], pool base, chroma DC token offsets
     static constexpr int OFF_BAR = OFF_MISC + 64;        // mbarrier
@@ -141,6 +141,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 
     // quantisation constants + histogram init
     if (tid < 128) qs[tid] = make_uint2(qd->recip[tid >> 6][tid & 63], qd->half[tid >> 6][tid & 63]);
+    else if (tid < 192) qs[tid] = make_uint2(0u, 0u);   // reciprocal 0: every coefficient of a dummy block quantises to 0
     if (do_hist)
         for (int i = tid; i < 1024; i += 256) hs[i] = 0;
 
@@ -303,8 +304,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply; the
         // results are kept as 16-bit pairs in zig-zag order (they live across the CTA scan below); the non-zero AC
         // coefficients are counted on the way (one token each)
-        const uint2 *qt = qs + tbl * 64;
-        int nnz = 0, zprev = 0;
+        const uint2 *qt = qs + ((C::HV > 1 && !real) ? 2 : tbl) * 64;
+        int nnz = 0, zprev = 0, qprev = 0;
 #pragma unroll
         for (int k = 0; k < 64; k++) {
             const int n = zigzag_nat(k);
@@ -313,12 +314,15 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             const int s = x >> 31;
             const uint32_t a = (uint32_t)((x ^ s) - s) + rq.y;
             const int qa = (int)__umulhi(a, rq.x);
-            int z = (qa ^ s) - s;
+            const int z = (qa ^ s) - s;
             if (k == 0) mydc = z;
-            if (C::HV > 1 && !real && k > 0) z = 0;
-            if (k > 0) nnz += (z != 0);
-            if (k & 1) pk[k >> 1] = __byte_perm((uint32_t)zprev, (uint32_t)z, 0x5410);
-            else zprev = z;
+            if (k & 1) {
+                pk[k >> 1] = __byte_perm((uint32_t)zprev, (uint32_t)z, 0x5410);
+                nnz += (k == 1 ? 0 : min(qprev, 1)) + min(qa, 1);   // AC only; one three-input add per pair
+            } else {
+                zprev = z;
+                qprev = qa;
+            }
         }
         ntok = 1 + nnz + ((pk[31] >> 16) == 0u ? 1 : 0);   // DC, one per non-zero AC, EOB iff the last coefficient is zero
         if constexpr (DUMP) {
@@ -418,20 +422,25 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     // ---- stage C: the run in output order -> final tokens, symbol statistics, coalesced stores
     {
         uint32_t *dst = pool + (size_t)misc[8];
+        uint32_t zrl = 0;   // ZRL symbols seen by this thread: luma in the low half, chroma in the high half
         for (uint32_t i = tid; i < total; i += 256) {
             uint32_t tk = tok[i];
             if (tk & TOK_RAWAC) {  // (chroma | run | value) -> (ZRL count | table | run/size symbol | value bits)
                 const uint32_t run = (tk >> 16) & 63u;
                 const int z = (int)(int16_t)(tk & 0xFFFFu);
                 const int nb = 32 - __clz(z < 0 ? -z : z);
-                const uint32_t actb = 1u + ((tk >> 23) & 2u);
+                const uint32_t cb = (tk >> 24) & 1u;
                 const uint32_t nz = run >> 4;
-                tk = (nz << 28) | (actb << 24) | ((((run & 15u) << 4) | (uint32_t)nb) << 16) |
+                zrl += nz << (cb * 16u);
+                tk = (nz << 28) | ((1u + 2u * cb) << 24) | ((((run & 15u) << 4) | (uint32_t)nb) << 16) |
                      ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
-                if (do_hist && nz) atomicAdd(&hs[(actb << 8) | 0xF0u], nz);
             }
             dst[i] = tk;
             if (do_hist && !(tk & TOK_RAWDC)) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
+        }
+        if (do_hist && zrl) {
+            if (zrl & 0xFFFFu) atomicAdd(&hs[0x1F0], zrl & 0xFFFFu);
+            if (zrl >> 16) atomicAdd(&hs[0x3F0], zrl >> 16);
         }
     }
 
