@@ -103,6 +103,52 @@ __device__ __forceinline__ void fdct8(int &d0, int &d1, int &d2, int &d3, int &d
     d1 = (t7 + z1 + z4 + RND) >> SH;
 }
 
+// ---- pass 1 (rows) on packed samples. Every jfdctint.c row output is an exact integer combination of the eight
+// samples followed by ONE descale, so it can be evaluated as four 2-way dot products (IDP.2A: signed 16-bit
+// coefficient pairs x unsigned 8-bit samples) straight on the packed bytes: no unpacking, no butterflies. The
+// coefficient matrix below is jfdctint.c's pass 1 applied to unit vectors (CONST_BITS 13, before the descale);
+// rows 0 and 4 (coefficients +-4, no descale) take two 4-way dot products each.
+__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#define B2J_PAIR(lo, hi) ((int)((((uint32_t)(hi)) << 16) | (((uint32_t)(lo)) & 0xFFFFu)))
+template <int K>
+__device__ __forceinline__ int fdct_row_out(uint32_t x03, uint32_t x47) {
+    constexpr int M[8][8] = {{4, 4, 4, 4, 4, 4, 4, 4},
+                             {11363, 9633, 6437, 2260, -2260, -6437, -9633, -11363},
+                             {10703, 4433, -4433, -10703, -10703, -4433, 4433, 10703},
+                             {9633, -2259, -11362, -6436, 6436, 11362, 2259, -9633},
+                             {4, -4, -4, 4, 4, -4, -4, 4},
+                             {6437, -11362, 2261, 9633, -9633, -2261, 11362, -6437},
+                             {4433, -10704, 10704, -4433, -4433, 10704, -10704, 4433},
+                             {2260, -6436, 9633, -11363, 11363, -9633, 6436, -2260}};
+    if (K == 0) return dp4a_us(x47, 0x04040404, dp4a_us(x03, 0x04040404, 0));
+    if (K == 4) return dp4a_us(x47, 0x04FCFC04, dp4a_us(x03, 0x04FCFC04, 0));
+    int a = 1024;   // DESCALE(x, CONST_BITS - PASS1_BITS) rounding
+    a = dp2a_lo_su(B2J_PAIR(M[K][0], M[K][1]), x03, a);
+    a = dp2a_hi_su(B2J_PAIR(M[K][2], M[K][3]), x03, a);
+    a = dp2a_lo_su(B2J_PAIR(M[K][4], M[K][5]), x47, a);
+    a = dp2a_hi_su(B2J_PAIR(M[K][6], M[K][7]), x47, a);
+    return a >> 11;
+}
+template <int K>
+__device__ __forceinline__ void fdct_rows_k(const uint32_t (&xin)[16], int (&v)[64]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r * 8 + K] = fdct_row_out<K>(xin[2 * r], xin[2 * r + 1]);
+}
+
 // jccolor.c rgb_ycc_convert, 16-bit fixed point
 __device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &cr) {
     y = (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
@@ -276,6 +322,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     int mydc = 0;
     uint32_t pk[32];   // quantised coefficients, zig-zag order, two per word
     int v[64];
+    uint32_t xin[16];   // the block's samples, one row per word pair
     if (active) {
         const uint8_t *src;
         int stride;
@@ -283,19 +330,15 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         else { src = (bn == C::HV ? Cbp : Crp) + m * 8; stride = C::C_STRIDE; }
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            uint2 w = *reinterpret_cast<const uint2 *>(src + r * stride);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                v[r * 8 + c] = (w.x >> (8 * c)) & 0xFF;       // level shift folded into the DC term below
-                v[r * 8 + 4 + c] = (w.y >> (8 * c)) & 0xFF;
-            }
+            const uint2 w = *reinterpret_cast<const uint2 *>(src + r * stride);
+            xin[2 * r] = w.x;       // level shift folded into the DC term below
+            xin[2 * r + 1] = w.y;
         }
     }
     __syncthreads();  // every sample is in registers: the planes are dead, the token area may be written
     if (active) {
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-            fdct8<false>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+        fdct_rows_k<0>(xin, v); fdct_rows_k<1>(xin, v); fdct_rows_k<2>(xin, v); fdct_rows_k<3>(xin, v);
+        fdct_rows_k<4>(xin, v); fdct_rows_k<5>(xin, v); fdct_rows_k<6>(xin, v); fdct_rows_k<7>(xin, v);
 #pragma unroll
         for (int c = 0; c < 8; c++)
             fdct8<true>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
