@@ -158,6 +158,37 @@ __device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &c
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : v); }
 
+// Stage C of k_fdct: entries (TOK_RAWAC | chroma << 24 | zero run << 16 | coefficient) become final tokens
+// (ZRL count | table | run/size symbol | value bits); DC and EOB tokens pass through. Branch-free: the conversion is
+// computed for every word and selected. Every token counts one symbol; the tile's three raw-DC tokens (first MCU)
+// land in bins 0x000 / 0x201 / 0x202 and are taken out again by thread 0 (k_dc_edge_hist counts their real symbols).
+template <bool HIST>
+__device__ __forceinline__ void stage_c(const uint32_t *tok, uint32_t *__restrict__ dst, uint32_t total, uint32_t *hs, int tid) {
+    uint32_t zrl = 0;   // ZRL symbols seen by this thread: luma in the low half, chroma in the high half
+#pragma unroll 4
+    for (uint32_t i = tid; i < total; i += 256) {
+        const uint32_t e = tok[i];
+        const uint32_t run = (e >> 16) & 63u;   // DC / EOB tokens: symbol < 16, so their "ZRL count" below is 0
+        const int z = (int)(int16_t)(e & 0xFFFFu);
+        uint32_t msb;
+        asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"((uint32_t)(z < 0 ? -z : z)));
+        const uint32_t nb = msb + 1u;           // bfind(0) = -1
+        const uint32_t cb = (e >> 24) & 1u;
+        const uint32_t nz = run >> 4;
+        zrl += nz << (cb * 16u);
+        const uint32_t conv = (nz << 28) | ((1u + 2u * cb) << 24) | ((((run & 15u) << 4) | nb) << 16) |
+                              ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
+        const uint32_t tk = (e & TOK_RAWAC) ? conv : e;
+        dst[i] = tk;
+        if (HIST) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
+    }
+    if (HIST) {
+        if (zrl & 0xFFFFu) atomicAdd(&hs[0x1F0], zrl & 0xFFFFu);
+        if (zrl >> 16) atomicAdd(&hs[0x3F0], zrl >> 16);
+        if (tid == 0) { atomicSub(&hs[0x000], 1u); atomicSub(&hs[0x201], 1u); atomicSub(&hs[0x202], 1u); }
+    }
+}
+
 template <int HS, int VS, bool DUMP>
 __global__ void __launch_bounds__(256, 3)
 k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__restrict__ qd,
@@ -463,29 +494,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     __syncthreads();
 
     // ---- stage C: the run in output order -> final tokens, symbol statistics, coalesced stores
-    {
-        uint32_t *dst = pool + (size_t)misc[8];
-        uint32_t zrl = 0;   // ZRL symbols seen by this thread: luma in the low half, chroma in the high half
-        for (uint32_t i = tid; i < total; i += 256) {
-            uint32_t tk = tok[i];
-            if (tk & TOK_RAWAC) {  // (chroma | run | value) -> (ZRL count | table | run/size symbol | value bits)
-                const uint32_t run = (tk >> 16) & 63u;
-                const int z = (int)(int16_t)(tk & 0xFFFFu);
-                const int nb = 32 - __clz(z < 0 ? -z : z);
-                const uint32_t cb = (tk >> 24) & 1u;
-                const uint32_t nz = run >> 4;
-                zrl += nz << (cb * 16u);
-                tk = (nz << 28) | ((1u + 2u * cb) << 24) | ((((run & 15u) << 4) | (uint32_t)nb) << 16) |
-                     ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
-            }
-            dst[i] = tk;
-            if (do_hist && !(tk & TOK_RAWDC)) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
-        }
-        if (do_hist && zrl) {
-            if (zrl & 0xFFFFu) atomicAdd(&hs[0x1F0], zrl & 0xFFFFu);
-            if (zrl >> 16) atomicAdd(&hs[0x3F0], zrl >> 16);
-        }
-    }
+    if (do_hist) stage_c<true>(tok, pool + (size_t)misc[8], total, hs, tid);
+    else stage_c<false>(tok, pool + (size_t)misc[8], total, hs, tid);
 
     if constexpr (DUMP) {  // quantised coefficients, scan order (parity tests)
         uint4 *cdst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM) * 64);
