@@ -118,6 +118,16 @@ __device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c) {
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -246,28 +256,32 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         const int ngx = nmcu * HS;
         const int rg = wid;
         for (int gx = lane; gx < ngx; gx += 32) {
-            int cbv[VS][8], crv[VS][8];
+            // jccolor.c rgb_ycc_convert on packed pixels: every component is two 2-way dot products (IDP.2A, 16-bit
+            // coefficients x the pixel's bytes [b, g | r, next b]); for the chroma planes t = (N + 32768) >> 16 with
+            // N = -(the libjpeg sum without its constant), so that cb = 128 - t exactly (floor identities).
+            int tbv[VS][8], trv[VS][8];
 #pragma unroll
             for (int v = 0; v < VS; v++) {
                 const int r = rg * VS + v;
                 const uint2 *p = reinterpret_cast<const uint2 *>(raw + r * C::RAW_STRIDE + gx * 24);
-                uint2 a = p[0], b = p[1], c = p[2];
-                uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                uint32_t yw[2] = {0, 0};
+                const uint2 a = p[0], b = p[1], c = p[2];
+                const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                uint32_t S[8];
 #pragma unroll
                 for (int px = 0; px < 8; px++) {
-                    int bb = (w[(3 * px) >> 2] >> (((3 * px) & 3) * 8)) & 0xFF;
-                    int gg = (w[(3 * px + 1) >> 2] >> (((3 * px + 1) & 3) * 8)) & 0xFF;
-                    int rr = (w[(3 * px + 2) >> 2] >> (((3 * px + 2) & 3) * 8)) & 0xFF;
-                    int y, cb, cr;
-                    ycc(bb, gg, rr, y, cb, cr);
-                    yw[px >> 2] |= (uint32_t)y << ((px & 3) * 8);
-                    cbv[v][px] = cb;
-                    crv[v][px] = cr;
+                    const int o = 3 * px, wi = o >> 2, bo = o & 3;
+                    // bytes [b, g, r, *] of pixel px (the fourth byte meets a zero coefficient)
+                    const uint32_t q = bo == 0 ? w[wi] : (bo == 1 ? (w[wi] >> 8) : __byte_perm(w[wi], w[wi + 1], bo == 2 ? 0x5432 : 0x6543));
+                    S[px] = dp2a_hi_uu(B2J_PAIR(19595, 0), q, dp2a_lo_uu(B2J_PAIR(7471, 38470), q, 32768u));
+                    tbv[v][px] = dp2a_hi_su(B2J_PAIR(11059, 0), q, dp2a_lo_su(B2J_PAIR(-32768, 21709), q, 32768)) >> 16;
+                    trv[v][px] = dp2a_hi_su(B2J_PAIR(-32768, 0), q, dp2a_lo_su(B2J_PAIR(5329, 27439), q, 32768)) >> 16;
                 }
-                *reinterpret_cast<uint2 *>(Yp + r * C::Y_STRIDE + gx * 8) = make_uint2(yw[0], yw[1]);
+                // y = S >> 16 (S < 2^24): byte 2 of every sum
+                const uint32_t y0 = __byte_perm(__byte_perm(S[0], S[1], 0x0062), __byte_perm(S[2], S[3], 0x0062), 0x5410);
+                const uint32_t y1 = __byte_perm(__byte_perm(S[4], S[5], 0x0062), __byte_perm(S[6], S[7], 0x0062), 0x5410);
+                *reinterpret_cast<uint2 *>(Yp + r * C::Y_STRIDE + gx * 8) = make_uint2(y0, y1);
             }
-            // jcsample.c: fullsize / h2v1 (bias 0,1) / h2v2 (bias 1,2) / int_downsample (h1v2, h4v1)
+            // jcsample.c: fullsize / h2v1 (bias 0,1) / h2v2 (bias 1,2) / int_downsample (h1v2, h4v1), with cb = 128 - t
             uint32_t ob[2] = {0, 0}, orr[2] = {0, 0};
 #pragma unroll
             for (int j = 0; j < 8 / HS; j++) {
@@ -276,15 +290,16 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
                 for (int v = 0; v < VS; v++)
 #pragma unroll
                     for (int h = 0; h < HS; h++) {
-                        sb += cbv[v][j * HS + h];
-                        sr += crv[v][j * HS + h];
+                        sb += tbv[v][j * HS + h];
+                        sr += trv[v][j * HS + h];
                     }
+                constexpr int K = 128 * HS * VS;
                 int ocb, ocr;
-                if (HS == 1 && VS == 1) { ocb = sb; ocr = sr; }
-                else if (HS == 2 && VS == 1) { ocb = (sb + (j & 1)) >> 1; ocr = (sr + (j & 1)) >> 1; }
-                else if (HS == 2 && VS == 2) { ocb = (sb + 1 + (j & 1)) >> 2; ocr = (sr + 1 + (j & 1)) >> 2; }
-                else if (HS == 1 && VS == 2) { ocb = (sb + 1) >> 1; ocr = (sr + 1) >> 1; }
-                else { ocb = (sb + 2) >> 2; ocr = (sr + 2) >> 2; }
+                if (HS == 1 && VS == 1) { ocb = K - sb; ocr = K - sr; }
+                else if (HS == 2 && VS == 1) { ocb = (K + (j & 1) - sb) >> 1; ocr = (K + (j & 1) - sr) >> 1; }
+                else if (HS == 2 && VS == 2) { ocb = (K + 1 + (j & 1) - sb) >> 2; ocr = (K + 1 + (j & 1) - sr) >> 2; }
+                else if (HS == 1 && VS == 2) { ocb = (K + 1 - sb) >> 1; ocr = (K + 1 - sr) >> 1; }
+                else { ocb = (K + 2 - sb) >> 2; ocr = (K + 2 - sr) >> 2; }
                 ob[j >> 2] |= (uint32_t)ocb << ((j & 3) * 8);
                 orr[j >> 2] |= (uint32_t)ocr << ((j & 3) * 8);
             }
