@@ -150,7 +150,8 @@ B2J_API int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flag
 B2J_API int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int world, int flags);
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
-enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4 };
+enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4,
+       B2J_DBG_TOKEN_COUNT = 5 /* uint32: run-length tokens of the last encode (4 bytes each between the two passes) */ };
 B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len);
 /* flags bit0 (B2J_DEBUG_COEF): the next encodes also store the quantised coefficients for B2J_DBG_COEF */
 enum { B2J_DEBUG_COEF = 1 };

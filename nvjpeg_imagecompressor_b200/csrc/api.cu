@@ -632,6 +632,7 @@ int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len) {
     case B2J_DBG_HIST: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_ctrl->hist; n = 4 * 257 * 4; break;
     case B2J_DBG_TABLES: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_huff; n = sizeof(HuffDev); break;
     case B2J_DBG_TILE_BITS: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_tile_bits; n = (size_t)ctx->g.ntiles * 4; break;
+    case B2J_DBG_TOKEN_COUNT: if (!ctx->enc_ready) return B2J_EINVAL; src = &ctx->d_ctrl->pool_count; n = 4; break;
     case B2J_DBG_DEC_COEF: if (!ctx->dec) return B2J_EINVAL; src = dec_coef_ptr(ctx->dec, &n); break;
     default: return B2J_EINVAL;
     }
