@@ -45,6 +45,12 @@ __host__ __device__ constexpr int zigzag_nat(int k) {
     return z[k];
 }
 
+// run-time index variant (one table in constant memory instead of a compile-time select chain)
+__device__ __constant__ const uint8_t c_zigzag_nat[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+__device__ __forceinline__ int zigzag_nat_rt(int k) { return c_zigzag_nat[k]; }
+
 // ---- device-side tables -------------------------------------------------------------------------------
 struct QuantDev {          // forward: q = umulhi(|c| + half, recip), natural order; [0] luma, [1] chroma
     uint32_t recip[2][64];

@@ -78,30 +78,59 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
             cs[j] = 0;
             grp[j] = i;
         }
+        // Fast selection while the two least frequencies are below 2^23: one 32-bit key per symbol, frequency in the
+        // upper 23 bits and (511 - index) below it, so "least frequency, ties to the larger index" is one REDUX.MIN;
+        // the lane that owned c1 offers its second-best key for c2. Larger frequencies take the four-reduction path.
+        constexpr uint32_t KEY_NONE = 0xffffffffu;
+        uint32_t key[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int i = lane + 32 * j;
+            key[j] = (f[j] != 0 && f[j] < (1u << 23)) ? ((f[j] << 9) | (uint32_t)(511 - i)) : KEY_NONE;
+        }
         for (int iter = 0; iter < 300; iter++) {
-            // c1
-            uint32_t bf = 0xffffffffu;
-            int bi = -1;
+            uint32_t b1 = KEY_NONE, b2 = KEY_NONE;   // this lane's two smallest keys
 #pragma unroll
-            for (int j = 0; j < 9; j++)
-                if (f[j] != 0 && f[j] <= 1000000000u && f[j] <= bf) { bf = f[j]; bi = lane + 32 * j; }
-            const uint32_t m1 = __reduce_min_sync(FULL, bf);
-            if (m1 == 0xffffffffu) break;
-            const int c1 = __reduce_max_sync(FULL, bf == m1 ? bi : -1);
-            // c2
-            bf = 0xffffffffu;
-            bi = -1;
+            for (int j = 0; j < 9; j++) {
+                const uint32_t k = key[j];
+                b2 = min(b2, max(b1, k));
+                b1 = min(b1, k);
+            }
+            const uint32_t k1 = __reduce_min_sync(FULL, b1);
+            const uint32_t k2 = k1 == KEY_NONE ? KEY_NONE : __reduce_min_sync(FULL, b1 == k1 ? b2 : b1);
+            uint32_t m1, m2;
+            int c1, c2;
+            if (k2 != KEY_NONE) {
+                m1 = k1 >> 9; c1 = 511 - (int)(k1 & 511u);
+                m2 = k2 >> 9; c2 = 511 - (int)(k2 & 511u);
+            } else {
+                // c1
+                uint32_t bf = 0xffffffffu;
+                int bi = -1;
 #pragma unroll
-            for (int j = 0; j < 9; j++)
-                if (f[j] != 0 && f[j] <= 1000000000u && f[j] <= bf && (lane + 32 * j) != c1) { bf = f[j]; bi = lane + 32 * j; }
-            const uint32_t m2 = __reduce_min_sync(FULL, bf);
-            if (m2 == 0xffffffffu) break;
-            const int c2 = __reduce_max_sync(FULL, bf == m2 ? bi : -1);
+                for (int j = 0; j < 9; j++)
+                    if (f[j] != 0 && f[j] <= 1000000000u && f[j] <= bf) { bf = f[j]; bi = lane + 32 * j; }
+                m1 = __reduce_min_sync(FULL, bf);
+                if (m1 == 0xffffffffu) break;
+                c1 = __reduce_max_sync(FULL, bf == m1 ? bi : -1);
+                // c2
+                bf = 0xffffffffu;
+                bi = -1;
+#pragma unroll
+                for (int j = 0; j < 9; j++)
+                    if (f[j] != 0 && f[j] <= 1000000000u && f[j] <= bf && (lane + 32 * j) != c1) { bf = f[j]; bi = lane + 32 * j; }
+                m2 = __reduce_min_sync(FULL, bf);
+                if (m2 == 0xffffffffu) break;
+                c2 = __reduce_max_sync(FULL, bf == m2 ? bi : -1);
+            }
 #pragma unroll
             for (int j = 0; j < 9; j++) {
                 const int i = lane + 32 * j;
-                if (i == c1) f[j] = m1 + m2;
-                if (i == c2) f[j] = 0;
+                if (i == c1) {
+                    f[j] = m1 + m2;
+                    key[j] = f[j] < (1u << 23) ? ((f[j] << 9) | (uint32_t)(511 - i)) : KEY_NONE;
+                }
+                if (i == c2) { f[j] = 0; key[j] = KEY_NONE; }
                 if (i <= 256 && (grp[j] == c1 || grp[j] == c2) && (cs[j] > 0 || i == c1 || i == c2)) {
                     cs[j]++;
                     grp[j] = c1;
@@ -150,48 +179,87 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
         if (lane == 0) s_nsym[t] = p;
     }
     __syncwarp();
-    // Annex C code assignment
-    if (lane == 0) {
-        int p = 0;
-        uint32_t code = 0;
-        for (int l = 1; l <= 16; l++) {
-            const int n = s_bits[t][l];
-            for (int i = 0; i < n; i++, p++, code++) s_enc[t][s_vals[t][p]] = (code << 8) | (uint32_t)l;
-            code <<= 1;
+    // Annex C code assignment: lane l (1..16) derives the first code and the first huffval index of length l from
+    // the counts, then every lane assigns the codes of its huffval positions
+    {
+        int cnt = (lane >= 1 && lane <= 16) ? (int)s_bits[t][lane] : 0;
+        int first_idx = cnt;   // exclusive prefix of the counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, first_idx, o);
+            if (lane >= o) first_idx += y;
+        }
+        first_idx -= cnt;
+        // first code of length l: code(l) = (code(l-1) + count(l-1)) << 1, code(1) = 0
+        uint32_t fc = 0;
+        for (int l = 2; l <= 16; l++) {
+            const uint32_t prev_cnt = (uint32_t)__shfl_sync(FULL, cnt, l - 1);
+            const uint32_t prev_fc = __shfl_sync(FULL, fc, l - 1);
+            if (lane == l) fc = (prev_fc + prev_cnt) << 1;
+        }
+        s_cs[t][lane] = first_idx;         // reuse: [0..31] first index, [32..63] first code (s_cs is dead here)
+        s_cs[t][32 + lane] = (int)fc;
+        __syncwarp();
+        const int ns = (int)s_nsym[t];
+        for (int p = lane; p < ns; p += 32) {
+            // length of position p: the largest l with first_idx(l) <= p among the lengths that have codes
+            int l = 1;
+#pragma unroll 1
+            for (int q = 1; q <= 16; q++)
+                if (s_bits[t][q] != 0 && s_cs[t][q] <= p) l = q;
+            const uint32_t code = (uint32_t)s_cs[t][32 + l] + (uint32_t)(p - s_cs[t][l]);
+            s_enc[t][s_vals[t][p]] = (code << 8) | (uint32_t)l;
         }
     }
     __syncthreads();
 
-    // ---- headers (jcmarker.c): SOI, JFIF APP0, 2 x DQT, SOF0, 4 x DHT, SOS
+    // ---- headers (jcmarker.c): SOI, JFIF APP0, 2 x DQT, SOF0, 4 x DHT, SOS -- section offsets by thread 0, bytes by
+    //      all threads
+    __shared__ uint32_t s_off[8];   // DQT0, DQT1, SOF0, DHT0..3, SOS
     if (threadIdx.x == 0) {
-        int n = 0;
-        if (emit_header) {
-            uint8_t *h = s_hdr;
-            const uint8_t app0[] = {0xFF, 0xD8, 0xFF, 0xE0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};
-            for (int i = 0; i < 20; i++) h[n++] = app0[i];
-            for (int q = 0; q < 2; q++) {
-                h[n++] = 0xFF; h[n++] = 0xDB; h[n++] = 0; h[n++] = 67; h[n++] = (uint8_t)q;
-                for (int k = 0; k < 64; k++) h[n++] = (uint8_t)qd->q[q][zigzag_nat(k)];
-            }
-            h[n++] = 0xFF; h[n++] = 0xC0; h[n++] = 0; h[n++] = 17; h[n++] = 8;
-            h[n++] = (uint8_t)(full_h >> 8); h[n++] = (uint8_t)full_h; h[n++] = (uint8_t)(full_w >> 8); h[n++] = (uint8_t)full_w;
-            h[n++] = 3;
-            h[n++] = 1; h[n++] = (uint8_t)((hs << 4) | vs); h[n++] = 0;
-            h[n++] = 2; h[n++] = 0x11; h[n++] = 1;
-            h[n++] = 3; h[n++] = 0x11; h[n++] = 1;
-            const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
-            for (int q = 0; q < 4; q++) {
-                const int ns = (int)s_nsym[q];
-                h[n++] = 0xFF; h[n++] = 0xC4; h[n++] = (uint8_t)((19 + ns) >> 8); h[n++] = (uint8_t)(19 + ns); h[n++] = tcth[q];
-                for (int l = 1; l <= 16; l++) h[n++] = s_bits[q][l];
-                for (int i = 0; i < ns; i++) h[n++] = s_vals[q][i];
-            }
-            const uint8_t sos[] = {0xFF, 0xDA, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
-            for (int i = 0; i < 14; i++) h[n++] = sos[i];
-        }
-        s_hdr_len = (uint32_t)n;
-        huff->hdr_len = (uint32_t)n;
+        uint32_t n = 20;
+        s_off[0] = n; n += 69; s_off[1] = n; n += 69; s_off[2] = n; n += 19;
+        for (int q = 0; q < 4; q++) { s_off[3 + q] = n; n += 21 + s_nsym[q]; }
+        s_off[7] = n; n += 14;
+        if (!emit_header) n = 0;
+        s_hdr_len = n;
+        huff->hdr_len = n;
         huff->err = s_err;
+    }
+    __syncthreads();
+    if (emit_header) {
+        uint8_t *h = s_hdr;
+        const int x = threadIdx.x;
+        if (x < 20) {
+            const uint8_t app0[20] = {0xFF, 0xD8, 0xFF, 0xE0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};
+            h[x] = app0[x];
+        }
+        {   // DQT: thread x -> table x >> 6, coefficient x & 63 (zig-zag order)
+            const int q = x >> 6, k = x & 63;
+            uint8_t *d = h + s_off[q];
+            if (k == 0) { d[0] = 0xFF; d[1] = 0xDB; d[2] = 0; d[3] = 67; d[4] = (uint8_t)q; }
+            d[5 + k] = (uint8_t)qd->q[q][zigzag_nat_rt(k)];
+        }
+        if (x == 32) {
+            uint8_t *d = h + s_off[2];
+            const uint8_t sof[19] = {0xFF, 0xC0, 0, 17, 8, (uint8_t)(full_h >> 8), (uint8_t)full_h, (uint8_t)(full_w >> 8), (uint8_t)full_w,
+                                     3, 1, (uint8_t)((hs << 4) | vs), 0, 2, 0x11, 1, 3, 0x11, 1};
+            for (int i = 0; i < 19; i++) d[i] = sof[i];
+        }
+        if (x == 64) {
+            uint8_t *d = h + s_off[7];
+            const uint8_t sos[14] = {0xFF, 0xDA, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
+            for (int i = 0; i < 14; i++) d[i] = sos[i];
+        }
+        {   // DHT q by warp q
+            const int q = x >> 5;
+            const int ns = (int)s_nsym[q];
+            uint8_t *d = h + s_off[3 + q];
+            const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
+            if (lane == 0) { d[0] = 0xFF; d[1] = 0xC4; d[2] = (uint8_t)((19 + ns) >> 8); d[3] = (uint8_t)(19 + ns); d[4] = tcth[q]; }
+            if (lane >= 1 && lane <= 16) d[4 + lane] = s_bits[q][lane];
+            for (int i = lane; i < ns; i += 32) d[21 + i] = s_vals[q][i];
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (int)s_hdr_len; i += 128) out[i] = s_hdr[i];
