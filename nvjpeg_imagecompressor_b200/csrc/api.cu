@@ -321,7 +321,7 @@ static int phase3_launch(b2j_ctx *ctx, int flags) {
     a.seam = ctx->d_ctrl->seam; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
     a.out = ctx->d_out; a.cap = ctx->out_cap; a.desc = ctx->d_desc; a.ticket = &ctx->d_ctrl->ticket;
     a.out_len = &ctx->d_ctrl->out_len; a.err = &ctx->d_ctrl->err;
-    CK(launch_stuff(a, 148 * 8, ctx->stream));
+    CK(launch_stuff(a, 148 * STUFF_CTAS, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 7);
     return B2J_OK;

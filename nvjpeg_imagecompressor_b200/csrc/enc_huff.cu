@@ -562,27 +562,124 @@ k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__res
 
 // ------------------------------------------------------------------------------------------------------
 // k_stuff: the strip's bit string (tile slots, concatenated virtually) -> shifted to the global bit phase ->
-// bytes -> 0xFF00 stuffing -> final position. Persistent CTAs take 4 KB chunks of unstuffed bytes in ticket order;
-// a decoupled look-back over the stuffed byte counts gives each chunk its output offset in the same pass.
+// bytes -> 0xFF00 stuffing -> final position. Persistent CTAs take chunks of unstuffed bytes in ticket order; a
+// decoupled look-back over the stuffed byte
+// counts gives each chunk its output offset while the other warps already stage their bytes at chunk-local offsets;
+// the copy-out re-aligns to 16-byte global vectors with funnel shifts.
 // Byte j of the strip = local bits [skip + 8j, skip + 8j + 8); bits past the strip's end come from `ext`
 // (the next strip's first bits) followed by 1-bits (jchuff.c flush_bits padding).
-__global__ void __launch_bounds__(STUFF_THREADS)
+constexpr int STUFF_TWIN = 72;   // tiles whose offsets are cached per chunk (a chunk of a flat image spans more)
+
+struct StuffTiles {
+    const uint64_t *s_toff;
+    const uint32_t *s_tbits;
+    const uint64_t *g_toff;
+    const uint32_t *g_tbits;
+    int tau0, ntiles;
+    __device__ __forceinline__ uint64_t off(int ti) const {
+        const int r = ti - tau0;
+        return r < STUFF_TWIN ? s_toff[r] : g_toff[min(ti, ntiles)];
+    }
+    __device__ __forceinline__ uint32_t bits(int ti) const {
+        const int r = ti - tau0;
+        return r < STUFF_TWIN ? s_tbits[r] : g_tbits[ti];
+    }
+};
+
+// 32 stream bits starting at bit p when they are not all inside one tile (tile seams, the strip's end)
+__device__ __noinline__ uint32_t stuff_seam_word(const StuffTiles &tl, const uint32_t *__restrict__ slots, uint64_t &p, int &tau,
+                                                 uint64_t T, int ext) {
+    uint32_t res = 0;
+    int got = 0;
+    while (got < 32) {
+        if (p >= T) {
+            const uint64_t e = p - T;
+            uint32_t x = 0xffffffffu;
+            if (e < 32) {
+                x = ((uint32_t)ext << 24) | 0x00ffffffu;
+                if (e) x = (x << e) | ((1u << e) - 1u);
+            }
+            res |= x >> got;
+            p += 32 - got;
+            got = 32;
+            break;
+        }
+        while (tl.off(tau + 1) <= p) tau++;
+        const uint32_t tb = tl.bits(tau);
+        const uint32_t qb = (uint32_t)(p - tl.off(tau));
+        const uint32_t rem = tb - qb;
+        const uint32_t *slot = slots + (size_t)tau * SLOT_WORDS;
+        const uint32_t wi = qb >> 5, sh = qb & 31u;
+        const uint32_t nw = (tb + 31u) >> 5;
+        const uint32_t w0 = slot[wi];
+        const uint32_t w1 = (sh && wi + 1 < nw) ? slot[wi + 1] : 0u;
+        uint32_t x = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;
+        const int take = min(32 - got, (int)min(rem, 32u));
+        if (take < 32) x &= ~(0xffffffffu >> take);
+        res |= x >> got;
+        got += take;
+        p += take;
+    }
+    return res;
+}
+
+// One 32-bit piece of the stream (w: first byte in bits 31..24) -> its bytes in memory order with a 0x00 after every
+// 0xFF, OR-ed into the zeroed staging buffer at byte offset o (any alignment). Branch-free: the byte expansion is two
+// PRMTs whose selectors come from a 16-entry table indexed by the word's 0xFF mask. Returns the bytes produced.
+__device__ __forceinline__ uint32_t stuff_place_word(uint32_t w, uint32_t o, uint32_t sbase, const uint32_t *s_lut) {
+    const uint32_t l = __byte_perm(w, 0, 0x0123);
+    uint32_t mm = l & (l >> 4) & 0x0F0F0F0Fu;   // a byte is 0xFF iff all eight bits survive the and-fold
+    mm &= mm >> 2;
+    mm &= mm >> 1;
+    mm &= 0x01010101u;
+    const uint32_t m4 = (mm * 0x01020408u) >> 24;   // bit i: byte i is 0xFF
+    const uint32_t sel = s_lut[m4];
+    const uint32_t lo = __byte_perm(l, 0, sel & 0xFFFFu), hi = __byte_perm(l, 0, sel >> 16);
+    const uint32_t bs = (o & 3u) * 8u;
+    const uint32_t addr = sbase + (o & ~3u);
+    const uint32_t x0 = lo << bs, x1 = __funnelshift_l(lo, hi, bs), x2 = __funnelshift_l(hi, 0u, bs);
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(x0) : "memory");
+    asm volatile("red.shared.or.b32 [%0+4], %1;" ::"r"(addr), "r"(x1) : "memory");
+    if (x2) asm volatile("red.shared.or.b32 [%0+8], %1;" ::"r"(addr), "r"(x2) : "memory");
+    return 4u + __popc(m4);
+}
+
+__global__ void __launch_bounds__(STUFF_THREADS, STUFF_CTAS)
 k_stuff(StuffArgs a) {
-    constexpr int TWIN = 72;
-    __shared__ uint64_t s_toff[TWIN];
-    __shared__ uint32_t s_tbits[TWIN];
+    constexpr int NWARP = STUFF_THREADS / 32;
+    constexpr int NP = STUFF_PIECES;                       // 16-byte pieces per thread and chunk
+    constexpr int PSTRIDE = STUFF_THREADS * 16;            // bytes between a thread's pieces
+    constexpr int OUT_WORDS = (2 * STUFF_CHUNK + 64) / 4;
+    __shared__ uint64_t s_toff[STUFF_TWIN];
+    __shared__ uint32_t s_tbits[STUFF_TWIN];
     __shared__ int s_chunk, s_tau0;
-    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_warp[NP][NWARP];
     __shared__ uint64_t s_goff;
-    __shared__ __align__(16) uint8_t s_out[2 * STUFF_CHUNK + 32];
+    __shared__ uint32_t s_lut[16];
+    __shared__ __align__(16) uint32_t s_out32[OUT_WORDS];
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_out32);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t T = a.tile_off[a.ntiles];
     const int a_skip = a.seam[0], a_ext = a.seam[1];
     const uint64_t NB = T > (uint64_t)a_skip ? (T - a_skip + 7) >> 3 : 0;
     const int nchunks = (int)max((uint64_t)1, (NB + STUFF_CHUNK - 1) / STUFF_CHUNK);
     const uint32_t hdr = a.huff->hdr_len;
+    const uint32_t sbase = smem_u32(s_out32);
+
+    if (tid < 16) {   // PRMT selectors: bytes 0..3 of the word in order, a zero byte (selector 4) after every 0xFF
+        uint32_t sel = 0;
+        int n = 0;
+        for (int i = 0; i < 4; i++) {
+            sel |= (uint32_t)i << (4 * n++);
+            if (tid & (1 << i)) sel |= 4u << (4 * n++);
+        }
+        for (; n < 8; n++) sel |= 4u << (4 * n);
+        s_lut[tid] = sel;
+    }
+    for (int i = tid; i < OUT_WORDS; i += STUFF_THREADS) s_out32[i] = 0;
 
     for (;;) {
+        // chunk ids are taken when the work starts (a ticket held back would make its successors spin in the look-back)
         if (tid == 0) s_chunk = (int)atomicAdd(a.ticket, 1u);
         __syncthreads();
         const int ch = s_chunk;
@@ -607,188 +704,157 @@ k_stuff(StuffArgs a) {
         }
         __syncthreads();
         const int tau0 = s_tau0;
-        for (int i = tid; i < TWIN; i += STUFF_THREADS) {
+        for (int i = tid; i < STUFF_TWIN; i += STUFF_THREADS) {
             const int ti = min(tau0 + i, a.ntiles);
             s_toff[i] = a.tile_off[ti];
             s_tbits[i] = ti < a.ntiles ? a.tile_bits[ti] : 0;
         }
         __syncthreads();
-        // tile offsets / sizes: shared window first, global memory beyond it (only flat images get there)
-        auto TOFF = [&](int ti) -> uint64_t { const int r = ti - tau0; return r < TWIN ? s_toff[r] : a.tile_off[min(ti, a.ntiles)]; };
-        auto TBITS = [&](int ti) -> uint32_t { const int r = ti - tau0; return r < TWIN ? s_tbits[r] : a.tile_bits[ti]; };
+        StuffTiles tl{s_toff, s_tbits, a.tile_off, a.tile_bits, tau0, a.ntiles};
 
-        // ---- STUFF_BPT bytes per thread: w[q] = stream bits [p + 32q, p + 32q + 32), MSB first
-        constexpr int NW = STUFF_BPT / 4;
-        const uint64_t j0 = j0c + (uint64_t)tid * STUFF_BPT;
-        const int nvalid = j0 >= NB ? 0 : (int)min((uint64_t)STUFF_BPT, NB - j0);
-        uint32_t w[NW];
+        // ---- NP pieces of 16 bytes per thread: w[i][q] = stream bits [p + 32q, p + 32q + 32) of piece i, MSB first
+        uint32_t w[NP][4];
+        int nvalid[NP];
+        uint32_t cnt[NP];
+        int tau = tau0;
 #pragma unroll
-        for (int q = 0; q < NW; q++) w[q] = 0;
-        if (nvalid > 0) {
-            uint64_t p = (uint64_t)a_skip + 8 * j0;
-            int tau = tau0;
-            while (TOFF(tau + 1) <= p) tau++;
-            const uint64_t tend = TOFF(tau + 1);
-            if (p + 32 * NW <= tend) {  // fast path: all bits inside one tile
-                const uint32_t qb = (uint32_t)(p - TOFF(tau));
-                const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS + (qb >> 5);
-                const uint32_t sh = qb & 31u;
-                uint32_t x[NW + 1];
+        for (int i = 0; i < NP; i++) {
+            const uint64_t jb = j0c + (uint64_t)i * PSTRIDE + (uint64_t)tid * 16;
+            nvalid[i] = jb >= NB ? 0 : (int)min((uint64_t)16, NB - jb);
 #pragma unroll
-                for (int q = 0; q < NW; q++) x[q] = slot[q];
-                x[NW] = sh ? slot[NW] : 0u;
+            for (int q = 0; q < 4; q++) w[i][q] = 0;
+            if (nvalid[i] > 0) {
+                uint64_t p = (uint64_t)a_skip + 8 * jb;
+                while (tl.off(tau + 1) <= p) tau++;
+                uint64_t tstart = tl.off(tau), tend = tl.off(tau + 1);
+                if (p + 128 <= tend) {  // all bits inside one tile
+                    const uint32_t qb = (uint32_t)(p - tstart);
+                    const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS + (qb >> 5);
+                    const uint32_t sh = qb & 31u;
+                    uint32_t x[5];
 #pragma unroll
-                for (int q = 0; q < NW; q++) w[q] = __funnelshift_l(x[q + 1], x[q], sh);
-            } else {
-#pragma unroll 1
-                for (int q = 0; q < NW; q++) {
-                    uint32_t res = 0;
-                    int got = 0;
-                    while (got < 32) {
-                        if (p >= T) {
-                            const uint64_t e = p - T;
-                            uint32_t x = 0xffffffffu;
-                            if (e < 32) {
-                                x = ((uint32_t)a_ext << 24) | 0x00ffffffu;
-                                if (e) x = (x << e) | ((1u << e) - 1u);
+                    for (int q = 0; q < 5; q++) x[q] = slot[q];   // slot[4] may belong to the next tile: shifted out when sh == 0
+#pragma unroll
+                    for (int q = 0; q < 4; q++) w[i][q] = __funnelshift_l(x[q + 1], x[q], sh);
+                } else {                // a tile seam (or the strip's end) inside these 16 bytes: word by word
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (p + 32 <= tend) {
+                            const uint32_t qb = (uint32_t)(p - tstart);
+                            const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS + (qb >> 5);
+                            w[i][q] = __funnelshift_l(slot[1], slot[0], qb & 31u);
+                            p += 32;
+                        } else {
+                            w[i][q] = stuff_seam_word(tl, a.slots, p, tau, T, a_ext);
+                            if (p < T) {
+                                while (tl.off(tau + 1) <= p) tau++;
+                                tstart = tl.off(tau);
+                                tend = tl.off(tau + 1);
+                            } else {
+                                tend = 0;   // past the strip's end: stay on the seam path
                             }
-                            res |= x >> got;
-                            p += 32 - got;
-                            got = 32;
-                            break;
                         }
-                        while (TOFF(tau + 1) <= p) tau++;
-                        const uint32_t tb = TBITS(tau);
-                        const uint32_t qb = (uint32_t)(p - TOFF(tau));
-                        const uint32_t rem = tb - qb;
-                        const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS;
-                        const uint32_t wi = qb >> 5, sh = qb & 31u;
-                        const uint32_t nw = (tb + 31u) >> 5;
-                        const uint32_t w0 = slot[wi];
-                        const uint32_t w1 = (sh && wi + 1 < nw) ? slot[wi + 1] : 0u;
-                        uint32_t x = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;
-                        const int take = min(32 - got, (int)min(rem, 32u));
-                        if (take < 32) x &= ~(0xffffffffu >> take);
-                        res |= x >> got;
-                        got += take;
-                        p += take;
                     }
-#pragma unroll
-                    for (int qq = 0; qq < NW; qq++) if (qq == q) w[qq] = res;
                 }
             }
-        }
-        // 0xFF bytes (per word: a byte is 0xFF iff all eight bits survive the and-fold)
-        int nff = 0;
+            // stuffed size of the piece
+            int nff = 0;
 #pragma unroll
-        for (int q = 0; q < NW; q++) {
-            uint32_t m = w[q] & (w[q] >> 4) & 0x0F0F0F0Fu;
-            m &= m >> 2;
-            m &= m >> 1;
-            m &= 0x01010101u;
-            if (nvalid < STUFF_BPT) {  // tail thread: ignore bytes past the end
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (4 * q + b >= nvalid) m &= ~(1u << (24 - 8 * b));
-            }
-            nff += __popc(m);
-        }
-        const uint32_t cnt = (uint32_t)(nvalid + nff);
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += y;
-        }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        uint32_t wbase = 0, total = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t x = s_warp[i];
-            if (i < wid) wbase += x;
-            total += x;
-        }
-        if (wid == 0) {
-            const uint64_t pre = lookback_exclusive(a.desc, ch, total, a.err);
-            if (lane == 0) s_goff = pre;
-        }
-        __syncthreads();
-        const uint64_t goff = (uint64_t)hdr + s_goff;
-        // shared staging is laid out so that s_out[k] <-> out[goff - pad + k] with (goff - pad) 16-byte aligned
-        const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + goff) & 15u);
-        uint32_t o = pad + wbase + inc - cnt;
-        if (nff == 0 && nvalid == STUFF_BPT) {
-            // little-endian words of the stream bytes, written at byte offset o: head bytes to the next word boundary,
-            // NW-1 whole words built with funnel shifts, tail bytes
-            uint32_t l[NW];
-#pragma unroll
-            for (int q = 0; q < NW; q++) l[q] = __byte_perm(w[q], 0, 0x0123);
-            const uint32_t al = o & 3u;
-            if (al == 0) {
-                uint32_t *d = reinterpret_cast<uint32_t *>(s_out + o);
-#pragma unroll
-                for (int q = 0; q < NW; q++) d[q] = l[q];
-            } else {
-                const uint32_t r = 32 - al * 8;
-                for (uint32_t b = 0; b < 4 - al; b++) s_out[o + b] = (uint8_t)(l[0] >> (8 * b));
-                uint32_t *d = reinterpret_cast<uint32_t *>(s_out + o + (4 - al));
-#pragma unroll
-                for (int q = 0; q < NW - 1; q++) d[q] = __funnelshift_r(l[q], l[q + 1], r);
-                for (uint32_t b = 0; b < al; b++) s_out[o + STUFF_BPT - al + b] = (uint8_t)(l[NW - 1] >> (r + 8 * b));
-            }
-        } else if (nvalid == STUFF_BPT) {
-            // some 0xFF in these 32 bytes (one thread in eight): whole words without one go out as four byte stores,
-            // only the word that holds it is walked byte by byte
-#pragma unroll
-            for (int q = 0; q < NW; q++) {
-                uint32_t m = w[q] & (w[q] >> 4) & 0x0F0F0F0Fu;
+            for (int q = 0; q < 4; q++) {
+                uint32_t m = w[i][q] & (w[i][q] >> 4) & 0x0F0F0F0Fu;
                 m &= m >> 2;
                 m &= m >> 1;
                 m &= 0x01010101u;
-                if (m == 0u) {
-                    s_out[o] = (uint8_t)(w[q] >> 24); s_out[o + 1] = (uint8_t)(w[q] >> 16);
-                    s_out[o + 2] = (uint8_t)(w[q] >> 8); s_out[o + 3] = (uint8_t)w[q];
-                    o += 4;
-                } else {
+                if (nvalid[i] < 16) {  // tail piece: ignore bytes past the end
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const uint32_t byte = (w[q] >> (24 - 8 * b)) & 0xFFu;
-                        s_out[o++] = (uint8_t)byte;
-                        if (byte == 0xFFu) s_out[o++] = 0;
-                    }
+                    for (int bb = 0; bb < 4; bb++)
+                        if (4 * q + bb >= nvalid[i]) m &= ~(1u << (24 - 8 * bb));
                 }
+                nff += __popc(m);
             }
-        } else {
+            cnt[i] = (uint32_t)(nvalid[i] + nff);
+        }
+        // ---- offsets: bytes are ordered piece-major (piece i of all threads, then piece i + 1)
+        uint32_t inc[NP];
 #pragma unroll
-            for (int i = 0; i < STUFF_BPT; i++) {
-                const uint32_t byte = (w[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
-                if (i < nvalid) {
-                    s_out[o++] = (uint8_t)byte;
-                    if (byte == 0xFFu) s_out[o++] = 0;
+        for (int i = 0; i < NP; i++) inc[i] = cnt[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc[i], o);
+                if (lane >= o) inc[i] += y;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) s_warp[i][wid] = inc[i];
+        }
+        __syncthreads();
+        uint32_t off[NP], total = 0;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            uint32_t wb = 0, tt = 0;
+#pragma unroll
+            for (int k = 0; k < NWARP; k++) {
+                const uint32_t x = s_warp[i][k];
+                if (k < wid) wb += x;
+                tt += x;
+            }
+            off[i] = total + wb + inc[i] - cnt[i];
+            total += tt;
+        }
+        if (wid == 0) {   // the other warps stage their bytes meanwhile
+            const uint64_t pre = lookback_exclusive(a.desc, ch, total, a.err);
+            if (lane == 0) s_goff = pre;
+        }
+        // ---- stage the stuffed bytes at their chunk-local offsets (the buffer is all zero here)
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            uint32_t o = off[i];
+            if (nvalid[i] == 16) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) o += stuff_place_word(w[i][q], o, sbase, s_lut);
+            } else {
+                for (int k = 0; k < nvalid[i]; k++) {
+                    uint32_t byte = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) if ((k >> 2) == q) byte = (w[i][q] >> (24 - 8 * (k & 3))) & 0xFFu;
+                    atomicOr(&s_out32[o >> 2], byte << ((o & 3u) * 8u));
+                    o += byte == 0xFFu ? 2u : 1u;
                 }
             }
         }
         __syncthreads();
+        // ---- copy out: 16-byte aligned global vectors assembled from the (unaligned) staged bytes
+        const uint64_t goff = (uint64_t)hdr + s_goff;
         const bool last = ch == nchunks - 1;
         const uint64_t end = goff + total + ((last && a.append_eoi) ? 2 : 0);
         if (end > a.cap) {
             if (tid == 0) *a.err = 3;
         } else {
-            uint8_t *base = a.out + goff - pad;  // 16-byte aligned
-            const uint32_t lim = pad + total;
-            for (uint32_t v = tid; v * 16 < lim; v += STUFF_THREADS) {
-                const uint32_t k0 = v * 16;
-                if (k0 >= pad && k0 + 16 <= lim) {
-                    *reinterpret_cast<uint4 *>(base + k0) = *reinterpret_cast<const uint4 *>(s_out + k0);
+            uint8_t *dst = a.out + goff;                     // byte k of the chunk -> dst[k]
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+            // vector v covers chunk bytes [16 v - mis, 16 v - mis + 16)
+            for (uint32_t v = tid; 16 * v < total + mis; v += STUFF_THREADS) {
+                const int k0 = (int)(16 * v) - (int)mis;
+                if (k0 >= 0 && (uint32_t)k0 + 16 <= total) {
+                    const uint32_t wi = (uint32_t)k0 >> 2, bs = ((uint32_t)k0 & 3u) * 8u;
+                    const uint32_t x0 = s_out32[wi], x1 = s_out32[wi + 1], x2 = s_out32[wi + 2], x3 = s_out32[wi + 3], x4 = s_out32[wi + 4];
+                    uint4 o4;
+                    o4.x = __funnelshift_r(x0, x1, bs); o4.y = __funnelshift_r(x1, x2, bs);
+                    o4.z = __funnelshift_r(x2, x3, bs); o4.w = __funnelshift_r(x3, x4, bs);
+                    *reinterpret_cast<uint4 *>(dst + k0) = o4;
                 } else {
-                    for (uint32_t k = max(k0, pad); k < min(k0 + 16, lim); k++) base[k] = s_out[k];
+                    for (int k = max(k0, 0); k < min(k0 + 16, (int)total); k++) dst[k] = s_out[k];
                 }
             }
             if (last && a.append_eoi && tid == 0) { a.out[goff + total] = 0xFF; a.out[goff + total + 1] = 0xD9; }
         }
         if (last && tid == 0) *a.out_len = end;
         __syncthreads();
+        // clear what was staged (the last stuffed byte may carry its 0x00 one byte further)
+        for (uint32_t i = tid; i * 16 < total + 20; i += STUFF_THREADS) reinterpret_cast<uint4 *>(s_out32)[i] = make_uint4(0, 0, 0, 0);
     }
 }
 
