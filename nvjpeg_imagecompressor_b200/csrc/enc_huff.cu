@@ -273,45 +273,53 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
 
 // ------------------------------------------------------------------------------------------------------
 // k_pack: token-parallel entropy coding (jchuff.c encode_one_block's emit_bits, without its run-length walk: that
-// happened once, in k_fdct). Persistent CTAs of PACK_WARPS warps walk the fdct tiles; all the work is convergent:
-//   1. length pass: warp w takes a contiguous share of the tile's token run; every lane loads PACK_K consecutive
-//      tokens per step (16-byte loads) and sums (code length + value bits); the warp totals give each warp its bit
-//      offset inside the tile and the tile's size                                     [the only CTA barrier per tile]
-//   2. scatter pass: the same walk; a warp scan of the lanes' bit counts gives every lane its bit position; the
-//      lane appends its PACK_K codes to a 64-bit accumulator and ORs every completed 32-bit word into the tile's
-//      bit buffer (predicated shared-memory reductions: the words at a lane's ends are shared with its neighbours)
-//   3. every warp copies the words that lie wholly inside its own bit range to the tile's fixed-size slot in
-//      global memory (tile t at t*SLOT_WORDS); the few words shared by two warps are copied after the NEXT tile's
-//      barrier, which is why the bit buffer is double-buffered
-// Tiles whose bit string exceeds the 64 kbit buffer take a fully synchronised path, one window at a time.
+// happened once, in k_fdct). Persistent CTAs of PACK_WARPS warps walk the fdct tiles; all the work is convergent and
+// every token is looked up ONCE:
+//   1. warp w takes a contiguous share of the tile's token run; every lane loads PACK_K consecutive tokens per step
+//      (16-byte loads); a warp scan of the lanes' bit counts gives every lane its bit position inside the share; the
+//      lane appends its codes to a 64-bit accumulator and ORs every completed 32-bit word into the warp's own bit
+//      buffer, which starts at bit 0 (predicated red.shared: the words at a lane's ends are shared with its
+//      neighbours). The share's length falls out of the walk.
+//   2. one CTA barrier: the warps' lengths give each share its bit offset inside the tile and the tile's size
+//   3. every warp shifts its buffer into place on the way out: words wholly inside its bit range go straight to the
+//      tile's fixed-size slot in global memory (tile t at t*SLOT_WORDS); the word it shares with a neighbour is
+//      OR-ed into a per-boundary cell that thread 0 writes after the NEXT tile's barrier (cells double-buffered)
+// Dense tiles (more tokens than the warp buffers are sure to hold, or a buffer that overflowed) take the two-pass
+// path: lengths first, then the bits are scattered window by window into one tile-wide buffer.
 // Raw-DC tokens were resolved by k_dc_edge_hist; ZRL prefixes (token bits 29:28) are emitted in a side branch.
-constexpr int WIN_WORDS = 2048;                  // 64 kbit bit-buffer window (a typical tile is ~30 kbit)
+constexpr int WIN_WORDS = 2048;                  // dense tiles: 64 kbit window of the tile's bit string
+constexpr int SUB_WORDS = 512;                   // per-warp bit buffer: 16 kbit (a typical share is ~7.5 kbit)
 constexpr int PACK_THREADS = 128;                // one CTA per tile at a time, PACK_WARPS contiguous shares
 constexpr int PACK_WARPS = PACK_THREADS / 32;
 constexpr int PACK_CTAS = 8;                     // resident CTAs per SM (register budget)
 constexpr int PACK_K = 8;                        // consecutive tokens per lane and step
 constexpr int PACK_STEP = 32 * PACK_K;           // tokens per warp and step
+constexpr uint32_t PACK_DENSE_TOKENS = 7000;     // above this the shares may not fit the warp buffers: two-pass path
 constexpr uint32_t TOK_NULL = 0x00100000u;       // DC0 symbol 0x10 does not exist: code length 0, no value bits
 
 struct PackShared {
-    uint32_t buf[2][WIN_WORDS];
+    uint32_t buf[WIN_WORDS];
+    uint32_t sub[PACK_WARPS][SUB_WORDS + 4];
     uint32_t enc[1024];
     uint32_t wlen[3][PACK_WARPS];                // bit counts of the warps' shares, three tiles deep
+    uint32_t bnd[2][PACK_WARPS + 1];             // words shared by two shares (cell b: the word holding the start of share b)
 };
 
 // One lane's contiguous piece of the bit string: bits are appended to a 64-bit accumulator and every completed
-// 32-bit word is OR-ed into the window. `cnt` = valid low bits of acc that are not flushed yet (< 32 between calls).
-// Fast variant: predicated red.shared (no branch); windowed variant: words outside the window are skipped.
+// 32-bit word is OR-ed into the buffer. `cnt` = valid low bits of acc that are not flushed yet (< 32 between calls).
+// WINDOWED: C++ path, words outside [0, WIN_WORDS) are skipped. Otherwise: predicated red.shared (no branch), words
+// at or beyond the byte address `limit` are dropped (the caller notices the overflow from the share's length).
 template <bool WINDOWED>
 struct LaneEmitter {
     uint64_t acc;
     uint32_t cnt;
-    uint32_t addr;   // fast: shared byte address of the current word
-    int wi;          // windowed: word index relative to the window
+    uint32_t addr, limit;   // fast: shared byte address of the current word / end of the buffer
+    int wi;                 // windowed: word index relative to the window
     uint32_t *buf;
-    __device__ __forceinline__ void start(uint32_t *b, int pos) {
+    __device__ __forceinline__ void start(uint32_t *b, int pos, uint32_t nwords) {
         buf = b; acc = 0; cnt = (uint32_t)pos & 31u; wi = pos >> 5;
         addr = smem_u32(b) + (uint32_t)(pos >> 5) * 4u;
+        limit = smem_u32(b) + nwords * 4u;
     }
     __device__ __forceinline__ void put(uint32_t bits, uint32_t n) {   // n <= 32
         acc = (acc << n) | bits;
@@ -324,15 +332,16 @@ struct LaneEmitter {
             }
         } else {
             const uint32_t wv = __funnelshift_r((uint32_t)acc, (uint32_t)(acc >> 32), cnt);   // acc >> (cnt - 32) if cnt >= 32
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, 32;\n\t@p red.shared.or.b32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t@p sub.u32 %1, %1, 32;\n\t}"
-                         : "+r"(addr), "+r"(cnt) : "r"(wv) : "memory");
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ge.u32 p, %1, 32;\n\tsetp.lt.and.u32 q, %0, %3, p;\n\t"
+                         "@q red.shared.or.b32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t@p sub.u32 %1, %1, 32;\n\t}"
+                         : "+r"(addr), "+r"(cnt) : "r"(wv), "r"(limit) : "memory");
         }
     }
     __device__ __forceinline__ void finish() {
         if (cnt) {
             const uint32_t wv = (uint32_t)acc << (32u - cnt);
             if (WINDOWED) { if ((uint32_t)wi < (uint32_t)WIN_WORDS) atomicOr(&buf[wi], wv); }
-            else asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(wv) : "memory");
+            else if (addr < limit) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(wv) : "memory");
         }
     }
 };
@@ -352,9 +361,10 @@ __device__ __forceinline__ void load_tokens(const uint4 *tk4, uint32_t v0, uint3
     }
 }
 
+// The warp's share [lo, hi) of the walk, coded into `buf` starting at bit `run`; returns the bit position after it.
 template <bool WINDOWED>
-__device__ __forceinline__ void pack_scatter(const uint32_t *enc, uint32_t *buf, const uint4 *tk4, uint32_t a, uint32_t lo,
-                                             uint32_t hi, int run, int lane, uint32_t zr_y, uint32_t zr_c) {
+__device__ __forceinline__ int pack_scatter(const uint32_t *enc, uint32_t *buf, uint32_t nwords, const uint4 *tk4, uint32_t a,
+                                            uint32_t lo, uint32_t hi, int run, int lane, uint32_t zr_y, uint32_t zr_c) {
     const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
     for (uint32_t s0 = lo; s0 < hi; s0 += PACK_STEP) {
         const uint32_t v0 = s0 + lane * PACK_K;
@@ -380,7 +390,7 @@ __device__ __forceinline__ void pack_scatter(const uint32_t *enc, uint32_t *buf,
             if (lane >= o) inc += y;
         }
         LaneEmitter<WINDOWED> e;
-        e.start(buf, run + (int)(inc - Lt));
+        e.start(buf, run + (int)(inc - Lt), nwords);
         run += (int)__shfl_sync(0xffffffffu, inc, 31);
 #pragma unroll
         for (int k = 0; k < PACK_K; k++) {
@@ -397,17 +407,45 @@ __device__ __forceinline__ void pack_scatter(const uint32_t *enc, uint32_t *buf,
         }
         e.finish();
     }
+    return run;
 }
 
-// words of the previous tile that two warps share (and its last, partial word): copy to the slot, clear
-__device__ __forceinline__ void pack_flush_shared_words(uint32_t *buf, const uint32_t *wlen, uint32_t *slot) {
-    uint32_t pos = 0, last = 0xffffffffu;
+// bits of the warp's share without coding them (two-pass path)
+__device__ __forceinline__ uint32_t pack_length(const uint32_t *enc, const uint4 *tk4, uint32_t a, uint32_t lo, uint32_t hi,
+                                                int lane, uint32_t zl_y, uint32_t zl_c) {
+    uint32_t len = 0;
+    for (uint32_t v0 = lo + lane * PACK_K; v0 < hi; v0 += PACK_STEP) {
+        uint32_t w[PACK_K];
+        load_tokens(tk4, v0, a, hi, w);
 #pragma unroll
-    for (int w = 0; w < PACK_WARPS; w++) {
-        pos += wlen[w];   // end of warp w = start of warp w + 1 (or the tile's end)
-        const uint32_t wi = pos >> 5;
-        if ((pos & 31u) && wi != last) { slot[wi] = buf[wi]; buf[wi] = 0; last = wi; }
+        for (int k = 0; k < PACK_K; k++)
+            len += (enc[(w[k] >> 16) & 0x3FFu] & 31u) + ((w[k] >> 16) & 15u) + (w[k] >> 28) * ((w[k] & (2u << 24)) ? zl_c : zl_y);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+    return len;
+}
+
+// the previous tile's shared words: cell b holds the bits of the word that contains the start of share b (and the end
+// of share b - 1); consecutive cells can name the same word when a share is shorter than a word
+__device__ __forceinline__ void pack_flush_shared_words(uint32_t *bnd, const uint32_t *wlen, uint32_t *slot) {
+    uint32_t pos = 0, last = 0xffffffffu, acc = 0;
+#pragma unroll
+    for (int b = 1; b <= PACK_WARPS; b++) {
+        pos += wlen[b - 1];
+        const uint32_t v = bnd[b];
+        bnd[b] = 0;
+        if (pos & 31u) {
+            const uint32_t wi = pos >> 5;
+            if (wi != last) {
+                if (last != 0xffffffffu) slot[last] = acc;
+                last = wi;
+                acc = 0;
+            }
+            acc |= v;
+        }
+    }
+    if (last != 0xffffffffu) slot[last] = acc;
 }
 
 __global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
@@ -416,12 +454,15 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
     __shared__ __align__(16) PackShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < 1024; i += PACK_THREADS) sh.enc[i] = huff->enc[i >> 8][i & 255];
-    for (int i = tid; i < 2 * WIN_WORDS; i += PACK_THREADS) sh.buf[0][i] = 0;
+    for (int i = tid; i < WIN_WORDS; i += PACK_THREADS) sh.buf[i] = 0;
+    for (int i = tid; i < PACK_WARPS * (SUB_WORDS + 4); i += PACK_THREADS) sh.sub[0][i] = 0;
+    if (tid < 2 * (PACK_WARPS + 1)) sh.bnd[0][tid] = 0;
     __syncthreads();
     const uint32_t zr_y = sh.enc[0x1F0], zr_c = sh.enc[0x3F0];   // ZRL (0xF0) codes of the two AC tables
     const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
+    uint32_t *sub = sh.sub[wid];
 
-    bool pend = false;      // the previous tile's shared words are still in its buffer
+    bool pend = false;      // the previous tile's shared words are still in their cells
     uint32_t *pslot = nullptr;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
@@ -434,7 +475,6 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
         // warp shares: contiguous, a multiple of PACK_STEP tokens; every lane owns PACK_K consecutive tokens per step
         const uint32_t per = (((vend + PACK_WARPS - 1u) / PACK_WARPS) + PACK_STEP - 1u) & ~(uint32_t)(PACK_STEP - 1);
         const uint32_t lo = min(vend, (uint32_t)wid * per), hi = min(vend, lo + per);
-
         // the next tile's token run on its way into L2 while this one is coded
         if (t + (int)gridDim.x < ntiles) {
             const TileRec nx = recs[t + gridDim.x];
@@ -444,58 +484,59 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         }
 
-        // ---- 1. length pass (loads run one step ahead of the table lookups)
-        uint32_t len = 0;
-        {
-            uint32_t v0 = lo + lane * PACK_K;
-            uint32_t w[PACK_K], wn[PACK_K];
-            if (v0 < hi) load_tokens(tk4, v0, a, hi, w);
-            while (v0 < hi) {
-                const uint32_t v1 = v0 + PACK_STEP;
-                if (v1 < hi) load_tokens(tk4, v1, a, hi, wn);
-#pragma unroll
-                for (int k = 0; k < PACK_K; k++)
-                    len += (sh.enc[(w[k] >> 16) & 0x3FFu] & 31u) + ((w[k] >> 16) & 15u) + (w[k] >> 28) * ((w[k] & (2u << 24)) ? zl_c : zl_y);
-#pragma unroll
-                for (int k = 0; k < PACK_K; k++) w[k] = wn[k];
-                v0 = v1;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+        // ---- 1. code the share into the warp's buffer (or only measure it: dense tiles)
+        const bool dense = rec.count > PACK_DENSE_TOKENS;
+        uint32_t len;
+        if (!dense) len = (uint32_t)pack_scatter<false>(sh.enc, sub, SUB_WORDS, tk4, a, lo, hi, 0, lane, zr_y, zr_c);
+        else len = pack_length(sh.enc, tk4, a, lo, hi, lane, zl_y, zl_c);
         if (lane == 0) sh.wlen[l3][wid] = len;
-        __syncthreads();   // also: every warp is done with the previous tile's buffer
-        if (pend && tid == 0) pack_flush_shared_words(sh.buf[cur ^ 1], sh.wlen[pl3], pslot);
+        __syncthreads();   // ---- 2. also: every warp is done with the previous tile's cells
+        if (pend && tid == 0) pack_flush_shared_words(sh.bnd[cur ^ 1], sh.wlen[pl3], pslot);
         uint32_t base = 0, total = 0;
+        bool two_pass = dense;
 #pragma unroll
-        for (int w = 0; w < PACK_WARPS; w++) { const uint32_t x = sh.wlen[l3][w]; if (w < wid) base += x; total += x; }
+        for (int w = 0; w < PACK_WARPS; w++) {
+            const uint32_t x = sh.wlen[l3][w];
+            if (w < wid) base += x;
+            total += x;
+            if (x > (uint32_t)SUB_WORDS * 32u) two_pass = true;   // a warp buffer overflowed: its bits were dropped
+        }
         if (tid == 0) tile_bits[t] = total;
-        const uint32_t nwords = (total + 31u) >> 5;
         uint32_t *slot = slots + (size_t)t * SLOT_WORDS;
-        uint32_t *buf = sh.buf[cur];
 
-        if (nwords <= (uint32_t)WIN_WORDS) {
-            // ---- 2. scatter pass (the buffer is all zero here)
-            pack_scatter<false>(sh.enc, buf, tk4, a, lo, hi, (int)base, lane, zr_y, zr_c);
+        if (!two_pass) {
+            // ---- 3. shift the share into place; clear the buffer behind
+            const uint32_t shv = base & 31u, fw = base >> 5;
+            const uint32_t nV = (shv + len + 31u) >> 5;
+            const uint32_t tailbits = (shv + len) & 31u;
+            for (uint32_t i = lane; i < nV; i += 32) {
+                const uint32_t hi_w = i ? sub[i - 1] : 0u, lo_w = sub[i];
+                const uint32_t v = __funnelshift_r(lo_w, hi_w, shv);
+                if (i == 0 && shv != 0u) atomicOr(&sh.bnd[cur][wid], v);
+                else if (i == nV - 1 && tailbits != 0u) atomicOr(&sh.bnd[cur][wid + 1], v);
+                else slot[fw + i] = v;
+            }
             __syncwarp();
-            // ---- 3. words wholly inside this warp's bit range: copy out and clear
-            const uint32_t fw = (base + 31u) >> 5, lw = (base + len) >> 5;
-            for (uint32_t i = fw + lane; i < lw; i += 32) { slot[i] = buf[i]; buf[i] = 0; }
+            for (uint32_t i = lane; i < nV + 1; i += 32) sub[i] = 0;
             pend = true;
             pslot = slot;
         } else {
+            if (!dense) {   // overflowed buffers hold a prefix of the share: clear them
+                for (uint32_t i = lane; i < (uint32_t)SUB_WORDS + 4u; i += 32) sub[i] = 0;
+            }
+            const uint32_t nwords = (total + 31u) >> 5;
             for (uint32_t wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
-                pack_scatter<true>(sh.enc, buf, tk4, a, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
+                pack_scatter<true>(sh.enc, sh.buf, WIN_WORDS, tk4, a, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
                 __syncthreads();
                 const uint32_t wn = min((uint32_t)WIN_WORDS, nwords - wbase);
-                for (uint32_t i = tid; i < wn; i += PACK_THREADS) { slot[wbase + i] = buf[i]; buf[i] = 0; }
+                for (uint32_t i = tid; i < wn; i += PACK_THREADS) { slot[wbase + i] = sh.buf[i]; sh.buf[i] = 0; }
                 __syncthreads();
             }
             pend = false;
         }
     }
     __syncthreads();
-    if (pend && tid == 0) pack_flush_shared_words(sh.buf[(it + 1) & 1], sh.wlen[(it + 2) % 3], pslot);
+    if (pend && tid == 0) pack_flush_shared_words(sh.bnd[(it + 1) & 1], sh.wlen[(it + 2) % 3], pslot);
 }
 
 // ------------------------------------------------------------------------------------------------------
