@@ -154,7 +154,9 @@ enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS
        B2J_DBG_TOKEN_COUNT = 5 /* uint32: run-length tokens of the last encode (4 bytes each between the two passes) */ };
 B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len);
 /* flags bit0 (B2J_DEBUG_COEF): the next encodes also store the quantised coefficients for B2J_DBG_COEF */
-enum { B2J_DEBUG_COEF = 1 };
+/* bit1 (B2J_DEBUG_SMALL_PACK_BUFFERS): the entropy coder's per-warp bit buffers overflow on purpose (tests its
+ * two-pass recovery path); output is unchanged */
+enum { B2J_DEBUG_COEF = 1, B2J_DEBUG_SMALL_PACK_BUFFERS = 2 };
 B2J_API int b2j_set_debug(b2j_ctx *ctx, int flags);
 
 /* per-stage device times (ms) of the last encode/decode, measured with CUDA events on the context stream */

@@ -303,7 +303,7 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
     CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, ctx->stream));
     tick(ctx, 4);
-    CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_slots, ctx->d_tile_bits, ctx->stream));
+    CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_slots, ctx->d_tile_bits, ctx->debug & 2, ctx->stream));
     tick(ctx, 5);
     CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->d_sdesc,
                          &ctx->d_ctrl->scan_ticket, &ctx->d_ctrl->err, ctx->stream));

@@ -450,7 +450,7 @@ __device__ __forceinline__ void pack_flush_shared_words(uint32_t *bnd, const uin
 
 __global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
 k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int ntiles, const HuffDev *__restrict__ huff,
-       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits) {
+       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits, uint32_t sub_words) {
     __shared__ __align__(16) PackShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < 1024; i += PACK_THREADS) sh.enc[i] = huff->enc[i >> 8][i & 255];
@@ -487,7 +487,7 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
         // ---- 1. code the share into the warp's buffer (or only measure it: dense tiles)
         const bool dense = rec.count > PACK_DENSE_TOKENS;
         uint32_t len;
-        if (!dense) len = (uint32_t)pack_scatter<false>(sh.enc, sub, SUB_WORDS, tk4, a, lo, hi, 0, lane, zr_y, zr_c);
+        if (!dense) len = (uint32_t)pack_scatter<false>(sh.enc, sub, sub_words, tk4, a, lo, hi, 0, lane, zr_y, zr_c);
         else len = pack_length(sh.enc, tk4, a, lo, hi, lane, zl_y, zl_c);
         if (lane == 0) sh.wlen[l3][wid] = len;
         __syncthreads();   // ---- 2. also: every warp is done with the previous tile's cells
@@ -499,7 +499,7 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
             const uint32_t x = sh.wlen[l3][w];
             if (w < wid) base += x;
             total += x;
-            if (x > (uint32_t)SUB_WORDS * 32u) two_pass = true;   // a warp buffer overflowed: its bits were dropped
+            if (x > sub_words * 32u) two_pass = true;   // a warp buffer overflowed: its bits were dropped
         }
         if (tid == 0) tile_bits[t] = total;
         uint32_t *slot = slots + (size_t)t * SLOT_WORDS;
@@ -906,9 +906,9 @@ cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, con
     return cudaGetLastError();
 }
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
-                        uint32_t *slots, uint32_t *tile_bits, cudaStream_t s) {
+                        uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s) {
     const int grid = min(g.ntiles, 148 * PACK_CTAS);
-    k_pack<<<grid, PACK_THREADS, 0, s>>>(pool, recs, g.ntiles, huff, slots, tile_bits);
+    k_pack<<<grid, PACK_THREADS, 0, s>>>(pool, recs, g.ntiles, huff, slots, tile_bits, small_buffers ? 24u : (uint32_t)SUB_WORDS);
     return cudaGetLastError();
 }
 int scan_desc_count(int ntiles) { return (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }

@@ -15,8 +15,9 @@ cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_
                                 int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, cudaStream_t s);
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
                           int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s);
+// small_buffers != 0 (tests): the per-warp bit buffers pretend to hold 24 words, forcing the overflow path
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
-                        uint32_t *slots, uint32_t *tile_bits, cudaStream_t s);
+                        uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s);
 // desc: scan_desc_count(ntiles) zeroed look-back descriptors; ticket: zeroed
 int scan_desc_count(int ntiles);
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,

@@ -74,6 +74,26 @@ def test_flat_and_extreme_images(P, oracle):
             eng.close()
 
 
+def test_pack_buffer_regimes(P, oracle):
+    """k_pack's three paths: single pass (shares fit the warp buffers), overflow of a warp buffer (long codes, few
+    tokens: redone in two passes) and the dense two-pass path (token count above the threshold)."""
+    rng = np.random.default_rng(21)
+    W, H = 1344, 48
+    noise = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    soft = (noise.astype(np.int32) // 8 + oracle.synth(W, H, 5, 8).astype(np.int32) * 7 // 8).astype(np.uint8)
+    for css in (0, 1):
+        for q in (60, 80, 90, 97, 100):
+            for opt in (1, 0):
+                eng = P.Engine(W, H, q, bool(opt), css)
+                for name, img in (("noise", noise), ("soft", soft)):
+                    want = oracle.encode(img, css, q, opt)
+                    for dbg in (0, 2):   # 2 = B2J_DEBUG_SMALL_PACK_BUFFERS: every warp buffer overflows -> recovery path
+                        eng.set_debug(dbg)
+                        jpg = eng.encode(img)
+                        assert jpg.size == want.size and np.array_equal(jpg, want), f"{name} css{css} q{q} opt{opt} dbg{dbg}"
+                eng.close()
+
+
 def test_golden_cases(P, golden, oracle):
     """End to end against digests written by libjpeg-turbo itself (tests/golden/make_golden.py)."""
     engines = {}
