@@ -19,7 +19,7 @@ build/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared -o $@ $(OBJS) -cudart static
+	$(NVCC) -shared -o $@ $(OBJS) -cudart static -lpthread
 
 oracle:
 	$(MAKE) -C oracle -s

@@ -312,6 +312,60 @@ def run_b200(args, rank, world, local_rank):
            "h2d_bytes_per_step": W * H * 3, "d2h_bytes_per_step": int(nbytes),
            "api": "b2j_encode (host BGR -> host JPEG), pinned buffers" if world == 1 else
                   "per rank: pinned H2D of its strip + b2j_strip_phase1..3 + pinned D2H of its bytes"}
+    # ---- the same call on PAGEABLE host memory (what the reference's cv::Mat / std::vector hand over): the library
+    #      stages row groups through pinned buffers with its own copy threads (hostpipe.h)
+    e2e_pageable = None
+    if world == 1:
+        try:
+            p_img = np.array(h_img.numpy(), copy=True)
+            p_out = np.empty(int(nbytes) + (1 << 20), np.uint8)
+            p_out[:] = 0   # touch the pages: the timed calls measure the codec, not the kernel's page faults
+            eng.encode(p_img, out=p_out)
+            kp = 3
+            t0 = time.perf_counter()
+            for _ in range(kp):
+                eng.encode(p_img, out=p_out)
+            dtp = (time.perf_counter() - t0) / kp
+            e2e_pageable = {"value": round(W * H / dtp / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dtp * 1e3, 2),
+                            "api": "b2j_encode (pageable host BGR -> pageable host JPEG)"}
+            del p_img, p_out
+        except Exception as e:
+            e2e_pageable = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- the metric's second half (BASELINE.json: "...; decode Mpix/s"): the JPEG just produced, host bytes ->
+    #      device BGR (b2j_decode_device, includes the H2D of the scan) and host bytes -> pinned host BGR (b2j_decode)
+    decode = None
+    if world == 1:
+        try:
+            jpg = h_out[:int(n2)].numpy()
+            d_rec = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+            kd = max(2, min(args.steps, 5))
+            with torch.cuda.stream(stream):
+                eng.decode_device(jpg, d_rec.data_ptr(), W * 3)
+                stream.synchronize()
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record(stream)
+                for _ in range(kd):
+                    eng.decode_device(jpg, d_rec.data_ptr(), W * 3)
+                d1.record(stream)
+                stream.synchronize()
+            dec_ms = d0.elapsed_time(d1) / kd
+            h_rec = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
+            eng.decode_ptr(jpg, h_rec.data_ptr(), W * 3)
+            t0 = time.perf_counter()
+            for _ in range(kd):
+                eng.decode_ptr(jpg, h_rec.data_ptr(), W * 3)
+            dth = (time.perf_counter() - t0) / kd
+            dt_st = {k: round(v, 3) for k, v in eng.timings().items() if k.startswith("dec_")}
+            decode = {"metric": "decode_mpix_per_s", "value": round(W * H / dec_ms / 1e3, 1), "unit": "Mpix/s",
+                      "ms_per_step": round(dec_ms, 3), "input": "host JPEG bytes (this run's output), output BGR in HBM",
+                      "e2e": {"value": round(W * H / dth / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dth * 1e3, 2),
+                              "h2d_bytes_per_step": int(n2), "d2h_bytes_per_step": W * H * 3,
+                              "api": "b2j_decode (host JPEG -> host BGR), pinned output"},
+                      "stages_ms": dt_st}
+            del d_rec, h_rec
+        except Exception as e:  # the encode line must survive a decode problem
+            decode = {"error": f"{type(e).__name__}: {e}"}
     if sampler:
         sampler.t_hi = time.time()
     clocks = sampler.finish() if sampler else None
@@ -326,6 +380,10 @@ def run_b200(args, rank, world, local_rank):
                        "exceed the 126 MB L2; no flush between steps", "parallelism": "single GPU" if world == 1 else
                        f"{world} MCU-row strips, 1 all_reduce + 2 all_gather per image"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if e2e_pageable is not None:
+        line["e2e_pageable"] = e2e_pageable
+    if decode is not None:
+        line["decode"] = decode
     if world == 1:
         from nvjpeg_imagecompressor_b200 import _native as NAT
         st = {k: v / args.steps for k, v in stage_acc.items()}

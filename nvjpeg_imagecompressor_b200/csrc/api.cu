@@ -12,6 +12,7 @@
 #include "../../include/b2jpeg.h"
 #include "common.cuh"
 #include "dec.h"
+#include "hostpipe.h"
 #include "kernels.h"
 
 using namespace b2j;
@@ -77,8 +78,13 @@ struct b2j_ctx {
     b2j::Decoder *dec;
     uint8_t *d_recon, *d_diff;
     size_t d_recon_bytes;
+    // pageable host buffers: copy threads + pinned staging ring (hostpipe.h), created on first use
+    b2j::CopyPool *pool;
+    b2j::StageRing ring;
     b2j_ctx *second;  // encoder for the difference image (secondary compression)
 };
+
+extern "C" { static int upload_linear(void *user, uint8_t *d_dst, const uint8_t *src, size_t n, cudaStream_t s); }
 
 #define CK(call)                                                                                        \
     do {                                                                                                \
@@ -225,6 +231,8 @@ void b2j_destroy(b2j_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->second) b2j_destroy(ctx->second);
     if (ctx->dec) dec_destroy(ctx->dec);
+    delete ctx->pool;
+    ctx->ring.release();
     cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_pool); cudaFree(ctx->d_recs); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
     cudaFree(ctx->d_tile_off); cudaFree(ctx->d_desc); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_pred_in);
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
@@ -413,6 +421,93 @@ static int ensure_img(b2j_ctx *ctx, size_t bytes) {
     return B2J_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ pageable host buffers
+static int ensure_hostpipe(b2j_ctx *ctx, size_t ring_bytes) {
+    if (!ctx->pool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        ctx->pool = new (std::nothrow) CopyPool((int)std::max(1u, std::min(8u, hc ? hc : 1u)));
+        if (!ctx->pool) return B2J_ENOMEM;
+    }
+    CK(ctx->ring.ensure(ring_bytes));
+    return B2J_OK;
+}
+
+static constexpr size_t RING_CHUNK = 32u << 20;   // staging granularity of the generic helpers
+
+// rows from the caller's (possibly pageable) memory to the device, asynchronously on `s`
+static int upload_2d(b2j_ctx *ctx, uint8_t *d_dst, size_t dstep, const uint8_t *src, size_t sstep, size_t row_bytes, size_t rows,
+                     cudaStream_t s) {
+    if (!is_pageable_host(src)) {
+        CK(cudaMemcpy2DAsync(d_dst, dstep, src, sstep, row_bytes, rows, cudaMemcpyHostToDevice, s));
+        return B2J_OK;
+    }
+    int rc = ensure_hostpipe(ctx, std::max(RING_CHUNK, row_bytes)); if (rc) return rc;
+    StageRing &r = ctx->ring;
+    const size_t rows_per = std::max<size_t>(1, r.bytes / row_bytes);
+    int k = 0;
+    for (size_t y = 0; y < rows; y += rows_per, k++) {
+        const size_t nr = std::min(rows_per, rows - y);
+        const int slot = k % StageRing::N;
+        if (r.busy[slot]) CK(cudaEventSynchronize(r.ev[slot]));
+        ctx->pool->copy2d(r.buf[slot], row_bytes, src + y * sstep, sstep, row_bytes, nr);
+        CK(cudaMemcpy2DAsync(d_dst + y * dstep, dstep, r.buf[slot], row_bytes, row_bytes, nr, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(r.ev[slot], s));
+        r.busy[slot] = true;
+    }
+    return B2J_OK;
+}
+
+// rows from the device to the caller's (possibly pageable) memory; returns after the data has landed
+static int download_2d(b2j_ctx *ctx, uint8_t *dst, size_t hstep, const uint8_t *d_src, size_t dstep, size_t row_bytes, size_t rows,
+                       cudaStream_t s) {
+    if (!is_pageable_host(dst)) {
+        CK(cudaMemcpy2DAsync(dst, hstep, d_src, dstep, row_bytes, rows, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return B2J_OK;
+    }
+    int rc = ensure_hostpipe(ctx, std::max(RING_CHUNK, row_bytes)); if (rc) return rc;
+    StageRing &r = ctx->ring;
+    for (int i = 0; i < StageRing::N; i++) if (r.busy[i]) { CK(cudaEventSynchronize(r.ev[i])); r.busy[i] = false; }
+    const size_t rows_per = std::max<size_t>(1, r.bytes / row_bytes);
+    const size_t ngroups = (rows + rows_per - 1) / rows_per;
+    // group k travels while group k - 1 is copied into the caller's pages
+    for (size_t k = 0; k <= ngroups; k++) {
+        if (k < ngroups) {
+            const size_t y = k * rows_per, nr = std::min(rows_per, rows - y);
+            const int slot = (int)(k % StageRing::N);
+            CK(cudaMemcpy2DAsync(r.buf[slot], row_bytes, d_src + y * dstep, dstep, row_bytes, nr, cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(r.ev[slot], s));
+        }
+        if (k > 0) {
+            const size_t y = (k - 1) * rows_per, nr = std::min(rows_per, rows - y);
+            const int slot = (int)((k - 1) % StageRing::N);
+            CK(cudaEventSynchronize(r.ev[slot]));
+            ctx->pool->copy2d(dst + y * hstep, hstep, r.buf[slot], row_bytes, row_bytes, nr);
+        }
+    }
+    return B2J_OK;
+}
+
+// linear buffers go through the same helpers as rows of 1 MB
+static int download_linear(b2j_ctx *ctx, uint8_t *dst, const uint8_t *d_src, size_t n, cudaStream_t s) {
+    constexpr size_t CH = 1u << 20;
+    const size_t rows = n / CH, rem = n - rows * CH;
+    int rc = B2J_OK;
+    if (rows) rc = download_2d(ctx, dst, CH, d_src, CH, CH, rows, s);
+    if (!rc && rem) rc = download_2d(ctx, dst + rows * CH, rem, d_src + rows * CH, rem, rem, 1, s);
+    return rc;
+}
+static int upload_linear(void *user, uint8_t *d_dst, const uint8_t *src, size_t n, cudaStream_t s) {
+    b2j_ctx *ctx = static_cast<b2j_ctx *>(user);
+    constexpr size_t CH = 1u << 20;
+    const size_t rows = n / CH, rem = n - rows * CH;
+    int rc = B2J_OK;
+    if (rows) rc = upload_2d(ctx, d_dst, CH, src, CH, CH, rows, s);
+    if (!rc && rem) rc = upload_2d(ctx, d_dst + rows * CH, rem, src + rows * CH, rem, rem, 1, s);
+    return rc;
+}
+
 int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
     if (!ctx || !bgr || !out || !len || step < (size_t)width * 3) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -427,6 +522,8 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
     // upload in MCU-row groups on the copy stream; the fdct of a group starts as soon as its rows have landed
     const int ngroups = std::max(1, std::min(32, g.mcuy / 64));
     const int rows_per = (g.mcuy + ngroups - 1) / ngroups;
+    const bool pageable_in = is_pageable_host(bgr);
+    if (pageable_in) { rc = ensure_hostpipe(ctx, (size_t)rows_per * 8 * g.vs * (size_t)width * 3); if (rc) return rc; }
     CK(cudaEventRecord(ctx->ev_copy[63], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[63], 0));
     const int mcu_h = 8 * g.vs;
@@ -434,8 +531,19 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
     for (int gi = 0, my0 = 0; my0 < g.mcuy; gi++, my0 += rows_per) {
         const int nr = std::min(rows_per, g.mcuy - my0);
         const int y0 = my0 * mcu_h, y1 = std::min(height, (my0 + nr) * mcu_h);
-        CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0,
-                             cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (pageable_in) {   // copy threads -> pinned ring -> DMA: the group goes up while the next one is being staged
+            StageRing &r = ctx->ring;
+            const int slot = gi % StageRing::N;
+            if (r.busy[slot]) CK(cudaEventSynchronize(r.ev[slot]));
+            ctx->pool->copy2d(r.buf[slot], (size_t)width * 3, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0);
+            CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, r.buf[slot], (size_t)width * 3, (size_t)width * 3, y1 - y0,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(r.ev[slot], ctx->copy_stream));
+            r.busy[slot] = true;
+        } else {
+            CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
         CK(cudaEventRecord(ctx->ev_copy[gi], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[gi], 0));
         CK(launch_fdct(ctx->d_img, dstep, g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, my0, nr, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
@@ -447,8 +555,8 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
     collect_timings(ctx);
     const size_t n = (size_t)ctx->h_ret->out_len;
     if (n > cap) { snprintf(ctx->err, sizeof(ctx->err), "output needs %zu bytes, buffer has %zu", n, cap); return B2J_ECAPACITY; }
-    CK(cudaMemcpyAsync(out, ctx->d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < StageRing::N; i++) ctx->ring.busy[i] = false;   // every upload has completed (fetch_ret synchronised)
+    rc = download_linear(ctx, out, ctx->d_out, n, ctx->stream); if (rc) return rc;
     *len = n;
     return B2J_OK;
 }
@@ -459,6 +567,7 @@ int b2j_last_timings(b2j_ctx *ctx, b2j_timings *t) { if (!ctx || !t) return B2J_
 static int dec_ensure(b2j_ctx *ctx) {
     if (ctx->dec) return B2J_OK;
     ctx->dec = dec_create(ctx->cap_g.nblocks, ctx->err, sizeof(ctx->err));
+    if (ctx->dec) dec_set_uploader(ctx->dec, upload_linear, ctx);   // pageable JPEG bytes go up through the staging ring
     return ctx->dec ? B2J_OK : B2J_ECUDA;
 }
 
@@ -511,8 +620,7 @@ int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_
     }
     rc = decode_parsed(ctx, jpg, len, info, ctx->d_recon, dstep);
     if (rc) return rc;
-    CK(cudaMemcpy2DAsync(bgr, step, ctx->d_recon, dstep, (size_t)info.W * 3, info.H, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    rc = download_2d(ctx, bgr, step, ctx->d_recon, dstep, (size_t)info.W * 3, info.H, ctx->stream); if (rc) return rc;
     rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
     return rc;
 }

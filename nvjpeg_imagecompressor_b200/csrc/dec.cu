@@ -41,6 +41,8 @@ struct Decoder {
     char *err;
     size_t errlen;
     cudaStream_t last_stream = nullptr;
+    dec_upload_fn upload = nullptr;
+    void *upload_user = nullptr;
 };
 
 #define DCK(call)                                                                                                  \
@@ -80,6 +82,8 @@ void dec_destroy(Decoder *d) {
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
     delete d;
 }
+
+void dec_set_uploader(Decoder *d, dec_upload_fn fn, void *user) { d->upload = fn; d->upload_user = user; }
 
 const void *dec_coef_ptr(Decoder *d, size_t *bytes) { *bytes = (size_t)d->nblocks_cap * 128; return d->d_coef; }
 
@@ -132,7 +136,12 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     if (tm) cudaEventRecord(d->ev[0], s);
     dec_build_tables(info, d->h_tb);
     DCK(cudaMemcpyAsync(d->d_tb, d->h_tb, dec_tables_size(), cudaMemcpyHostToDevice, s));
-    DCK(cudaMemcpyAsync(d->d_scan, jpg + info.scan_offset, n, cudaMemcpyHostToDevice, s));
+    if (d->upload) {
+        const int urc = d->upload(d->upload_user, d->d_scan, jpg + info.scan_offset, n, s);
+        if (urc) return urc;
+    } else {
+        DCK(cudaMemcpyAsync(d->d_scan, jpg + info.scan_offset, n, cudaMemcpyHostToDevice, s));
+    }
     DCK(cudaMemsetAsync(d->d_ctrl, 0, sizeof(DecCtrl), s));
     DCK(cudaMemsetAsync(d->d_desc, 0, d->desc_cap * 5 * 8, s));
     DCK(cudaMemsetAsync(d->d_nblk, 0, (nsub_max + 1) * 4, s));

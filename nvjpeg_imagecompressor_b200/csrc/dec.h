@@ -26,6 +26,10 @@ void dec_destroy(Decoder *d);
 int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
             cudaStream_t s, b2j_timings *tm, uint64_t *launches);
 int dec_check(Decoder *d, char *err, size_t errlen);
+// optional: how host bytes reach the device (the API layer stages pageable memory through pinned buffers); the
+// function returns a B2J_* status and must leave the copy ordered on stream s
+typedef int (*dec_upload_fn)(void *user, uint8_t *d_dst, const uint8_t *src, size_t n, cudaStream_t s);
+void dec_set_uploader(Decoder *d, dec_upload_fn fn, void *user);
 const void *dec_coef_ptr(Decoder *d, size_t *bytes);
 
 }  // namespace b2j
