@@ -314,7 +314,7 @@ k_scan_u32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n
 __global__ void __launch_bounds__(256)
 k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__restrict__ desc_all,
           uint32_t *__restrict__ ticket_all, size_t desc_stride, uint32_t *__restrict__ err) {
-    constexpr int ITEMS = 4, CH = 256 * ITEMS;
+    constexpr int ITEMS = 16, CH = 256 * ITEMS;   // 4096 blocks per look-back unit: few, long chunks keep the walk short
     __shared__ int s_chunk;
     __shared__ int s_warp[8];
     __shared__ uint64_t s_goff;
@@ -325,6 +325,11 @@ k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__
     const size_t n = nmcu * per;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = (int)((n + CH - 1) / CH);
+    auto index_of = [&](size_t e) -> size_t {   // coefficient index of the DC of block e of this component
+        const size_t m = comp == 0 ? e / hv : e;
+        const int sub = comp == 0 ? (int)(e - m * hv) : hv + comp - 1;
+        return (m * bpm + sub) * 64;
+    };
     for (;;) {
         if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
         __syncthreads();
@@ -332,14 +337,10 @@ k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__
         if (ch >= nchunks) break;
         const size_t base = (size_t)ch * CH + (size_t)tid * ITEMS;
         int v[ITEMS], sum = 0;
-        size_t idx[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const size_t e = base + j;
-            const size_t m = comp == 0 ? e / hv : e;
-            const int sub = comp == 0 ? (int)(e - m * hv) : hv + comp - 1;
-            idx[j] = (m * bpm + sub) * 64;
-            v[j] = e < n ? (int)coef[idx[j]] : 0;
+            v[j] = e < n ? (int)coef[index_of(e)] : 0;
             sum += v[j];
         }
         int inc = sum;
@@ -362,7 +363,7 @@ k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             run += v[j];
-            if (base + j < n) coef[idx[j]] = (int16_t)run;
+            if (base + j < n) coef[index_of(base + j)] = (int16_t)run;
         }
         __syncthreads();
     }
