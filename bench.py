@@ -342,11 +342,12 @@ def run_b200(args, rank, world, local_rank):
             kd = max(2, min(args.steps, 5))
             with torch.cuda.stream(stream):
                 eng.decode_device(jpg, d_rec.data_ptr(), W * 3)
-                stream.synchronize()
+                eng.decode_finish()
                 d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 d0.record(stream)
                 for _ in range(kd):
                     eng.decode_device(jpg, d_rec.data_ptr(), W * 3)
+                    eng.decode_finish()
                 d1.record(stream)
                 stream.synchronize()
             dec_ms = d0.elapsed_time(d1) / kd

@@ -110,6 +110,10 @@ B2J_API int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bg
 /* Host JPEG bytes -> device BGR (d_bgr: device pointer, pitch step); asynchronous after the header parse. */
 B2J_API int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_bgr, size_t step,
                               int *width, int *height);
+/* Completes the last b2j_decode_device: waits for it and validates it. The decode runs a fixed schedule of Huffman
+ * synchronisation launches without asking the host; in the rare case that was too short the image is decoded again
+ * here with the checked schedule. `jpg` of the b2j_decode_device call must stay valid until this returns. */
+B2J_API int b2j_decode_finish(b2j_ctx *ctx);
 
 /* Difference map and PSNR over n bytes (host pointers). */
 B2J_API int b2j_diff(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, int mode, uint8_t *out);
@@ -156,7 +160,9 @@ B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t
 /* flags bit0 (B2J_DEBUG_COEF): the next encodes also store the quantised coefficients for B2J_DBG_COEF */
 /* bit1 (B2J_DEBUG_SMALL_PACK_BUFFERS): the entropy coder's per-warp bit buffers overflow on purpose (tests its
  * two-pass recovery path); output is unchanged */
-enum { B2J_DEBUG_COEF = 1, B2J_DEBUG_SMALL_PACK_BUFFERS = 2 };
+/* bit2 (B2J_DEBUG_SHORT_DECODE_SCHEDULE): the decoder's unchecked synchronisation schedule is cut to one launch, so
+ * every multi-chunk image takes the validated retry; output is unchanged */
+enum { B2J_DEBUG_COEF = 1, B2J_DEBUG_SMALL_PACK_BUFFERS = 2, B2J_DEBUG_SHORT_DECODE_SCHEDULE = 4 };
 B2J_API int b2j_set_debug(b2j_ctx *ctx, int flags);
 
 /* per-stage device times (ms) of the last encode/decode, measured with CUDA events on the context stream */

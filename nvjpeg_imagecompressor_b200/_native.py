@@ -38,7 +38,7 @@ class HuffDev(C.Structure):
 # every symbol include/b2jpeg.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["b2j_default_params", "b2j_create", "b2j_destroy", "b2j_last_error", "b2j_version", "b2j_set_stream",
            "b2j_encode_bound", "b2j_encode", "b2j_encode_device", "b2j_encode_finish", "b2j_peek", "b2j_decode",
-           "b2j_decode_device", "b2j_diff", "b2j_psnr", "b2j_diff_psnr_device", "b2j_secondary",
+           "b2j_decode_device", "b2j_decode_finish", "b2j_diff", "b2j_psnr", "b2j_diff_psnr_device", "b2j_secondary",
            "b2j_strip_state_get", "b2j_strip_phase1", "b2j_strip_phase1b", "b2j_strip_phase2", "b2j_strip_phase3", "b2j_strip_phase3_dev",
            "b2j_debug_read", "b2j_set_debug", "b2j_last_timings", "b2j_enable_timing", "b2j_launch_count", "b2j_host_alloc",
            "b2j_host_free"]
@@ -82,6 +82,7 @@ def lib():
     L.b2j_peek.argtypes = [u8p, sz, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.b2j_decode.argtypes = [vp, u8p, sz, u8p, sz, C.POINTER(i), C.POINTER(i)]
     L.b2j_decode_device.argtypes = [vp, u8p, sz, u8p, sz, C.POINTER(i), C.POINTER(i)]
+    L.b2j_decode_finish.argtypes = [vp]
     L.b2j_diff.argtypes = [vp, u8p, u8p, sz, i, u8p]
     L.b2j_psnr.argtypes = [vp, u8p, u8p, sz, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.b2j_diff_psnr_device.argtypes = [vp, u8p, u8p, sz, i, u8p, C.POINTER(vp)]

@@ -81,6 +81,10 @@ struct b2j_ctx {
     // pageable host buffers: copy threads + pinned staging ring (hostpipe.h), created on first use
     b2j::CopyPool *pool;
     b2j::StageRing ring;
+    // last b2j_decode_device call (for b2j_decode_finish)
+    const uint8_t *last_jpg;
+    size_t last_len, last_step;
+    uint8_t *last_bgr;
     b2j_ctx *second;  // encoder for the difference image (secondary compression)
 };
 
@@ -581,11 +585,12 @@ int b2j_peek(const uint8_t *jpg, size_t len, int *width, int *height, int *css) 
     return B2J_OK;
 }
 
-static int decode_parsed(b2j_ctx *ctx, const uint8_t *jpg, size_t len, const JpegInfo &info, uint8_t *d_bgr, size_t step) {
+static int decode_parsed(b2j_ctx *ctx, const uint8_t *jpg, size_t len, const JpegInfo &info, uint8_t *d_bgr, size_t step, bool careful) {
     if (step < (size_t)info.W * 3) return B2J_EINVAL;
     int rc = dec_ensure(ctx); if (rc) return rc;
     Geom g; rc = make_geom(info.W, info.H, info.css, &g); if (rc) return rc;
-    return dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches);
+    dec_set_spec_launches(ctx->dec, (ctx->debug & 4) ? 1 : 3);
+    return dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches, careful);
 }
 
 static int parse_for(b2j_ctx *ctx, const uint8_t *jpg, size_t len, JpegInfo *info, int *width, int *height) {
@@ -602,7 +607,24 @@ int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_b
     JpegInfo info;
     int rc = parse_for(ctx, jpg, len, &info, width, height); if (rc) return rc;
     if (!d_bgr) return B2J_OK;
-    return decode_parsed(ctx, jpg, len, info, d_bgr, step);
+    // remembered for b2j_decode_finish: the caller keeps `jpg` alive until then
+    ctx->last_jpg = jpg; ctx->last_len = len; ctx->last_bgr = d_bgr; ctx->last_step = step;
+    return decode_parsed(ctx, jpg, len, info, d_bgr, step, false);
+}
+
+int b2j_decode_finish(b2j_ctx *ctx) {
+    if (!ctx) return B2J_EINVAL;
+    if (!ctx->dec || !ctx->last_jpg) return B2J_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
+    if (rc == DEC_RETRY) {   // the speculative synchronisation schedule was too short for this stream: decode again, checked
+        JpegInfo info;
+        rc = parse_for(ctx, ctx->last_jpg, ctx->last_len, &info, nullptr, nullptr); if (rc) return rc;
+        rc = decode_parsed(ctx, ctx->last_jpg, ctx->last_len, info, ctx->last_bgr, ctx->last_step, true); if (rc) return rc;
+        rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
+    }
+    ctx->last_jpg = nullptr;
+    return rc;
 }
 
 int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *width, int *height) {
@@ -618,10 +640,13 @@ int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_
         CK(cudaMalloc(&ctx->d_recon, dstep * info.H));
         ctx->d_recon_bytes = dstep * info.H;
     }
-    rc = decode_parsed(ctx, jpg, len, info, ctx->d_recon, dstep);
-    if (rc) return rc;
-    rc = download_2d(ctx, bgr, step, ctx->d_recon, dstep, (size_t)info.W * 3, info.H, ctx->stream); if (rc) return rc;
-    rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        rc = decode_parsed(ctx, jpg, len, info, ctx->d_recon, dstep, attempt == 1);
+        if (rc) return rc;
+        rc = download_2d(ctx, bgr, step, ctx->d_recon, dstep, (size_t)info.W * 3, info.H, ctx->stream); if (rc) return rc;
+        rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
+        if (rc != DEC_RETRY) break;   // else: the speculative synchronisation schedule was too short: once more, checked
+    }
     return rc;
 }
 
@@ -695,7 +720,11 @@ int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int 
     }
     cudaFree(ctx->d_diff); ctx->d_diff = nullptr;
     CK(cudaMalloc(&ctx->d_diff, bytes));
-    rc = b2j_decode_device(ctx, o1, n1, ctx->d_recon, dstep, nullptr, nullptr); if (rc) return rc;
+    {
+        JpegInfo info;
+        rc = parse_for(ctx, o1, n1, &info, nullptr, nullptr); if (rc) return rc;
+        rc = decode_parsed(ctx, o1, n1, info, ctx->d_recon, dstep, true); if (rc) return rc;
+    }
     // 3. difference map + SSD; the pitch padding of both device images is zero-filled so it adds nothing
     if (dstep != (size_t)width * 3) {
         CK(cudaMemset2DAsync(ctx->d_img + (size_t)width * 3, dstep, 0, dstep - (size_t)width * 3, height, ctx->stream));

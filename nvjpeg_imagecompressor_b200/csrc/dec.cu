@@ -43,6 +43,8 @@ struct Decoder {
     cudaStream_t last_stream = nullptr;
     dec_upload_fn upload = nullptr;
     void *upload_user = nullptr;
+    bool speculated = false;   // the last run issued a fixed number of synchronisation launches without looking
+    int spec_launches = 3;     // that number (tests shorten it to force the retry path)
 };
 
 #define DCK(call)                                                                                                  \
@@ -84,6 +86,7 @@ void dec_destroy(Decoder *d) {
 }
 
 void dec_set_uploader(Decoder *d, dec_upload_fn fn, void *user) { d->upload = fn; d->upload_user = user; }
+void dec_set_spec_launches(Decoder *d, int n) { d->spec_launches = n < 1 ? 1 : n; }
 
 const void *dec_coef_ptr(Decoder *d, size_t *bytes) { *bytes = (size_t)d->nblocks_cap * 128; return d->d_coef; }
 
@@ -123,7 +126,7 @@ static int ensure(Decoder *d, size_t scan_len, const Geom &g) {
 }
 
 int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
-            cudaStream_t s, b2j_timings *tm, uint64_t *launches) {
+            cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful) {
     if (info.restart_interval != 0) { snprintf(d->err, d->errlen, "restart markers (DRI=%d) are not supported yet", info.restart_interval); return B2J_EFORMAT; }
     if (g.nblocks > d->nblocks_cap) { snprintf(d->err, d->errlen, "image exceeds the context's size"); return B2J_ESIZE; }
     if (info.scan_offset + info.scan_len > len || info.scan_len == 0) return B2J_EFORMAT;
@@ -149,18 +152,37 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     if (tm) cudaEventRecord(d->ev[1], s);
     DCK(launch_destuff(d->d_scan, n, d->d_u, d->d_desc, &d->d_ctrl->ticket[0], &d->d_ctrl->u_len, &d->d_ctrl->err, s));
     if (launches) (*launches)++;
-    // ---- self-synchronisation: launches of 8 in-CTA rounds until no end state moves
+    // ---- self-synchronisation: launches of 8 in-CTA rounds until no end state moves.
+    // Speculative mode (default): DEC_SPEC_LAUNCHES launches back to back, the "still moving" flag of the last one is
+    // fetched asynchronously and looked at in dec_check -- no host round trip inside the decode, so several decoders
+    // on different streams overlap. Streams with long synchronisation distances (about 200+ bits per block: blocks
+    // rarely end with EOB) and retries take the careful mode: the host looks at the flag after every launch.
+    const int DEC_SPEC_LAUNCHES = d->spec_launches;
+    const bool spec = !careful && (double)n * 8.0 / (double)g.nblocks < 200.0;
+    d->speculated = spec;
+    d->h_flag[2] = 0;
     int rounds = 0;
-    for (;; rounds++) {
-        if (rounds >= 256) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
-        DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
-        DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, rounds == 0,
-                            &d->d_ctrl->changed, nsub_max, s));
-        if (launches) (*launches)++;
-        if (rounds == 0) continue;  // the first launch always moves states
-        DCK(cudaMemcpyAsync(d->h_flag, &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
-        DCK(cudaStreamSynchronize(s));
-        if (d->h_flag[0] == 0) break;
+    if (spec) {
+        for (; rounds < DEC_SPEC_LAUNCHES; rounds++) {
+            DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
+            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, rounds == 0,
+                                &d->d_ctrl->changed, nsub_max, s));
+            if (launches) (*launches)++;
+        }
+        DCK(cudaMemcpyAsync(&d->h_flag[2], &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
+        rounds--;
+    } else {
+        for (;; rounds++) {
+            if (rounds >= 256) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
+            DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
+            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, rounds == 0,
+                                &d->d_ctrl->changed, nsub_max, s));
+            if (launches) (*launches)++;
+            if (rounds == 0) continue;  // the first launch always moves states
+            DCK(cudaMemcpyAsync(d->h_flag, &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
+            DCK(cudaStreamSynchronize(s));
+            if (d->h_flag[0] == 0) break;
+        }
     }
     d->last_rounds = rounds + 1;
     if (tm) cudaEventRecord(d->ev[2], s);
@@ -196,6 +218,7 @@ int dec_check(Decoder *d, char *err, size_t errlen) {
         snprintf(err, errlen, "%s in dec_check", cudaGetErrorString(cudaGetLastError()));
         return B2J_ECUDA;
     }
+    if (d->speculated && d->h_flag[2]) return DEC_RETRY;   // the fixed number of launches was not enough: run again, carefully
     if (d->h_flag[1]) { snprintf(err, errlen, "decoder consistency check failed (err=%u)", d->h_flag[1]); return B2J_EINTERNAL; }
     return B2J_OK;
 }

@@ -23,13 +23,16 @@ int parse_jpeg(const uint8_t *jpg, size_t len, JpegInfo *info);
 struct Decoder;
 Decoder *dec_create(int nblocks_cap, char *err, size_t errlen);
 void dec_destroy(Decoder *d);
+// careful = false: no host synchronisation inside (dec_check may then answer DEC_RETRY: run again with careful = true)
 int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
-            cudaStream_t s, b2j_timings *tm, uint64_t *launches);
-int dec_check(Decoder *d, char *err, size_t errlen);
+            cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful);
+constexpr int DEC_RETRY = 1;
+int dec_check(Decoder *d, char *err, size_t errlen);   // synchronises the decode's stream
 // optional: how host bytes reach the device (the API layer stages pageable memory through pinned buffers); the
 // function returns a B2J_* status and must leave the copy ordered on stream s
 typedef int (*dec_upload_fn)(void *user, uint8_t *d_dst, const uint8_t *src, size_t n, cudaStream_t s);
 void dec_set_uploader(Decoder *d, dec_upload_fn fn, void *user);
+void dec_set_spec_launches(Decoder *d, int n);   // speculative synchronisation launches (default 3)
 const void *dec_coef_ptr(Decoder *d, size_t *bytes);
 
 }  // namespace b2j

@@ -126,10 +126,16 @@ class Engine:
         return n.value
 
     def decode_device(self, jpg, d_ptr, step):
+        """Asynchronous; call decode_finish() before using the pixels (it validates the decode and keeps `jpg` alive)."""
         jpg = np.ascontiguousarray(jpg, np.uint8)
+        self._pending_jpg = jpg
         W, H = C.c_int(0), C.c_int(0)
         self._ck(self._L.b2j_decode_device(self._h, _ptr(jpg), jpg.size, C.c_void_p(d_ptr), step, C.byref(W), C.byref(H)))
         return W.value, H.value
+
+    def decode_finish(self):
+        self._ck(self._L.b2j_decode_finish(self._h))
+        self._pending_jpg = None
 
     def diff_psnr_device(self, a_ptr, b_ptr, n, mode, out_ptr):
         s = C.c_void_p()

@@ -62,11 +62,16 @@ for k in range(nuniq):
 outs = [torch.empty((H, W, 3), dtype=torch.uint8, device=dev) for _ in engs]
 for k, e in enumerate(engs):
     e.decode_device(jpgs[k % nuniq], outs[k].data_ptr(), W * 3)
-torch.cuda.synchronize()
+for e in engs:
+    e.decode_finish()
 t0 = time.perf_counter()
 for i in range(len(mine)):
-    engs[i % len(engs)].decode_device(jpgs[i % nuniq], outs[i % len(engs)].data_ptr(), W * 3)
-torch.cuda.synchronize()
+    e = engs[i % len(engs)]
+    if i >= len(engs):
+        e.decode_finish()                              # the engine's previous image: validated, pixels usable
+    e.decode_device(jpgs[i % nuniq], outs[i % len(engs)].data_ptr(), W * 3)
+for e in engs:
+    e.decode_finish()
 dtd = time.perf_counter() - t0
 res = torch.tensor([dt, dtd], dtype=torch.float64, device=dev)
 if world > 1:

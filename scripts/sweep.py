@@ -59,7 +59,7 @@ for css, q, opt in cases:
             e0.record(st)
             eng.decode_device(jpg.numpy(), rec.data_ptr(), W * 3)
             e1.record(st)
-            st.synchronize()
+            eng.decode_finish()
             if i:
                 dec_ms.append(e0.elapsed_time(e1))
         dt = eng.timings()

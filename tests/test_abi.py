@@ -16,7 +16,7 @@ def header_symbols():
 
 def test_header_declares_expected_entry_points():
     syms = header_symbols()
-    for s in ("b2j_create", "b2j_destroy", "b2j_encode", "b2j_encode_device", "b2j_decode", "b2j_diff", "b2j_psnr",
+    for s in ("b2j_create", "b2j_destroy", "b2j_encode", "b2j_encode_device", "b2j_decode", "b2j_decode_device", "b2j_decode_finish", "b2j_diff", "b2j_psnr",
               "b2j_secondary", "b2j_strip_phase1", "b2j_strip_phase2", "b2j_strip_phase3", "b2j_strip_phase3_dev"):
         assert s in syms
 

@@ -45,6 +45,27 @@ def test_golden_files(P, oracle, golden):
     eng.close()
 
 
+def test_decode_schedules(P, oracle):
+    """The three synchronisation schedules give the same pixels: the unchecked fixed schedule (default), its validated
+    retry (forced by cutting the schedule to one launch) and the checked loop (long synchronisation distance: q100),
+    through the synchronous call and through decode_device + decode_finish."""
+    import torch
+    W, H = 1600, 640   # several decoder chunks (256 subsequences of 1024 bits each)
+    img = oracle.synth(W, H, 11, 8)
+    eng = P.Engine(W, H, 95, True, "444")   # sized for the largest block count of the cases below
+    for css, q in ((1, 95), (3, 85), (0, 100)):
+        jpg = oracle.encode(img, css, q, 1)
+        want = oracle.decode(jpg)
+        for dbg in (0, 4):   # 4 = B2J_DEBUG_SHORT_DECODE_SCHEDULE
+            eng.set_debug(dbg)
+            assert np.array_equal(eng.decode(jpg), want), (css, q, dbg, "decode")
+            out = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+            eng.decode_device(jpg, out.data_ptr(), W * 3)
+            eng.decode_finish()
+            assert np.array_equal(out.cpu().numpy(), want), (css, q, dbg, "decode_device")
+    eng.close()
+
+
 def test_small_sizes_all_modes(P, oracle):
     rng = np.random.default_rng(6)
     sizes = [(64, 96), (48, 64), (50, 70), (17, 33), (135, 121), (8, 8), (1, 1), (257, 63), (33, 17), (2, 2), (3, 5), (5, 3), (4, 4)]
