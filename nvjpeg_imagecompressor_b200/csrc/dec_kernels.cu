@@ -114,7 +114,11 @@ struct DecShared {
     int32_t maxcode[4][18];
     int32_t valoff[4][17];
     uint8_t vals[4][256];
-    uint64_t state[DEC_THREADS + 1];
+    uint64_t state[DEC_THREADS + 1];           // [i + 1] = end state of subsequence i; [0] = state entering the chunk
+    uint64_t used[DEC_THREADS];                // the start state that produced state[i + 1]
+    uint32_t nblk[DEC_THREADS];
+    uint16_t list[DEC_THREADS];                // subsequences to decode this round, compacted
+    uint32_t wcnt[DEC_THREADS / 32];
 };
 
 // state word: bit position << 16 | block-in-MCU << 8 | zig-zag index
@@ -189,13 +193,15 @@ __device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__r
 // One synchronisation launch: every CTA iterates up to `inner` rounds over its 256 subsequences (states in shared
 // memory), then publishes the end states. st_out[i] = state after subsequence i; st_in[i] = the start state that
 // produced it. `changed` is raised when a CTA did not converge or its last end state moved.
+// From the third round on only a few subsequences still see a new start state: every round first compacts the
+// subsequences that need decoding into a list, and the threads take list entries, so the warps stay full.
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
            uint64_t *__restrict__ st_in, uint64_t *__restrict__ st_out, uint32_t *__restrict__ nblk, int bpm, int hv,
            int inner, int first_launch, uint32_t *__restrict__ changed) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t nbytes = *u_len;
     const uint64_t total_bits = nbytes * 8;
     const size_t cta = blockIdx.x;
@@ -208,31 +214,48 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
     const bool live = my_bit0 < total_bits;
     // incoming state of the CTA's first subsequence; initial guess = "a block starts exactly at my first bit"
     if (tid == 0) sh.state[0] = cta == 0 ? pack_state(0, 0, 0) : (first_launch ? pack_state(chunk_bit0, 0, 0) : st_out[i - 1]);
-    uint64_t used = first_launch ? ~0ull : st_in[i];
-    uint64_t mine = first_launch ? pack_state(my_end, 0, 0) : st_out[i];
-    const uint64_t before = mine;
-    uint32_t my_nblk = first_launch ? 0 : nblk[i];
-    sh.state[tid + 1] = mine;
+    sh.used[tid] = first_launch ? ~0ull : st_in[i];
+    const uint64_t before = first_launch ? pack_state(my_end, 0, 0) : st_out[i];
+    sh.nblk[tid] = first_launch ? 0 : nblk[i];
+    sh.state[tid + 1] = before;
     __syncthreads();
     int any = 1;
     for (int round = 0; round < inner && any; round++) {
-        const uint64_t in = sh.state[tid];
+        // ---- who needs decoding: start state differs from the one used last time
+        const bool need = live && sh.state[tid] != sh.used[tid];
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) sh.wcnt[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < DEC_THREADS / 32; w++) { const uint32_t x = sh.wcnt[w]; if (w < wid) wbase += x; total += x; }
+        if (need) sh.list[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)tid;
+        __syncthreads();
+        // ---- decode the listed subsequences (their start states are read before anybody writes an end state)
         int ch = 0;
-        uint64_t outst = mine;
-        if (live && in != used) {
-            outst = decode_range<false>(sh, chunk_bit0, in, my_end, total_bits, bpm, hv, my_nblk, nullptr, 0, 0);
-            used = in;
-            ch = outst != mine;
-            mine = outst;
+        uint64_t outst = 0, in = 0;
+        uint32_t nb = 0;
+        int t = -1;
+        if ((uint32_t)tid < total) {
+            t = sh.list[tid];
+            in = sh.state[t];
+            const uint64_t t_end = chunk_bit0 + (uint64_t)(t + 1) * SUB_BITS;
+            outst = decode_range<false>(sh, chunk_bit0, in, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0);
         }
         __syncthreads();
-        sh.state[tid + 1] = mine;
+        if (t >= 0) {
+            ch = outst != sh.state[t + 1];
+            sh.state[t + 1] = outst;
+            sh.used[t] = in;
+            sh.nblk[t] = nb;
+        }
         any = __syncthreads_or(ch);
     }
+    const uint64_t mine = sh.state[tid + 1], used = sh.used[tid];
     if (live) {
         st_in[i] = used;
         st_out[i] = mine;
-        nblk[i] = my_nblk;
+        nblk[i] = sh.nblk[tid];
     }
     // not converged inside the CTA, or the state handed to the next CTA moved
     const bool last_live = tid == DEC_THREADS - 1 || my_end >= total_bits;
