@@ -124,53 +124,64 @@ struct DecShared {
 // state word: bit position << 16 | block-in-MCU << 8 | zig-zag index
 __device__ __forceinline__ uint64_t pack_state(uint64_t p, int c, int k) { return (p << 16) | ((uint64_t)c << 8) | (uint64_t)k; }
 
+// codes longer than the LUT covers (rare), or an invalid code (only while unsynchronised): canonical search
+__device__ __noinline__ uint32_t huff_sym_long(const DecShared &sh, uint32_t t, uint32_t top16) {
+#pragma unroll 1
+    for (int l = DEC_LUT_BITS + 1; l <= 16; l++) {
+        const int code = (int)(top16 >> (16 - l));
+        if (code <= sh.maxcode[t][l]) return ((uint32_t)l << 8) | sh.vals[t][(sh.valoff[t][l] + code) & 255];
+    }
+    return 0xFFFFu;  // invalid: skip one bit and keep going
+}
+
+// Decodes from `start_state` up to `end_bit` (jdhuff.c decode_mcu, one symbol per iteration). Positions are kept
+// relative to the chunk (32-bit); the block state machine (DC / coefficient / ZRL / EOB) is branch-free.
 template <bool WRITE>
 __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t chunk_bit0, uint64_t start_state,
                                                  uint64_t end_bit, uint64_t total_bits, int bpm, int hv,
                                                  uint32_t &nblk_out, int16_t *__restrict__ coef, uint32_t blk_base,
                                                  uint32_t nblocks) {
-    uint64_t p = start_state >> 16;
+    uint32_t q = (uint32_t)((start_state >> 16) - chunk_bit0);
     int c = (int)((start_state >> 8) & 0xFF), k = (int)(start_state & 0xFF);
     uint32_t nblk = 0;
-    const uint64_t stop = end_bit < total_bits ? end_bit : total_bits;
-    while (p < stop) {
-        const uint32_t q = (uint32_t)(p - chunk_bit0);
+    const uint64_t left = total_bits - chunk_bit0;
+    const uint32_t tot = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;          // end of the stream, clamped
+    const uint32_t stop = min((uint32_t)(end_bit - chunk_bit0), tot);
+    const uint16_t *lut = &sh.lut[0][0];
+    while (q < stop) {
         const uint32_t g = q >> 5, o = q & 31u;
         const uint32_t w0 = sh.words[(g & 31u) * (DEC_THREADS + 1) + (g >> 5)];
         const uint32_t g1 = g + 1;
         const uint32_t w1 = sh.words[(g1 & 31u) * (DEC_THREADS + 1) + (g1 >> 5)];
-        const uint32_t win = __funnelshift_l(w1, w0, o);  // 32 bits starting at p
-        const int t = (c < hv ? 0 : 2) + (k ? 1 : 0);
-        int len;
-        const uint32_t sym = huff_sym(sh.lut[t], sh.maxcode[t], sh.valoff[t], sh.vals[t], win >> 16, len);
-        if (sym > 0xFFu) { p += 1; continue; }
-        const int s = (int)(sym & 15u);
-        if (p + len + s > total_bits) { p = total_bits; break; }  // padding bits at the very end
+        const uint32_t win = __funnelshift_l(w1, w0, o);  // 32 bits starting at q
+        const bool dc = k == 0;
+        const uint32_t t = (c < hv ? 0u : 2u) + (dc ? 0u : 1u);
+        uint32_t e = lut[(t << DEC_LUT_BITS) + (win >> (32 - DEC_LUT_BITS))];
+        if (e == 0) e = huff_sym_long(sh, t, win >> 16);
+        if (e == 0xFFFFu) { q += 1; continue; }            // invalid code
+        const uint32_t len = e >> 8, s = e & 15u, r = (e >> 4) & 15u;
+        if (q + len + s > tot) { q = tot; break; }         // padding bits at the very end
         int val = 0;
         if (s) {
             const uint32_t v = (win << len) >> (32 - s);
             val = v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v;  // jdhuff.c HUFF_EXTEND
         }
-        p += len + s;
-        bool done = false;
-        if (k == 0) {
-            if (WRITE) { const uint32_t b = blk_base + nblk; if (b < nblocks && val) coef[(size_t)b * 64] = (int16_t)val; }
-            k = 1;
-        } else {
-            const int r = (int)(sym >> 4);
-            if (s == 0) {
-                if (r == 15) k += 16; else done = true;
-            } else {
-                k += r;
-                if (WRITE) { const uint32_t b = blk_base + nblk; if (k < 64 && b < nblocks) coef[(size_t)b * 64 + k] = (int16_t)val; }
-                k++;
-            }
-            if (k > 63) done = true;
+        q += len + s;
+        // DC: k = 1. Coefficient: stored at k + r, k += r + 1. ZRL: k += 16. EOB: block done. k > 63: block done.
+        int knew = s ? k + (int)r + 1 : (r == 15u ? k + 16 : 64);
+        if (dc) knew = 1;
+        if (WRITE && s) {
+            const uint32_t b = blk_base + nblk;
+            const int idx = dc ? 0 : k + (int)r;
+            if (idx < 64 && b < nblocks) coef[(size_t)b * 64 + idx] = (int16_t)val;
         }
-        if (done) { k = 0; c = c + 1 == bpm ? 0 : c + 1; nblk++; }
+        const bool done = knew > 63;
+        k = done ? 0 : knew;
+        c = done ? (c + 1 == bpm ? 0 : c + 1) : c;
+        nblk += done ? 1u : 0u;
     }
     nblk_out = nblk;
-    return pack_state(p, c, k);
+    return pack_state(chunk_bit0 + q, c, k);
 }
 
 __device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__restrict__ u, uint64_t nbytes_padded,
