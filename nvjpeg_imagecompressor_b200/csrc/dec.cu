@@ -14,7 +14,9 @@ namespace b2j {
 
 struct DecCtrl {
     uint64_t u_len;
-    uint32_t ticket[8];  // 0 destuff, 1 nblk scan, 2..4 dc scan
+    uint64_t avail;      // bytes de-stuffed so far (pipelined front end)
+    uint32_t ticket[8];  // 0 unused, 1 nblk scan, 2..4 dc scan
+    uint32_t dticket[32];  // one counter per de-stuff launch
     uint32_t err;
     uint32_t changed;
 };
@@ -28,7 +30,10 @@ struct Decoder {
     size_t desc_cap = 0;       // entries per descriptor array (5 arrays)
     uint64_t *d_st_in = nullptr, *d_st_out = nullptr;
     uint32_t *d_nblk = nullptr, *d_blk_start = nullptr;
+    uint8_t *d_done = nullptr;   // per decoder chunk (256 subsequences): first synchronisation pass has run
     size_t nsub_cap = 0;
+    cudaStream_t up_stream = nullptr;   // uploads of the scan pieces
+    cudaEvent_t ev_up[33] = {};
     DecCtrl *d_ctrl = nullptr;
     void *d_tb = nullptr;
     void *h_tb = nullptr;      // pinned
@@ -66,6 +71,8 @@ Decoder *dec_create(int nblocks_cap, char *err, size_t errlen) {
               cudaHostAlloc(&d->h_flag, 16, cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&d->d_coef, (size_t)nblocks_cap * 128) == cudaSuccess;
     for (auto &e : d->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&d->up_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &e : d->ev_up) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         snprintf(err, errlen, "decoder allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         dec_destroy(d);
@@ -82,6 +89,9 @@ void dec_destroy(Decoder *d) {
     if (d->h_tb) cudaFreeHost(d->h_tb);
     if (d->h_flag) cudaFreeHost(d->h_flag);
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : d->ev_up) if (e) cudaEventDestroy(e);
+    if (d->up_stream) cudaStreamDestroy(d->up_stream);
+    cudaFree(d->d_done);
     delete d;
 }
 
@@ -100,13 +110,14 @@ static int ensure(Decoder *d, size_t scan_len, const Geom &g) {
     }
     const size_t nsub = (scan_len * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS + 256;
     if (nsub > d->nsub_cap) {
-        cudaFree(d->d_st_in); cudaFree(d->d_st_out); cudaFree(d->d_nblk); cudaFree(d->d_blk_start);
-        d->d_st_in = d->d_st_out = nullptr; d->d_nblk = d->d_blk_start = nullptr; d->nsub_cap = 0;
+        cudaFree(d->d_st_in); cudaFree(d->d_st_out); cudaFree(d->d_nblk); cudaFree(d->d_blk_start); cudaFree(d->d_done);
+        d->d_st_in = d->d_st_out = nullptr; d->d_nblk = d->d_blk_start = nullptr; d->d_done = nullptr; d->nsub_cap = 0;
         const size_t cap = nsub + nsub / 4;
         DCK(cudaMalloc(&d->d_st_in, cap * 8));
         DCK(cudaMalloc(&d->d_st_out, cap * 8));
         DCK(cudaMalloc(&d->d_nblk, (cap + 1) * 4));
         DCK(cudaMalloc(&d->d_blk_start, (cap + 1) * 4));
+        DCK(cudaMalloc(&d->d_done, cap / 256 + 64));
         d->nsub_cap = cap;
     }
     // descriptor arrays: destuff chunks (4 KB), nblk scan chunks (2048), dc scan chunks (1024 blocks) x 3
@@ -139,21 +150,14 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     if (tm) cudaEventRecord(d->ev[0], s);
     dec_build_tables(info, d->h_tb);
     DCK(cudaMemcpyAsync(d->d_tb, d->h_tb, dec_tables_size(), cudaMemcpyHostToDevice, s));
-    if (d->upload) {
-        const int urc = d->upload(d->upload_user, d->d_scan, jpg + info.scan_offset, n, s);
-        if (urc) return urc;
-    } else {
-        DCK(cudaMemcpyAsync(d->d_scan, jpg + info.scan_offset, n, cudaMemcpyHostToDevice, s));
-    }
     DCK(cudaMemsetAsync(d->d_ctrl, 0, sizeof(DecCtrl), s));
     DCK(cudaMemsetAsync(d->d_desc, 0, d->desc_cap * 5 * 8, s));
     DCK(cudaMemsetAsync(d->d_nblk, 0, (nsub_max + 1) * 4, s));
+    DCK(cudaMemsetAsync(d->d_done, 0, nsub_max / 256 + 64, s));
     DCK(cudaMemsetAsync(d->d_coef, 0, (size_t)g.nblocks * 128, s));
-    if (tm) cudaEventRecord(d->ev[1], s);
-    DCK(launch_destuff(d->d_scan, n, d->d_u, d->d_desc, &d->d_ctrl->ticket[0], &d->d_ctrl->u_len, &d->d_ctrl->err, s));
-    if (launches) (*launches)++;
+
     // ---- self-synchronisation: launches of 8 in-CTA rounds until no end state moves.
-    // Speculative mode (default): DEC_SPEC_LAUNCHES launches back to back, the "still moving" flag of the last one is
+    // Speculative mode (default): a fixed number of launches back to back, the "still moving" flag of the last one is
     // fetched asynchronously and looked at in dec_check -- no host round trip inside the decode, so several decoders
     // on different streams overlap. Streams with long synchronisation distances (about 200+ bits per block: blocks
     // rarely end with EOB) and retries take the careful mode: the host looks at the flag after every launch.
@@ -161,11 +165,46 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     const bool spec = !careful && (double)n * 8.0 / (double)g.nblocks < 200.0;
     d->speculated = spec;
     d->h_flag[2] = 0;
+
+    // ---- front end, pipelined: the scan goes up in pieces on its own stream; every piece is de-stuffed as soon as it
+    // has landed and the first synchronisation pass runs on the decoder chunks whose bytes are complete, so most of
+    // that pass hides behind the upload (large scans, speculative mode).
+    const int nch = (int)((n + 4095) / 4096);
+    const int npieces = (spec && n >= (16u << 20)) ? 8 : 1;   // fewer, larger pieces: a piece should fill the GPU
+    const size_t piece = ((n + npieces - 1) / npieces + 4095) & ~(size_t)4095;
+    DCK(cudaEventRecord(d->ev_up[32], s));                       // the scan buffer is free once earlier work on s is done
+    DCK(cudaStreamWaitEvent(d->up_stream, d->ev_up[32], 0));
+    for (int j = 0; j < npieces; j++) {
+        const size_t b0 = std::min(n, (size_t)j * piece), b1 = std::min(n, b0 + piece);
+        if (b1 > b0) {
+            if (d->upload) {
+                const int urc = d->upload(d->upload_user, d->d_scan + b0, jpg + info.scan_offset + b0, b1 - b0, d->up_stream);
+                if (urc) return urc;
+            } else {
+                DCK(cudaMemcpyAsync(d->d_scan + b0, jpg + info.scan_offset + b0, b1 - b0, cudaMemcpyHostToDevice, d->up_stream));
+            }
+        }
+        DCK(cudaEventRecord(d->ev_up[j], d->up_stream));
+        DCK(cudaStreamWaitEvent(s, d->ev_up[j], 0));
+        const int c0 = (int)(b0 / 4096), c1 = j == npieces - 1 ? nch : (int)(b1 / 4096);
+        if (c1 > c0) {
+            DCK(launch_destuff(d->d_scan, n, d->d_u, d->d_desc, &d->d_ctrl->dticket[j], c0, c1, &d->d_ctrl->u_len, &d->d_ctrl->avail,
+                               &d->d_ctrl->err, s));
+            if (launches) (*launches)++;
+        }
+        if (npieces > 1 && j < npieces - 1) {
+            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->avail, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 1, d->d_done,
+                                &d->d_ctrl->changed, (b1 * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS, s));
+            if (launches) (*launches)++;
+        }
+    }
+    if (tm) cudaEventRecord(d->ev[1], s);
     int rounds = 0;
     if (spec) {
-        for (; rounds < DEC_SPEC_LAUNCHES; rounds++) {
+        const int nl = npieces > 1 ? std::max(1, DEC_SPEC_LAUNCHES - 1) : DEC_SPEC_LAUNCHES;
+        for (; rounds < nl; rounds++) {
             DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
-            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, rounds == 0,
+            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 0, d->d_done,
                                 &d->d_ctrl->changed, nsub_max, s));
             if (launches) (*launches)++;
         }
@@ -175,7 +214,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         for (;; rounds++) {
             if (rounds >= 256) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
             DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
-            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, rounds == 0,
+            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 0, d->d_done,
                                 &d->d_ctrl->changed, nsub_max, s));
             if (launches) (*launches)++;
             if (rounds == 0) continue;  // the first launch always moves states

@@ -7,6 +7,8 @@
 // Appendix A.9, pixel-exactly. The stream has no restart markers, so the Huffman stage is the self-synchronising
 // scheme of Weissenberger & Schmidt (ICPP'18): every thread decodes a fixed 1024-bit subsequence from a guessed
 // state, then re-decodes from its predecessor's end state until the states stop changing.
+#include <algorithm>
+
 #include "common.cuh"
 #include "dec.h"
 #include "dec_kernels.h"
@@ -16,9 +18,13 @@ namespace b2j {
 // ------------------------------------------------------------------------------------------------------
 // k_destuff: drop the 0x00 that follows every 0xFF. 16 bytes per thread, 4 KB per chunk, persistent CTAs with
 // ticketed chunks and a decoupled look-back over the kept-byte counts. Output is padded with 0xFF bytes (1-bits).
+// One launch handles the 4 KB chunks [c0, c1) of the scan (the bytes before them are already there: a byte only looks
+// at its predecessor), so the scan can be de-stuffed piece by piece while it is still being uploaded; look-back
+// descriptors carry over, `ticket` is a fresh counter per launch, *avail = bytes produced up to the end of the launch.
 __global__ void __launch_bounds__(256)
 k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint64_t *__restrict__ desc,
-          uint32_t *__restrict__ ticket, uint64_t *__restrict__ out_len, uint32_t *__restrict__ err) {
+          uint32_t *__restrict__ ticket, int c0, int c1, uint64_t *__restrict__ out_len, uint64_t *__restrict__ avail,
+          uint32_t *__restrict__ err) {
     __shared__ int s_chunk;
     __shared__ uint32_t s_warp[8];
     __shared__ uint64_t s_goff;
@@ -26,10 +32,10 @@ k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, u
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = (int)((n + 4095) / 4096);
     for (;;) {
-        if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
+        if (tid == 0) s_chunk = c0 + (int)atomicAdd(ticket, 1u);
         __syncthreads();
         const int ch = s_chunk;
-        if (ch >= nchunks) break;
+        if (ch >= c1) break;
         const size_t base = (size_t)ch * 4096 + (size_t)tid * 16;
         uint8_t b[17];
         b[0] = base > 0 && base <= n ? in[base - 1] : 0;
@@ -66,6 +72,7 @@ k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, u
         __syncthreads();
         uint8_t *dst = out + s_goff;
         for (uint32_t i = tid; i < total; i += 256) dst[i] = s_out[i];
+        if (ch == c1 - 1 && tid == 0) *avail = s_goff + total;
         if (ch == nchunks - 1) {
             if (tid < 64) dst[total + tid] = 0xFF;  // padding the bit reader may peek into
             if (tid == 0) *out_len = s_goff + total;
@@ -209,16 +216,25 @@ __device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__r
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
            uint64_t *__restrict__ st_in, uint64_t *__restrict__ st_out, uint32_t *__restrict__ nblk, int bpm, int hv,
-           int inner, int first_launch, uint32_t *__restrict__ changed) {
+           int inner, int mode, uint8_t *__restrict__ done, uint32_t *__restrict__ changed) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t nbytes = *u_len;
-    const uint64_t total_bits = nbytes * 8;
     const size_t cta = blockIdx.x;
     const uint64_t chunk_bit0 = (uint64_t)cta * SUB_BITS * DEC_THREADS;
+    // mode 0: the whole stream is there (*u_len = its length); a chunk whose first pass has not run yet runs it now.
+    // mode 1 (stream still arriving, *u_len = bytes de-stuffed so far): only the first pass, only for chunks whose
+    //         bytes (and the words the bit reader may peek into) are complete; everything else returns.
+    const bool first_launch = done[cta] == 0;
+    uint64_t nbytes = *u_len;
+    if (mode == 1) {
+        if (!first_launch) return;
+        if ((chunk_bit0 >> 3) + (uint64_t)(SUB_BITS / 8) * DEC_THREADS + 64 > nbytes) return;
+        nbytes = ~0ull >> 8;   // no end of stream inside this chunk
+    }
+    const uint64_t total_bits = nbytes * 8;
     if (chunk_bit0 >= total_bits) return;
-    dec_load_chunk(sh, u, (nbytes + 64) & ~(uint64_t)3, cta, tb);
+    dec_load_chunk(sh, u, mode == 1 ? *u_len & ~(uint64_t)3 : (nbytes + 64) & ~(uint64_t)3, cta, tb);
     const size_t i = cta * DEC_THREADS + tid;
     const uint64_t my_bit0 = chunk_bit0 + (uint64_t)tid * SUB_BITS;
     const uint64_t my_end = my_bit0 + SUB_BITS;
@@ -268,6 +284,7 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
         st_out[i] = mine;
         nblk[i] = sh.nblk[tid];
     }
+    if (tid == 0) done[cta] = 1;
     // not converged inside the CTA, or the state handed to the next CTA moved
     const bool last_live = tid == DEC_THREADS - 1 || my_end >= total_bits;
     if (any || (live && last_live && mine != before) || (live && sh.state[tid] != used)) atomicOr(changed, 1u);
@@ -571,9 +588,10 @@ k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const
 // ------------------------------------------------------------------------------------------------------
 size_t dec_sync_smem() { return sizeof(DecShared); }
 
-cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, uint64_t *out_len,
-                           uint32_t *err, cudaStream_t s) {
-    k_destuff<<<148 * 6, 256, 0, s>>>(in, n, out, desc, ticket, out_len, err);
+cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,
+                           uint64_t *out_len, uint64_t *avail, uint32_t *err, cudaStream_t s) {
+    const int grid = std::max(1, std::min(148 * 6, c1 - c0));
+    k_destuff<<<grid, 256, 0, s>>>(in, n, out, desc, ticket, c0, c1, out_len, avail, err);
     return cudaGetLastError();
 }
 
@@ -589,13 +607,14 @@ static cudaError_t dec_attr() {
 }
 
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
-                            uint32_t *nblk, int bpm, int hv, int inner, int first, uint32_t *changed, size_t nsub_max,
-                            cudaStream_t s) {
+                            uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
+                            size_t nsub, cudaStream_t s) {
     cudaError_t e = dec_attr();
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((nsub_max + DEC_THREADS - 1) / DEC_THREADS);
+    const unsigned grid = (unsigned)((nsub + DEC_THREADS - 1) / DEC_THREADS);
+    if (grid == 0) return cudaSuccess;
     k_dec_sync<<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv, inner,
-                                                            first, changed);
+                                                            mode, done, changed);
     return cudaGetLastError();
 }
 

@@ -11,11 +11,14 @@ constexpr int DEC_SUB_BITS = 1024;
 size_t dec_tables_size();
 void dec_build_tables(const JpegInfo &info, void *dst_host);
 
-cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, uint64_t *out_len,
-                           uint32_t *err, cudaStream_t s);
+// 4 KB chunks [c0, c1) of the n-byte scan; `ticket`: a zeroed counter per launch; *avail = bytes produced so far
+cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,
+                           uint64_t *out_len, uint64_t *avail, uint32_t *err, cudaStream_t s);
+// mode 0: whole stream present (*u_len final); mode 1: stream still arriving (*u_len = bytes so far), first pass of the
+// complete chunks only. done[chunk] (zeroed per decode) marks chunks whose first pass has run. nsub: subsequences covered.
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
-                            uint32_t *nblk, int bpm, int hv, int inner, int first, uint32_t *changed, size_t nsub_max,
-                            cudaStream_t s);
+                            uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
+                            size_t nsub, cudaStream_t s);
 cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
                              const uint32_t *blk_start, int bpm, int hv, int16_t *coef, uint32_t nblocks, uint32_t *err,
                              size_t nsub_max, cudaStream_t s);
