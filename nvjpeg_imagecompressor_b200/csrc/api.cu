@@ -22,14 +22,18 @@ namespace {
 struct Ctrl {  // zeroed before every encode with one memset
     uint32_t hist[4 * 257];
     uint32_t ticket;
-    uint32_t err;
     uint32_t pool_count;
     uint32_t scan_ticket;
+    uint32_t pad0;
+    // ---- fetched by the host in one copy (same layout as HostRet)
     uint64_t out_len;
     uint64_t strip_bits[2];
     uint64_t ssd;
+    uint32_t err;        // k_stuff / look-backs
+    uint32_t huff_err;   // k_tables
+    // ----
     int16_t last_dc[4];
-    int seam[2];
+    int seam[2];         // [0] skip bits, [1] ext byte XOR 0xFF (so that all-zero means "whole image": skip 0, pad with ones)
 };
 
 struct HostRet {  // pinned
@@ -313,7 +317,7 @@ int b2j_strip_phase1b(b2j_ctx *ctx) {
 int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
     // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
-    CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, ctx->stream));
+    CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, &ctx->d_ctrl->huff_err, ctx->stream));
     tick(ctx, 4);
     CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_slots, ctx->d_tile_bits, ctx->debug & 2, ctx->stream));
     tick(ctx, 5);
@@ -341,8 +345,10 @@ static int phase3_launch(b2j_ctx *ctx, int flags) {
 
 int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
     if (!ctx || !ctx->enc_ready || skip_bits < 0 || skip_bits > 7) return B2J_EINVAL;
-    CK(launch_set_seam(ctx->d_ctrl->seam, skip_bits, ext_byte & 0xFF, ctx->stream));
-    ctx->launches += 1;
+    if (skip_bits != 0 || (ext_byte & 0xFF) != 0xFF) {   // the zeroed control block already says "skip 0, pad with ones"
+        CK(launch_set_seam(ctx->d_ctrl->seam, skip_bits, ext_byte & 0xFF, ctx->stream));
+        ctx->launches += 1;
+    }
     return phase3_launch(ctx, flags);
 }
 
@@ -388,10 +394,8 @@ int b2j_encode_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width
 }
 
 static int fetch_ret(b2j_ctx *ctx) {
-    CK(cudaMemcpyAsync(&ctx->h_ret->out_len, &ctx->d_ctrl->out_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&ctx->h_ret->strip_bits, &ctx->d_ctrl->strip_bits, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&ctx->h_ret->err, &ctx->d_ctrl->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&ctx->h_ret->huff_err, &ctx->d_huff->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    static_assert(sizeof(HostRet) == 40, "HostRet mirrors the fetched block of Ctrl");
+    CK(cudaMemcpyAsync(ctx->h_ret, &ctx->d_ctrl->out_len, sizeof(HostRet), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_ret->err || ctx->h_ret->huff_err) {
         snprintf(ctx->err, sizeof(ctx->err), "device check failed: stuff err=%u tables err=%u", ctx->h_ret->err, ctx->h_ret->huff_err);

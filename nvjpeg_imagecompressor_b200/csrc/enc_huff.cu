@@ -47,7 +47,7 @@ __constant__ uint8_t c_std_ac_val[2][162] = {
 // group id per symbol so "increment codesize along the others chain" becomes "increment every member".
 __global__ void __launch_bounds__(128)
 k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ huff, const QuantDev *__restrict__ qd,
-         int full_w, int full_h, int hs, int vs, uint8_t *__restrict__ out, int emit_header) {
+         int full_w, int full_h, int hs, int vs, uint8_t *__restrict__ out, int emit_header, uint32_t *__restrict__ err_out) {
     __shared__ uint8_t s_bits[4][17];
     __shared__ uint8_t s_vals[4][256];
     __shared__ uint32_t s_enc[4][256];
@@ -225,6 +225,7 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
         s_hdr_len = n;
         huff->hdr_len = n;
         huff->err = s_err;
+        *err_out = s_err;
     }
     __syncthreads();
     if (emit_header) {
@@ -701,7 +702,7 @@ k_stuff(StuffArgs a) {
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_out32);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t T = a.tile_off[a.ntiles];
-    const int a_skip = a.seam[0], a_ext = a.seam[1];
+    const int a_skip = a.seam[0], a_ext = a.seam[1] ^ 0xFF;   // the ext byte is stored inverted: zeroed control block = whole image
     const uint64_t NB = T > (uint64_t)a_skip ? (T - a_skip + 7) >> 3 : 0;
     const int nchunks = (int)max((uint64_t)1, (NB + STUFF_CHUNK - 1) / STUFF_CHUNK);
     const uint32_t hdr = a.huff->hdr_len;
@@ -901,8 +902,8 @@ k_stuff(StuffArgs a) {
 
 // ------------------------------------------------------------------------------------------------------
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
-                          int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s) {
-    k_tables<<<1, 128, 0, s>>>(hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header);
+                          int hs, int vs, uint8_t *out, int emit_header, uint32_t *err_out, cudaStream_t s) {
+    k_tables<<<1, 128, 0, s>>>(hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header, err_out);
     return cudaGetLastError();
 }
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
@@ -918,7 +919,7 @@ cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *t
     k_scan_tiles<<<grid, 1024, 0, s>>>(tile_bits, ntiles, tile_off, slots, strip_bits, desc, ticket, err);
     return cudaGetLastError();
 }
-__global__ void k_set_seam(int *seam, int skip, int ext) { seam[0] = skip; seam[1] = ext; }
+__global__ void k_set_seam(int *seam, int skip, int ext) { seam[0] = skip; seam[1] = ext ^ 0xFF; }
 
 // bits_all[k] = {entropy bits of strip k, its first 32 bits (top-aligned)}: strip `rank` starts at global bit G =
 // sum of the bit counts before it; it skips the (8 - G % 8) % 8 bits that complete the previous strip's last byte and
@@ -927,7 +928,7 @@ __global__ void k_seam_from_bits(int *seam, const int64_t *__restrict__ bits_all
     uint64_t G = 0;
     for (int k = 0; k < rank; k++) G += (uint64_t)bits_all[2 * k];
     seam[0] = (int)((8u - (uint32_t)(G & 7u)) & 7u);
-    seam[1] = rank == world - 1 ? 0xFF : (int)(((uint64_t)bits_all[2 * (rank + 1) + 1] >> 24) & 0xFFu);
+    seam[1] = (rank == world - 1 ? 0xFF : (int)(((uint64_t)bits_all[2 * (rank + 1) + 1] >> 24) & 0xFFu)) ^ 0xFF;
 }
 
 cudaError_t launch_set_seam(int *seam, int skip, int ext, cudaStream_t s) {

@@ -14,7 +14,7 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
                                 int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, cudaStream_t s);
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
-                          int hs, int vs, uint8_t *out, int emit_header, cudaStream_t s);
+                          int hs, int vs, uint8_t *out, int emit_header, uint32_t *err_out, cudaStream_t s);
 // small_buffers != 0 (tests): the per-warp bit buffers pretend to hold 24 words, forcing the overflow path
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s);
@@ -28,7 +28,7 @@ struct StuffArgs {
     const uint64_t *tile_off;   // [ntiles+1]
     int ntiles;
     const int *seam;            // device: [0] skip = leading bits owned by the previous strip's last byte,
-                                //         [1] ext = next strip's first 8 bits (0xFF: pad with ones)
+                                //         [1] ext ^ 0xFF, ext = next strip's first 8 bits (0xFF: pad with ones)
     int append_eoi;
     const HuffDev *huff;        // hdr_len
     uint8_t *out;
