@@ -154,7 +154,6 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     DCK(cudaMemsetAsync(d->d_desc, 0, d->desc_cap * 5 * 8, s));
     DCK(cudaMemsetAsync(d->d_nblk, 0, (nsub_max + 1) * 4, s));
     DCK(cudaMemsetAsync(d->d_done, 0, nsub_max / 256 + 64, s));
-    DCK(cudaMemsetAsync(d->d_coef, 0, (size_t)g.nblocks * 128, s));
 
     // ---- self-synchronisation: launches of 8 in-CTA rounds until no end state moves.
     // Speculative mode (default): a fixed number of launches back to back, the "still moving" flag of the last one is

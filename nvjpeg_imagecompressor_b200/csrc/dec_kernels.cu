@@ -132,7 +132,8 @@ struct DecShared {
 __device__ __forceinline__ uint64_t pack_state(uint64_t p, int c, int k) { return (p << 16) | ((uint64_t)c << 8) | (uint64_t)k; }
 
 // codes longer than the LUT covers (rare), or an invalid code (only while unsynchronised): canonical search
-__device__ __noinline__ uint32_t huff_sym_long(const DecShared &sh, uint32_t t, uint32_t top16) {
+template <class SH>
+__device__ __noinline__ uint32_t huff_sym_long(const SH &sh, uint32_t t, uint32_t top16) {
 #pragma unroll 1
     for (int l = DEC_LUT_BITS + 1; l <= 16; l++) {
         const int code = (int)(top16 >> (16 - l));
@@ -290,29 +291,124 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
     if (any || (live && last_live && mine != before) || (live && sh.state[tid] != used)) atomicOr(changed, 1u);
 }
 
-// Final pass: decode every subsequence from its synchronised start state and scatter the non-zero coefficients
-// (zig-zag order, DC still differential) into the zero-filled coefficient array.
+// Final pass: decode every subsequence from its synchronised start state and write whole coefficient blocks
+// (zig-zag order, DC still differential). A block belongs to the thread in whose subsequence it STARTS: that thread
+// keeps decoding past its last bit until the block is complete (a block is at most 1665 bits: two subsequences of
+// lookahead are staged), and skips the tail of the block that was running when its subsequence began. The owner
+// collects the block's coefficients in a 128-byte cell of shared memory; the warp runs in lock step, one symbol per
+// lane and iteration, and after every iteration the lanes that completed a block have it written out by the whole
+// warp: one coalesced 128-byte store per block, zeros included -- no memset of the array, no scattered 2-byte stores.
+constexpr int WR_STRIDE = DEC_THREADS + 3;           // columns: 256 subsequences + 2 of lookahead, odd stride
+struct DecWriteShared {
+    uint32_t words[SUB_WORDS * WR_STRIDE];           // [word-in-subsequence][subsequence]
+    uint16_t lut[4][1 << DEC_LUT_BITS];
+    int32_t maxcode[4][18];
+    int32_t valoff[4][17];
+    uint8_t vals[4][256];
+    uint32_t blk[DEC_THREADS][32];                   // word w of thread t's block at [t][w ^ (t & 31)]
+};
+
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
             const uint64_t *__restrict__ st_out, const uint32_t *__restrict__ blk_start, int bpm, int hv,
             int16_t *__restrict__ coef, uint32_t nblocks, uint32_t *__restrict__ err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
-    const int tid = threadIdx.x;
+    DecWriteShared &sh = *reinterpret_cast<DecWriteShared *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t nbytes = *u_len;
     const uint64_t total_bits = nbytes * 8;
     const size_t cta = blockIdx.x;
     const uint64_t chunk_bit0 = (uint64_t)cta * SUB_BITS * DEC_THREADS;
     if (chunk_bit0 >= total_bits) return;
-    dec_load_chunk(sh, u, (nbytes + 64) & ~(uint64_t)3, cta, tb);
+    {   // the chunk's words + two subsequences of lookahead, tables, empty block cells
+        const uint32_t *uw = reinterpret_cast<const uint32_t *>(u);
+        const size_t w0 = cta * (size_t)(SUB_WORDS * DEC_THREADS);
+        const size_t nwords = (size_t)(((nbytes + 64) & ~(uint64_t)3) >> 2);
+        for (int i = tid; i < SUB_WORDS * (DEC_THREADS + 2); i += DEC_THREADS) {
+            const size_t gw = w0 + i;
+            const uint32_t w = gw < nwords ? uw[gw] : 0xFFFFFFFFu;
+            sh.words[(i & 31) * WR_STRIDE + (i >> 5)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
+        }
+        for (int i = tid; i < 4 * (1 << DEC_LUT_BITS); i += DEC_THREADS) (&sh.lut[0][0])[i] = (&tb->lut[0][0])[i];
+        for (int i = tid; i < 4 * 18; i += DEC_THREADS) (&sh.maxcode[0][0])[i] = (&tb->maxcode[0][0])[i];
+        for (int i = tid; i < 4 * 17; i += DEC_THREADS) (&sh.valoff[0][0])[i] = (&tb->valoff[0][0])[i];
+        for (int i = tid; i < 4 * 256; i += DEC_THREADS) (&sh.vals[0][0])[i] = (&tb->vals[0][0])[i];
+#pragma unroll
+        for (int w = 0; w < 32; w++) sh.blk[tid][w ^ lane] = 0;
+    }
     __syncthreads();
     const size_t i = cta * DEC_THREADS + tid;
     const uint64_t my_bit0 = chunk_bit0 + (uint64_t)tid * SUB_BITS;
-    if (my_bit0 >= total_bits) return;
-    const uint64_t in = i == 0 ? pack_state(0, 0, 0) : st_out[i - 1];
-    uint32_t n = 0;
-    const uint64_t o = decode_range<true>(sh, chunk_bit0, in, my_bit0 + SUB_BITS, total_bits, bpm, hv, n, coef, blk_start[i], nblocks);
-    if (o != st_out[i]) atomicOr(err, 4u);  // the states were not a fixed point
+    const bool live = my_bit0 < total_bits;
+    const uint64_t in = (!live || i == 0) ? pack_state(live ? 0 : my_bit0, 0, 0) : st_out[i - 1];
+    uint32_t q = (uint32_t)((in >> 16) - chunk_bit0);
+    int c = (int)((in >> 8) & 0xFF), k = (int)(in & 0xFF);
+    const uint64_t left = total_bits - chunk_bit0;
+    const uint32_t tot = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;
+    const uint32_t stop = min((uint32_t)(tid + 1) * SUB_BITS, tot);
+    uint32_t b_cur = live ? blk_start[i] : 0;   // index of the block that is running (or starts) at q
+    bool owning = k == 0;                        // a block that starts here is mine; a running one is my predecessor's
+    bool active = live && !(k == 0 && q >= stop);
+    bool crossed = q >= stop;                    // the state at the first symbol boundary at or past `stop` must be st_out[i]
+    uint64_t end_state = in;
+    const uint16_t *lut = &sh.lut[0][0];
+    uint32_t *cell = sh.blk[tid];
+    while (__any_sync(0xffffffffu, active)) {
+        bool flush = false;
+        if (active) {
+            const uint32_t g = q >> 5, o = q & 31u;
+            const uint32_t w0 = sh.words[(g & 31u) * WR_STRIDE + (g >> 5)];
+            const uint32_t g1 = g + 1;
+            const uint32_t w1 = sh.words[(g1 & 31u) * WR_STRIDE + (g1 >> 5)];
+            const uint32_t win = __funnelshift_l(w1, w0, o);
+            const bool dc = k == 0;
+            const uint32_t t = (c < hv ? 0u : 2u) + (dc ? 0u : 1u);
+            uint32_t e = lut[(t << DEC_LUT_BITS) + (win >> (32 - DEC_LUT_BITS))];
+            if (e == 0) e = huff_sym_long(sh, t, win >> 16);
+            const uint32_t len = e >> 8, s = e & 15u, r = (e >> 4) & 15u;
+            if (e == 0xFFFFu || q + len + s > tot) {   // cannot happen on synchronised states except in the final padding
+                q = tot;
+                active = false;
+            } else {
+                int val = 0;
+                if (s) {
+                    const uint32_t v = (win << len) >> (32 - s);
+                    val = v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v;  // jdhuff.c HUFF_EXTEND
+                }
+                q += len + s;
+                int knew = s ? k + (int)r + 1 : (r == 15u ? k + 16 : 64);
+                if (dc) knew = 1;
+                if (owning && s) {
+                    const int idx = dc ? 0 : k + (int)r;
+                    if (idx < 64) reinterpret_cast<int16_t *>(&cell[(idx >> 1) ^ lane])[idx & 1] = (int16_t)val;
+                }
+                const bool done = knew > 63;
+                k = done ? 0 : knew;
+                c = done ? (c + 1 == bpm ? 0 : c + 1) : c;
+                if (done) {
+                    flush = owning;
+                    if (!owning) { b_cur++; owning = true; }   // my predecessor's block is over; the next one is mine
+                    if (q >= stop) active = false;             // blocks that start at or past my last bit are not mine
+                }
+            }
+            if (!crossed && q >= stop) { crossed = true; end_state = pack_state(chunk_bit0 + q, c, k); }
+        }
+        // ---- completed blocks: the whole warp writes each one (128 bytes, coalesced) and clears its cell
+        __syncwarp();
+        unsigned fl = __ballot_sync(0xffffffffu, flush);
+        while (fl) {
+            const int L = __ffs(fl) - 1;
+            fl &= fl - 1;
+            const uint32_t b = __shfl_sync(0xffffffffu, b_cur, L);
+            uint32_t *src = sh.blk[(tid & ~31) + L];
+            const uint32_t w = src[lane ^ L];
+            src[lane ^ L] = 0;
+            if (b < nblocks) reinterpret_cast<uint32_t *>(coef)[(size_t)b * 32 + lane] = w;
+        }
+        if (flush) b_cur++;
+        __syncwarp();
+    }
+    if (live && (!crossed || end_state != st_out[i])) atomicOr(err, 4u);  // the states were not a fixed point
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -600,7 +696,7 @@ static cudaError_t dec_attr() {
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    e = cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWriteShared));
     if (e != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
@@ -624,7 +720,7 @@ cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void
     cudaError_t e = dec_attr();
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((nsub_max + DEC_THREADS - 1) / DEC_THREADS);
-    k_dec_write<<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm, hv, coef,
+    k_dec_write<<<grid, DEC_THREADS, sizeof(DecWriteShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm, hv, coef,
                                                              nblocks, err);
     return cudaGetLastError();
 }
