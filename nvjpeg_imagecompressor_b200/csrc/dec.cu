@@ -39,6 +39,7 @@ struct Decoder {
     void *h_tb = nullptr;      // pinned
     uint32_t *h_flag = nullptr;  // pinned: [0] changed, [1] err
     int16_t *d_coef = nullptr;
+    int16_t *d_dc = nullptr;     // one DC per block: differences from k_dec_write, un-differenced in place by k_dc_scan
     uint8_t *d_planes = nullptr;
     size_t planes_cap = 0;
     cudaEvent_t ev[8];
@@ -69,7 +70,8 @@ Decoder *dec_create(int nblocks_cap, char *err, size_t errlen) {
     bool ok = cudaMalloc(&d->d_ctrl, sizeof(DecCtrl)) == cudaSuccess && cudaMalloc(&d->d_tb, dec_tables_size()) == cudaSuccess &&
               cudaHostAlloc(&d->h_tb, dec_tables_size(), cudaHostAllocDefault) == cudaSuccess &&
               cudaHostAlloc(&d->h_flag, 16, cudaHostAllocDefault) == cudaSuccess &&
-              cudaMalloc(&d->d_coef, (size_t)nblocks_cap * 128) == cudaSuccess;
+              cudaMalloc(&d->d_coef, (size_t)nblocks_cap * 128) == cudaSuccess &&
+              cudaMalloc(&d->d_dc, (size_t)nblocks_cap * 2 + 64) == cudaSuccess;
     for (auto &e : d->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&d->up_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &e : d->ev_up) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -84,7 +86,7 @@ Decoder *dec_create(int nblocks_cap, char *err, size_t errlen) {
 void dec_destroy(Decoder *d) {
     if (!d) return;
     cudaFree(d->d_scan); cudaFree(d->d_u); cudaFree(d->d_desc); cudaFree(d->d_st_in); cudaFree(d->d_st_out);
-    cudaFree(d->d_nblk); cudaFree(d->d_blk_start); cudaFree(d->d_ctrl); cudaFree(d->d_tb); cudaFree(d->d_coef);
+    cudaFree(d->d_nblk); cudaFree(d->d_blk_start); cudaFree(d->d_ctrl); cudaFree(d->d_tb); cudaFree(d->d_coef); cudaFree(d->d_dc);
     cudaFree(d->d_planes);
     if (d->h_tb) cudaFreeHost(d->h_tb);
     if (d->h_flag) cudaFreeHost(d->h_flag);
@@ -225,14 +227,14 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     d->last_rounds = rounds + 1;
     if (tm) cudaEventRecord(d->ev[2], s);
     DCK(launch_scan_u32(d->d_nblk, d->d_blk_start, nsub_max, d->d_desc + d->desc_cap, &d->d_ctrl->ticket[1], &d->d_ctrl->err, s));
-    DCK(launch_dec_write(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_out, d->d_blk_start, g.bpm, hv, d->d_coef, (uint32_t)g.nblocks,
+    DCK(launch_dec_write(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_out, d->d_blk_start, g.bpm, hv, d->d_coef, d->d_dc, (uint32_t)g.nblocks,
                          &d->d_ctrl->err, nsub_max, s));
-    DCK(launch_dc_scan(d->d_coef, g, d->d_desc + 2 * d->desc_cap, &d->d_ctrl->ticket[2], d->desc_cap, &d->d_ctrl->err, s));
+    DCK(launch_dc_scan(d->d_dc, g, d->d_desc + 2 * d->desc_cap, &d->d_ctrl->ticket[2], d->desc_cap, &d->d_ctrl->err, s));
     if (tm) cudaEventRecord(d->ev[3], s);
     uint8_t *py = d->d_planes;
     uint8_t *pcb = py + (((size_t)g.mcux * 8 * g.hs * g.mcuy * 8 * g.vs + 63) & ~(size_t)63);
     uint8_t *pcr = pcb + (((size_t)g.mcux * 8 * g.mcuy * 8 + 63) & ~(size_t)63);
-    DCK(launch_idct(d->d_coef, g, d->d_tb, py, pcb, pcr, s));
+    DCK(launch_idct(d->d_coef, d->d_dc, g, d->d_tb, py, pcb, pcr, s));
     if (tm) cudaEventRecord(d->ev[4], s);
     DCK(launch_upcolor(py, pcb, pcr, g, d_bgr, step, s));
     if (tm) cudaEventRecord(d->ev[5], s);

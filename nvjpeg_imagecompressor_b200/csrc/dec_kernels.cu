@@ -311,7 +311,7 @@ struct DecWriteShared {
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
             const uint64_t *__restrict__ st_out, const uint32_t *__restrict__ blk_start, int bpm, int hv,
-            int16_t *__restrict__ coef, uint32_t nblocks, uint32_t *__restrict__ err) {
+            int16_t *__restrict__ coef, int16_t *__restrict__ dcarr, uint32_t nblocks, uint32_t *__restrict__ err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecWriteShared &sh = *reinterpret_cast<DecWriteShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -403,7 +403,10 @@ k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, c
             uint32_t *src = sh.blk[(tid & ~31) + L];
             const uint32_t w = src[lane ^ L];
             src[lane ^ L] = 0;
-            if (b < nblocks) reinterpret_cast<uint32_t *>(coef)[(size_t)b * 32 + lane] = w;
+            if (b < nblocks) {
+                reinterpret_cast<uint32_t *>(coef)[(size_t)b * 32 + lane] = w;
+                if (lane == 0) dcarr[b] = (int16_t)(w & 0xFFFFu);   // the DC differences also go to a compact array (k_dc_scan)
+            }
         }
         if (flush) b_cur++;
         __syncwarp();
@@ -457,7 +460,8 @@ k_scan_u32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n
 
 // ------------------------------------------------------------------------------------------------------
 // DC un-differencing: inclusive prefix sum of the DC differences of one component over its blocks in scan order
-// (jdhuff.c decode_mcu: s += last_dc_val). blockIdx.y = component; chunked look-back per component.
+// (jdhuff.c decode_mcu: s += last_dc_val), on the compact array of DCs (one int16 per block) that k_dec_write fills;
+// k_idct takes the DC from there. blockIdx.y = component; chunked look-back per component.
 __global__ void __launch_bounds__(256)
 k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__restrict__ desc_all,
           uint32_t *__restrict__ ticket_all, size_t desc_stride, uint32_t *__restrict__ err) {
@@ -472,10 +476,10 @@ k_dc_scan(int16_t *__restrict__ coef, int bpm, int hv, size_t nmcu, uint64_t *__
     const size_t n = nmcu * per;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nchunks = (int)((n + CH - 1) / CH);
-    auto index_of = [&](size_t e) -> size_t {   // coefficient index of the DC of block e of this component
+    auto index_of = [&](size_t e) -> size_t {   // block index (= index into the compact DC array) of element e of this component
         const size_t m = comp == 0 ? e / hv : e;
         const int sub = comp == 0 ? (int)(e - m * hv) : hv + comp - 1;
-        return (m * bpm + sub) * 64;
+        return m * bpm + sub;
     };
     for (;;) {
         if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
@@ -554,8 +558,8 @@ __device__ __forceinline__ void idct8(int &i0, int &i1, int &i2, int &i3, int &i
 }
 
 __global__ void __launch_bounds__(256, 2)
-k_idct(const int16_t *__restrict__ coef, Geom g, const DecTables *__restrict__ tb, uint8_t *__restrict__ py,
-       uint8_t *__restrict__ pcb, uint8_t *__restrict__ pcr) {
+k_idct(const int16_t *__restrict__ coef, const int16_t *__restrict__ dcarr, Geom g, const DecTables *__restrict__ tb,
+       uint8_t *__restrict__ py, uint8_t *__restrict__ pcb, uint8_t *__restrict__ pcr) {
     __shared__ __align__(16) uint4 s_c[256 * 8];
     __shared__ uint16_t s_q[2][64];
     const int tid = threadIdx.x;
@@ -587,6 +591,7 @@ k_idct(const int16_t *__restrict__ coef, Geom g, const DecTables *__restrict__ t
             v[n] = cv * (int)q[n];
         }
     }
+    v[0] = (int)dcarr[b] * (int)q[0];   // the un-differenced DC (the coefficient array holds the difference)
 #pragma unroll
     for (int c = 0; c < 8; c++) idct8<11>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
     uint8_t *dst;
@@ -715,13 +720,13 @@ cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void 
 }
 
 cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
-                             const uint32_t *blk_start, int bpm, int hv, int16_t *coef, uint32_t nblocks, uint32_t *err,
-                             size_t nsub_max, cudaStream_t s) {
+                             const uint32_t *blk_start, int bpm, int hv, int16_t *coef, int16_t *dcarr, uint32_t nblocks,
+                             uint32_t *err, size_t nsub_max, cudaStream_t s) {
     cudaError_t e = dec_attr();
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((nsub_max + DEC_THREADS - 1) / DEC_THREADS);
     k_dec_write<<<grid, DEC_THREADS, sizeof(DecWriteShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm, hv, coef,
-                                                             nblocks, err);
+                                                                  dcarr, nblocks, err);
     return cudaGetLastError();
 }
 
@@ -738,9 +743,9 @@ cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_
     return cudaGetLastError();
 }
 
-cudaError_t launch_idct(const int16_t *coef, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb, uint8_t *pcr,
-                        cudaStream_t s) {
-    k_idct<<<g.ntiles, 256, 0, s>>>(coef, g, (const DecTables *)tb, py, pcb, pcr);
+cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb,
+                        uint8_t *pcr, cudaStream_t s) {
+    k_idct<<<g.ntiles, 256, 0, s>>>(coef, dcarr, g, (const DecTables *)tb, py, pcb, pcr);
     return cudaGetLastError();
 }
 

@@ -20,14 +20,15 @@ cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void 
                             uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
                             size_t nsub, cudaStream_t s);
 cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
-                             const uint32_t *blk_start, int bpm, int hv, int16_t *coef, uint32_t nblocks, uint32_t *err,
-                             size_t nsub_max, cudaStream_t s);
+                             const uint32_t *blk_start, int bpm, int hv, int16_t *coef, int16_t *dcarr, uint32_t nblocks,
+                             uint32_t *err, size_t nsub_max, cudaStream_t s);
 cudaError_t launch_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint64_t *desc, uint32_t *ticket, uint32_t *err,
                             cudaStream_t s);
+// coef here = the compact DC array (one int16 per block)
 cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_t *ticket, size_t desc_stride, uint32_t *err,
                            cudaStream_t s);
-cudaError_t launch_idct(const int16_t *coef, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb, uint8_t *pcr,
-                        cudaStream_t s);
+cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb,
+                        uint8_t *pcr, cudaStream_t s);
 cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr, size_t step,
                            cudaStream_t s);
 
