@@ -646,6 +646,59 @@ __device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, size_t s
     return i > 0 ? (3 * s + 3 * r0[i - 1] + r1[i - 1] + 8) >> 4 : (4 * s + 8) >> 4;
 }
 
+// the same eight upsampled chroma samples for an INTERIOR group (every neighbour exists): word loads, no edge tests
+template <int HS, int VS>
+__device__ __forceinline__ void chroma8_interior(const uint8_t *__restrict__ p, size_t stride, int dh, int x0, int y, int (&c)[8]) {
+    auto six = [](const uint8_t *row, int i0, int (&s)[6]) {   // samples i0 - 1 .. i0 + 4 (i0 % 4 == 0)
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(row + i0);
+        s[0] = row[i0 - 1];
+        s[1] = w & 0xFF; s[2] = (w >> 8) & 0xFF; s[3] = (w >> 16) & 0xFF; s[4] = w >> 24;
+        s[5] = row[i0 + 4];
+    };
+    if (HS == 1 && VS == 1) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(p + (size_t)y * stride + x0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { c[i] = (w.x >> (8 * i)) & 0xFF; c[4 + i] = (w.y >> (8 * i)) & 0xFF; }
+    } else if (HS == 4) {
+        const uint8_t *row = p + (size_t)y * stride + (x0 >> 2);
+        const int s0 = row[0], s1 = row[1];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { c[i] = s0; c[4 + i] = s1; }
+    } else if (HS == 2 && VS == 1) {
+        int s[6];
+        six(p + (size_t)y * stride, x0 >> 1, s);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            c[2 * j] = (3 * s[j + 1] + s[j] + 1) >> 2;
+            c[2 * j + 1] = (3 * s[j + 1] + s[j + 2] + 2) >> 2;
+        }
+    } else if (HS == 1 && VS == 2) {
+        const int r = y >> 1;
+        const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+        const uint2 a = *reinterpret_cast<const uint2 *>(p + (size_t)r * stride + x0);
+        const uint2 bq = *reinterpret_cast<const uint2 *>(p + (size_t)rn * stride + x0);
+        const int bias = (y & 1) ? 2 : 1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            c[i] = (3 * (int)((a.x >> (8 * i)) & 0xFF) + (int)((bq.x >> (8 * i)) & 0xFF) + bias) >> 2;
+            c[4 + i] = (3 * (int)((a.y >> (8 * i)) & 0xFF) + (int)((bq.y >> (8 * i)) & 0xFF) + bias) >> 2;
+        }
+    } else {   // h2v2
+        const int r = y >> 1;
+        const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+        int s0[6], s1[6], t[6];
+        six(p + (size_t)r * stride, x0 >> 1, s0);
+        six(p + (size_t)rn * stride, x0 >> 1, s1);
+#pragma unroll
+        for (int j = 0; j < 6; j++) t[j] = 3 * s0[j] + s1[j];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            c[2 * j] = (3 * t[j + 1] + t[j] + 8) >> 4;
+            c[2 * j + 1] = (3 * t[j + 1] + t[j + 2] + 7) >> 4;
+        }
+    }
+}
+
 template <int HS, int VS>
 __global__ void __launch_bounds__(256)
 k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const uint8_t *__restrict__ pcr, Geom g,
@@ -656,7 +709,35 @@ k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const
     if (x0 >= g.W) return;
     const size_t ys = (size_t)g.mcux * 8 * HS, cs = (size_t)g.mcux * 8;
     const int dw = g.dw[1], dh = g.dh[1];
+    uint8_t *dst = bgr + (size_t)y * step + (size_t)x0 * 3;
     uint8_t o[24];
+    // interior groups (all neighbours of all eight pixels exist, 8-byte aligned destination): vector loads and stores
+    if (x0 >= 8 && x0 + 16 <= g.W && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        const uint2 yw = *reinterpret_cast<const uint2 *>(py + (size_t)y * ys + x0);
+        int cbv[8], crv[8];
+        chroma8_interior<HS, VS>(pcb, cs, dh, x0, y, cbv);
+        chroma8_interior<HS, VS>(pcr, cs, dh, x0, y, crv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int Y = (int)(((i < 4 ? yw.x : yw.y) >> (8 * (i & 3))) & 0xFF);
+            const int cb = cbv[i] - 128, cr = crv[i] - 128;
+            const int r = Y + ((91881 * cr + 32768) >> 16);
+            const int b = Y + ((116130 * cb + 32768) >> 16);
+            const int gg = Y + ((-22554 * cb - 46802 * cr + 32768) >> 16);
+            o[3 * i] = (uint8_t)min(255, max(0, b));
+            o[3 * i + 1] = (uint8_t)min(255, max(0, gg));
+            o[3 * i + 2] = (uint8_t)min(255, max(0, r));
+        }
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) { lo |= (uint32_t)o[8 * j + c] << (8 * c); hi |= (uint32_t)o[8 * j + 4 + c] << (8 * c); }
+            d2[j] = make_uint2(lo, hi);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int x = min(x0 + i, g.W - 1);
@@ -670,20 +751,8 @@ k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const
         o[3 * i + 1] = (uint8_t)min(255, max(0, gg));
         o[3 * i + 2] = (uint8_t)min(255, max(0, r));
     }
-    uint8_t *dst = bgr + (size_t)y * step + (size_t)x0 * 3;
     const int nv = min(8, g.W - x0);
-    if (nv == 8 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) { lo |= (uint32_t)o[8 * j + c] << (8 * c); hi |= (uint32_t)o[8 * j + 4 + c] << (8 * c); }
-            d2[j] = make_uint2(lo, hi);
-        }
-    } else {
-        for (int j = 0; j < nv * 3; j++) dst[j] = o[j];
-    }
+    for (int j = 0; j < nv * 3; j++) dst[j] = o[j];
 }
 
 // ------------------------------------------------------------------------------------------------------
