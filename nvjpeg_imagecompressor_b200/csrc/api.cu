@@ -81,7 +81,7 @@ struct b2j_ctx {
     // decoder + secondary state
     b2j::Decoder *dec;
     uint8_t *d_recon, *d_diff;
-    size_t d_recon_bytes;
+    size_t d_recon_bytes, d_diff_bytes;
     // pageable host buffers: copy threads + pinned staging ring (hostpipe.h), created on first use
     b2j::CopyPool *pool;
     b2j::StageRing ring;
@@ -722,8 +722,11 @@ int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int 
         cudaFree(ctx->d_recon); ctx->d_recon = nullptr; ctx->d_recon_bytes = 0;
         CK(cudaMalloc(&ctx->d_recon, bytes)); ctx->d_recon_bytes = bytes;
     }
-    cudaFree(ctx->d_diff); ctx->d_diff = nullptr;
-    CK(cudaMalloc(&ctx->d_diff, bytes));
+    if (ctx->d_diff_bytes < bytes) {   // grow-only, like the other per-context buffers
+        cudaFree(ctx->d_diff); ctx->d_diff = nullptr; ctx->d_diff_bytes = 0;
+        CK(cudaMalloc(&ctx->d_diff, bytes));
+        ctx->d_diff_bytes = bytes;
+    }
     {
         JpegInfo info;
         rc = parse_for(ctx, o1, n1, &info, nullptr, nullptr); if (rc) return rc;

@@ -101,7 +101,7 @@ class Engine:
     def secondary(self, img, diff_mode=1, want_recon=True):
         img = np.asarray(img)
         H, W = img.shape[:2]
-        cap = W * H * 3 * 2 + 65536
+        cap = min(self._L.b2j_encode_bound(self._h), W * H * 3 + 65536)
         j1, j2 = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
         n1, n2, ps = C.c_size_t(0), C.c_size_t(0), C.c_double(0)
         recon = np.empty((H, W, 3), np.uint8) if want_recon else None
