@@ -155,7 +155,7 @@ B2J_API int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int ra
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
 enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4,
-       B2J_DBG_TOKEN_COUNT = 5 /* uint32: run-length tokens of the last encode (4 bytes each between the two passes) */ };
+       B2J_DBG_TOKEN_COUNT = 5 /* DEC_COEF: decoded blocks, zig-zag order, DC as difference. TOKEN_COUNT: uint32: run-length tokens of the last encode (4 bytes each between the two passes) */ };
 B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len);
 /* flags bit0 (B2J_DEBUG_COEF): the next encodes also store the quantised coefficients for B2J_DBG_COEF */
 /* bit1 (B2J_DEBUG_SMALL_PACK_BUFFERS): the entropy coder's per-warp bit buffers overflow on purpose (tests its
