@@ -177,6 +177,31 @@ def run_reference(args, rank, world):
                     raise RuntimeError("ref_encode_resident failed")
                 if i >= args.warmup:
                     gpu_ms.append(ms.value)
+            # the reference's decode of the JPEG it just wrote (DecodeWorker + getCVImageOnCPU: ImageCompressorImpl.cu:311-385,
+            # :184-232): device phase (host JPEG -> planar BGR in HBM, cudaEvent bracket) and the whole call (3 x D2H + CPU
+            # interleave into a host BGR image)
+            ref_decode = None
+            try:
+                if L.ref_build_decode_env(h) == 0:
+                    jpg = out[: n.value].copy()
+                    rec = np.empty((H, W, 3), np.uint8)
+                    w_, h_, gms = C.c_int(0), C.c_int(0), C.c_float(0)
+                    dev_ms, wall_ms = [], []
+                    for i in range(3):
+                        t0 = time.perf_counter()
+                        rc = L.ref_decode(h, C.c_void_p(jpg.ctypes.data), C.c_size_t(jpg.size), C.c_void_p(rec.ctypes.data),
+                                          C.c_size_t(W * 3), C.byref(w_), C.byref(h_), C.byref(gms))
+                        if rc != 0:
+                            raise RuntimeError(f"ref_decode rc={rc}")
+                        if i:
+                            dev_ms.append(gms.value)
+                            wall_ms.append((time.perf_counter() - t0) * 1e3)
+                    ref_decode = {"metric": "decode_mpix_per_s", "value": round(W * H / float(np.mean(dev_ms)) / 1e3, 1), "unit": "Mpix/s",
+                                  "ms_per_step": round(float(np.mean(dev_ms)), 2),
+                                  "e2e": {"value": round(W * H / float(np.mean(wall_ms)) / 1e3, 1), "unit": "Mpix/s",
+                                          "ms_per_step": round(float(np.mean(wall_ms)), 1)}}
+            except Exception as e:
+                ref_decode = {"error": f"{type(e).__name__}: {e}"}
             L.ref_destroy(h)
             ms = float(np.mean(gpu_ms))
             e2e = float(np.mean(e2e_ms))
@@ -189,6 +214,8 @@ def run_reference(args, rank, world):
                                            "4:2:2, q95, optimized Huffman) on this GPU; n_gpus ignored (single-GPU library)",
                          "jpeg_bytes": int(n.value)})
             line["vs_baseline"] = round(line["value"] / PUBLISHED_MPIX_S, 2)
+            if ref_decode is not None:
+                line["decode"] = ref_decode
             line["cpu_baseline"] = cpu_baseline()
             return line
         except Exception as e:  # fall through to the CPU arm
