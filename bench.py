@@ -302,6 +302,11 @@ def run_b200(args, rank, world, local_rank):
             ms_total = float(t.item())
             lens = enc.gather_lengths()
             nbytes = int(lens.sum())
+            try:   # stage times of this rank's last step (CUDA events inside the library)
+                eng.encode_finish()
+                stage_acc = {k: v * args.steps for k, v in eng.timings().items()}
+            except Exception:
+                stage_acc = {}
             lt = torch.tensor([launches], device=dev, dtype=torch.int64)
             dist.all_reduce(lt)
             launches = int(lt.item())
@@ -413,6 +418,12 @@ def run_b200(args, rank, world, local_rank):
                        "exceed the 126 MB L2; no flush between steps", "parallelism": "single GPU" if world == 1 else
                        f"{world} MCU-row strips, 1 all_reduce + 2 all_gather per image"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if world > 1 and stage_acc:
+        st = {k: v / args.steps for k, v in stage_acc.items()}
+        ksum = sum(st.get(k, 0.0) for k in ("fdct", "hist_edge", "tables", "pack", "scan", "stuff"))
+        line["stages_ms_rank0"] = {k: round(st[k], 4) for k in ("fdct", "hist_edge", "tables", "pack", "scan", "stuff") if k in st}
+        line["stages_ms_rank0"]["kernels"] = round(ksum, 4)
+        line["stages_ms_rank0"]["collectives_and_gaps"] = round(ms - ksum, 4)
     if e2e_pageable is not None:
         line["e2e_pageable"] = e2e_pageable
     if decode is not None:
