@@ -138,6 +138,7 @@ typedef struct b2j_strip_state {
     uint64_t *d_strip_bits; /* [2]: entropy bits of this strip (unstuffed), first 32 bits of its bit string */
     uint64_t *d_out_len;    /* bytes this strip produced in d_out (header included on first strip) */
     uint8_t *d_out;
+    void *d_record;         /* b2j_strip_record of this strip (one-collective schedule: allgather source) */
 } b2j_strip_state;
 
 B2J_API int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st);
@@ -152,6 +153,25 @@ B2J_API int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flag
 /* Same, with the seam derived on the device (no host synchronisation in the multi-GPU step): d_bits_all is the
  * all-gathered table [world][2] of int64 {d_strip_bits[0], d_strip_bits[1]} of every strip, in strip order. */
 B2J_API int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int world, int flags);
+
+/* One-collective schedule (what StripEncoder uses on GPUs): phase1x, ONE allgather of the strips' records, phase2x.
+ * The record carries the strip's symbol counts (always taken), its first/last DCs and its first tokens; with all
+ * records every rank derives the image histogram, the DC symbols at the strip starts, every strip's entropy bit
+ * count (histogram x code lengths: the bit phase of a strip does not wait for the other strips' entropy coders) and
+ * the bits that complete its last byte. phase2x = tables + entropy coding + seam + byte stuffing of this strip;
+ * the predicted bit count is checked against the coded one on the device (b2j_encode_finish reports a mismatch). */
+#define B2J_STRIP_RECORD_BYTES 4176
+typedef struct b2j_strip_record {
+    uint32_t hist[4 * 257]; /* DC0, AC0, DC1, AC1; the DC symbols of the strip's first MCU are not included */
+    int16_t first_dc[4];    /* quantised DC of the strip's first Y, Cb, Cr blocks */
+    int16_t last_dc[4];     /* ... of its last Y, Cb, Cr blocks */
+    uint32_t tok[8];        /* first entropy tokens of the strip (engine-internal format) */
+    uint32_t ntok;
+    uint32_t pad[3];
+} b2j_strip_record;
+B2J_API int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows);
+B2J_API int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int world, int full_width,
+                              int full_height, int flags);
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
 enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4,

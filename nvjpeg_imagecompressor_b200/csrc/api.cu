@@ -20,7 +20,10 @@ using namespace b2j;
 namespace {
 
 struct Ctrl {  // zeroed before every encode with one memset
-    uint32_t hist[4 * 257];
+    union {
+        uint32_t hist[4 * 257];
+        StripRecord rec;   // the strip exchange record starts with the histogram
+    };
     uint32_t ticket;
     uint32_t pool_count;
     uint32_t scan_ticket;
@@ -32,7 +35,6 @@ struct Ctrl {  // zeroed before every encode with one memset
     uint32_t err;        // k_stuff / look-backs
     uint32_t huff_err;   // k_tables
     // ----
-    int16_t last_dc[4];
     int seam[2];         // [0] skip bits, [1] ext byte XOR 0xFF (so that all-zero means "whole image": skip 0, pad with ones)
 };
 
@@ -300,7 +302,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
     rc = enc_reset(ctx); if (rc) return rc;
     tick(ctx, 1);
     CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, 0, ctx->d_pool, 0, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 0, ctx->d_pool, 0, nullptr, ctx->stream));
     ctx->launches += 2;
     tick(ctx, 2);
     return B2J_OK;
@@ -308,7 +310,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
 
 int b2j_strip_phase1b(b2j_ctx *ctx) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->last_dc, ctx->p.optimize, ctx->d_pool, 1, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, ctx->p.optimize, ctx->d_pool, 1, nullptr, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 3);
     return B2J_OK;
@@ -330,8 +332,8 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
 
 __global__ void k_set_hdr_len(HuffDev *h, uint32_t v) { h->hdr_len = v; }
 
-static int phase3_launch(b2j_ctx *ctx, int flags) {
-    if (!(flags & 1)) { k_set_hdr_len<<<1, 1, 0, ctx->stream>>>(ctx->d_huff, 0); ctx->launches++; }
+static int phase3_launch(b2j_ctx *ctx, int flags, bool hdr_done = false) {
+    if (!(flags & 1) && !hdr_done) { k_set_hdr_len<<<1, 1, 0, ctx->stream>>>(ctx->d_huff, 0); ctx->launches++; }
     StuffArgs a;
     a.slots = ctx->d_slots; a.tile_bits = ctx->d_tile_bits; a.tile_off = ctx->d_tile_off; a.ntiles = ctx->g.ntiles;
     a.seam = ctx->d_ctrl->seam; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
@@ -359,11 +361,39 @@ int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int 
     return phase3_launch(ctx, flags);
 }
 
+// One-collective schedule: phase1x -> all-gather of d_record -> phase2x (everything else, no further exchange).
+int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows) {
+    if (!ctx || !d_bgr) return B2J_EINVAL;
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    rc = set_strip_geom(ctx, width, rows); if (rc) return rc;
+    rc = enc_reset(ctx); if (rc) return rc;
+    tick(ctx, 1);
+    // symbol counts are always taken: they also give every strip's bit count once the tables are known
+    CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, 1, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
+    tick(ctx, 2);
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 1, ctx->d_pool, 1, &ctx->d_ctrl->rec, ctx->stream));
+    ctx->launches += 2;
+    tick(ctx, 3);
+    return B2J_OK;
+}
+
+int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int world, int full_w, int full_h, int flags) {
+    if (!ctx || !ctx->enc_ready || !d_records_all || rank < 0 || rank >= world || world > 256) return B2J_EINVAL;
+    const StripRecord *rec = static_cast<const StripRecord *>(d_records_all);
+    CK(launch_strip_merge(rec, rank, world, ctx->d_ctrl->hist, ctx->d_pool, ctx->d_recs, ctx->stream));
+    ctx->launches += 1;
+    int rc = b2j_strip_phase2(ctx, full_w, full_h); if (rc) return rc;
+    CK(launch_strip_seam(rec, rank, world, ctx->d_huff, !(flags & 1), ctx->d_ctrl->seam, ctx->d_ctrl->strip_bits, &ctx->d_ctrl->err, ctx->stream));
+    ctx->launches += 1;
+    return phase3_launch(ctx, flags, true);
+}
+
 int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st) {
     if (!ctx || !st) return B2J_EINVAL;
     int rc = enc_alloc(ctx); if (rc) return rc;
-    st->d_hist = ctx->d_ctrl->hist; st->d_last_dc = ctx->d_ctrl->last_dc; st->d_pred_in = ctx->d_pred_in;
+    st->d_hist = ctx->d_ctrl->hist; st->d_last_dc = ctx->d_ctrl->rec.last_dc; st->d_pred_in = ctx->d_pred_in;
     st->d_strip_bits = ctx->d_ctrl->strip_bits; st->d_out_len = &ctx->d_ctrl->out_len; st->d_out = ctx->d_out;
+    st->d_record = &ctx->d_ctrl->rec;
     return B2J_OK;
 }
 

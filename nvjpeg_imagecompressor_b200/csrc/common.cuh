@@ -31,6 +31,19 @@ struct TileRec {                               // one per fdct tile (<= 256 bloc
     uint16_t pos_cb, pos_cr;                   // run offsets of the first MCU's Cb / Cr DC tokens (Y: offset 0)
 };
 
+// What the strips of one image tell each other (multi-GPU encode, one all-gather of this record per image;
+// include/b2jpeg.h: b2j_strip_record). The DC symbols of the strip's first MCU are NOT in hist: their predictors live
+// in the previous strip, every rank derives them for every strip from first_dc / last_dc after the exchange.
+struct StripRecord {
+    uint32_t hist[4 * 257];   // symbol counts of this strip: DC0, AC0, DC1, AC1
+    int16_t first_dc[4];      // quantised DC of the strip's first Y, Cb, Cr blocks
+    int16_t last_dc[4];       // ... of its last Y, Cb, Cr blocks
+    uint32_t tok[8];          // first tokens of the strip (raw-DC tokens unresolved): the next 8+ bits after the seam
+    uint32_t ntok;
+    uint32_t pad[3];
+};
+static_assert(sizeof(StripRecord) == 4176, "b2j_strip_record layout");
+
 constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)
 constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
 constexpr int STUFF_THREADS = 256;

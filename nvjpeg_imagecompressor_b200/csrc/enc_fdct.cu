@@ -531,17 +531,18 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 // DC-difference symbols of each fdct tile's first MCU (their predecessor block lives in the previous tile; the
 // strip's very first MCU takes pred_in), plus the strip's last DCs for the next strip. With `resolve` the three
 // raw-DC tokens of every tile are rewritten in the pool as final difference tokens, so the entropy coder sees one
-// uniform token format.
+// uniform token format. With `xr` (one-collective strip exchange) the strip's first MCU is left alone -- its
+// predictors arrive with the exchange, k_strip_merge finishes it -- and the record's DC / first-token fields are filled.
 __global__ void __launch_bounds__(256)
 k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restrict__ pred_in,
                uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist,
-               uint32_t *__restrict__ pool, int resolve) {
+               uint32_t *__restrict__ pool, int resolve, StripRecord *__restrict__ xr) {
     __shared__ uint32_t s_h[2][16];   // DC categories 0..11 of the two DC tables, aggregated per CTA
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ntile = g.tiles_x * g.mcuy;
     if (threadIdx.x < 32) s_h[threadIdx.x >> 4][threadIdx.x & 15] = 0;
     __syncthreads();
-    if (t < ntile * 3 && (do_hist || resolve)) {
+    if (t < ntile * 3 && (do_hist || resolve) && !(xr && t < 3)) {
         const int tile = t / 3, c = t - tile * 3;
         const TileRec r = recs[tile];
         const int dc = r.first_dc[c];
@@ -555,6 +556,14 @@ k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restri
         }
     }
     if (t < 3) last_dc[t] = recs[ntile - 1].last_dc[t];
+    if (xr) {
+        if (t < 3) xr->first_dc[t] = recs[0].first_dc[t];
+        if (t >= 32 && t < 40) {   // tile 0 only: the other tiles' first tokens are being rewritten by this launch
+            const uint32_t n = min(recs[0].count, 8u), j = (uint32_t)t - 32u;
+            xr->tok[j] = j < n ? pool[recs[0].base + j] : 0u;
+            if (j == 0) xr->ntok = n;
+        }
+    }
     __syncthreads();
     if (do_hist && threadIdx.x < 32) {
         const uint32_t n = s_h[threadIdx.x >> 4][threadIdx.x & 15];
@@ -609,9 +618,9 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 }
 
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, cudaStream_t s) {
-    const int n = max(3, g.tiles_x * g.mcuy * 3);
-    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(recs, g, pred_in, hist, last_dc, do_hist, pool, resolve);
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, cudaStream_t s) {
+    const int n = max(64, g.tiles_x * g.mcuy * 3);
+    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr);
     return cudaGetLastError();
 }
 

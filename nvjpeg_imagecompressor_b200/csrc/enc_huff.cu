@@ -931,6 +931,109 @@ __global__ void k_seam_from_bits(int *seam, const int64_t *__restrict__ bits_all
     seam[1] = (rank == world - 1 ? 0xFF : (int)(((uint64_t)bits_all[2 * (rank + 1) + 1] >> 24) & 0xFFu)) ^ 0xFF;
 }
 
+// ---- one-collective strip exchange -------------------------------------------------------------------------
+// After the all-gather of every strip's StripRecord each rank has what the three-collective schedule exchanged:
+// the image histogram is the sum of the strips' plus the DC symbols at the strip starts (derived from first_dc /
+// last_dc of neighbouring records); a strip's entropy bit count is its histogram weighted with the code lengths,
+// so the bit phase of every strip is known without waiting for the others' entropy coders; the byte completing a
+// strip's last byte is the head of the next strip's record tokens coded with the (identical) tables.
+__device__ __forceinline__ uint32_t dc_token(int c, int diff) {
+    const int nb = 32 - __clz(diff < 0 ? -diff : diff);
+    return ((uint32_t)(c ? 2 : 0) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+}
+
+__global__ void __launch_bounds__(1024)
+k_strip_merge(const StripRecord *__restrict__ rec, int rank, int world, uint32_t *__restrict__ hist,
+              uint32_t *__restrict__ pool, const TileRec *__restrict__ recs) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * 257; i += 1024) {
+        uint32_t s = 0;
+        for (int k = 0; k < world; k++) s += rec[k].hist[i];
+        hist[i] = s;
+    }
+    __syncthreads();
+    if (tid < world * 3) {
+        const int k = tid / 3, c = tid - k * 3;
+        const int diff = (int)rec[k].first_dc[c] - (k ? (int)rec[k - 1].last_dc[c] : 0);
+        const uint32_t tk = dc_token(c, diff);
+        atomicAdd(&hist[(c ? 2 : 0) * 257 + ((tk >> 16) & 15u)], 1u);
+        if (k == rank) {   // this strip's own first MCU: the raw-DC tokens k_dc_edge_hist left alone
+            const TileRec r = recs[0];
+            pool[r.base + (c == 0 ? 0u : (c == 1 ? r.pos_cb : r.pos_cr))] = tk;
+        }
+    }
+}
+
+// seam[] of strip `rank` from the gathered records and the final code tables; also checks the strip's predicted bit
+// count against what its entropy coder produced (strip_bits[0]).
+__global__ void __launch_bounds__(1024)
+k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *__restrict__ huff, int drop_header,
+             int *__restrict__ seam, const uint64_t *__restrict__ strip_bits, uint32_t *__restrict__ err) {
+    __shared__ unsigned long long s_red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t = tid >> 8, sym = tid & 255;
+    const uint32_t len = huff->enc[t][sym] & 0xFFu;
+    const uint32_t cost = len + ((t & 1) ? (uint32_t)(sym & 15) : (uint32_t)sym);
+    unsigned long long before = 0, own = rec[rank].hist[t * 257 + sym];
+    for (int k = 0; k < rank; k++) before += rec[k].hist[t * 257 + sym];
+    uint32_t bad = (before + own) && !len;   // a counted symbol without a code
+    before *= cost; own *= cost;
+    if (tid <= rank * 3 + 2) {               // DC symbols at the strip starts 0..rank
+        const int k = tid / 3, c = tid - k * 3;
+        const uint32_t tk = dc_token(c, (int)rec[k].first_dc[c] - (k ? (int)rec[k - 1].last_dc[c] : 0));
+        const uint32_t nb = (tk >> 16) & 15u, l = huff->enc[c ? 2 : 0][nb] & 0xFFu;
+        bad |= !l;
+        if (k < rank) before += l + nb; else own += l + nb;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        own += __shfl_xor_sync(0xffffffffu, own, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) { s_red[0][wid] = before; s_red[1][wid] = own | ((unsigned long long)bad << 63); }
+    __syncthreads();
+    if (tid) return;
+    before = own = 0;
+    for (int w = 0; w < 32; w++) { before += s_red[0][w]; own += s_red[1][w] & ~(1ull << 63); bad |= (uint32_t)(s_red[1][w] >> 63); }
+    seam[0] = (int)((8u - (uint32_t)(before & 7u)) & 7u);
+    uint32_t ext = 0xFF;
+    if (rank + 1 < world) {   // head of the next strip's bit string
+        const StripRecord &nx = rec[rank + 1];
+        uint64_t acc = 0; int n = 0;
+        for (uint32_t j = 0; j < nx.ntok && n < 8; j++) {
+            uint32_t tk = nx.tok[j];
+            if (tk & TOK_RAWDC) {
+                const int c = (tk >> 16) & 3u;
+                tk = dc_token(c, (int)(int16_t)(tk & 0xFFFFu) - (int)rec[rank].last_dc[c]);
+            }
+            const uint32_t tb = (tk >> 24) & 3u, sy = (tk >> 16) & 0xFFu;
+            const uint32_t zr = huff->enc[tb][0xF0];
+            for (uint32_t z = 0; z < ((tk >> 28) & 3u); z++) { acc = (acc << (zr & 0xFFu)) | (zr >> 8); n += zr & 0xFFu; }
+            const uint32_t en = huff->enc[tb][sy], nv = (tb & 1u) ? (sy & 15u) : sy;
+            acc = (acc << (en & 0xFFu)) | (en >> 8); n += en & 0xFFu;
+            acc = (acc << nv) | (tk & 0xFFFFu); n += nv;
+            bad |= !(en & 0xFFu);
+        }
+        if (n < 8) { bad = 1; n = 8; }   // a strip shorter than one byte cannot supply the seam
+        ext = (uint32_t)(acc >> (n - 8)) & 0xFFu;
+    }
+    seam[1] = (int)(ext ^ 0xFFu);
+    if (drop_header) huff->hdr_len = 0;   // only the first strip's output starts with SOI..SOS
+    if (bad || own != strip_bits[0]) atomicMax(err, 7u);
+}
+
+cudaError_t launch_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *hist, uint32_t *pool,
+                               const TileRec *recs, cudaStream_t s) {
+    k_strip_merge<<<1, 1024, 0, s>>>(rec, rank, world, hist, pool, recs);
+    return cudaGetLastError();
+}
+cudaError_t launch_strip_seam(const StripRecord *rec, int rank, int world, HuffDev *huff, int drop_header, int *seam,
+                              const uint64_t *strip_bits, uint32_t *err, cudaStream_t s) {
+    k_strip_seam<<<1, 1024, 0, s>>>(rec, rank, world, huff, drop_header, seam, strip_bits, err);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_set_seam(int *seam, int skip, int ext, cudaStream_t s) {
     k_set_seam<<<1, 1, 0, s>>>(seam, skip, ext);
     return cudaGetLastError();

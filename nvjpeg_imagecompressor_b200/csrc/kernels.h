@@ -10,9 +10,10 @@ int fdct_tm_max(int hs, int vs);
 cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const QuantDev *qd, uint32_t *pool,
                         uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
                         int16_t *coef_dump, cudaStream_t s);
+// xr != NULL: one-collective strip exchange (first MCU left to k_strip_merge, record fields filled)
 // resolve != 0: also rewrite each tile's three raw-DC tokens in `pool` as final DC-difference tokens
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, cudaStream_t s);
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, cudaStream_t s);
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
                           int hs, int vs, uint8_t *out, int emit_header, uint32_t *err_out, cudaStream_t s);
 // small_buffers != 0 (tests): the per-warp bit buffers pretend to hold 24 words, forcing the overflow path
@@ -42,6 +43,11 @@ cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s);
 // seam[0..1] from host scalars, or from the all-gathered per-strip (bit count, first 32 bits) table on the device
 cudaError_t launch_set_seam(int *seam, int skip, int ext, cudaStream_t s);
 cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, int world, cudaStream_t s);
+// one-collective strip exchange: rec = the all-gathered records [world]
+cudaError_t launch_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *hist, uint32_t *pool,
+                               const TileRec *recs, cudaStream_t s);
+cudaError_t launch_strip_seam(const StripRecord *rec, int rank, int world, HuffDev *huff, int drop_header, int *seam,
+                              const uint64_t *strip_bits, uint32_t *err, cudaStream_t s);
 
 // decode
 struct DecArgs;

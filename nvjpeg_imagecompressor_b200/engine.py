@@ -164,6 +164,12 @@ class Engine:
     def strip_phase3_dev(self, d_bits_all, rank, world, flags):
         self._ck(self._L.b2j_strip_phase3_dev(self._h, C.c_void_p(d_bits_all), rank, world, flags))
 
+    def strip_phase1x(self, d_ptr, step, W, rows):
+        self._ck(self._L.b2j_strip_phase1x(self._h, C.c_void_p(d_ptr), step, W, rows))
+
+    def strip_phase2x(self, d_records_all, rank, world, full_w, full_h, flags):
+        self._ck(self._L.b2j_strip_phase2x(self._h, C.c_void_p(d_records_all), rank, world, full_w, full_h, flags))
+
     # introspection
     def debug_read(self, what, dtype, count_hint=None):
         n = C.c_size_t(0)

@@ -11,6 +11,12 @@ Not in the reference (single GPU, no communication: SURVEY.md 2a); this is BASEL
 Strip k then byte-stuffs its own bits shifted to phase G_k mod 8; it owns every output byte whose FIRST bit it holds,
 so the concatenation [headers | strip 0 | ... | strip N-1 | EOI] is the single-GPU stream, byte for byte.
 
+On GPUs (EngineBackend) the three exchanges are folded into ONE all_gather of a 4 KB record per strip (its own symbol
+counts, first/last DCs, first tokens: include/b2jpeg.h b2j_strip_record): with every strip's counts and the final code
+lengths each rank computes every strip's bit count itself, so nothing waits for another rank's entropy coder
+(`phase1x` -> all_gather -> `phase2x`). The three-step schedule above is what the host-visible phases implement and
+what the CPU tests drive.
+
 `backend` abstracts the device: EngineBackend drives libb2jpeg.so on a GPU; the CPU tests plug a checker-backed
 backend into the same host logic over gloo.
 """
@@ -74,6 +80,7 @@ class EngineBackend:
         self.strip_bits = _view(st.d_strip_bits, (2,), "<i8", self.device)
         self.out_len = _view(st.d_out_len, (1,), "<i8", self.device)
         self._d_out = st.d_out
+        self.record = _view(st.d_record, (N.STRIP_RECORD_BYTES,), "|u1", self.device)
 
     def set_stream(self, s):
         self.eng.set_stream(s)
@@ -93,6 +100,13 @@ class EngineBackend:
     def phase3_dev(self, bits_all, rank, world, flags):
         """bits_all: device int64 [world][2] (all-gathered strip_bits); the seam is derived on the device."""
         self.eng.strip_phase3_dev(bits_all.data_ptr(), rank, world, flags)
+
+    def phase1x(self, d_ptr, step, W, rows):
+        self.eng.strip_phase1x(d_ptr, step, W, rows)
+
+    def phase2x(self, records_all, rank, world, W, H, flags):
+        """records_all: device uint8 [world][STRIP_RECORD_BYTES], the all-gathered `record`s in strip order."""
+        self.eng.strip_phase2x(records_all.data_ptr(), rank, world, W, H, flags)
 
     def out_view(self, n):
         return _view(self._d_out, (int(n),), "|u1", self.device)
@@ -117,10 +131,19 @@ class StripEncoder:
         self._dc_all = torch.zeros((self.world, 4), dtype=torch.int16, device=dev)
         self._bits_all = torch.zeros((self.world, 2), dtype=torch.int64, device=dev)
         self._len_all = torch.zeros((self.world, 1), dtype=torch.int64, device=dev)
+        self.one_collective = hasattr(self.b, "phase2x") and self.world > 1
+        if self.one_collective:
+            self._rec_all = torch.zeros((self.world, N.STRIP_RECORD_BYTES), dtype=torch.uint8, device=dev)
 
     def encode_strip(self, d_ptr, step):
         """d_ptr: this rank's strip (rows [y0, y1) of the image). Returns (stuffed byte count, all ranks' counts)."""
         b, w, r = self.b, self.world, self.rank
+        flags = (1 if r == 0 else 0) | (2 if r == w - 1 else 0)
+        if self.one_collective:
+            b.phase1x(d_ptr, step, self.W, self.y1 - self.y0)
+            dist.all_gather_into_tensor(self._rec_all.view(-1), b.record, group=self.group)
+            b.phase2x(self._rec_all, r, w, self.W, self.H, flags)
+            return b.out_len
         b.phase1(d_ptr, step, self.W, self.y1 - self.y0)
         if w > 1:
             dist.all_gather_into_tensor(self._dc_all.view(torch.uint8).view(-1), b.last_dc.view(torch.uint8), group=self.group)
@@ -134,7 +157,6 @@ class StripEncoder:
         if w > 1 and self.optimize:
             dist.all_reduce(b.hist, op=dist.ReduceOp.SUM, group=self.group)
         b.phase2(self.W, self.H)
-        flags = (1 if r == 0 else 0) | (2 if r == w - 1 else 0)
         if w > 1:
             dist.all_gather_into_tensor(self._bits_all.view(-1), b.strip_bits, group=self.group)
             if hasattr(b, "phase3_dev"):   # GPU backend: seam parameters derived on the device, no host sync

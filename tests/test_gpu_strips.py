@@ -51,6 +51,29 @@ def encode_strips_one_gpu(img, css, q, opt, nstrips, dev_seam=False):
     return np.concatenate(parts)
 
 
+def encode_strips_one_collective(img, css, q, opt, nstrips):
+    """phase1x -> (all_gather of the records) -> phase2x: the schedule StripEncoder runs over NCCL."""
+    from nvjpeg_imagecompressor_b200.strips import EngineBackend, strip_rows
+    H, W = img.shape[:2]
+    d = torch.from_numpy(img).cuda()
+    rows = strip_rows(H, css, nstrips)
+    bs = [EngineBackend(W, max(b - a for a, b in rows), q, bool(opt), css, 0) for _ in rows]
+    for b, (y0, y1) in zip(bs, rows):
+        b.phase1x(d[y0:y1].data_ptr(), W * 3, W, y1 - y0)
+    torch.cuda.synchronize()
+    rec_all = torch.stack([b.record for b in bs]).contiguous()
+    torch.cuda.synchronize()
+    for k, b in enumerate(bs):
+        b.phase2x(rec_all, k, nstrips, W, H, (1 if k == 0 else 0) | (2 if k == nstrips - 1 else 0))
+    torch.cuda.synchronize()
+    parts = []
+    for b in bs:
+        n = b.eng.encode_finish()          # raises when a device check (predicted vs coded bit count) failed
+        parts.append(b.out_view(n).cpu().numpy())
+        b.eng.close()
+    return np.concatenate(parts)
+
+
 @pytest.mark.parametrize("W,H,css,q,opt,n", [(256, 320, 1, 95, 1, 2), (256, 320, 1, 95, 1, 8), (200, 333, 3, 90, 1, 4),
                                            (129, 200, 0, 75, 0, 3), (96, 250, 2, 95, 1, 5), (160, 64, 4, 100, 1, 8)])
 def test_strips_equal_single_stream(oracle, W, H, css, q, opt, n):
@@ -59,6 +82,8 @@ def test_strips_equal_single_stream(oracle, W, H, css, q, opt, n):
     for dev_seam in (False, True):
         out = encode_strips_one_gpu(img, css, q, opt, n, dev_seam)
         assert out.size == want.size and np.array_equal(out, want), f"dev_seam={dev_seam}"
+    out = encode_strips_one_collective(img, css, q, opt, n)
+    assert out.size == want.size and np.array_equal(out, want), "one-collective schedule"
 
 
 def test_strips_headline_slab(oracle, golden):
@@ -67,3 +92,15 @@ def test_strips_headline_slab(oracle, golden):
     c = golden["slab"][0]
     out = encode_strips_one_gpu(img, c["css"], c["quality"], c["optimize"], 8, dev_seam=True)
     assert out.size == c["jpeg_len"] and hashlib.sha256(out.tobytes()).hexdigest() == c["jpeg_sha256"]
+    out = encode_strips_one_collective(img, c["css"], c["quality"], c["optimize"], 8)
+    assert out.size == c["jpeg_len"] and hashlib.sha256(out.tobytes()).hexdigest() == c["jpeg_sha256"]
+
+
+def test_one_collective_flat_and_tiny_strips(oracle):
+    """Constant image (every code 1-2 bits, seams inside the first tokens) and strips of a single MCU row."""
+    for img, css, n in ((np.full((64, 48, 3), 77, np.uint8), 1, 4), (oracle.synth(40, 64, 3, 8), 0, 8),
+                        (np.zeros((128, 16, 3), np.uint8), 3, 8)):
+        for opt in (0, 1):
+            want = oracle.encode(img, css, 90, opt)
+            out = encode_strips_one_collective(img, css, 90, opt, n)
+            assert out.size == want.size and np.array_equal(out, want), (img.shape, css, opt)
