@@ -405,14 +405,31 @@ def run_b200(args, rank, world, local_rank):
     if sampler:
         sampler.t_hi = time.time()
     clocks = sampler.finish() if sampler else None
+    # the bytes themselves: one digest for every N (N>1: the strips' bytes concatenated on rank 0) -- same image, same stream
+    import hashlib
+    if world == 1:
+        digest = hashlib.sha256(h_out[:int(n2)].numpy().tobytes()).hexdigest()
+    else:
+        with torch.cuda.stream(stream):
+            whole = enc.gather_jpeg(0)
+            stream.synchronize()
+        digest = hashlib.sha256(whole.cpu().numpy().tobytes()).hexdigest() if rank == 0 else None
     if rank != 0:
         return None
+    bit_exact = None
+    try:   # libjpeg-turbo's digest of this very encode (tests/golden/make_golden.py, cv2.imencode in the build container)
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "golden.json")) as f:
+            for c in json.load(f)["headline"]["encodes"]:
+                if (c["css"], c["quality"], c["optimize"]) == ({"444": 0, "422": 1, "440": 2, "420": 3, "411": 4}[CSS], QUALITY, int(OPT)):
+                    bit_exact = bool(c["jpeg_len"] == int(nbytes) and digest[:32] == c["jpeg_sha256_128"])
+    except Exception:
+        pass
 
     peak, which = measured_peak()
     line = {"metric": "encode_mpix_per_s", "value": round(W * H / ms / 1e3, 1), "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": round(W * H / ms / 1e3 / PUBLISHED_MPIX_S, 2), "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "jpeg_bytes": int(nbytes),
+            "config": {"workload": WORKLOAD, "jpeg_bytes": int(nbytes), "jpeg_sha256": digest, "bit_exact_vs_libjpeg_turbo": bit_exact,
                        "vs_baseline_basis": "BASELINE.md section 1: the reference README's 201.45 ms = 1652 Mpix/s for this configuration "
                                             "(8320x40000, 4:2:2, q95, optimised Huffman) on an RTX 3060, its own images", "l2": "inputs (998 MB image, ~0.8 GB token pool) "
                        "exceed the 126 MB L2; no flush between steps", "parallelism": "single GPU" if world == 1 else
