@@ -181,6 +181,21 @@ static int ensure_tiles(b2j_ctx *ctx, const Geom &g) {
     return B2J_OK;
 }
 
+// Everything an encode needs zeroed lives in ONE allocation, cleared by one memset per image:
+// [Ctrl | pred_in (16 B) | tile-scan descriptors (nsdesc) | byte-stuffing descriptors (ndesc, used prefix cleared)]
+constexpr size_t ARENA_CTRL = (sizeof(Ctrl) + 15) & ~(size_t)15;
+static int alloc_zero_arena(b2j_ctx *ctx, size_t nsdesc) {
+    if (ctx->d_ctrl) { cudaFree(ctx->d_ctrl); ctx->d_ctrl = nullptr; }
+    ctx->nsdesc = nsdesc;
+    uint8_t *p = nullptr;
+    CK(cudaMalloc(&p, ARENA_CTRL + 16 + (ctx->nsdesc + ctx->ndesc) * 8));
+    ctx->d_ctrl = reinterpret_cast<Ctrl *>(p);
+    ctx->d_pred_in = reinterpret_cast<int16_t *>(p + ARENA_CTRL);
+    ctx->d_sdesc = reinterpret_cast<uint64_t *>(p + ARENA_CTRL + 16);
+    ctx->d_desc = ctx->d_sdesc + ctx->nsdesc;
+    return B2J_OK;
+}
+
 static int enc_alloc(b2j_ctx *ctx) {
     if (ctx->enc_ready) return B2J_OK;
     const Geom &g = ctx->cap_g;
@@ -189,12 +204,9 @@ static int enc_alloc(b2j_ctx *ctx) {
     ctx->out_cap = (size_t)g.nblocks * 208 + 4096;
     CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
     ctx->ndesc = ctx->out_cap / STUFF_CHUNK + 4;
-    CK(cudaMalloc(&ctx->d_desc, ctx->ndesc * 8));
-    ctx->nsdesc = (size_t)scan_desc_count(g.ntiles) + 64;
-    CK(cudaMalloc(&ctx->d_sdesc, ctx->nsdesc * 8));
-    CK(cudaMalloc(&ctx->d_ctrl, sizeof(Ctrl)));
-    CK(cudaMalloc(&ctx->d_pred_in, 16));
-    CK(cudaMemset(ctx->d_pred_in, 0, 16));
+    // 1024 scan descriptors cover 4M tiles: no geometry within the configured size re-allocates (b2j_strip_state
+    // hands out pointers into this arena)
+    rc = alloc_zero_arena(ctx, std::max<size_t>((size_t)scan_desc_count(g.ntiles) + 64, 1024)); if (rc) return rc;
     CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
     CK(cudaMalloc(&ctx->d_quant, sizeof(QuantDev)));
     CK(cudaMemcpy(ctx->d_quant, &ctx->hq, sizeof(QuantDev), cudaMemcpyHostToDevice));
@@ -244,7 +256,7 @@ void b2j_destroy(b2j_ctx *ctx) {
     delete ctx->pool;
     ctx->ring.release();
     cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_pool); cudaFree(ctx->d_recs); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
-    cudaFree(ctx->d_tile_off); cudaFree(ctx->d_desc); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_pred_in);
+    cudaFree(ctx->d_tile_off); cudaFree(ctx->d_ctrl);   // d_pred_in, d_sdesc, d_desc live in d_ctrl's allocation
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
     if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -279,17 +291,14 @@ static int set_strip_geom(b2j_ctx *ctx, int width, int rows) {
     return ensure_debug(ctx);
 }
 
-static int enc_reset(b2j_ctx *ctx) {
-    CK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(Ctrl), ctx->stream));
+static int enc_reset(b2j_ctx *ctx) {   // also zeroes pred_in: strip hosts fill it AFTER phase1
+    if ((size_t)scan_desc_count(ctx->g.ntiles) > ctx->nsdesc) {   // strips with more (smaller) tiles than the configured image
+        CK(cudaStreamSynchronize(ctx->stream));
+        int rc = alloc_zero_arena(ctx, (size_t)scan_desc_count(ctx->g.ntiles) + 64); if (rc) return rc;
+    }
     // descriptors actually reachable for this image: bounded by its worst-case entropy bytes
     size_t nd = std::min(ctx->ndesc, ((size_t)ctx->g.nblocks * 208) / STUFF_CHUNK + 4);
-    CK(cudaMemsetAsync(ctx->d_desc, 0, nd * 8, ctx->stream));
-    if ((size_t)scan_desc_count(ctx->g.ntiles) > ctx->nsdesc) {   // strips with more (smaller) tiles than the configured image
-        cudaFree(ctx->d_sdesc); ctx->d_sdesc = nullptr;
-        ctx->nsdesc = (size_t)scan_desc_count(ctx->g.ntiles) + 64;
-        CK(cudaMalloc(&ctx->d_sdesc, ctx->nsdesc * 8));
-    }
-    CK(cudaMemsetAsync(ctx->d_sdesc, 0, (size_t)scan_desc_count(ctx->g.ntiles) * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctrl, 0, ARENA_CTRL + 16 + (ctx->nsdesc + nd) * 8, ctx->stream));
     return B2J_OK;
 }
 
@@ -410,7 +419,6 @@ int b2j_encode_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width
     CK(cudaSetDevice(ctx->device));
     int rc = enc_alloc(ctx); if (rc) return rc;
     rc = set_strip_geom(ctx, width, height); if (rc) return rc;
-    CK(cudaMemsetAsync(ctx->d_pred_in, 0, 16, ctx->stream));
     tick(ctx, 0);
     rc = enc_reset(ctx); if (rc) return rc;
     tick(ctx, 1);
@@ -554,7 +562,6 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
     const Geom &g = ctx->g;
     const size_t dstep = ((size_t)width * 3 + 15) & ~(size_t)15;  // 16-byte pitch keeps the TMA path for any width
     rc = ensure_img(ctx, dstep * height); if (rc) return rc;
-    CK(cudaMemsetAsync(ctx->d_pred_in, 0, 16, ctx->stream));
     tick(ctx, 0);
     rc = enc_reset(ctx); if (rc) return rc;
     // upload in MCU-row groups on the copy stream; the fdct of a group starts as soon as its rows have landed
