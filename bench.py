@@ -262,9 +262,9 @@ def run_b200(args, rank, world, local_rank):
         eng = P.Engine(W, H, QUALITY, bool(OPT), CSS, device=local_rank)
         eng.set_stream(stream.cuda_stream)
 
-        def step():
+        def step():   # asynchronous, like the strip step: the length word stays in HBM next to the bytes
             eng.encode_device(img.data_ptr(), W * 3, W, H)
-            return eng.encode_finish()
+            return 0
     else:
         enc = StripEncoder(W, H, QUALITY, bool(OPT), CSS, device=local_rank)
         eng = enc.b.eng
@@ -293,12 +293,12 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         ms_total = e0.elapsed_time(e1)
         launches = eng.launch_count() - launches0
+        nbytes = eng.encode_finish()   # device-side checks of the last encode + its length (N>1: this rank's strip)
         eng.enable_timing(True)
         ks = args.steps if world == 1 else max(1, min(args.steps, 5))
         for _ in range(ks):
             step()
-            if world > 1:
-                eng.encode_finish()
+            eng.encode_finish()
             for k, v in eng.timings().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v * args.steps / ks
         eng.enable_timing(False)

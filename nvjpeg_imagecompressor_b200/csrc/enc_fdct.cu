@@ -538,6 +538,8 @@ k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restri
                uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist,
                uint32_t *__restrict__ pool, int resolve, StripRecord *__restrict__ xr) {
     __shared__ uint32_t s_h[2][16];   // DC categories 0..11 of the two DC tables, aggregated per CTA
+    pdl_trigger();
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ntile = g.tiles_x * g.mcuy;
     if (threadIdx.x < 32) s_h[threadIdx.x >> 4][threadIdx.x & 15] = 0;
@@ -620,8 +622,7 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
                                 int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, cudaStream_t s) {
     const int n = max(64, g.tiles_x * g.mcuy * 3);
-    k_dc_edge_hist<<<(n + 255) / 256, 256, 0, s>>>(recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr);
-    return cudaGetLastError();
+    return launch_pdl(k_dc_edge_hist, dim3((n + 255) / 256), dim3(256), 0, s, recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr);
 }
 
 }  // namespace b2j

@@ -59,9 +59,11 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
     __shared__ uint32_t s_hdr_len;
     const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
+    pdl_trigger();   // k_pack's CTAs clear their buffers meanwhile
     if (threadIdx.x == 0) s_err = 0;
     for (int i = lane; i < 256; i += 32) { s_vals[t][i] = 0; s_enc[t][i] = 0; }
     __syncthreads();
+    pdl_wait();
 
     if (!optimize) {
         if (lane < 17) s_bits[t][lane] = c_std_bits[t][lane];
@@ -454,10 +456,11 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
        uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits, uint32_t sub_words) {
     __shared__ __align__(16) PackShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < 1024; i += PACK_THREADS) sh.enc[i] = huff->enc[i >> 8][i & 255];
     for (int i = tid; i < WIN_WORDS; i += PACK_THREADS) sh.buf[i] = 0;
     for (int i = tid; i < PACK_WARPS * (SUB_WORDS + 4); i += PACK_THREADS) sh.sub[0][i] = 0;
     if (tid < 2 * (PACK_WARPS + 1)) sh.bnd[0][tid] = 0;
+    pdl_wait();   // everything above ran under k_tables
+    for (int i = tid; i < 1024; i += PACK_THREADS) sh.enc[i] = huff->enc[i >> 8][i & 255];
     __syncthreads();
     const uint32_t zr_y = sh.enc[0x1F0], zr_c = sh.enc[0x3F0];   // ZRL (0xF0) codes of the two AC tables
     const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
@@ -553,6 +556,8 @@ k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__res
     __shared__ uint64_t s_carry;
     __shared__ int s_chunk;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_trigger();   // k_stuff (or k_strip_seam) sets up meanwhile
+    pdl_wait();
     if (tid == 0) s_chunk = (int)atomicAdd(ticket, 1u);
     __syncthreads();
     const int ch = s_chunk;
@@ -701,11 +706,6 @@ k_stuff(StuffArgs a) {
     __shared__ __align__(16) uint32_t s_out32[OUT_WORDS];
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_out32);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t T = a.tile_off[a.ntiles];
-    const int a_skip = a.seam[0], a_ext = a.seam[1] ^ 0xFF;   // the ext byte is stored inverted: zeroed control block = whole image
-    const uint64_t NB = T > (uint64_t)a_skip ? (T - a_skip + 7) >> 3 : 0;
-    const int nchunks = (int)max((uint64_t)1, (NB + STUFF_CHUNK - 1) / STUFF_CHUNK);
-    const uint32_t hdr = a.huff->hdr_len;
     const uint32_t sbase = smem_u32(s_out32);
 
     if (tid < 16) {   // PRMT selectors: bytes 0..3 of the word in order, a zero byte (selector 4) after every 0xFF
@@ -719,6 +719,12 @@ k_stuff(StuffArgs a) {
         s_lut[tid] = sel;
     }
     for (int i = tid; i < OUT_WORDS; i += STUFF_THREADS) s_out32[i] = 0;
+    pdl_wait();   // the set-up above ran under the tile scan
+    const uint64_t T = a.tile_off[a.ntiles];
+    const int a_skip = a.seam[0], a_ext = a.seam[1] ^ 0xFF;   // the ext byte is stored inverted: zeroed control block = whole image
+    const uint64_t NB = T > (uint64_t)a_skip ? (T - a_skip + 7) >> 3 : 0;
+    const int nchunks = (int)max((uint64_t)1, (NB + STUFF_CHUNK - 1) / STUFF_CHUNK);
+    const uint32_t hdr = a.huff->hdr_len;
 
     for (;;) {
         // chunk ids are taken when the work starts (a ticket held back would make its successors spin in the look-back)
@@ -903,21 +909,18 @@ k_stuff(StuffArgs a) {
 // ------------------------------------------------------------------------------------------------------
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
                           int hs, int vs, uint8_t *out, int emit_header, uint32_t *err_out, cudaStream_t s) {
-    k_tables<<<1, 128, 0, s>>>(hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header, err_out);
-    return cudaGetLastError();
+    return launch_pdl(k_tables, dim3(1), dim3(128), 0, s, hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header, err_out);
 }
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s) {
     const int grid = min(g.ntiles, 148 * PACK_CTAS);
-    k_pack<<<grid, PACK_THREADS, 0, s>>>(pool, recs, g.ntiles, huff, slots, tile_bits, small_buffers ? 24u : (uint32_t)SUB_WORDS);
-    return cudaGetLastError();
+    return launch_pdl(k_pack, dim3(grid), dim3(PACK_THREADS), 0, s, pool, recs, g.ntiles, huff, slots, tile_bits, small_buffers ? 24u : (uint32_t)SUB_WORDS);
 }
 int scan_desc_count(int ntiles) { return (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
                               uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *err, cudaStream_t s) {
     const int grid = max(1, (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    k_scan_tiles<<<grid, 1024, 0, s>>>(tile_bits, ntiles, tile_off, slots, strip_bits, desc, ticket, err);
-    return cudaGetLastError();
+    return launch_pdl(k_scan_tiles, dim3(grid), dim3(1024), 0, s, tile_bits, ntiles, tile_off, slots, strip_bits, desc, ticket, err);
 }
 __global__ void k_set_seam(int *seam, int skip, int ext) { seam[0] = skip; seam[1] = ext ^ 0xFF; }
 
@@ -946,6 +949,8 @@ __global__ void __launch_bounds__(1024)
 k_strip_merge(const StripRecord *__restrict__ rec, int rank, int world, uint32_t *__restrict__ hist,
               uint32_t *__restrict__ pool, const TileRec *__restrict__ recs) {
     const int tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     for (int i = tid; i < 4 * 257; i += 1024) {
         uint32_t s = 0;
         for (int k = 0; k < world; k++) s += rec[k].hist[i];
@@ -972,6 +977,8 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
     __shared__ unsigned long long s_red[2][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int t = tid >> 8, sym = tid & 255;
+    pdl_trigger();   // k_stuff sets up meanwhile
+    pdl_wait();
     const uint32_t len = huff->enc[t][sym] & 0xFFu;
     const uint32_t cost = len + ((t & 1) ? (uint32_t)(sym & 15) : (uint32_t)sym);
     unsigned long long before = 0, own = rec[rank].hist[t * 257 + sym];
@@ -1025,13 +1032,11 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
 
 cudaError_t launch_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *hist, uint32_t *pool,
                                const TileRec *recs, cudaStream_t s) {
-    k_strip_merge<<<1, 1024, 0, s>>>(rec, rank, world, hist, pool, recs);
-    return cudaGetLastError();
+    return launch_pdl(k_strip_merge, dim3(1), dim3(1024), 0, s, rec, rank, world, hist, pool, recs);
 }
 cudaError_t launch_strip_seam(const StripRecord *rec, int rank, int world, HuffDev *huff, int drop_header, int *seam,
                               const uint64_t *strip_bits, uint32_t *err, cudaStream_t s) {
-    k_strip_seam<<<1, 1024, 0, s>>>(rec, rank, world, huff, drop_header, seam, strip_bits, err);
-    return cudaGetLastError();
+    return launch_pdl(k_strip_seam, dim3(1), dim3(1024), 0, s, rec, rank, world, huff, drop_header, seam, strip_bits, err);
 }
 
 cudaError_t launch_set_seam(int *seam, int skip, int ext, cudaStream_t s) {
@@ -1043,8 +1048,7 @@ cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, 
     return cudaGetLastError();
 }
 cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s) {
-    k_stuff<<<grid, STUFF_THREADS, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(k_stuff, dim3(grid), dim3(STUFF_THREADS), 0, s, a);
 }
 
 }  // namespace b2j
