@@ -169,6 +169,16 @@ typedef struct b2j_strip_record {
     uint32_t ntok;
     uint32_t pad[3];
 } b2j_strip_record;
+/* Peer-memory variant (GPUs of one node with P2P access, one process per GPU): no collective at all. Set-up, once:
+ * every rank calls b2j_peer_export (allocates its arena, returns a 64-byte cudaIpcMemHandle_t), the host exchanges the
+ * handles, each rank maps the others' with b2j_peer_open and calls b2j_peer_connect(rank, world, arenas[world])
+ * (arenas[rank] is ignored), then a host barrier. From then on b2j_strip_phase1x also stores the record into every
+ * rank's arena over NVLink and raises a flag there, and b2j_strip_phase2x(ctx, NULL, ...) waits (bounded: error 9 after
+ * ~2 s, never a hang) for the world's flags of this image before merging. All ranks must encode the same number of
+ * images. Same-process callers (tests) pass raw arena pointers from b2j_peer_export to b2j_peer_connect. */
+B2J_API int b2j_peer_export(b2j_ctx *ctx, void *ipc_handle_64, void **d_arena);
+B2J_API int b2j_peer_open(b2j_ctx *ctx, const void *ipc_handle_64, void **d_ptr);
+B2J_API int b2j_peer_connect(b2j_ctx *ctx, int rank, int world, void *const *d_arenas);
 B2J_API int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows);
 B2J_API int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int world, int full_width,
                               int full_height, int flags);

@@ -92,6 +92,12 @@ struct b2j_ctx {
     size_t last_len, last_step;
     uint8_t *last_bgr;
     b2j_ctx *second;  // encoder for the difference image (secondary compression)
+    // peer-memory exchange of the strip records (multi-GPU encode without a collective)
+    XchgArena *d_arena;            // this rank's arena (peers store into it)
+    XchgArena **d_peers;           // device array [peer_world] of every rank's arena
+    void *peer_opened[XCHG_MAX_WORLD];   // mappings from b2j_peer_open (closed in b2j_destroy)
+    int n_opened, peer_rank, peer_world;
+    uint32_t xseq;                 // images exchanged so far (identical on every rank)
 };
 
 extern "C" { static int upload_linear(void *user, uint8_t *d_dst, const uint8_t *src, size_t n, cudaStream_t s); }
@@ -256,6 +262,8 @@ void b2j_destroy(b2j_ctx *ctx) {
     delete ctx->pool;
     ctx->ring.release();
     cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_pool); cudaFree(ctx->d_recs); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
+    for (int i = 0; i < ctx->n_opened; i++) cudaIpcCloseMemHandle(ctx->peer_opened[i]);
+    cudaFree(ctx->d_arena); cudaFree(ctx->d_peers);
     cudaFree(ctx->d_tile_off); cudaFree(ctx->d_ctrl);   // d_pred_in, d_sdesc, d_desc live in d_ctrl's allocation
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
     if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
@@ -382,19 +390,77 @@ int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width
     tick(ctx, 2);
     CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 1, ctx->d_pool, 1, &ctx->d_ctrl->rec, ctx->stream));
     ctx->launches += 2;
+    if (ctx->peer_world > 0) {   // connected: the record goes straight into every rank's arena
+        ctx->xseq++;
+        CK(launch_strip_push(&ctx->d_ctrl->rec, ctx->d_peers, ctx->peer_rank, ctx->peer_world, ctx->xseq, ctx->stream));
+        ctx->launches += 1;
+    }
     tick(ctx, 3);
     return B2J_OK;
 }
 
 int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int world, int full_w, int full_h, int flags) {
-    if (!ctx || !ctx->enc_ready || !d_records_all || rank < 0 || rank >= world || world > 256) return B2J_EINVAL;
+    if (!ctx || !ctx->enc_ready || rank < 0 || rank >= world || world > 256) return B2J_EINVAL;
     const StripRecord *rec = static_cast<const StripRecord *>(d_records_all);
-    CK(launch_strip_merge(rec, rank, world, ctx->d_ctrl->hist, ctx->d_pool, ctx->d_recs, ctx->stream));
+    const uint32_t *xflags = nullptr;
+    if (!rec) {   // peer exchange: the records of this image are (or will be) in this rank's arena
+        if (ctx->peer_world != world || ctx->peer_rank != rank || ctx->xseq == 0) return B2J_EINVAL;
+        const int set = (int)(ctx->xseq % XCHG_SETS);
+        rec = ctx->d_arena->rec[set];
+        xflags = ctx->d_arena->flags[set];
+    }
+    CK(launch_strip_merge(rec, rank, world, ctx->d_ctrl->hist, ctx->d_pool, ctx->d_recs, xflags, ctx->xseq, &ctx->d_ctrl->err, ctx->stream));
     ctx->launches += 1;
     int rc = b2j_strip_phase2(ctx, full_w, full_h); if (rc) return rc;
     CK(launch_strip_seam(rec, rank, world, ctx->d_huff, !(flags & 1), ctx->d_ctrl->seam, ctx->d_ctrl->strip_bits, &ctx->d_ctrl->err, ctx->stream));
     ctx->launches += 1;
     return phase3_launch(ctx, flags, true);
+}
+
+// ---- peer-memory exchange set-up (GPUs of one node, one process per GPU) ----------------------------------------
+int b2j_peer_export(b2j_ctx *ctx, void *ipc_handle_64, void **d_arena) {
+    if (!ctx) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_arena) {
+        CK(cudaMalloc(&ctx->d_arena, sizeof(XchgArena)));
+        CK(cudaMemset(ctx->d_arena, 0, sizeof(XchgArena)));
+    }
+    if (ipc_handle_64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->d_arena));
+        memcpy(ipc_handle_64, &h, 64);
+    }
+    if (d_arena) *d_arena = ctx->d_arena;
+    return B2J_OK;
+}
+
+int b2j_peer_open(b2j_ctx *ctx, const void *ipc_handle_64, void **d_ptr) {
+    if (!ctx || !ipc_handle_64 || !d_ptr || ctx->n_opened >= XCHG_MAX_WORLD) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_opened[ctx->n_opened++] = p;
+    *d_ptr = p;
+    return B2J_OK;
+}
+
+int b2j_peer_connect(b2j_ctx *ctx, int rank, int world, void *const *d_arenas) {
+    if (!ctx || !d_arenas || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world || !ctx->d_arena) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    XchgArena *host[XCHG_MAX_WORLD];
+    for (int r = 0; r < world; r++) {
+        host[r] = r == rank ? ctx->d_arena : static_cast<XchgArena *>(d_arenas[r]);
+        if (!host[r]) return B2J_EINVAL;
+    }
+    if (!ctx->d_peers) CK(cudaMalloc(&ctx->d_peers, sizeof(XchgArena *) * XCHG_MAX_WORLD));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->d_peers, host, sizeof(XchgArena *) * world, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_arena, 0, sizeof(XchgArena)));   // every rank connects before any rank encodes (host barrier)
+    ctx->peer_rank = rank; ctx->peer_world = world; ctx->xseq = 0;
+    return B2J_OK;
 }
 
 int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st) {

@@ -44,6 +44,16 @@ struct StripRecord {
 };
 static_assert(sizeof(StripRecord) == 4176, "b2j_strip_record layout");
 
+// Peer-memory exchange of the records (GPUs of one node): every rank owns one arena; peers store their record of
+// image `seq` straight into set (seq % SETS), slot [their rank], over NVLink and then raise flags[set][rank] = seq.
+constexpr int XCHG_SETS = 4;                   // images in flight before a slot is reused (2 would do: DESIGN.md 5)
+constexpr int XCHG_MAX_WORLD = 16;
+struct XchgArena {
+    uint32_t flags[XCHG_SETS][XCHG_MAX_WORLD];
+    uint32_t pad[64 - XCHG_SETS * XCHG_MAX_WORLD > 0 ? 64 - XCHG_SETS * XCHG_MAX_WORLD : 64];
+    StripRecord rec[XCHG_SETS][XCHG_MAX_WORLD];
+};
+
 constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)
 constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
 constexpr int STUFF_THREADS = 256;

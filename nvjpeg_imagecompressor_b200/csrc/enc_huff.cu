@@ -945,12 +945,45 @@ __device__ __forceinline__ uint32_t dc_token(int c, int diff) {
     return ((uint32_t)(c ? 2 : 0) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Peer exchange, sending side: CTA p stores this strip's record into rank p's arena (its own included) and raises
+// the flag there. The flag store follows a system-scope fence that follows every data store of the CTA.
+__global__ void __launch_bounds__(256)
+k_strip_push(const StripRecord *__restrict__ mine, XchgArena *const *__restrict__ peers, int rank, uint32_t seq) {
+    pdl_trigger();
+    pdl_wait();
+    XchgArena *dst = peers[blockIdx.x];
+    const int set = (int)(seq % XCHG_SETS);
+    const uint4 *src = reinterpret_cast<const uint4 *>(mine);
+    uint4 *d4 = reinterpret_cast<uint4 *>(&dst->rec[set][rank]);
+    for (int i = threadIdx.x; i < (int)(sizeof(StripRecord) / 16); i += 256) d4[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->flags[set][rank]), "r"(seq) : "memory");
+}
+
 __global__ void __launch_bounds__(1024)
-k_strip_merge(const StripRecord *__restrict__ rec, int rank, int world, uint32_t *__restrict__ hist,
-              uint32_t *__restrict__ pool, const TileRec *__restrict__ recs) {
+k_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *__restrict__ hist,
+              uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const uint32_t *flags, uint32_t seq,
+              uint32_t *__restrict__ err) {
     const int tid = threadIdx.x;
     pdl_trigger();
     pdl_wait();
+    if (flags) {   // peer exchange: the records of image `seq` arrive from the other GPUs (bounded wait, never a hang)
+        if (tid < world) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u32(flags + tid) != seq) {
+                if (clock64() - t0 > (4ll << 30)) { atomicMax(err, 9u); break; }   // ~2 s
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
     for (int i = tid; i < 4 * 257; i += 1024) {
         uint32_t s = 0;
         for (int k = 0; k < world; k++) s += rec[k].hist[i];
@@ -1031,8 +1064,11 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
 }
 
 cudaError_t launch_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *hist, uint32_t *pool,
-                               const TileRec *recs, cudaStream_t s) {
-    return launch_pdl(k_strip_merge, dim3(1), dim3(1024), 0, s, rec, rank, world, hist, pool, recs);
+                               const TileRec *recs, const uint32_t *flags, uint32_t seq, uint32_t *err, cudaStream_t s) {
+    return launch_pdl(k_strip_merge, dim3(1), dim3(1024), 0, s, rec, rank, world, hist, pool, recs, flags, seq, err);
+}
+cudaError_t launch_strip_push(const StripRecord *mine, XchgArena *const *peers, int rank, int world, uint32_t seq, cudaStream_t s) {
+    return launch_pdl(k_strip_push, dim3(world), dim3(256), 0, s, mine, peers, rank, seq);
 }
 cudaError_t launch_strip_seam(const StripRecord *rec, int rank, int world, HuffDev *huff, int drop_header, int *seam,
                               const uint64_t *strip_bits, uint32_t *err, cudaStream_t s) {

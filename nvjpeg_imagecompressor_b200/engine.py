@@ -168,7 +168,25 @@ class Engine:
         self._ck(self._L.b2j_strip_phase1x(self._h, C.c_void_p(d_ptr), step, W, rows))
 
     def strip_phase2x(self, d_records_all, rank, world, full_w, full_h, flags):
+        """d_records_all = None: peer-memory exchange (after peer_connect)."""
         self._ck(self._L.b2j_strip_phase2x(self._h, C.c_void_p(d_records_all), rank, world, full_w, full_h, flags))
+
+    # peer-memory exchange set-up
+    def peer_export(self):
+        """-> (64-byte IPC handle, raw device pointer of this context's arena)."""
+        h = C.create_string_buffer(64)
+        p = C.c_void_p(0)
+        self._ck(self._L.b2j_peer_export(self._h, h, C.byref(p)))
+        return h.raw, p.value
+
+    def peer_open(self, handle):
+        p = C.c_void_p(0)
+        self._ck(self._L.b2j_peer_open(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def peer_connect(self, rank, world, arenas):
+        arr = (C.c_void_p * world)(*[C.c_void_p(a or 0) for a in arenas])
+        self._ck(self._L.b2j_peer_connect(self._h, rank, world, arr))
 
     # introspection
     def debug_read(self, what, dtype, count_hint=None):

@@ -14,12 +14,16 @@ so the concatenation [headers | strip 0 | ... | strip N-1 | EOI] is the single-G
 On GPUs (EngineBackend) the three exchanges are folded into ONE all_gather of a 4 KB record per strip (its own symbol
 counts, first/last DCs, first tokens: include/b2jpeg.h b2j_strip_record): with every strip's counts and the final code
 lengths each rank computes every strip's bit count itself, so nothing waits for another rank's entropy coder
-(`phase1x` -> all_gather -> `phase2x`). The three-step schedule above is what the host-visible phases implement and
+(`phase1x` -> all_gather -> `phase2x`). When the GPUs can map each other's memory (CUDA IPC, one node) even that
+collective goes: `phase1x` stores the record into every rank's arena over NVLink and raises a flag, `phase2x` waits for
+the world's flags (B2J_STRIP_EXCHANGE=nccl keeps the all_gather). The three-step schedule above is what the host-visible phases implement and
 what the CPU tests drive.
 
 `backend` abstracts the device: EngineBackend drives libb2jpeg.so on a GPU; the CPU tests plug a checker-backed
 backend into the same host logic over gloo.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -106,7 +110,7 @@ class EngineBackend:
 
     def phase2x(self, records_all, rank, world, W, H, flags):
         """records_all: device uint8 [world][STRIP_RECORD_BYTES], the all-gathered `record`s in strip order."""
-        self.eng.strip_phase2x(records_all.data_ptr(), rank, world, W, H, flags)
+        self.eng.strip_phase2x(None if records_all is None else records_all.data_ptr(), rank, world, W, H, flags)
 
     def out_view(self, n):
         return _view(self._d_out, (int(n),), "|u1", self.device)
@@ -114,7 +118,7 @@ class EngineBackend:
 
 class StripEncoder:
     def __init__(self, W, H, quality=95, optimize=True, css="422", rank=None, world=None, backend=None, device=None,
-                 group=None):
+                 group=None, peer=None):
         self.W, self.H = W, H
         self.css = N.CSS[css] if isinstance(css, str) else int(css)
         self.optimize = bool(optimize)
@@ -132,8 +136,36 @@ class StripEncoder:
         self._bits_all = torch.zeros((self.world, 2), dtype=torch.int64, device=dev)
         self._len_all = torch.zeros((self.world, 1), dtype=torch.int64, device=dev)
         self.one_collective = hasattr(self.b, "phase2x") and self.world > 1
+        self.exchange = "three collectives"
         if self.one_collective:
             self._rec_all = torch.zeros((self.world, N.STRIP_RECORD_BYTES), dtype=torch.uint8, device=dev)
+            self.exchange = "one all_gather"
+            if peer is None:
+                peer = os.environ.get("B2J_STRIP_EXCHANGE", "peer") == "peer"
+            if peer and self._connect_peers():
+                self.exchange = "peer memory"
+
+    def _connect_peers(self):
+        """Map every rank's exchange arena (CUDA IPC) so that records travel as plain NVLink stores. All ranks decide
+        together: one rank that cannot map a peer sends everybody back to the all_gather schedule."""
+        b, w, r = self.b, self.world, self.rank
+        ok, arenas = 1, [None] * w
+        try:
+            handle, _ = b.eng.peer_export()
+            handles = [None] * w
+            dist.all_gather_object(handles, handle, group=self.group)
+            for k in range(w):
+                if k != r:
+                    arenas[k] = b.eng.peer_open(handles[k])
+        except Exception:
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=b.last_dc.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        if int(t.item()) == 0:
+            return False
+        b.eng.peer_connect(r, w, arenas)
+        dist.barrier(group=self.group)   # nobody pushes before every arena is mapped and zeroed
+        return True
 
     def encode_strip(self, d_ptr, step):
         """d_ptr: this rank's strip (rows [y0, y1) of the image). Returns (stuffed byte count, all ranks' counts)."""
@@ -141,6 +173,9 @@ class StripEncoder:
         flags = (1 if r == 0 else 0) | (2 if r == w - 1 else 0)
         if self.one_collective:
             b.phase1x(d_ptr, step, self.W, self.y1 - self.y0)
+            if self.exchange == "peer memory":   # phase1x already stored the record into every rank's arena
+                b.phase2x(None, r, w, self.W, self.H, flags)
+                return b.out_len
             dist.all_gather_into_tensor(self._rec_all.view(-1), b.record, group=self.group)
             b.phase2x(self._rec_all, r, w, self.W, self.H, flags)
             return b.out_len

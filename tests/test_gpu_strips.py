@@ -51,6 +51,32 @@ def encode_strips_one_gpu(img, css, q, opt, nstrips, dev_seam=False):
     return np.concatenate(parts)
 
 
+def encode_strips_peer(img, css, q, opt, nstrips, images=3):
+    """Peer-memory exchange with every 'rank' a context on this one GPU (arenas connected by raw pointers): all
+    pushes are issued before any merge waits, so nothing here spins. Several images in a row exercise the sequence
+    numbers and the arena sets."""
+    from nvjpeg_imagecompressor_b200.strips import EngineBackend, strip_rows
+    H, W = img.shape[:2]
+    d = torch.from_numpy(img).cuda()
+    rows = strip_rows(H, css, nstrips)
+    bs = [EngineBackend(W, max(b - a for a, b in rows), q, bool(opt), css, 0) for _ in rows]
+    arenas = [b.eng.peer_export()[1] for b in bs]
+    for k, b in enumerate(bs):
+        b.eng.peer_connect(k, nstrips, arenas)
+    outs = []
+    for it in range(images):
+        for b, (y0, y1) in zip(bs, rows):
+            b.phase1x(d[y0:y1].data_ptr(), W * 3, W, y1 - y0)
+        torch.cuda.synchronize()
+        for k, b in enumerate(bs):
+            b.phase2x(None, k, nstrips, W, H, (1 if k == 0 else 0) | (2 if k == nstrips - 1 else 0))
+        torch.cuda.synchronize()
+        outs.append(np.concatenate([b.out_view(b.eng.encode_finish()).cpu().numpy() for b in bs]))
+    for b in bs:
+        b.eng.close()
+    return outs
+
+
 def encode_strips_one_collective(img, css, q, opt, nstrips):
     """phase1x -> (all_gather of the records) -> phase2x: the schedule StripEncoder runs over NCCL."""
     from nvjpeg_imagecompressor_b200.strips import EngineBackend, strip_rows
@@ -84,6 +110,27 @@ def test_strips_equal_single_stream(oracle, W, H, css, q, opt, n):
         assert out.size == want.size and np.array_equal(out, want), f"dev_seam={dev_seam}"
     out = encode_strips_one_collective(img, css, q, opt, n)
     assert out.size == want.size and np.array_equal(out, want), "one-collective schedule"
+    for i, out in enumerate(encode_strips_peer(img, css, q, opt, n, images=6)):
+        assert out.size == want.size and np.array_equal(out, want), f"peer-memory exchange, image {i}"
+
+
+def test_peer_exchange_times_out_instead_of_hanging():
+    """A rank whose peers never push gets error 9 from the bounded wait (about 2 s), not a hung GPU."""
+    import time
+    import nvjpeg_imagecompressor_b200 as P
+    from nvjpeg_imagecompressor_b200.strips import EngineBackend
+    img = torch.zeros((64, 64, 3), dtype=torch.uint8, device="cuda")
+    b0, b1 = (EngineBackend(64, 32, 90, True, 1, 0) for _ in range(2))
+    arenas = [b.eng.peer_export()[1] for b in (b0, b1)]
+    b0.eng.peer_connect(0, 2, arenas)
+    b1.eng.peer_connect(1, 2, arenas)
+    b0.phase1x(img.data_ptr(), 64 * 3, 64, 32)      # rank 1 never encodes
+    t0 = time.time()
+    b0.phase2x(None, 0, 2, 64, 64, 1)
+    with pytest.raises(P.B2JError):
+        b0.eng.encode_finish()
+    assert time.time() - t0 < 20
+    b0.eng.close(); b1.eng.close()
 
 
 def test_strips_headline_slab(oracle, golden):
