@@ -3,7 +3,7 @@
 per GPU; images are independent, no collective on the data path). Every rank encodes and decodes its share with a few
 engines on separate streams so that launch latency of one image hides behind the kernels of another.
 
-    python scripts/batch_1080p.py [--images 512] [--engines 4]            # one GPU
+    python scripts/batch_1080p.py [--images 512] [--engines 8]            # one GPU
     torchrun --nproc-per-node 8 scripts/batch_1080p.py --images 4096      # 512 per GPU
 """
 import argparse, json, os, sys, time
@@ -13,7 +13,7 @@ import nvjpeg_imagecompressor_b200 as P
 from nvjpeg_imagecompressor_b200.synth import synth_rows
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--images", type=int, default=512); ap.add_argument("--engines", type=int, default=4)
+ap.add_argument("--images", type=int, default=512); ap.add_argument("--engines", type=int, default=8)
 ap.add_argument("--css", default="420"); ap.add_argument("--quality", type=int, default=95); ap.add_argument("--optimize", type=int, default=1)
 a = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -58,7 +58,9 @@ dt = time.perf_counter() - t0
 jpgs = []
 for k in range(nuniq):
     j = engs[0].encode(imgs[k].cpu().numpy())
-    jpgs.append(np.array(j, copy=True))
+    keep = torch.empty(len(j), dtype=torch.uint8, pin_memory=True)   # pinned JPEG bytes: the upload is a plain DMA
+    keep.numpy()[:] = j
+    jpgs.append(keep.numpy())
 outs = [torch.empty((H, W, 3), dtype=torch.uint8, device=dev) for _ in engs]
 for k, e in enumerate(engs):
     e.decode_device(jpgs[k % nuniq], outs[k].data_ptr(), W * 3)
