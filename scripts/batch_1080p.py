@@ -14,6 +14,7 @@ from nvjpeg_imagecompressor_b200.synth import synth_rows
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--images", type=int, default=512); ap.add_argument("--engines", type=int, default=8)
+ap.add_argument("--threads", type=int, default=0, help="host threads per GPU, one engine each (0: one thread drives all engines)")
 ap.add_argument("--css", default="420"); ap.add_argument("--quality", type=int, default=95); ap.add_argument("--optimize", type=int, default=1)
 a = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -27,6 +28,8 @@ W, H = 1920, 1080
 mine = list(range(rank, a.images, world))            # image ids = synth seeds
 nuniq = min(len(mine), 16)                           # distinct images kept resident; the batch cycles through them
 imgs = [synth_rows(W, H, 0, H, seed, 8, dev) for seed in mine[:nuniq]]
+if a.threads:
+    a.engines = a.threads
 engs = [P.Engine(W, H, a.quality, bool(a.optimize), a.css, device=lr) for _ in range(a.engines)]
 streams = [torch.cuda.Stream(device=dev) for _ in engs]
 for e, s in zip(engs, streams):
@@ -34,7 +37,33 @@ for e, s in zip(engs, streams):
 torch.cuda.synchronize()
 
 
+def per_thread(fn):
+    """One host thread per engine (ctypes releases the GIL inside the library): fn(engine index, image indices)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(engs)) as ex:
+        return sum(ex.map(lambda k: fn(k, range(k, len(mine), len(engs))), range(len(engs))))
+
+
+def enc_worker(k, idx):
+    torch.cuda.set_device(lr)
+    n = 0
+    for i in idx:
+        engs[k].encode_device(imgs[i % nuniq].data_ptr(), W * 3, W, H)
+        n += engs[k].encode_finish()
+    return n
+
+
+def dec_worker(k, idx):
+    torch.cuda.set_device(lr)
+    for i in idx:
+        engs[k].decode_device(jpgs[i % nuniq], outs[k].data_ptr(), W * 3)
+        engs[k].decode_finish()
+    return 0
+
+
 def run_encode():
+    if a.threads:
+        return per_thread(enc_worker)
     n = 0
     for i in range(len(mine)):
         e = engs[i % len(engs)]
@@ -67,20 +96,23 @@ for k, e in enumerate(engs):
 for e in engs:
     e.decode_finish()
 t0 = time.perf_counter()
-for i in range(len(mine)):
-    e = engs[i % len(engs)]
-    if i >= len(engs):
-        e.decode_finish()                              # the engine's previous image: validated, pixels usable
-    e.decode_device(jpgs[i % nuniq], outs[i % len(engs)].data_ptr(), W * 3)
-for e in engs:
-    e.decode_finish()
+if a.threads:
+    per_thread(dec_worker)
+else:
+    for i in range(len(mine)):
+        e = engs[i % len(engs)]
+        if i >= len(engs):
+            e.decode_finish()                              # the engine's previous image: validated, pixels usable
+        e.decode_device(jpgs[i % nuniq], outs[i % len(engs)].data_ptr(), W * 3)
+    for e in engs:
+        e.decode_finish()
 dtd = time.perf_counter() - t0
 res = torch.tensor([dt, dtd], dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
 if rank == 0:
     mp = a.images * W * H / 1e6
-    print(json.dumps({"case": "batch 1920x1080", "images": a.images, "n_gpus": world, "engines_per_gpu": a.engines, "css": a.css,
+    print(json.dumps({"case": "batch 1920x1080", "images": a.images, "n_gpus": world, "engines_per_gpu": a.engines, "host_threads_per_gpu": a.threads or 1, "css": a.css,
                       "quality": a.quality, "optimize": a.optimize, "encode_mpix_s": round(mp / float(res[0]), 1),
                       "encode_images_s": round(a.images / float(res[0]), 1), "decode_mpix_s": round(mp / float(res[1]), 1),
                       "decode_images_s": round(a.images / float(res[1]), 1), "jpeg_bytes_per_image": int(nbytes / len(mine))}))
