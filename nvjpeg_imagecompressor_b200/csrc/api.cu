@@ -3,6 +3,7 @@
 // env setup/teardown, :269-294 CompressWorker, :311-385 DecodeWorker) with nvJPEG replaced by this library's kernels.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -538,7 +539,9 @@ static int ensure_img(b2j_ctx *ctx, size_t bytes) {
 static int ensure_hostpipe(b2j_ctx *ctx, size_t ring_bytes) {
     if (!ctx->pool) {
         unsigned hc = std::thread::hardware_concurrency();
-        ctx->pool = new (std::nothrow) CopyPool((int)std::max(1u, std::min(8u, hc ? hc : 1u)));
+        unsigned want = std::min(12u, std::max(1u, (hc ? hc : 1u) * 3u / 4u));   // 12 of 16 cores measured best on the B200 host
+        if (const char *e = getenv("B2J_COPY_THREADS")) want = (unsigned)std::max(1, std::min(64, atoi(e)));
+        ctx->pool = new (std::nothrow) CopyPool((int)std::max(1u, want));
         if (!ctx->pool) return B2J_ENOMEM;
     }
     CK(ctx->ring.ensure(ring_bytes));

@@ -5,7 +5,38 @@
 
 #include <algorithm>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define B2J_HAVE_NT 1
+#endif
+
 namespace b2j {
+
+// Streaming copy: the destination is written with non-temporal stores (whole 64-byte lines), so the copy costs one read
+// and one write of memory instead of read + read-for-ownership + write, and the staging ring / the caller's image do
+// not evict each other from the caches. Rows of an image are far below the size at which memcpy() switches by itself.
+static inline void copy_stream(uint8_t *dst, const uint8_t *src, size_t n) {
+#ifdef B2J_HAVE_NT
+    if (n >= 256) {
+        const size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+        if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+        const size_t lines = n / 64;
+        for (size_t i = 0; i < lines; i++) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 0);
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 1);
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 2);
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 3);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 0, a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 1, b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 2, c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 3, d);
+            src += 64; dst += 64;
+        }
+        n -= lines * 64;
+    }
+#endif
+    if (n) memcpy(dst, src, n);
+}
 
 CopyPool::CopyPool(int nthreads) {
     const int n = std::max(0, nthreads - 1);
@@ -28,11 +59,14 @@ void CopyPool::run_slices(const Job &j, std::atomic<size_t> &next) {
         if (r0 >= j.rows) break;
         const size_t r1 = std::min(j.rows, r0 + j.rows_per);
         if (j.dstep == j.row_bytes && j.sstep == j.row_bytes) {
-            memcpy(j.dst + r0 * j.dstep, j.src + r0 * j.sstep, (r1 - r0) * j.row_bytes);
+            copy_stream(j.dst + r0 * j.dstep, j.src + r0 * j.sstep, (r1 - r0) * j.row_bytes);
         } else {
-            for (size_t r = r0; r < r1; r++) memcpy(j.dst + r * j.dstep, j.src + r * j.sstep, j.row_bytes);
+            for (size_t r = r0; r < r1; r++) copy_stream(j.dst + r * j.dstep, j.src + r * j.sstep, j.row_bytes);
         }
     }
+#ifdef B2J_HAVE_NT
+    _mm_sfence();   // the streamed lines are globally visible before the DMA engine (or the caller) reads them
+#endif
 }
 
 void CopyPool::worker() {
