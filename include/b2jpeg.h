@@ -174,7 +174,7 @@ typedef struct b2j_strip_record {
  * handles, each rank maps the others' with b2j_peer_open and calls b2j_peer_connect(rank, world, arenas[world])
  * (arenas[rank] is ignored), then a host barrier. From then on b2j_strip_phase1x also stores the record into every
  * rank's arena over NVLink and raises a flag there, and b2j_strip_phase2x(ctx, NULL, ...) waits (bounded: error 9 after
- * ~2 s, never a hang) for the world's flags of this image before merging. All ranks must encode the same number of
+ * B2J_PEER_TIMEOUT_MS, default 10 s, never a hang) for the world's flags of this image before merging. All ranks must encode the same number of
  * images. Same-process callers (tests) pass raw arena pointers from b2j_peer_export to b2j_peer_connect. */
 B2J_API int b2j_peer_export(b2j_ctx *ctx, void *ipc_handle_64, void **d_arena);
 B2J_API int b2j_peer_open(b2j_ctx *ctx, const void *ipc_handle_64, void **d_ptr);

@@ -99,6 +99,7 @@ struct b2j_ctx {
     void *peer_opened[XCHG_MAX_WORLD];   // mappings from b2j_peer_open (closed in b2j_destroy)
     int n_opened, peer_rank, peer_world;
     uint32_t xseq;                 // images exchanged so far (identical on every rank)
+    unsigned long long peer_timeout_ns;   // bound of the wait for the peers' records (B2J_PEER_TIMEOUT_MS, default 10 s)
 };
 
 extern "C" { static int upload_linear(void *user, uint8_t *d_dst, const uint8_t *src, size_t n, cudaStream_t s); }
@@ -410,7 +411,7 @@ int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int wor
         rec = ctx->d_arena->rec[set];
         xflags = ctx->d_arena->flags[set];
     }
-    CK(launch_strip_merge(rec, rank, world, ctx->d_ctrl->hist, ctx->d_pool, ctx->d_recs, xflags, ctx->xseq, &ctx->d_ctrl->err, ctx->stream));
+    CK(launch_strip_merge(rec, rank, world, ctx->d_ctrl->hist, ctx->d_pool, ctx->d_recs, xflags, ctx->xseq, ctx->peer_timeout_ns, &ctx->d_ctrl->err, ctx->stream));
     ctx->launches += 1;
     int rc = b2j_strip_phase2(ctx, full_w, full_h); if (rc) return rc;
     CK(launch_strip_seam(rec, rank, world, ctx->d_huff, !(flags & 1), ctx->d_ctrl->seam, ctx->d_ctrl->strip_bits, &ctx->d_ctrl->err, ctx->stream));
@@ -461,6 +462,8 @@ int b2j_peer_connect(b2j_ctx *ctx, int rank, int world, void *const *d_arenas) {
     CK(cudaMemcpy(ctx->d_peers, host, sizeof(XchgArena *) * world, cudaMemcpyHostToDevice));
     CK(cudaMemset(ctx->d_arena, 0, sizeof(XchgArena)));   // every rank connects before any rank encodes (host barrier)
     ctx->peer_rank = rank; ctx->peer_world = world; ctx->xseq = 0;
+    const char *e = getenv("B2J_PEER_TIMEOUT_MS");
+    ctx->peer_timeout_ns = 1000000ull * (unsigned long long)std::max(1, e ? atoi(e) : 10000);
     return B2J_OK;
 }
 

@@ -970,15 +970,17 @@ k_strip_push(const StripRecord *__restrict__ mine, XchgArena *const *__restrict_
 __global__ void __launch_bounds__(1024)
 k_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *__restrict__ hist,
               uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, const uint32_t *flags, uint32_t seq,
-              uint32_t *__restrict__ err) {
+              unsigned long long timeout_ns, uint32_t *__restrict__ err) {
     const int tid = threadIdx.x;
     pdl_trigger();
     pdl_wait();
     if (flags) {   // peer exchange: the records of image `seq` arrive from the other GPUs (bounded wait, never a hang)
         if (tid < world) {
-            const long long t0 = clock64();
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
             while (ld_acquire_sys_u32(flags + tid) != seq) {
-                if (clock64() - t0 > (4ll << 30)) { atomicMax(err, 9u); break; }   // ~2 s
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > timeout_ns) { atomicMax(err, 9u); break; }
                 __nanosleep(100);
             }
         }
@@ -1064,8 +1066,9 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
 }
 
 cudaError_t launch_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *hist, uint32_t *pool,
-                               const TileRec *recs, const uint32_t *flags, uint32_t seq, uint32_t *err, cudaStream_t s) {
-    return launch_pdl(k_strip_merge, dim3(1), dim3(1024), 0, s, rec, rank, world, hist, pool, recs, flags, seq, err);
+                               const TileRec *recs, const uint32_t *flags, uint32_t seq, unsigned long long timeout_ns,
+                               uint32_t *err, cudaStream_t s) {
+    return launch_pdl(k_strip_merge, dim3(1), dim3(1024), 0, s, rec, rank, world, hist, pool, recs, flags, seq, timeout_ns, err);
 }
 cudaError_t launch_strip_push(const StripRecord *mine, XchgArena *const *peers, int rank, int world, uint32_t seq, cudaStream_t s) {
     return launch_pdl(k_strip_push, dim3(world), dim3(256), 0, s, mine, peers, rank, seq);

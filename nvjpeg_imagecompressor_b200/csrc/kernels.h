@@ -46,7 +46,8 @@ cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, 
 // one-collective strip exchange: rec = the all-gathered records [world]
 // flags != NULL: wait (bounded) until flags[0..world) == seq before reading rec (peer-memory exchange)
 cudaError_t launch_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *hist, uint32_t *pool,
-                               const TileRec *recs, const uint32_t *flags, uint32_t seq, uint32_t *err, cudaStream_t s);
+                               const TileRec *recs, const uint32_t *flags, uint32_t seq, unsigned long long timeout_ns,
+                               uint32_t *err, cudaStream_t s);
 // store this strip's record into every rank's arena (peers[world], device array) and raise the flags
 cudaError_t launch_strip_push(const StripRecord *mine, XchgArena *const *peers, int rank, int world, uint32_t seq, cudaStream_t s);
 cudaError_t launch_strip_seam(const StripRecord *rec, int rank, int world, HuffDev *huff, int drop_header, int *seam,
