@@ -232,3 +232,66 @@ class StripEncoder:
             return total
         dist.send(mine.contiguous(), dst=dst, group=self.group)
         return None
+
+
+class StripSecondary:
+    """Secondary compression of ONE image on N GPUs (BASELINE.json config 4): encode -> reconstruct -> difference map ->
+    encode(difference) + PSNR, every step on the rank's own MCU-row strip; both JPEG streams are stitched single-image
+    streams (two StripEncoders), the PSNR comes from an all_reduce of the strips' exact integer SSDs.
+
+    Reconstruction needs no exchange when the sampling has no vertical subsampling (444 / 422 / 411): quantisation,
+    IDCT and the horizontal triangle upsampling never look across an MCU row, so the strip encoded and decoded as an
+    image of its own gives exactly the rows the whole image's decode would give (tests/test_gpu_strips.py). 420 / 440
+    upsample vertically across strip borders and are refused for world > 1.
+    """
+
+    def __init__(self, W, H, quality=95, optimize=True, css="422", diff_mode=1, rank=None, world=None, device=None,
+                 group=None):
+        from .engine import Engine
+        self.W, self.H, self.mode, self.group = W, H, int(diff_mode), group
+        css_id = N.CSS[css] if isinstance(css, str) else int(css)
+        self.enc1 = StripEncoder(W, H, quality, optimize, css_id, rank, world, None, device, group)
+        self.enc2 = StripEncoder(W, H, quality, optimize, css_id, rank, world, None, device, group)
+        self.rank, self.world = self.enc1.rank, self.enc1.world
+        if self.world > 1 and _VS[css_id] != 1:
+            raise ValueError("secondary compression over strips needs a sampling without vertical subsampling")
+        self.y0, self.y1 = self.enc1.y0, self.enc1.y1
+        rows_max = max(b - a for a, b in self.enc1.rows)
+        dev = self.enc1.b.device
+        self.solo = Engine(W, rows_max, quality, optimize, css_id, device=dev.index)
+        self.recon = torch.empty((rows_max, W, 3), dtype=torch.uint8, device=dev)
+        self.diff = torch.empty((rows_max, W, 3), dtype=torch.uint8, device=dev)
+        self._host = torch.empty(rows_max * W * 3 // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)
+        self._ssd = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._solo_out = self.solo.strip_state().d_out
+        # one stream for the three encoder states, the decoder and torch's copies / collectives
+        self.stream = torch.cuda.Stream(device=dev)
+        for e in (self.enc1.b.eng, self.enc2.b.eng, self.solo):
+            e.set_stream(self.stream.cuda_stream)
+
+    def run(self, d_ptr, step):
+        """d_ptr: this rank's strip (rows [y0, y1)), pitch W*3. -> (primary strip bytes, secondary strip bytes, PSNR);
+        the byte counts are device tensors, the strips' bytes are in enc1.b / enc2.b (gather_jpeg stitches them)."""
+        assert step == self.W * 3, "the difference map runs over contiguous rows"
+        self.stream.wait_stream(torch.cuda.current_stream(self.recon.device))
+        with torch.cuda.stream(self.stream):
+            return self._run(d_ptr, step)
+
+    def _run(self, d_ptr, step):
+        rows, W = self.y1 - self.y0, self.W
+        n1 = self.enc1.encode_strip(d_ptr, step)
+        # the strip as an image of its own -> its pixels as every decoder will reconstruct them
+        self.solo.encode_device(d_ptr, step, W, rows)
+        n = self.solo.encode_finish()
+        self._host[:n].copy_(_view(self._solo_out, (n,), "|u1", self.recon.device), non_blocking=True)
+        self.stream.synchronize()
+        self.solo.decode_device(self._host[:n].numpy(), self.recon.data_ptr(), W * 3)
+        self.solo.decode_finish()
+        ssd_ptr = self.solo.diff_psnr_device(d_ptr, self.recon.data_ptr(), rows * W * 3, self.mode, self.diff.data_ptr())
+        self._ssd.copy_(_view(ssd_ptr, (1,), "<i8", self.recon.device))
+        if self.world > 1:
+            dist.all_reduce(self._ssd, op=dist.ReduceOp.SUM, group=self.group)
+        n2 = self.enc2.encode_strip(self.diff.data_ptr(), W * 3)
+        ssd = int(self._ssd.item())
+        psnr = 20.0 * np.log10(255.0 / (np.sqrt(ssd / (self.W * self.H * 3)) + 2.220446049250313e-16))   # cv::PSNR
+        return n1, n2, float(psnr)

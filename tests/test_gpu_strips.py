@@ -154,3 +154,37 @@ def test_one_collective_flat_and_tiny_strips(oracle):
             want = oracle.encode(img, css, 90, opt)
             out = encode_strips_one_collective(img, css, 90, opt, n)
             assert out.size == want.size and np.array_equal(out, want), (img.shape, css, opt)
+
+
+@pytest.mark.parametrize("css", ["444", "422", "411"])
+def test_strip_decodes_alone_to_the_images_rows(oracle, css):
+    """No vertical subsampling: a strip encoded and decoded as an image of its own = its rows of the whole decode."""
+    import nvjpeg_imagecompressor_b200 as P
+    img = oracle.synth(200, 160, 5, 8)
+    full = P.Engine(200, 160, 90, True, css)
+    whole = full.decode(full.encode(img))
+    for y0, y1 in ((0, 40), (40, 104), (104, 160)):
+        e = P.Engine(200, y1 - y0, 90, True, css)
+        part = e.decode(e.encode(np.ascontiguousarray(img[y0:y1])))
+        assert np.array_equal(part, whole[y0:y1]), (css, y0, y1)
+        e.close()
+    full.close()
+
+
+def test_strip_secondary_world1_equals_b2j_secondary(oracle):
+    import nvjpeg_imagecompressor_b200 as P
+    from nvjpeg_imagecompressor_b200.strips import StripSecondary
+    W, H = 256, 192
+    img = oracle.synth(W, H, 9, 8)
+    eng = P.Engine(W, H, 95, True, "422")
+    j1, j2, recon, psnr = eng.secondary(img, diff_mode=1)
+    sec = StripSecondary(W, H, 95, True, "422", diff_mode=1, rank=0, world=1, device=0)
+    d = torch.from_numpy(img).cuda()
+    n1, n2, ps = sec.run(d.data_ptr(), W * 3)
+    torch.cuda.synchronize()
+    a = sec.enc1.gather_jpeg(0).cpu().numpy()
+    b = sec.enc2.gather_jpeg(0).cpu().numpy()
+    assert np.array_equal(a, j1) and np.array_equal(b, j2)
+    assert abs(ps - psnr) < 1e-9
+    assert np.array_equal(sec.recon[:H].cpu().numpy(), recon)
+    eng.close()
