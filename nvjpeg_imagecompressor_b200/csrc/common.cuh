@@ -49,8 +49,7 @@ static_assert(sizeof(StripRecord) == 4176, "b2j_strip_record layout");
 constexpr int XCHG_SETS = 4;                   // images in flight before a slot is reused (2 would do: DESIGN.md 5)
 constexpr int XCHG_MAX_WORLD = 16;
 struct XchgArena {
-    uint32_t flags[XCHG_SETS][XCHG_MAX_WORLD];
-    uint32_t pad[64 - XCHG_SETS * XCHG_MAX_WORLD > 0 ? 64 - XCHG_SETS * XCHG_MAX_WORLD : 64];
+    uint32_t flags[XCHG_SETS][XCHG_MAX_WORLD];   // [set][sender] = sequence number of the image whose record is in place
     StripRecord rec[XCHG_SETS][XCHG_MAX_WORLD];
 };
 
