@@ -68,6 +68,7 @@ struct b2j_ctx {
     int debug;
     uint32_t *d_slots, *d_tile_bits;
     uint64_t *d_tile_off, *d_desc, *d_sdesc;   // look-back descriptors: byte stuffing, tile scan
+    uint32_t *d_chunk_tile;                    // [ndesc] tile holding the first bit of every k_stuff chunk (written by the scan)
     size_t ndesc, nsdesc;
     Ctrl *d_ctrl;
     int16_t *d_pred_in;
@@ -215,6 +216,7 @@ static int enc_alloc(b2j_ctx *ctx) {
     // 1024 scan descriptors cover 4M tiles: no geometry within the configured size re-allocates (b2j_strip_state
     // hands out pointers into this arena)
     rc = alloc_zero_arena(ctx, std::max<size_t>((size_t)scan_desc_count(g.ntiles) + 64, 1024)); if (rc) return rc;
+    CK(cudaMalloc(&ctx->d_chunk_tile, ctx->ndesc * 4));
     CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
     CK(cudaMalloc(&ctx->d_quant, sizeof(QuantDev)));
     CK(cudaMemcpy(ctx->d_quant, &ctx->hq, sizeof(QuantDev), cudaMemcpyHostToDevice));
@@ -266,6 +268,7 @@ void b2j_destroy(b2j_ctx *ctx) {
     cudaFree(ctx->d_img); cudaFree(ctx->d_coef); cudaFree(ctx->d_pool); cudaFree(ctx->d_recs); cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits);
     for (int i = 0; i < ctx->n_opened; i++) cudaIpcCloseMemHandle(ctx->peer_opened[i]);
     cudaFree(ctx->d_arena); cudaFree(ctx->d_peers);
+    cudaFree(ctx->d_chunk_tile);
     cudaFree(ctx->d_tile_off); cudaFree(ctx->d_ctrl);   // d_pred_in, d_sdesc, d_desc live in d_ctrl's allocation
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
     if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
@@ -343,7 +346,7 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_slots, ctx->d_tile_bits, ctx->debug & 2, ctx->stream));
     tick(ctx, 5);
     CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->d_sdesc,
-                         &ctx->d_ctrl->scan_ticket, &ctx->d_ctrl->err, ctx->stream));
+                         &ctx->d_ctrl->scan_ticket, ctx->d_chunk_tile, (uint32_t)ctx->ndesc, &ctx->d_ctrl->err, ctx->stream));
     ctx->launches += 3;
     tick(ctx, 6);
     return B2J_OK;
@@ -355,6 +358,7 @@ static int phase3_launch(b2j_ctx *ctx, int flags, bool hdr_done = false) {
     if (!(flags & 1) && !hdr_done) { k_set_hdr_len<<<1, 1, 0, ctx->stream>>>(ctx->d_huff, 0); ctx->launches++; }
     StuffArgs a;
     a.slots = ctx->d_slots; a.tile_bits = ctx->d_tile_bits; a.tile_off = ctx->d_tile_off; a.ntiles = ctx->g.ntiles;
+    a.chunk_tile = ctx->d_chunk_tile;
     a.seam = ctx->d_ctrl->seam; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
     a.out = ctx->d_out; a.cap = ctx->out_cap; a.desc = ctx->d_desc; a.ticket = &ctx->d_ctrl->ticket;
     a.out_len = &ctx->d_ctrl->out_len; a.err = &ctx->d_ctrl->err;

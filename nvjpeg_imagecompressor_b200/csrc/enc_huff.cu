@@ -551,7 +551,7 @@ constexpr int SCAN_CHUNK = 4096;
 __global__ void __launch_bounds__(1024)
 k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__restrict__ tile_off,
              const uint32_t *__restrict__ slots, uint64_t *__restrict__ strip_bits, uint64_t *__restrict__ desc,
-             uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
+             uint32_t *__restrict__ ticket, uint32_t *__restrict__ chunk_tile, uint32_t nchunk_cap, uint32_t *__restrict__ err) {
     __shared__ uint32_t s_w[32];
     __shared__ uint64_t s_carry;
     __shared__ int s_chunk;
@@ -594,9 +594,14 @@ k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__res
     __syncthreads();
     const uint64_t carry = s_carry;
     uint64_t run = carry + wbase + (inc - mine);
+    constexpr uint64_t CHB = (uint64_t)STUFF_CHUNK * 8;   // bits per k_stuff chunk
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (i0 + k < ntiles) tile_off[i0 + k] = run;
+        if (i0 + k < ntiles) {
+            tile_off[i0 + k] = run;
+            // the k_stuff chunks whose first bit (at seam skip 0; k_stuff steps over a tile end within 7 bits) is in this tile
+            for (uint64_t c = (run + CHB - 1) / CHB; c * CHB < run + v[k] && c < nchunk_cap; c++) chunk_tile[c] = (uint32_t)(i0 + k);
+        }
         run += v[k];
     }
     if (ch == (int)gridDim.x - 1 && tid == 0) {
@@ -699,7 +704,7 @@ k_stuff(StuffArgs a) {
     constexpr int OUT_WORDS = (2 * STUFF_CHUNK + 64) / 4;
     __shared__ uint64_t s_toff[STUFF_TWIN];
     __shared__ uint32_t s_tbits[STUFF_TWIN];
-    __shared__ int s_chunk, s_tau0;
+    __shared__ int s_chunk;
     __shared__ uint32_t s_warp[NP][NWARP];
     __shared__ uint64_t s_goff;
     __shared__ uint32_t s_lut[16];
@@ -734,24 +739,9 @@ k_stuff(StuffArgs a) {
         if (ch >= nchunks) break;
         const uint64_t j0c = (uint64_t)ch * STUFF_CHUNK;
         const uint64_t p0c = (uint64_t)a_skip + 8 * j0c;
-        if (wid == 0) {  // tile containing the chunk's first bit: largest tau with tile_off[tau] <= p0c (32-ary search)
-            int lo = 0, hi = a.ntiles;  // invariant: tile_off[lo] <= p0c < tile_off[hi]
-            while (hi - lo > 1) {
-                const int span = hi - lo;
-                const int stepw = (span + 31) >> 5;
-                const int probe = min(hi, lo + (lane + 1) * stepw);
-                const bool le = probe < hi && a.tile_off[probe] <= p0c;
-                const unsigned m = __ballot_sync(0xffffffffu, le);
-                const int nle = __popc(m);  // probes are monotone: the first nle lanes are <=
-                const int nlo = lo + nle * stepw;
-                const int nhi = min(hi, lo + (nle + 1) * stepw);
-                lo = min(nlo, hi - 1);
-                hi = max(nhi, lo + 1);
-            }
-            if (lane == 0) s_tau0 = lo;
-        }
-        __syncthreads();
-        const int tau0 = s_tau0;
+        // tile holding the chunk's first bit: the tile scan left it in chunk_tile (for skip 0; with a seam skip the first
+        // bit may lie up to 7 bits further, i.e. in the next tile: the pieces' own tile walk steps over that)
+        const int tau0 = (int)a.chunk_tile[ch];
         for (int i = tid; i < STUFF_TWIN; i += STUFF_THREADS) {
             const int ti = min(tau0 + i, a.ntiles);
             s_toff[i] = a.tile_off[ti];
@@ -918,9 +908,10 @@ cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g
 }
 int scan_desc_count(int ntiles) { return (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
-                              uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *err, cudaStream_t s) {
+                              uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *chunk_tile, uint32_t nchunk_cap,
+                              uint32_t *err, cudaStream_t s) {
     const int grid = max(1, (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    return launch_pdl(k_scan_tiles, dim3(grid), dim3(1024), 0, s, tile_bits, ntiles, tile_off, slots, strip_bits, desc, ticket, err);
+    return launch_pdl(k_scan_tiles, dim3(grid), dim3(1024), 0, s, tile_bits, ntiles, tile_off, slots, strip_bits, desc, ticket, chunk_tile, nchunk_cap, err);
 }
 __global__ void k_set_seam(int *seam, int skip, int ext) { seam[0] = skip; seam[1] = ext ^ 0xFF; }
 

@@ -19,14 +19,17 @@ cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, con
 // small_buffers != 0 (tests): the per-warp bit buffers pretend to hold 24 words, forcing the overflow path
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s);
-// desc: scan_desc_count(ntiles) zeroed look-back descriptors; ticket: zeroed
+// desc: scan_desc_count(ntiles) zeroed look-back descriptors; ticket: zeroed. Also writes, for every k_stuff chunk
+// c < nchunk_cap that starts inside the strip, the tile that holds its first bit (k_stuff starts there: no search)
 int scan_desc_count(int ntiles);
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
-                              uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *err, cudaStream_t s);
+                              uint64_t *strip_bits, uint64_t *desc, uint32_t *ticket, uint32_t *chunk_tile,
+                              uint32_t nchunk_cap, uint32_t *err, cudaStream_t s);
 struct StuffArgs {
     const uint32_t *slots;
     const uint32_t *tile_bits;
     const uint64_t *tile_off;   // [ntiles+1]
+    const uint32_t *chunk_tile; // tile holding bit c * 8 * STUFF_CHUNK of the strip's bit string (from the tile scan)
     int ntiles;
     const int *seam;            // device: [0] skip = leading bits owned by the previous strip's last byte,
                                 //         [1] ext ^ 0xFF, ext = next strip's first 8 bits (0xFF: pad with ones)
