@@ -53,6 +53,7 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
     __shared__ uint32_t s_enc[4][256];
     __shared__ int s_cs[4][257];
     __shared__ int s_cnt[4][33];
+    __shared__ int s_base[4][33];
     __shared__ uint32_t s_nsym[4];
     __shared__ uint32_t s_err;
     __shared__ uint8_t s_hdr[1024];
@@ -91,12 +92,19 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
             key[j] = (f[j] != 0 && f[j] < (1u << 23)) ? ((f[j] << 9) | (uint32_t)(511 - i)) : KEY_NONE;
         }
         for (int iter = 0; iter < 300; iter++) {
-            uint32_t b1 = KEY_NONE, b2 = KEY_NONE;   // this lane's two smallest keys
-#pragma unroll
-            for (int j = 0; j < 9; j++) {
-                const uint32_t k = key[j];
-                b2 = min(b2, max(b1, k));
-                b1 = min(b1, k);
+            // this lane's two smallest keys: a tournament (depth 7) instead of a 9-step insertion chain (depth 18),
+            // the loop is one long dependency chain per table
+            uint32_t b1, b2;
+            {
+                const uint32_t l01 = min(key[0], key[1]), h01 = max(key[0], key[1]);
+                const uint32_t l23 = min(key[2], key[3]), h23 = max(key[2], key[3]);
+                const uint32_t l45 = min(key[4], key[5]), h45 = max(key[4], key[5]);
+                const uint32_t l67 = min(key[6], key[7]), h67 = max(key[6], key[7]);
+                const uint32_t a1 = min(l01, l23), a2 = min(max(l01, l23), min(h01, h23));
+                const uint32_t c1 = min(l45, l67), c2 = min(max(l45, l67), min(h45, h67));
+                const uint32_t d1 = min(a1, c1), d2 = min(max(a1, c1), min(a2, c2));
+                b1 = min(d1, key[8]);
+                b2 = min(max(d1, key[8]), d2);
             }
             const uint32_t k1 = __reduce_min_sync(FULL, b1);
             const uint32_t k2 = k1 == KEY_NONE ? KEY_NONE : __reduce_min_sync(FULL, b1 == k1 ? b2 : b1);
@@ -151,6 +159,22 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
             }
         }
         __syncwarp();
+        // huffval: symbols 0..255 sorted by (natural codesize, symbol). First slot of every codesize from the counts
+        // (taken before the length limiting below rewrites them; the reserved symbol 256 holds no slot), then per 32
+        // symbols the lanes of equal codesize rank themselves with MATCH.ANY.
+        {
+            const int l = lane + 1;   // codesize 1..32
+            const int n = s_cnt[t][l] - (s_cs[t][256] == l ? 1 : 0);
+            int inc = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += y;
+            }
+            s_base[t][l] = inc - n;
+            if (lane == 31) s_nsym[t] = (uint32_t)inc;
+        }
+        __syncwarp();
         if (lane == 0) {
             int *bits = s_cnt[t];
             for (int i = 32; i > 16; i--)
@@ -168,17 +192,19 @@ k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ 
             s_bits[t][0] = 0;
             for (int l = 1; l <= 16; l++) s_bits[t][l] = (uint8_t)bits[l];
         }
-        // huffval: symbols 0..255 sorted by (natural codesize, symbol)
-        int p = 0;
-        for (int len = 1; len <= 32; len++)
-            for (int c = 0; c < 8; c++) {
-                const int sym = c * 32 + lane;
-                const bool hit = s_cs[t][sym] == len;
-                const unsigned bal = __ballot_sync(FULL, hit);
-                if (hit) s_vals[t][p + __popc(bal & ((1u << lane) - 1))] = (uint8_t)sym;
-                p += __popc(bal);
+        // huffval, second half: per 32 symbols the lanes of equal codesize rank themselves with MATCH.ANY
+        for (int c = 0; c < 8; c++) {
+            const int sym = c * 32 + lane;
+            const int v = s_cs[t][sym] <= 32 ? s_cs[t][sym] : 0;   // > 32: error already flagged (s_err = 2)
+            const unsigned same = __match_any_sync(FULL, v);
+            const int base = v > 0 ? s_base[t][v] : 0;
+            __syncwarp();
+            if (v > 0) {
+                s_vals[t][base + __popc(same & ((1u << lane) - 1u))] = (uint8_t)sym;
+                if ((same & ((1u << lane) - 1u)) == 0) s_base[t][v] = base + __popc(same);
             }
-        if (lane == 0) s_nsym[t] = p;
+            __syncwarp();
+        }
     }
     __syncwarp();
     // Annex C code assignment: lane l (1..16) derives the first code and the first huffval index of length l from
