@@ -152,14 +152,15 @@ def headers(W, H, css, qt, bits, vals):
     return out[:n].copy()
 
 
-def encode(img, css, quality, optimize):
+def encode(img, css, quality, optimize, restart_interval=0):
+    """restart_interval: MCUs between RSTn markers (0 = none), as cv2's IMWRITE_JPEG_RST_INTERVAL."""
     img = np.ascontiguousarray(img)
     H, W = img.shape[:2]
-    cap = W * H * 3 * 4 + 4096
+    cap = W * H * 3 * 4 + 4096 + (2 * W * H // 64 if restart_interval else 0)
     out = np.empty(cap, np.uint8)
     n = C.c_size_t(0)
-    rc = lib().orc_encode(_p(img), C.c_size_t(img.strides[0]), W, H, int(css), int(quality), int(bool(optimize)),
-                          _p(out), C.c_size_t(cap), C.byref(n))
+    rc = lib().orc_encode_rst(_p(img), C.c_size_t(img.strides[0]), W, H, int(css), int(quality), int(bool(optimize)),
+                              int(restart_interval), _p(out), C.c_size_t(cap), C.byref(n))
     if rc:
         raise RuntimeError(f"orc_encode rc={rc}")
     return out[: n.value].copy()

@@ -1,11 +1,11 @@
 /*
  * jpeg_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see jpeg_oracle.h).
  *
- * Plain-C restatement of libjpeg-turbo 3.1.2 baseline JPEG (DCT_ISLOW, fancy upsampling, no restarts
- * on encode) following SURVEY.md Appendix A section by section. The reference repository contains no
+ * Plain-C restatement of libjpeg-turbo 3.1.2 baseline JPEG (DCT_ISLOW, fancy upsampling; restart intervals
+ * in orc_encode_rst / the decoder) following SURVEY.md Appendix A section by section. The reference repository contains no
  * JPEG arithmetic of its own (it calls nvjpegEncodeImage at ImageCompressorImpl.cu:280 and the
  * nvjpegDecodeJpeg* trio at :364-366); the north-star pins results to libjpeg-turbo instead.
- * Pinned by tests/test_oracle_vs_cv2.py (live cv2 = libjpeg-turbo 3.1.2) and tests/golden/.
+ * Pinned by tests/test_oracle_golden.py (live cv2 = libjpeg-turbo 3.1.2) and tests/golden/.
  */
 #include "jpeg_oracle.h"
 
@@ -409,8 +409,8 @@ size_t orc_stuff(const uint8_t *in, uint64_t nbits, uint8_t *out, size_t cap) {
 
 /* ------------------------------------------------------------------ A.8 markers (jcmarker.c) */
 
-size_t orc_headers(int W, int H, int css, const uint16_t qt[2][64], const uint8_t bits[4][17],
-                   const uint8_t vals[4][256], uint8_t *out, size_t cap) {
+static size_t headers_ri(int W, int H, int css, const uint16_t qt[2][64], const uint8_t bits[4][17],
+                         const uint8_t vals[4][256], int restart_interval, uint8_t *out, size_t cap) {
     orc_geom g; if (orc_geometry(W, H, css, &g)) return 0;
     uint8_t buf[2048]; size_t n = 0;
 #define PUT(b) buf[n++] = (uint8_t)(b)
@@ -432,12 +432,20 @@ size_t orc_headers(int W, int H, int css, const uint16_t qt[2][64], const uint8_
         for (int l = 1; l <= 16; l++) PUT(bits[t][l]);
         for (int i = 0; i < ns; i++) PUT(vals[t][i]);
     }
+    if (restart_interval) { /* jcmarker.c write_scan_header: emit_dri after the scan's DHTs, before SOS */
+        PUT(0xFF); PUT(0xDD); PUT(0); PUT(4); PUT(restart_interval >> 8); PUT(restart_interval & 255);
+    }
     PUT(0xFF); PUT(0xDA); PUT(0); PUT(12); PUT(3); PUT(1); PUT(0x00); PUT(2); PUT(0x11); PUT(3); PUT(0x11);
     PUT(0); PUT(63); PUT(0);
 #undef PUT
     if (n > cap) return 0;
     memcpy(out, buf, n);
     return n;
+}
+
+size_t orc_headers(int W, int H, int css, const uint16_t qt[2][64], const uint8_t bits[4][17],
+                   const uint8_t vals[4][256], uint8_t *out, size_t cap) {
+    return headers_ri(W, H, css, qt, bits, vals, 0, out, cap);
 }
 
 int orc_encode(const uint8_t *bgr, size_t step, int W, int H, int css, int quality, int optimize, uint8_t *out,
@@ -471,6 +479,57 @@ int orc_encode(const uint8_t *bgr, size_t step, int W, int H, int css, int quali
     if (hl + sl + 2 > cap) return -6;
     out[hl + sl] = 0xFF; out[hl + sl + 1] = 0xD9;
     *len = hl + sl + 2;
+    return 0;
+}
+
+/* Restart intervals (jchuff.c emit_restart, jcmarker.c emit_dri): every `ri` MCUs the bit buffer is flushed (1-padding
+ * to a byte boundary, stuffing applies to the padded byte), RSTn (n = 0..7 cycling) is written unstuffed and the DC
+ * predictors return to 0; no marker follows the last interval. Symbol statistics use the same predictor resets. */
+int orc_encode_rst(const uint8_t *bgr, size_t step, int W, int H, int css, int quality, int optimize, int ri,
+                   uint8_t *out, size_t cap, size_t *len) {
+    if (ri <= 0) return orc_encode(bgr, step, W, H, css, quality, optimize, out, cap, len);
+    if (ri > 65535) return -1;
+    orc_geom g; if (orc_geometry(W, H, css, &g)) return -1;
+    if (W > 65535 || H > 65535) return -1;
+    int16_t *coef = (int16_t *)malloc((size_t)g.nblocks * 128);
+    if (!coef) return -2;
+    int rc = orc_forward(bgr, step, W, H, css, quality, coef);
+    if (rc) { free(coef); return rc; }
+    uint16_t qt[2][64]; orc_quant_tables(quality, qt);
+    uint8_t bits[4][17], vals[4][256];
+    const long long nmcu = (long long)g.mcux * g.mcuy;
+    if (optimize) {
+        uint32_t hist[4][257], h1[4][257];
+        memset(hist, 0, sizeof(hist));
+        for (long long m0 = 0; m0 < nmcu; m0 += ri) {
+            long long nm = nmcu - m0 < ri ? nmcu - m0 : ri;
+            orc_histogram(coef + m0 * g.bpm * 64, nm * g.bpm, g.bpm, NULL, h1);
+            for (int t = 0; t < 4; t++) for (int i = 0; i < 257; i++) hist[t][i] += h1[t][i];
+        }
+        for (int t = 0; t < 4; t++) if (orc_gen_optimal_table(hist[t], bits[t], vals[t]) < 0) { free(coef); return -3; }
+    } else {
+        for (int t = 0; t < 4; t++) orc_std_table(t, bits[t], vals[t]);
+    }
+    size_t o = headers_ri(W, H, css, qt, bits, vals, ri, out, cap);
+    if (!o) { free(coef); return -4; }
+    size_t raw_cap = (size_t)ri * g.bpm * 208 + 16;
+    uint8_t *raw = (uint8_t *)malloc(raw_cap);
+    if (!raw) { free(coef); return -2; }
+    int rstn = 0;
+    for (long long m0 = 0; m0 < nmcu; m0 += ri) {
+        long long nm = nmcu - m0 < ri ? nmcu - m0 : ri;
+        uint64_t nbits = 0;
+        rc = orc_entropy_bits(coef + m0 * g.bpm * 64, nm * g.bpm, g.bpm, NULL, bits, vals, raw, raw_cap, &nbits);
+        if (rc) { free(coef); free(raw); return -5; }
+        size_t sl = orc_stuff(raw, nbits, out + o, cap > o ? cap - o : 0);
+        o += sl;
+        if (o + 2 > cap) { free(coef); free(raw); return -6; }
+        if (m0 + ri < nmcu) { out[o++] = 0xFF; out[o++] = (uint8_t)(0xD0 + rstn); rstn = (rstn + 1) & 7; }
+    }
+    free(coef); free(raw);
+    if (o + 2 > cap) return -6;
+    out[o++] = 0xFF; out[o++] = 0xD9;
+    *len = o;
     return 0;
 }
 

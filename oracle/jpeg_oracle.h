@@ -82,6 +82,10 @@ size_t orc_headers(int W, int H, int css, const uint16_t qt[2][64], const uint8_
 /* Whole encoder: returns 0 on success */
 int  orc_encode(const uint8_t *bgr, size_t step, int W, int H, int css, int quality, int optimize,
                 uint8_t *out, size_t cap, size_t *len);
+/* Same with restart markers every `restart_interval` MCUs (0 = none): DRI before SOS, RSTn between the intervals,
+ * DC predictors and the bit buffer restart (jchuff.c emit_restart). Pinned against cv2 IMWRITE_JPEG_RST_INTERVAL. */
+int  orc_encode_rst(const uint8_t *bgr, size_t step, int W, int H, int css, int quality, int optimize,
+                    int restart_interval, uint8_t *out, size_t cap, size_t *len);
 
 /* Parsed header info */
 typedef struct {

@@ -145,6 +145,40 @@ def test_live_cv2_sweep(oracle):
     assert np.array_equal(oracle.decode(ref.ravel()), cv2.imdecode(ref, cv2.IMREAD_COLOR))
 
 
+def test_restart_interval_golden(oracle):
+    """Row N2's checker half: streams with DRI / RSTn (jchuff.c emit_restart) == cv2 IMWRITE_JPEG_RST_INTERVAL digests,
+    and their decode == cv2.imdecode digests (tests/golden/make_golden_rst.py)."""
+    import json
+    with open(os.path.join(HERE, "golden", "golden_rst.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 100
+    for c in cases:
+        img = oracle.synth(c["W"], c["H"], c["seed"], c["amp"])
+        jpg = oracle.encode(img, c["css"], c["quality"], c["optimize"], c["restart_interval"])
+        assert jpg.size == c["jpeg_len"] and sha(jpg)[:32] == c["jpeg_sha256_128"], c
+        if c["W"] * c["H"] < 100000:
+            assert sha(oracle.decode(jpg))[:32] == c["decoded_sha256_128"], c
+
+
+def test_restart_interval_live_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    sf = {0: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 1: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+          2: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, 3: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+          4: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}
+    rng = np.random.default_rng(5)
+    for (W, H) in ((50, 70), (8, 8), (33, 90)):
+        for img in (oracle.synth(W, H, 4, 8), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)):
+            for css in range(5):
+                for q, opt, ri in ((95, 1, 1), (80, 0, 4), (100, 1, 7), (90, 1, 500)):
+                    ok, ref = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_OPTIMIZE, opt,
+                                                         cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf[css],
+                                                         cv2.IMWRITE_JPEG_RST_INTERVAL, ri])
+                    ref = ref.ravel()
+                    assert np.array_equal(oracle.encode(img, css, q, opt, ri), ref), (W, H, css, q, opt, ri)
+                    assert np.array_equal(oracle.decode(ref), cv2.imdecode(ref, cv2.IMREAD_COLOR)), (W, H, css, q, opt, ri)
+
+
 def test_diff_psnr(oracle):
     rng = np.random.default_rng(3)
     a = rng.integers(0, 256, (40, 30, 3), dtype=np.uint8)
