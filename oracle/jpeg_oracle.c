@@ -817,9 +817,206 @@ int orc_inverse(const int16_t *coef, const orc_info *info, uint8_t *bgr, size_t 
     return 0;
 }
 
+/* ------------------------------------------------------------------ progressive (SOF2) decode: jdphuff.c
+ * What the reference as shipped writes (NVJPEG_ENCODING_PROGRESSIVE_DCT_HUFFMAN, ImageCompressorImpl.cu:28; SURVEY.md
+ * 8f N4). All scans are absorbed into the coefficient array (jdapimin.c without buffered-image mode), then the baseline
+ * back end (IDCT, upsampling, colour) runs: block smoothing never triggers on a complete file. */
+typedef struct { int ncomp, comp[3], td[3], ta[3], Ss, Se, Ah, Al; } pscan;
+
+static size_t block_index(const orc_geom *g, int c, int bx, int by) {
+    int h = c ? 1 : g->hs, v = c ? 1 : g->vs;
+    int mx = bx / h, my = by / v;
+    int blkn = c ? g->bpm - 3 + c : (by % v) * h + (bx % h);
+    return ((size_t)my * g->mcux + mx) * g->bpm + blkn;
+}
+
+static void prog_restart(bitr *r, int pred[3], int *eobrun) {
+    r->cnt = 0;
+    if (r->marker) { r->pos += 2; r->marker = 0; }
+    else if (r->pos + 1 < r->n && r->d[r->pos] == 0xFF && r->d[r->pos + 1] >= 0xD0 && r->d[r->pos + 1] <= 0xD7) r->pos += 2;
+    pred[0] = pred[1] = pred[2] = 0; *eobrun = 0;
+}
+
+static void prog_block(bitr *r, const pscan *sc, int ci, const dtbl *dc, const dtbl *ac, int16_t *blk, int *pred, int *eobrun) {
+    const int Al = sc->Al, p1 = 1 << Al, m1 = -(1 << Al);
+    if (sc->Ss == 0) {
+        if (sc->Ah == 0) { /* decode_mcu_DC_first */
+            int s = decode_sym(r, dc);
+            int diff = s ? extend(get_bits(r, s), s) : 0;
+            pred[ci] += diff;
+            blk[0] = (int16_t)(pred[ci] * (1 << Al));
+        } else {           /* decode_mcu_DC_refine */
+            if (get_bit(r)) blk[0] |= (int16_t)p1;
+        }
+        return;
+    }
+    if (sc->Ah == 0) {     /* decode_mcu_AC_first */
+        if (*eobrun > 0) { (*eobrun)--; return; }
+        for (int k = sc->Ss; k <= sc->Se; k++) {
+            int rs = decode_sym(r, ac), rr = rs >> 4, ss = rs & 15;
+            if (ss) {
+                k += rr;
+                int v = extend(get_bits(r, ss), ss);
+                if (k <= 63) blk[k] = (int16_t)(v * (1 << Al));
+            } else {
+                if (rr == 15) k += 15;
+                else { *eobrun = 1 << rr; if (rr) *eobrun += get_bits(r, rr); (*eobrun)--; break; }
+            }
+        }
+        return;
+    }
+    /* decode_mcu_AC_refine */
+    int k = sc->Ss;
+    if (*eobrun == 0) {
+        for (; k <= sc->Se; k++) {
+            int rs = decode_sym(r, ac), rr = rs >> 4, ss = rs & 15, val = 0;
+            if (ss) val = get_bit(r) ? p1 : m1;       /* size of a new coefficient is always 1 */
+            else if (rr != 15) { *eobrun = 1 << rr; if (rr) *eobrun += get_bits(r, rr); break; }
+            /* advance over already-nonzero coefficients and rr still-zero ones, refining the nonzero ones */
+            do {
+                int16_t *cp = blk + k;
+                if (*cp != 0) {
+                    if (get_bit(r) && (*cp & p1) == 0) *cp = (int16_t)(*cp + (*cp >= 0 ? p1 : m1));
+                } else {
+                    if (--rr < 0) break;
+                }
+                k++;
+            } while (k <= sc->Se);
+            if (val && k <= 63) blk[k] = (int16_t)val;
+        }
+    }
+    if (*eobrun > 0) {
+        for (; k <= sc->Se; k++) {
+            int16_t *cp = blk + k;
+            if (*cp != 0 && get_bit(r) && (*cp & p1) == 0) *cp = (int16_t)(*cp + (*cp >= 0 ? p1 : m1));
+        }
+        (*eobrun)--;
+    }
+}
+
+int orc_decode_progressive(const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *W, int *H) {
+    if (len < 4 || jpg[0] != 0xFF || jpg[1] != 0xD8) return -1;
+    orc_info info; memset(&info, 0, sizeof(info));
+    uint16_t qtabs[4][64]; int have_q[4] = {0, 0, 0, 0};
+    static uint8_t hb[2][4][17], hv[2][4][256];
+    memset(hb, 0, sizeof(hb)); memset(hv, 0, sizeof(hv));
+    int comp_id[3] = {0, 0, 0}, comp_hv[3] = {0, 0, 0}, comp_tq[3] = {0, 0, 0}, ncomp = 0, ri = 0, have_sof = 0;
+    orc_geom g; memset(&g, 0, sizeof(g));
+    int16_t *coef = NULL;
+    size_t p = 2;
+    int rc = -15;
+    while (p + 2 <= len) {
+        if (jpg[p] != 0xFF) { rc = -2; break; }
+        int m = jpg[p + 1];
+        if (m == 0xFF) { p++; continue; }
+        p += 2;
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        if (m == 0xD9) { rc = have_sof && coef ? 0 : -3; break; }
+        if (p + 2 > len) { rc = -4; break; }
+        int L = rd16(jpg + p);
+        if (p + L > len) { rc = -4; break; }
+        const uint8_t *s = jpg + p + 2; int n = L - 2;
+        if (m == 0xDB) {
+            while (n > 0) {
+                int pq = s[0] >> 4, tq = s[0] & 15; s++; n--;
+                if (tq > 3) { rc = -5; goto done; }
+                for (int k = 0; k < 64; k++) qtabs[tq][ZIGZAG[k]] = (uint16_t)(pq ? rd16(s + 2 * k) : s[k]);
+                s += pq ? 128 : 64; n -= pq ? 128 : 64; have_q[tq] = 1;
+            }
+        } else if (m == 0xC2) {
+            if (s[0] != 8) { rc = -6; break; }
+            info.H = rd16(s + 1); info.W = rd16(s + 3); ncomp = s[5];
+            if (ncomp != 3) { rc = -7; break; }
+            for (int c = 0; c < 3; c++) { comp_id[c] = s[6 + 3 * c]; comp_hv[c] = s[7 + 3 * c]; comp_tq[c] = s[8 + 3 * c]; }
+            if (comp_hv[1] != 0x11 || comp_hv[2] != 0x11 || comp_tq[1] != comp_tq[2]) { rc = -11; break; }
+            info.hs = comp_hv[0] >> 4; info.vs = comp_hv[0] & 15;
+            static const int HS[5] = {1, 2, 1, 2, 4}, VS[5] = {1, 1, 2, 2, 1};
+            info.css = -1;
+            for (int i = 0; i < 5; i++) if (HS[i] == info.hs && VS[i] == info.vs) info.css = i;
+            if (info.css < 0 || orc_geometry(info.W, info.H, info.css, &g)) { rc = -13; break; }
+            if (W) *W = info.W;
+            if (H) *H = info.H;
+            if (!bgr) return 0;
+            coef = (int16_t *)calloc((size_t)g.nblocks * 64, 2);
+            if (!coef) return -2;
+            have_sof = 1;
+        } else if (m == 0xC0 || m == 0xC1) {
+            rc = -8; break;   /* not progressive: orc_decode handles it */
+        } else if (m == 0xC4) {
+            while (n > 0) {
+                int tc = s[0] >> 4, th = s[0] & 15; s++; n--;
+                if (tc > 1 || th > 3) { rc = -9; goto done; }
+                int ns = 0; hb[tc][th][0] = 0;
+                for (int l = 1; l <= 16; l++) { hb[tc][th][l] = s[l - 1]; ns += s[l - 1]; }
+                s += 16; n -= 16;
+                if (ns > 256) { rc = -9; goto done; }
+                memset(hv[tc][th], 0, 256); memcpy(hv[tc][th], s, ns); s += ns; n -= ns;
+            }
+        } else if (m == 0xDD) {
+            ri = rd16(s);
+        } else if (m == 0xDA) {
+            if (!have_sof) { rc = -10; break; }
+            pscan sc; sc.ncomp = s[0];
+            if (sc.ncomp < 1 || sc.ncomp > 3) { rc = -10; break; }
+            for (int i = 0; i < sc.ncomp; i++) {
+                int id = s[1 + 2 * i]; sc.comp[i] = -1;
+                for (int c = 0; c < 3; c++) if (comp_id[c] == id) sc.comp[i] = c;
+                if (sc.comp[i] < 0) { rc = -10; goto done; }
+                sc.td[i] = s[2 + 2 * i] >> 4; sc.ta[i] = s[2 + 2 * i] & 15;
+            }
+            sc.Ss = s[1 + 2 * sc.ncomp]; sc.Se = s[2 + 2 * sc.ncomp];
+            sc.Ah = s[3 + 2 * sc.ncomp] >> 4; sc.Al = s[3 + 2 * sc.ncomp] & 15;
+            if (sc.Ss > sc.Se || sc.Se > 63 || (sc.Ss == 0 && sc.Se != 0) || (sc.Ss > 0 && sc.ncomp != 1)) { rc = -16; break; }
+            for (int c = 0; c < 3; c++) if (!have_q[comp_tq[c]]) { rc = -14; goto done; }
+            memcpy(info.qt[0], qtabs[comp_tq[0]], 128); memcpy(info.qt[1], qtabs[comp_tq[1]], 128);
+            /* entropy-coded segment of this scan */
+            size_t e0 = p + L, e = e0;
+            while (e + 1 < len) {
+                if (jpg[e] == 0xFF && jpg[e + 1] != 0x00 && !(jpg[e + 1] >= 0xD0 && jpg[e + 1] <= 0xD7)) break;
+                e++;
+            }
+            if (e + 1 >= len) e = len;
+            bitr r = {jpg + e0, e - e0, 0, 0, 0, 0};
+            dtbl dct[3], act[3];
+            for (int i = 0; i < sc.ncomp; i++) {
+                make_dtbl(hb[0][sc.td[i]], hv[0][sc.td[i]], &dct[i]);
+                make_dtbl(hb[1][sc.ta[i]], hv[1][sc.ta[i]], &act[i]);
+            }
+            int pred[3] = {0, 0, 0}, eobrun = 0, togo = ri;
+            if (sc.ncomp > 1) {            /* interleaved: MCU order, every block of the MCU (padding blocks too) */
+                for (long long mi = 0; mi < (long long)g.mcux * g.mcuy; mi++) {
+                    if (ri && togo == 0) { prog_restart(&r, pred, &eobrun); togo = ri; }
+                    for (int i = 0; i < sc.ncomp; i++) {
+                        int c = sc.comp[i], nb = c ? 1 : g.hs * g.vs, b0 = c ? g.bpm - 3 + c : 0;
+                        for (int b = 0; b < nb; b++)
+                            prog_block(&r, &sc, i, &dct[i], &act[i], coef + ((size_t)mi * g.bpm + b0 + b) * 64, pred, &eobrun);
+                    }
+                    if (ri) togo--;
+                }
+            } else {                       /* one component: raster order over its own blocks (real data only) */
+                int c = sc.comp[0];
+                for (int by = 0; by < g.hib[c]; by++)
+                    for (int bx = 0; bx < g.wib[c]; bx++) {
+                        if (ri && togo == 0) { prog_restart(&r, pred, &eobrun); togo = ri; }
+                        prog_block(&r, &sc, 0, &dct[0], &act[0], coef + block_index(&g, c, bx, by) * 64, pred, &eobrun);
+                        if (ri) togo--;
+                    }
+            }
+            p = e;
+            continue;
+        }
+        p += L;
+    }
+done:
+    if (rc == 0) rc = orc_inverse(coef, &info, bgr, step);
+    free(coef);
+    return rc;
+}
+
 int orc_decode(const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *W, int *H) {
     orc_info info;
     int rc = orc_parse(jpg, len, &info);
+    if (rc == -8) return orc_decode_progressive(jpg, len, bgr, step, W, H);
     if (rc) return rc;
     if (W) *W = info.W;
     if (H) *H = info.H;

@@ -107,6 +107,9 @@ int  orc_decode_coefs(const uint8_t *jpg, size_t len, const orc_info *info, int1
 /* Stage 5: coefficients -> BGR (islow IDCT, fancy upsampling, jdcolor) */
 int  orc_inverse(const int16_t *coef, const orc_info *info, uint8_t *bgr, size_t step);
 
+/* Progressive (SOF2) streams: all scans absorbed, then the baseline back end (jdphuff.c). orc_decode dispatches here. */
+int  orc_decode_progressive(const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *W, int *H);
+
 /* Whole decoder; *W,*H returned; bgr may be NULL to query size */
 int  orc_decode(const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *W, int *H);
 

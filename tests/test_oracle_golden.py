@@ -179,6 +179,38 @@ def test_restart_interval_live_cv2(oracle):
                     assert np.array_equal(oracle.decode(ref), cv2.imdecode(ref, cv2.IMREAD_COLOR)), (W, H, css, q, opt, ri)
 
 
+def test_progressive_decode_golden(oracle):
+    """Row N4's checker half: progressive (SOF2) streams, the format the reference as shipped writes
+    (ImageCompressorImpl.cu:28), decode to cv2.imdecode's pixels (fixtures: tests/golden/make_golden_prog.py)."""
+    import json
+    with open(os.path.join(HERE, "golden", "golden_prog.json")) as f:
+        files = json.load(f)["files"]
+    assert len(files) >= 5
+    for c in files:
+        jpg = np.fromfile(os.path.join(HERE, "golden", c["file"]), np.uint8)
+        assert sha(jpg) == c["jpeg_sha256"]
+        dec = oracle.decode(jpg)
+        assert dec.shape == (c["H"], c["W"], 3) and sha(dec) == c["decoded_sha256"], c
+
+
+def test_progressive_decode_live_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    sf = {0: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 1: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+          2: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, 3: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+          4: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}
+    rng = np.random.default_rng(8)
+    for (W, H) in ((50, 70), (8, 8), (1, 1), (135, 121)):
+        for img in (oracle.synth(W, H, 6, 8), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)):
+            for css in range(5):
+                for q, opt, ri in ((95, 1, 0), (50, 0, 0), (100, 1, 7)):
+                    p = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_OPTIMIZE, opt, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf[css],
+                         cv2.IMWRITE_JPEG_PROGRESSIVE, 1] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, ri] if ri else [])
+                    ok, ref = cv2.imencode(".jpg", img, p)
+                    ref = ref.ravel()
+                    assert np.array_equal(oracle.decode(ref), cv2.imdecode(ref, cv2.IMREAD_COLOR)), (W, H, css, q, opt, ri)
+
+
 def test_diff_psnr(oracle):
     rng = np.random.default_rng(3)
     a = rng.integers(0, 256, (40, 30, 3), dtype=np.uint8)
