@@ -319,6 +319,7 @@ static inline void tick(b2j_ctx *ctx, int i) { if (ctx->timing) cudaEventRecord(
 
 int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows) {
     if (!ctx || !d_bgr) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     int rc = enc_alloc(ctx); if (rc) return rc;
     rc = set_strip_geom(ctx, width, rows); if (rc) return rc;
     rc = enc_reset(ctx); if (rc) return rc;
@@ -332,6 +333,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
 
 int b2j_strip_phase1b(b2j_ctx *ctx) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, ctx->p.optimize, ctx->d_pool, 1, nullptr, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 3);
@@ -340,6 +342,7 @@ int b2j_strip_phase1b(b2j_ctx *ctx) {
 
 int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
     CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, &ctx->d_ctrl->huff_err, ctx->stream));
     tick(ctx, 4);
@@ -370,6 +373,7 @@ static int phase3_launch(b2j_ctx *ctx, int flags, bool hdr_done = false) {
 
 int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
     if (!ctx || !ctx->enc_ready || skip_bits < 0 || skip_bits > 7) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     if (skip_bits != 0 || (ext_byte & 0xFF) != 0xFF) {   // the zeroed control block already says "skip 0, pad with ones"
         CK(launch_set_seam(ctx->d_ctrl->seam, skip_bits, ext_byte & 0xFF, ctx->stream));
         ctx->launches += 1;
@@ -379,6 +383,7 @@ int b2j_strip_phase3(b2j_ctx *ctx, int skip_bits, int ext_byte, int flags) {
 
 int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int world, int flags) {
     if (!ctx || !ctx->enc_ready || !d_bits_all || rank < 0 || rank >= world) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     CK(launch_seam_from_bits(ctx->d_ctrl->seam, d_bits_all, rank, world, ctx->stream));
     ctx->launches += 1;
     return phase3_launch(ctx, flags);
@@ -387,6 +392,7 @@ int b2j_strip_phase3_dev(b2j_ctx *ctx, const int64_t *d_bits_all, int rank, int 
 // One-collective schedule: phase1x -> all-gather of d_record -> phase2x (everything else, no further exchange).
 int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows) {
     if (!ctx || !d_bgr) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     int rc = enc_alloc(ctx); if (rc) return rc;
     rc = set_strip_geom(ctx, width, rows); if (rc) return rc;
     rc = enc_reset(ctx); if (rc) return rc;
@@ -407,6 +413,7 @@ int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width
 
 int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int world, int full_w, int full_h, int flags) {
     if (!ctx || !ctx->enc_ready || rank < 0 || rank >= world || world > 256) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     const StripRecord *rec = static_cast<const StripRecord *>(d_records_all);
     const uint32_t *xflags = nullptr;
     if (!rec) {   // peer exchange: the records of this image are (or will be) in this rank's arena
@@ -473,6 +480,7 @@ int b2j_peer_connect(b2j_ctx *ctx, int rank, int world, void *const *d_arenas) {
 
 int b2j_strip_state_get(b2j_ctx *ctx, b2j_strip_state *st) {
     if (!ctx || !st) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     int rc = enc_alloc(ctx); if (rc) return rc;
     st->d_hist = ctx->d_ctrl->hist; st->d_last_dc = ctx->d_ctrl->rec.last_dc; st->d_pred_in = ctx->d_pred_in;
     st->d_strip_bits = ctx->d_ctrl->strip_bits; st->d_out_len = &ctx->d_ctrl->out_len; st->d_out = ctx->d_out;
