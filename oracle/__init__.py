@@ -166,6 +166,20 @@ def encode(img, css, quality, optimize, restart_interval=0):
     return out[: n.value].copy()
 
 
+def encode_progressive(img, css, quality):
+    """cv2.imencode(..., IMWRITE_JPEG_PROGRESSIVE=1) restated (progressive mode always optimises its tables)."""
+    img = np.ascontiguousarray(img)
+    H, W = img.shape[:2]
+    cap = W * H * 3 * 4 + 8192
+    out = np.empty(cap, np.uint8)
+    n = C.c_size_t(0)
+    rc = lib().orc_encode_progressive(_p(img), C.c_size_t(img.strides[0]), W, H, int(css), int(quality), _p(out),
+                                      C.c_size_t(cap), C.byref(n))
+    if rc:
+        raise RuntimeError(f"orc_encode_progressive rc={rc}")
+    return out[: n.value].copy()
+
+
 def parse(jpg):
     jpg = np.ascontiguousarray(jpg, np.uint8)
     info = Info()

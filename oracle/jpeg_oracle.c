@@ -2,7 +2,8 @@
  * jpeg_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see jpeg_oracle.h).
  *
  * Plain-C restatement of libjpeg-turbo 3.1.2 baseline JPEG (DCT_ISLOW, fancy upsampling; restart intervals
- * in orc_encode_rst / the decoder) following SURVEY.md Appendix A section by section. The reference repository contains no
+ * in orc_encode_rst / the decoder; progressive mode in orc_encode_progressive / orc_decode_progressive) following
+ * SURVEY.md Appendix A section by section. The reference repository contains no
  * JPEG arithmetic of its own (it calls nvjpegEncodeImage at ImageCompressorImpl.cu:280 and the
  * nvjpegDecodeJpeg* trio at :364-366); the north-star pins results to libjpeg-turbo instead.
  * Pinned by tests/test_oracle_golden.py (live cv2 = libjpeg-turbo 3.1.2) and tests/golden/.
@@ -533,6 +534,215 @@ int orc_encode_rst(const uint8_t *bgr, size_t step, int W, int H, int css, int q
     return 0;
 }
 
+/* scan parameters and the scan-order index of block (bx, by) of component c (shared by both progressive halves) */
+typedef struct { int ncomp, comp[3], td[3], ta[3], Ss, Se, Ah, Al; } pscan;
+
+static size_t block_index(const orc_geom *g, int c, int bx, int by) {
+    int h = c ? 1 : g->hs, v = c ? 1 : g->vs;
+    int mx = bx / h, my = by / v;
+    int blkn = c ? g->bpm - 3 + c : (by % v) * h + (bx % h);
+    return ((size_t)my * g->mcux + mx) * g->bpm + blkn;
+}
+
+/* ------------------------------------------------------------------ progressive (SOF2) encode: jcphuff.c
+ * jpeg_simple_progression's 10-scan script for YCbCr (jcparam.c), every scan with its own optimal Huffman tables
+ * (progressive mode forces optimize_coding): each scan is walked twice, first counting symbols, then emitting. */
+typedef struct {
+    int gather;                 /* pass 1: count symbols; pass 2: emit */
+    uint32_t count[257];        /* the scan's AC table, or (DC scans) indexed through cnt_dc */
+    uint32_t cnt_dc[2][257];
+    uint16_t code[2][256]; uint8_t size[2][256];   /* [0] = DC/AC luma table of this scan, [1] = chroma */
+    bitw w;
+    unsigned eobrun; int be; uint8_t bebuf[1024];
+} penc;
+
+static void p_sym(penc *e, int tbl, int sym, int is_dc) {
+    if (e->gather) { if (is_dc) e->cnt_dc[tbl][sym]++; else e->count[sym]++; }
+    else put_bits(&e->w, e->code[tbl][sym], e->size[tbl][sym]);
+}
+static void p_bits(penc *e, unsigned v, int n) { if (!e->gather && n) put_bits(&e->w, v & ((1u << n) - 1), n); }
+static void p_buffered(penc *e, const uint8_t *b, int n) { if (!e->gather) for (int i = 0; i < n; i++) put_bits(&e->w, b[i], 1); }
+static void p_eobrun(penc *e, int tbl) {
+    if (e->eobrun > 0) {
+        unsigned t = e->eobrun; int nb = 0;
+        while (t >>= 1) nb++;
+        p_sym(e, tbl, nb << 4, 0);
+        if (nb) p_bits(e, e->eobrun, nb);
+        e->eobrun = 0;
+        p_buffered(e, e->bebuf, e->be);
+        e->be = 0;
+    }
+}
+
+static void p_ac_first(penc *e, int tbl, const int16_t *blk, int Ss, int Se, int Al) {
+    int r = 0;
+    for (int k = Ss; k <= Se; k++) {
+        int t = blk[k], t2;
+        if (t == 0) { r++; continue; }
+        if (t < 0) { t = -t; t >>= Al; t2 = ~t; } else { t >>= Al; t2 = t; }
+        if (t == 0) { r++; continue; }
+        if (e->eobrun > 0) p_eobrun(e, tbl);
+        while (r > 15) { p_sym(e, tbl, 0xF0, 0); r -= 16; }
+        int nb = nbits_of(t);
+        p_sym(e, tbl, (r << 4) + nb, 0);
+        p_bits(e, (unsigned)t2, nb);
+        r = 0;
+    }
+    if (r > 0) { e->eobrun++; if (e->eobrun == 0x7FFF) p_eobrun(e, tbl); }
+}
+
+static void p_ac_refine(penc *e, int tbl, const int16_t *blk, int Ss, int Se, int Al) {
+    int absv[64], EOB = 0;
+    for (int k = Ss; k <= Se; k++) {
+        int t = blk[k]; if (t < 0) t = -t;
+        t >>= Al; absv[k] = t;
+        if (t == 1) EOB = k;
+    }
+    int r = 0, br = 0;
+    uint8_t *brbuf = e->bebuf + e->be;
+    for (int k = Ss; k <= Se; k++) {
+        int t = absv[k];
+        if (t == 0) { r++; continue; }
+        while (r > 15 && k <= EOB) {
+            p_eobrun(e, tbl);
+            p_sym(e, tbl, 0xF0, 0);
+            r -= 16;
+            p_buffered(e, brbuf, br);
+            brbuf = e->bebuf; br = 0;
+        }
+        if (t > 1) { brbuf[br++] = (uint8_t)(t & 1); continue; }
+        p_eobrun(e, tbl);
+        p_sym(e, tbl, (r << 4) + 1, 0);
+        p_bits(e, blk[k] < 0 ? 0u : 1u, 1);
+        p_buffered(e, brbuf, br);
+        brbuf = e->bebuf; br = 0;
+        r = 0;
+    }
+    if (r > 0 || br > 0) {
+        e->eobrun++;
+        e->be += br;
+        if (e->eobrun == 0x7FFF || e->be > 1000 - 64 + 1) p_eobrun(e, tbl);
+    }
+}
+
+/* one scan, one pass (gather or emit) over the coefficient array */
+static void p_scan(penc *e, const orc_geom *g, const int16_t *coef, const pscan *sc, int ri) {
+    int pred[3] = {0, 0, 0};
+    (void)ri;   /* restart intervals: not restated for progressive encode */
+    e->eobrun = 0; e->be = 0;
+    if (sc->ncomp > 1) {
+        for (long long mi = 0; mi < (long long)g->mcux * g->mcuy; mi++) {
+            for (int i = 0; i < sc->ncomp; i++) {
+                int c = sc->comp[i], nb = c ? 1 : g->hs * g->vs, b0 = c ? g->bpm - 3 + c : 0, tblc = c ? 1 : 0;
+                for (int b = 0; b < nb; b++) {
+                    const int16_t *blk = coef + ((size_t)mi * g->bpm + b0 + b) * 64;
+                    if (sc->Ah == 0) {
+                        int t2 = blk[0] >> sc->Al, d = t2 - pred[c];
+                        pred[c] = t2;
+                        int n = nbits_of(d), v = d < 0 ? d - 1 : d;
+                        p_sym(e, tblc, n, 1);
+                        p_bits(e, (unsigned)v, n);
+                    } else {
+                        p_bits(e, (unsigned)(blk[0] >> sc->Al) & 1u, 1);
+                    }
+                }
+            }
+        }
+    } else {
+        int c = sc->comp[0], tblc = c ? 1 : 0;
+        for (int by = 0; by < g->hib[c]; by++)
+            for (int bx = 0; bx < g->wib[c]; bx++) {
+                const int16_t *blk = coef + block_index(g, c, bx, by) * 64;
+                if (sc->Ss == 0) {
+                    if (sc->Ah == 0) {
+                        int t2 = blk[0] >> sc->Al, d = t2 - pred[c];
+                        pred[c] = t2;
+                        int n = nbits_of(d), v = d < 0 ? d - 1 : d;
+                        p_sym(e, tblc, n, 1);
+                        p_bits(e, (unsigned)v, n);
+                    } else p_bits(e, (unsigned)(blk[0] >> sc->Al) & 1u, 1);
+                } else if (sc->Ah == 0) p_ac_first(e, tblc, blk, sc->Ss, sc->Se, sc->Al);
+                else p_ac_refine(e, tblc, blk, sc->Ss, sc->Se, sc->Al);
+            }
+        p_eobrun(e, tblc);
+    }
+}
+
+int orc_encode_progressive(const uint8_t *bgr, size_t step, int W, int H, int css, int quality, uint8_t *out,
+                           size_t cap, size_t *len) {
+    orc_geom g; if (orc_geometry(W, H, css, &g)) return -1;
+    if (W > 65535 || H > 65535) return -1;
+    int16_t *coef = (int16_t *)malloc((size_t)g.nblocks * 128);
+    if (!coef) return -2;
+    int rc = orc_forward(bgr, step, W, H, css, quality, coef);
+    if (rc) { free(coef); return rc; }
+    uint16_t qt[2][64]; orc_quant_tables(quality, qt);
+    size_t n = 0;
+#define PUT(b) do { if (n < cap) out[n] = (uint8_t)(b); n++; } while (0)
+    PUT(0xFF); PUT(0xD8);
+    PUT(0xFF); PUT(0xE0); PUT(0); PUT(16); PUT('J'); PUT('F'); PUT('I'); PUT('F'); PUT(0); PUT(1); PUT(1); PUT(0);
+    PUT(0); PUT(1); PUT(0); PUT(1); PUT(0); PUT(0);
+    for (int t = 0; t < 2; t++) {
+        PUT(0xFF); PUT(0xDB); PUT(0); PUT(67); PUT(t);
+        for (int k = 0; k < 64; k++) PUT(qt[t][ZIGZAG[k]]);
+    }
+    PUT(0xFF); PUT(0xC2); PUT(0); PUT(17); PUT(8); PUT(H >> 8); PUT(H & 255); PUT(W >> 8); PUT(W & 255); PUT(3);
+    PUT(1); PUT((g.hs << 4) | g.vs); PUT(0);
+    PUT(2); PUT(0x11); PUT(1);
+    PUT(3); PUT(0x11); PUT(1);
+    /* jcparam.c jpeg_simple_progression, YCbCr: {comps, Ss, Se, Ah, Al} */
+    static const int script[10][5] = {{-1, 0, 0, 0, 1}, {0, 1, 5, 0, 2}, {2, 1, 63, 0, 1}, {1, 1, 63, 0, 1}, {0, 6, 63, 0, 2},
+                                      {0, 1, 63, 2, 1}, {-1, 0, 0, 1, 0}, {2, 1, 63, 1, 0}, {1, 1, 63, 1, 0}, {0, 1, 63, 1, 0}};
+    size_t raw_cap = (size_t)g.nblocks * 208 + 64;
+    uint8_t *raw = (uint8_t *)malloc(raw_cap);
+    penc *e = (penc *)malloc(sizeof(penc));
+    if (!raw || !e) { free(coef); free(raw); free(e); return -2; }
+    for (int si = 0; si < 10; si++) {
+        pscan sc; memset(&sc, 0, sizeof(sc));
+        if (script[si][0] < 0) { sc.ncomp = 3; sc.comp[0] = 0; sc.comp[1] = 1; sc.comp[2] = 2; }
+        else { sc.ncomp = 1; sc.comp[0] = script[si][0]; }
+        sc.Ss = script[si][1]; sc.Se = script[si][2]; sc.Ah = script[si][3]; sc.Al = script[si][4];
+        const int is_dc = sc.Ss == 0, need_tbl = !(is_dc && sc.Ah != 0);
+        memset(e, 0, sizeof(*e));
+        uint8_t bits[2][17], vals[2][256];
+        if (need_tbl) {
+            e->gather = 1;
+            p_scan(e, &g, coef, &sc, 0);
+            for (int t = 0; t < 2; t++) {
+                const uint32_t *cnt = is_dc ? e->cnt_dc[t] : e->count;
+                int used = is_dc ? 1 : (t == (sc.comp[0] ? 1 : 0));
+                if (!used) continue;
+                if (orc_gen_optimal_table(cnt, bits[t], vals[t]) < 0) { free(coef); free(raw); free(e); return -3; }
+                orc_derive_codes(bits[t], vals[t], e->code[t], e->size[t]);
+                int ns = 0; for (int l = 1; l <= 16; l++) ns += bits[t][l];
+                PUT(0xFF); PUT(0xC4); PUT((19 + ns) >> 8); PUT((19 + ns) & 255); PUT((is_dc ? 0x00 : 0x10) | t);
+                for (int l = 1; l <= 16; l++) PUT(bits[t][l]);
+                for (int i = 0; i < ns; i++) PUT(vals[t][i]);
+            }
+        }
+        PUT(0xFF); PUT(0xDA); PUT(0); PUT(6 + 2 * sc.ncomp); PUT(sc.ncomp);
+        for (int i = 0; i < sc.ncomp; i++) {
+            int c = sc.comp[i], t = c ? 1 : 0;
+            PUT(c + 1);
+            PUT(is_dc ? (sc.Ah == 0 ? (t << 4) : 0) : t);
+        }
+        PUT(sc.Ss); PUT(sc.Se); PUT((sc.Ah << 4) | sc.Al);
+        e->gather = 0;
+        memset(raw, 0, raw_cap);
+        e->w.out = raw; e->w.cap = raw_cap; e->w.nbits = 0; e->w.overflow = 0;
+        p_scan(e, &g, coef, &sc, 0);
+        if (e->w.overflow) { free(coef); free(raw); free(e); return -5; }
+        size_t sl = orc_stuff(raw, e->w.nbits, n < cap ? out + n : out, n < cap ? cap - n : 0);
+        n += sl;
+    }
+    PUT(0xFF); PUT(0xD9);
+#undef PUT
+    free(coef); free(raw); free(e);
+    if (n > cap) return -6;
+    *len = n;
+    return 0;
+}
+
 /* ------------------------------------------------------------------ decoder: markers (jdmarker.c) */
 
 static int rd16(const uint8_t *p) { return (p[0] << 8) | p[1]; }
@@ -821,15 +1031,6 @@ int orc_inverse(const int16_t *coef, const orc_info *info, uint8_t *bgr, size_t 
  * What the reference as shipped writes (NVJPEG_ENCODING_PROGRESSIVE_DCT_HUFFMAN, ImageCompressorImpl.cu:28; SURVEY.md
  * 8f N4). All scans are absorbed into the coefficient array (jdapimin.c without buffered-image mode), then the baseline
  * back end (IDCT, upsampling, colour) runs: block smoothing never triggers on a complete file. */
-typedef struct { int ncomp, comp[3], td[3], ta[3], Ss, Se, Ah, Al; } pscan;
-
-static size_t block_index(const orc_geom *g, int c, int bx, int by) {
-    int h = c ? 1 : g->hs, v = c ? 1 : g->vs;
-    int mx = bx / h, my = by / v;
-    int blkn = c ? g->bpm - 3 + c : (by % v) * h + (bx % h);
-    return ((size_t)my * g->mcux + mx) * g->bpm + blkn;
-}
-
 static void prog_restart(bitr *r, int pred[3], int *eobrun) {
     r->cnt = 0;
     if (r->marker) { r->pos += 2; r->marker = 0; }

@@ -107,6 +107,11 @@ int  orc_decode_coefs(const uint8_t *jpg, size_t len, const orc_info *info, int1
 /* Stage 5: coefficients -> BGR (islow IDCT, fancy upsampling, jdcolor) */
 int  orc_inverse(const int16_t *coef, const orc_info *info, uint8_t *bgr, size_t step);
 
+/* Progressive (SOF2) encode: jpeg_simple_progression's 10 scans, optimal tables per scan (jcphuff.c); what
+ * cv2.imencode(IMWRITE_JPEG_PROGRESSIVE) writes and the mode the reference hard-codes (ImageCompressorImpl.cu:28). */
+int  orc_encode_progressive(const uint8_t *bgr, size_t step, int W, int H, int css, int quality, uint8_t *out,
+                            size_t cap, size_t *len);
+
 /* Progressive (SOF2) streams: all scans absorbed, then the baseline back end (jdphuff.c). orc_decode dispatches here. */
 int  orc_decode_progressive(const uint8_t *jpg, size_t len, uint8_t *bgr, size_t step, int *W, int *H);
 

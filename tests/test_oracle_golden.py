@@ -191,6 +191,26 @@ def test_progressive_decode_golden(oracle):
         assert sha(jpg) == c["jpeg_sha256"]
         dec = oracle.decode(jpg)
         assert dec.shape == (c["H"], c["W"], 3) and sha(dec) == c["decoded_sha256"], c
+        if c["restart_interval"] == 0:   # and the same file is what the checker's progressive encoder writes
+            img = oracle.synth(c["W"], c["H"], 11, 8)
+            assert np.array_equal(oracle.encode_progressive(img, c["css"], c["quality"]), jpg), c
+
+
+def test_progressive_encode_live_cv2(oracle):
+    """jcphuff.c restated (jpeg_simple_progression, per-scan optimal tables): bytes == cv2 IMWRITE_JPEG_PROGRESSIVE."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    sf = {0: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 1: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+          2: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, 3: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+          4: cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}
+    rng = np.random.default_rng(9)
+    for (W, H) in ((50, 70), (8, 8), (1, 1), (135, 121), (257, 63)):
+        for img in (oracle.synth(W, H, 6, 8), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)):
+            for css in range(5):
+                for q in (50, 95, 100):
+                    ok, ref = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf[css],
+                                                         cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+                    assert np.array_equal(oracle.encode_progressive(img, css, q), ref.ravel()), (W, H, css, q)
 
 
 def test_progressive_decode_live_cv2(oracle):
