@@ -45,10 +45,21 @@ public:
     NvjpegCompressRunner(const NvjpegCompressRunner &) = delete;
     NvjpegCompressRunner &operator=(const NvjpegCompressRunner &) = delete;
 
+    // CV_8UC3 BGR pixels (any row step) -> complete JFIF bytes. Empty vector and *run_state = 0 on failure (empty or
+    // oversized image, CUDA error), 1 on success; run_state may be null. Replaces ImageCompressor.cpp:45-61 /
+    // ImageCompressorImpl.cu:269-294 (cv::split + 3 x cudaMemcpy + nvjpegEncodeImage + retrieve): b2j_encode, pageable
+    // pixels are staged by the engine's copy threads. Prints the reference's "[INFO] ... Cost Time" line unless B2J_QUIET=1.
     std::vector<unsigned char> compress(cv::Mat image, int *run_state);
+    // JPEG file -> CV_8UC3 BGR. Empty Mat and *run_state = 0 when the file cannot be opened or decoded
+    // (ImageCompressor.cpp:63-88, ImageCompressorImpl.cu:311-385 + getCVImageOnCPU :184-232): b2j_decode, the
+    // planar->interleaved step happens in the kernel's store.
     cv::Mat decode(std::string image_path, int *run_state);
+    // Binary write of the bytes (ImageCompressor.cpp:90-101; the size is not narrowed to int here).
     void save(std::string save_path, std::vector<unsigned char> obuffer);
 
+    // The reference's environment protocol (ImageCompressor.h:38-41): build before use, delete when done. Here one
+    // engine context serves both directions; building twice is harmless, using an unbuilt environment fails cleanly
+    // (*run_state = 0) instead of dereferencing uninitialised nvJPEG handles.
     void buildCompressEnv();
     void buildDecodeEnv();
     void deleteCompressEnv();
