@@ -182,11 +182,14 @@ static int ensure_tiles(b2j_ctx *ctx, const Geom &g) {
     cudaFree(ctx->d_slots); cudaFree(ctx->d_tile_bits); cudaFree(ctx->d_tile_off); cudaFree(ctx->d_recs);
     ctx->d_slots = nullptr; ctx->d_tile_bits = nullptr; ctx->d_tile_off = nullptr; ctx->d_recs = nullptr; ctx->tiles_cap = 0;
     const int n = g.ntiles + g.ntiles / 8 + 16;
+    const bool was_ready = ctx->enc_ready;
+    ctx->enc_ready = false;   // stays false if an allocation below fails: no phase launches with null tile buffers
     CK(cudaMalloc(&ctx->d_slots, (size_t)n * SLOT_WORDS * 4));
     CK(cudaMalloc(&ctx->d_tile_bits, (size_t)(n + 1) * 4));
     CK(cudaMalloc(&ctx->d_tile_off, (size_t)(n + 2) * 8));
     CK(cudaMalloc(&ctx->d_recs, (size_t)(n + 1) * sizeof(TileRec)));
     ctx->tiles_cap = n;
+    ctx->enc_ready = was_ready;
     return B2J_OK;
 }
 
@@ -208,17 +211,18 @@ static int alloc_zero_arena(b2j_ctx *ctx, size_t nsdesc) {
 static int enc_alloc(b2j_ctx *ctx) {
     if (ctx->enc_ready) return B2J_OK;
     const Geom &g = ctx->cap_g;
-    CK(cudaMalloc(&ctx->d_pool, (size_t)g.nblocks * 64 * 4 + 64));  // +64: k_pack reads whole 16-byte groups
+    // every buffer is allocated only while its pointer is null: a call that failed half way can be repeated
+    if (!ctx->d_pool) CK(cudaMalloc(&ctx->d_pool, (size_t)g.nblocks * 64 * 4 + 64));  // +64: k_pack reads whole 16-byte groups
     int rc = ensure_tiles(ctx, g); if (rc) return rc;
     ctx->out_cap = (size_t)g.nblocks * 208 + 4096;
-    CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
+    if (!ctx->d_out) CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
     ctx->ndesc = ctx->out_cap / STUFF_CHUNK + 4;
     // 1024 scan descriptors cover 4M tiles: no geometry within the configured size re-allocates (b2j_strip_state
     // hands out pointers into this arena)
-    rc = alloc_zero_arena(ctx, std::max<size_t>((size_t)scan_desc_count(g.ntiles) + 64, 1024)); if (rc) return rc;
-    CK(cudaMalloc(&ctx->d_chunk_tile, ctx->ndesc * 4));
-    CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
-    CK(cudaMalloc(&ctx->d_quant, sizeof(QuantDev)));
+    if (!ctx->d_ctrl) { rc = alloc_zero_arena(ctx, std::max<size_t>((size_t)scan_desc_count(g.ntiles) + 64, 1024)); if (rc) return rc; }
+    if (!ctx->d_chunk_tile) CK(cudaMalloc(&ctx->d_chunk_tile, ctx->ndesc * 4));
+    if (!ctx->d_huff) CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
+    if (!ctx->d_quant) CK(cudaMalloc(&ctx->d_quant, sizeof(QuantDev)));
     CK(cudaMemcpy(ctx->d_quant, &ctx->hq, sizeof(QuantDev), cudaMemcpyHostToDevice));
     ctx->enc_ready = true;
     return B2J_OK;
@@ -247,7 +251,7 @@ int b2j_create(const b2j_params *p, b2j_ctx **out) {
     e = cudaGetDevice(&ctx->device);
     if (e != cudaSuccess) { delete ctx; return B2J_ECUDA; }  // no CUDA device: fail loudly, there is no CPU path
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B2J_ECUDA; }
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { b2j_destroy(ctx); return B2J_ECUDA; }
     ctx->stream = ctx->own_stream;
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->ev_copy) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -732,6 +736,8 @@ int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_b
     JpegInfo info;
     int rc = parse_for(ctx, jpg, len, &info, width, height); if (rc) return rc;
     if (!d_bgr) return B2J_OK;
+    // one decode in flight per context: an unfinished predecessor is finished (validated, retried if needed) first
+    if (ctx->last_jpg) { rc = b2j_decode_finish(ctx); if (rc) return rc; }
     // remembered for b2j_decode_finish: the caller keeps `jpg` alive until then
     ctx->last_jpg = jpg; ctx->last_len = len; ctx->last_bgr = d_bgr; ctx->last_step = step;
     return decode_parsed(ctx, jpg, len, info, d_bgr, step, false);

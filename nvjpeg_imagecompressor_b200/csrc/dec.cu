@@ -47,6 +47,7 @@ struct Decoder {
     char *err;
     size_t errlen;
     cudaStream_t last_stream = nullptr;
+    bool in_flight = false;     // a decode was issued and dec_check has not drained it yet
     dec_upload_fn upload = nullptr;
     void *upload_user = nullptr;
     bool speculated = false;   // the last run issued a fixed number of synchronisation launches without looking
@@ -145,12 +146,15 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     if (info.scan_offset + info.scan_len > len || info.scan_len == 0) return B2J_EFORMAT;
     int rc = ensure(d, info.scan_len, g);
     if (rc) return rc;
-    d->last_stream = s;
     const size_t n = info.scan_len;
     const size_t nsub_max = (n * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
     const int hv = g.bpm - 2;
     if (tm) cudaEventRecord(d->ev[0], s);
-    dec_build_tables(info, d->h_tb);
+    // h_tb / h_flag are rewritten by the host below: a previous decode on this decoder must have drained first
+    if (d->in_flight) { DCK(cudaStreamSynchronize(d->last_stream)); d->in_flight = false; }
+    if (dec_build_tables(info, d->h_tb) != B2J_OK) { snprintf(d->err, d->errlen, "invalid Huffman table"); return B2J_EFORMAT; }
+    d->last_stream = s;
+    d->in_flight = true;
     DCK(cudaMemcpyAsync(d->d_tb, d->h_tb, dec_tables_size(), cudaMemcpyHostToDevice, s));
     DCK(cudaMemsetAsync(d->d_ctrl, 0, sizeof(DecCtrl), s));
     DCK(cudaMemsetAsync(d->d_desc, 0, d->desc_cap * 5 * 8, s));
@@ -258,6 +262,7 @@ int dec_check(Decoder *d, char *err, size_t errlen) {
         snprintf(err, errlen, "%s in dec_check", cudaGetErrorString(cudaGetLastError()));
         return B2J_ECUDA;
     }
+    d->in_flight = false;
     if (d->speculated && d->h_flag[2]) return DEC_RETRY;   // the fixed number of launches was not enough: run again, carefully
     if (d->h_flag[1]) { snprintf(err, errlen, "decoder consistency check failed (err=%u)", d->h_flag[1]); return B2J_EINTERNAL; }
     return B2J_OK;

@@ -8,6 +8,7 @@
 // scheme of Weissenberger & Schmidt (ICPP'18): every thread decodes a fixed 1024-bit subsequence from a guessed
 // state, then re-decodes from its predecessor's end state until the states stop changing.
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 #include "dec.h"
@@ -83,14 +84,6 @@ k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, u
 
 // ------------------------------------------------------------------------------------------------------
 // Huffman decoding of one symbol from the top 16 bits of a window (jdhuff.c jpeg_huff_decode, table-driven)
-struct DecTables {                 // device copy, one per decode
-    uint16_t lut[4][1 << DEC_LUT_BITS];  // (len << 8) | symbol for codes of length <= DEC_LUT_BITS, else 0
-    int32_t maxcode[4][18];        // maxcode[l] = largest code of length l, -1 if none; [17] = sentinel
-    int32_t valoff[4][17];         // valptr[l] - mincode[l]
-    uint8_t vals[4][256];
-    uint16_t q[2][64];             // dequantisation table, natural order
-};
-
 __device__ __forceinline__ uint32_t huff_sym(const uint16_t *lut, const int32_t *maxcode, const int32_t *valoff,
                                              const uint8_t *vals, uint32_t top16, int &len) {
     const uint32_t e = lut[top16 >> (16 - DEC_LUT_BITS)];
@@ -766,13 +759,17 @@ cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *
 }
 
 static cudaError_t dec_attr() {
-    static bool done = false;
-    if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    static std::atomic<uint64_t> done{0};   // one bit per device ordinal: the attribute is per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWriteShared));
     if (e != cudaSuccess) return e;
-    done = true;
+    done.fetch_or(bit, std::memory_order_release);
     return cudaSuccess;
 }
 
@@ -834,32 +831,6 @@ cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t 
     if (g.hs == 2 && g.vs == 2) return upcolor_one<2, 2>(py, pcb, pcr, g, bgr, step, s);
     if (g.hs == 4 && g.vs == 1) return upcolor_one<4, 1>(py, pcb, pcr, g, bgr, step, s);
     return cudaErrorInvalidValue;
-}
-
-size_t dec_tables_size() { return sizeof(DecTables); }
-
-// host-side construction of the decode tables (jdhuff.c jpeg_make_d_derived_tbl)
-void dec_build_tables(const JpegInfo &info, void *dst) {
-    DecTables *t = (DecTables *)dst;
-    memset(t, 0, sizeof(*t));
-    for (int ti = 0; ti < 4; ti++) {
-        int code = 0, p = 0;
-        for (int l = 1; l <= 16; l++) {
-            const int n = info.bits[ti][l];
-            t->valoff[ti][l] = p - code;
-            for (int i = 0; i < n; i++, p++, code++) {
-                if (l <= DEC_LUT_BITS) {
-                    const int lo = code << (DEC_LUT_BITS - l), cnt = 1 << (DEC_LUT_BITS - l);
-                    for (int j = 0; j < cnt; j++) t->lut[ti][lo + j] = (uint16_t)((l << 8) | info.vals[ti][p]);
-                }
-            }
-            t->maxcode[ti][l] = n ? code - 1 : -1;
-            code <<= 1;
-        }
-        t->maxcode[ti][17] = 0x7fffffff;
-        memcpy(t->vals[ti], info.vals[ti], 256);
-    }
-    memcpy(t->q, info.qt, sizeof(t->q));
 }
 
 }  // namespace b2j

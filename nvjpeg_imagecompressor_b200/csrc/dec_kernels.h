@@ -8,8 +8,16 @@ namespace b2j {
 constexpr int DEC_LUT_BITS = 10;
 constexpr int DEC_SUB_BITS = 1024;
 
+struct DecTables {                 // device copy, one per decode
+    uint16_t lut[4][1 << DEC_LUT_BITS];  // (len << 8) | symbol for codes of length <= DEC_LUT_BITS, else 0
+    int32_t maxcode[4][18];        // maxcode[l] = largest code of length l, -1 if none; [17] = sentinel
+    int32_t valoff[4][17];         // valptr[l] - mincode[l]
+    uint8_t vals[4][256];
+    uint16_t q[2][64];             // dequantisation table, natural order
+};
 size_t dec_tables_size();
-void dec_build_tables(const JpegInfo &info, void *dst_host);
+// host side (dec_parse.cpp); B2J_EFORMAT for a table with more codes than its lengths allow
+int dec_build_tables(const JpegInfo &info, void *dst_host);
 
 // 4 KB chunks [c0, c1) of the n-byte scan; `ticket`: a zeroed counter per launch; *avail = bytes produced so far
 cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "dec.h"
+#include "dec_kernels.h"
 
 namespace b2j {
 
@@ -59,6 +60,12 @@ int parse_jpeg(const uint8_t *jpg, size_t len, JpegInfo *info) {
                 hb[tc][th][0] = 0;
                 for (int l = 1; l <= 16; l++) { hb[tc][th][l] = s[l]; ns += s[l]; }
                 if (ns > 256 || n < 17 + ns) return B2J_EFORMAT;
+                // jdhuff.c jpeg_make_d_derived_tbl: a length may not hold more codes than the prefix code space leaves
+                for (int l = 1, code = 0; l <= 16; l++) {
+                    code += s[l];
+                    if (code > (1 << l)) return B2J_EFORMAT;
+                    code <<= 1;
+                }
                 memset(hv[tc][th], 0, 256);
                 memcpy(hv[tc][th], s + 17, ns);
                 have_h[tc][th] = true;
@@ -115,6 +122,36 @@ int parse_jpeg(const uint8_t *jpg, size_t len, JpegInfo *info) {
         p += L;
     }
     return B2J_EFORMAT;
+}
+
+size_t dec_tables_size() { return sizeof(DecTables); }
+
+// host-side construction of the decode tables (jdhuff.c jpeg_make_d_derived_tbl). parse_jpeg has already rejected
+// over-full tables; the bounds are checked again here because the tables index shared memory on the device.
+int dec_build_tables(const JpegInfo &info, void *dst) {
+    DecTables *t = (DecTables *)dst;
+    memset(t, 0, sizeof(*t));
+    for (int ti = 0; ti < 4; ti++) {
+        int code = 0, p = 0;
+        for (int l = 1; l <= 16; l++) {
+            const int n = info.bits[ti][l];
+            if (code + n > (1 << l) || p + n > 256) return B2J_EFORMAT;
+            t->valoff[ti][l] = p - code;
+            for (int i = 0; i < n; i++, p++, code++) {
+                if (l <= DEC_LUT_BITS) {
+                    const int lo = code << (DEC_LUT_BITS - l), cnt = 1 << (DEC_LUT_BITS - l);
+                    if (lo + cnt > (1 << DEC_LUT_BITS)) return B2J_EFORMAT;
+                    for (int j = 0; j < cnt; j++) t->lut[ti][lo + j] = (uint16_t)((l << 8) | info.vals[ti][p]);
+                }
+            }
+            t->maxcode[ti][l] = n ? code - 1 : -1;
+            code <<= 1;
+        }
+        t->maxcode[ti][17] = 0x7fffffff;
+        memcpy(t->vals[ti], info.vals[ti], 256);
+    }
+    memcpy(t->q, info.qt, sizeof(t->q));
+    return B2J_OK;
 }
 
 }  // namespace b2j

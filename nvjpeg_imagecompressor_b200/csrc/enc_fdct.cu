@@ -17,6 +17,8 @@
 //            bits), symbol statistics with full-warp shared atomics, coalesced stores to the token pool
 // The entropy coder (enc_huff.cu k_pack) then works token-parallel: uniform work per lane instead of a divergent
 // per-coefficient branch. With DUMP the quantised coefficients are also written (parity tests only).
+#include <atomic>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -579,11 +581,16 @@ static cudaError_t launch_one2(const uint8_t *img, size_t step, const Geom &g, c
                                int16_t *coef, cudaStream_t s) {
     using C = K1<HS, VS>;
     constexpr int SM = DUMP ? C::SMEM_DUMP : C::SMEM;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_fdct<HS, VS, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+    // the attribute is per device: one bit per device ordinal (a process may hold contexts on several GPUs)
+    static std::atomic<uint64_t> attr_done{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+        e = cudaFuncSetAttribute(k_fdct<HS, VS, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.fetch_or(bit, std::memory_order_release);
     }
     // TMA bulk copies need 16-byte aligned global addresses and sizes for every row of every interior tile
     const int row_unit = g.tm * C::MCU_W * 3;  // byte offset between tiles in a row

@@ -1,4 +1,4 @@
-// ASAN fuzz harness for the product's JPEG header parser (csrc/dec_parse.cpp): every mutated input is copied into an
+// ASAN fuzz harness for the product's JPEG header parser (csrc/dec_parse.cpp: parse_jpeg + dec_build_tables): every mutated input is copied into an
 // exact-size heap block so that any read past the end is reported.
 #include <cstdio>
 #include <cstdlib>
@@ -6,6 +6,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../nvjpeg_imagecompressor_b200/csrc/dec.h"
+#include "../../nvjpeg_imagecompressor_b200/csrc/dec_kernels.h"
 static uint32_t st = 99;
 static uint32_t rnd() { st = st * 1664525u + 1013904223u; return st >> 8; }
 int main(int argc, char **argv) {
@@ -35,6 +36,10 @@ int main(int argc, char **argv) {
         if (rc == 0) {
             ok++;
             if (info.scan_offset + info.scan_len > s.size()) { printf("BAD RANGE it=%d\n", it); return 2; }
+            // the table builder writes a fixed-size block: exact-size heap copy so ASAN sees any overflow
+            void *tb = malloc(b2j::dec_tables_size());
+            b2j::dec_build_tables(info, tb);
+            free(tb);
             if (info.W <= 0 || info.H <= 0 || info.css < 0 || info.css > 4) { printf("BAD INFO it=%d\n", it); return 2; }
         }
         total++;
