@@ -185,7 +185,7 @@ B2J_API int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank,
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
 enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4,
-       B2J_DBG_TOKEN_COUNT = 5 /* DEC_COEF: decoded blocks, zig-zag order, DC as difference. TOKEN_COUNT: uint32: run-length tokens of the last encode (4 bytes each between the two passes) */ };
+       B2J_DBG_TOKEN_COUNT = 5, B2J_DBG_TOKENS = 6, B2J_DBG_TILE_RECS = 7, B2J_DBG_SLOTS = 8 /* SLOTS: the per-tile bit buffers (SLOT_WORDS = 13312 uint32 per tile, MSB first). TOKENS: the token pool (uint32 each, csrc/common.cuh); TILE_RECS: one 24-byte record per fdct tile. DEC_COEF: decoded blocks, zig-zag order, DC as difference. TOKEN_COUNT: uint32: run-length tokens of the last encode (4 bytes each between the two passes) */ };
 B2J_API int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len);
 /* flags bit0 (B2J_DEBUG_COEF): the next encodes also store the quantised coefficients for B2J_DBG_COEF */
 /* bit1 (B2J_DEBUG_SMALL_PACK_BUFFERS): the entropy coder's per-warp bit buffers overflow on purpose (tests its

@@ -12,7 +12,7 @@ CSS = {"444": 0, "422": 1, "440": 2, "420": 3, "411": 4}
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ECAPACITY", -5: "EFORMAT", -6: "EINTERNAL", -7: "ESIZE"}
 
 FLAG_NO_PINNED, FLAG_ENCODE, FLAG_DECODE = 1, 2, 4
-DBG_COEF, DBG_HIST, DBG_TABLES, DBG_TILE_BITS, DBG_DEC_COEF, DBG_TOKEN_COUNT = 0, 1, 2, 3, 4, 5
+DBG_COEF, DBG_HIST, DBG_TABLES, DBG_TILE_BITS, DBG_DEC_COEF, DBG_TOKEN_COUNT, DBG_TOKENS, DBG_TILE_RECS, DBG_SLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class Params(C.Structure):

@@ -162,8 +162,7 @@ static void make_quant(int quality, QuantDev *q) {
             if (v > 255) v = 255;
             const uint32_t d = 8u * (uint32_t)v;
             q->q[t][i] = (uint16_t)v;
-            q->half[t][i] = d >> 1;
-            q->recip[t][i] = (uint32_t)((1ull << 32) / d) + 1u;  // exact floor(x/d) for x*d < 2^32
+            q->finv[t][i] = (float)((1.0 / (double)d) * (1.0 + 1.0 / 1048576.0));   // see k_fdct: exact for |c| <= 2^18
         }
 }
 
@@ -904,6 +903,9 @@ int b2j_debug_read(b2j_ctx *ctx, int what, void *dst, size_t cap, size_t *len) {
     case B2J_DBG_TABLES: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_huff; n = sizeof(HuffDev); break;
     case B2J_DBG_TILE_BITS: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_tile_bits; n = (size_t)ctx->g.ntiles * 4; break;
     case B2J_DBG_TOKEN_COUNT: if (!ctx->enc_ready) return B2J_EINVAL; src = &ctx->d_ctrl->pool_count; n = 4; break;
+    case B2J_DBG_TOKENS: { if (!ctx->enc_ready) return B2J_EINVAL; uint32_t cnt = 0; CK(cudaMemcpy(&cnt, &ctx->d_ctrl->pool_count, 4, cudaMemcpyDeviceToHost)); src = ctx->d_pool; n = (size_t)cnt * 4; break; }
+    case B2J_DBG_TILE_RECS: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_recs; n = (size_t)ctx->g.ntiles * sizeof(TileRec); break;
+    case B2J_DBG_SLOTS: if (!ctx->enc_ready) return B2J_EINVAL; src = ctx->d_slots; n = (size_t)ctx->g.ntiles * SLOT_WORDS * 4; break;
     case B2J_DBG_DEC_COEF: if (!ctx->dec) return B2J_EINVAL; src = dec_coef_ptr(ctx->dec, &n); break;
     default: return B2J_EINVAL;
     }

@@ -20,11 +20,17 @@ struct Geom {
     int ntiles;        // fdct/pack tiles = tiles_x * mcuy
 };
 
-// One token per coded coefficient / EOB: [29:28] number of ZRL (0xF0) symbols that precede it, [25:24] table (0 DC0,
-// 1 AC0, 2 DC1, 3 AC1), [23:16] symbol (run<<4 | size), [15:0] value bits (already masked to `size` bits). TOK_RAWDC: DC of a block whose predecessor lives in the
-// previous tile; [17:16] = component, [15:0] = the quantised DC itself (k_dc_edge_hist rewrites it as a difference token).
-constexpr uint32_t TOK_RAWDC = 1u << 26;
-constexpr uint32_t TOK_RAWAC = 1u << 27;   // k_fdct-internal: [21:16] zig-zag position, [15:0] coefficient; never leaves the kernel
+// One token per coded coefficient / EOB / DC difference:
+//   [27:26] number of ZRL (0xF0) symbols that precede it (zero run >> 4)   [25:22] zero run & 15
+//   [21:20] table (0 DC0, 1 AC0, 2 DC1, 3 AC1)                            [19:16] size (bits of |value|)
+//   [15:0]  value bits (already masked to `size` bits)
+// Bits [25:16] index the symbol (TOK_SYM: the histogram bins of k_fdct and the code table of k_pack use this order).
+// TOK_RAWDC: DC of a block whose predecessor lives in the previous tile; [21:20] table, [17:16] component, [15:0] the
+// quantised DC itself (k_dc_edge_hist rewrites it as a difference token).
+constexpr uint32_t TOK_RAWDC = 1u << 28;
+__host__ __device__ constexpr uint32_t tok_bin(uint32_t table, uint32_t sym) {   // bin of (table, JPEG symbol)
+    return (table & 1u) ? (((sym >> 4) << 6) | (table << 4) | (sym & 15u)) : ((table << 4) | (sym & 15u));
+}
 struct TileRec {                               // one per fdct tile (<= 256 blocks, one MCU-row segment)
     uint32_t base, count;                      // token run in the pool
     int16_t first_dc[3], last_dc[3];           // DCs of the tile's first / last MCU (last Y block, Cb, Cr)
@@ -76,9 +82,8 @@ __device__ __constant__ const uint8_t c_zigzag_nat[64] = {0,  1,  8,  16, 9,  2,
 __device__ __forceinline__ int zigzag_nat_rt(int k) { return c_zigzag_nat[k]; }
 
 // ---- device-side tables -------------------------------------------------------------------------------
-struct QuantDev {          // forward: q = umulhi(|c| + half, recip), natural order; [0] luma, [1] chroma
-    uint32_t recip[2][64];
-    uint32_t half[2][64];
+struct QuantDev {          // forward: q = low half of fma(c, finv, 1.5 * 2^23), natural order; [0] luma, [1] chroma
+    float finv[2][64];
     uint16_t q[2][64];     // natural order quant values (dequantisation + DQT marker)
 };
 

@@ -44,8 +44,8 @@ struct K1 {
     static constexpr int OFF_Y = (RAW_BYTES + 15) & ~15;
     static constexpr int OFF_CB = OFF_Y + Y_BYTES;
     static constexpr int OFF_CR = OFF_CB + C_BYTES;
-    static constexpr int OFF_Q = TOK_BYTES;              // uint2[3][64]: luma, chroma, all-zero (dummy blocks)
-    static constexpr int OFF_HIST = OFF_Q + 1536;        // uint32[4][256]
+    static constexpr int OFF_Q = TOK_BYTES;              // float[3][64] (+ pad): luma, chroma, all-zero (dummy blocks)
+    static constexpr int OFF_HIST = OFF_Q + 1536;        // uint32[1024], index = token bits [25:16]
     static constexpr int OFF_DC = OFF_HIST + 4096;       // int16[256]
     static constexpr int OFF_MISC = OFF_DC + 512;        // warp totals[8], pool base, chroma DC token offsets
     static constexpr int OFF_BAR = OFF_MISC + 64;        // mbarrier
@@ -170,35 +170,30 @@ __device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &c
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : v); }
 
-// Stage C of k_fdct: entries (TOK_RAWAC | chroma << 24 | zero run << 16 | coefficient) become final tokens
-// (ZRL count | table | run/size symbol | value bits); DC and EOB tokens pass through. Branch-free: the conversion is
-// computed for every word and selected. Every token counts one symbol; the tile's three raw-DC tokens (first MCU)
-// land in bins 0x000 / 0x201 / 0x202 and are taken out again by thread 0 (k_dc_edge_hist counts their real symbols).
+// Stage C of k_fdct: entries (run << 22 | table << 20 | coefficient, DC difference or 0 for EOB) become final tokens
+// (common.cuh: ZRL count | run & 15 | table | size | value bits) with ONE formula for DC, AC and EOB entries: the
+// size is the bit length of |value|, the value bits are jchuff.c's (value, or value - 1 if negative, masked). Raw-DC
+// tokens (first MCU of the tile) pass through. Every token counts one symbol in the bin given by its bits [25:16];
+// the three raw-DC tokens land in bins 0x000 / 0x021 / 0x022 and are taken out again by thread 0 (k_dc_edge_hist
+// counts their real symbols).
 template <bool HIST>
 __device__ __forceinline__ void stage_c(const uint32_t *tok, uint32_t *__restrict__ dst, uint32_t total, uint32_t *hs, int tid) {
-    uint32_t zrl = 0;   // ZRL symbols seen by this thread: luma in the low half, chroma in the high half
 #pragma unroll 4
     for (uint32_t i = tid; i < total; i += 256) {
         const uint32_t e = tok[i];
-        const uint32_t run = (e >> 16) & 63u;   // DC / EOB tokens: symbol < 16, so their "ZRL count" below is 0
         const int z = (int)(int16_t)(e & 0xFFFFu);
-        uint32_t msb;
-        asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"((uint32_t)(z < 0 ? -z : z)));
-        const uint32_t nb = msb + 1u;           // bfind(0) = -1
-        const uint32_t cb = (e >> 24) & 1u;
-        const uint32_t nz = run >> 4;
-        zrl += nz << (cb * 16u);
-        const uint32_t conv = (nz << 28) | ((1u + 2u * cb) << 24) | ((((run & 15u) << 4) | nb) << 16) |
-                              ((uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u));
-        const uint32_t tk = (e & TOK_RAWAC) ? conv : e;
+        const uint32_t nb = 32u - (uint32_t)__clz(abs(z));
+        const uint32_t vb = (uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u);
+        const uint32_t conv = (e & 0xFFF00000u) | (nb << 16) | vb;
+        const uint32_t tk = (e & TOK_RAWDC) ? e : conv;
         dst[i] = tk;
-        if (HIST) atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
+        if (HIST) {
+            atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
+            const uint32_t nz = (tk >> 26) & 3u;        // ZRL (0xF0) symbols ahead of this coefficient: about one token in sixty
+            if (nz) atomicAdd(&hs[(15u << 6) | (tk >> 16 & 0x30u)], nz);
+        }
     }
-    if (HIST) {
-        if (zrl & 0xFFFFu) atomicAdd(&hs[0x1F0], zrl & 0xFFFFu);
-        if (zrl >> 16) atomicAdd(&hs[0x3F0], zrl >> 16);
-        if (tid == 0) { atomicSub(&hs[0x000], 1u); atomicSub(&hs[0x201], 1u); atomicSub(&hs[0x202], 1u); }
-    }
+    if (HIST && tid == 0) { atomicSub(&hs[0x000], 1u); atomicSub(&hs[0x021], 1u); atomicSub(&hs[0x022], 1u); }
 }
 
 template <int HS, int VS, bool DUMP>
@@ -211,7 +206,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     uint8_t *raw = smem;
     uint32_t *tok = reinterpret_cast<uint32_t *>(smem);
     uint8_t *Yp = smem + C::OFF_Y, *Cbp = smem + C::OFF_CB, *Crp = smem + C::OFF_CR;
-    uint2 *qs = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
+    float *qs = reinterpret_cast<float *>(smem + C::OFF_Q);
     uint32_t *hs = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
     int16_t *dcs = reinterpret_cast<int16_t *>(smem + C::OFF_DC);
     uint32_t *misc = reinterpret_cast<uint32_t *>(smem + C::OFF_MISC);
@@ -229,8 +224,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     const int tile = my * g.tiles_x + blockIdx.x;
 
     // quantisation constants + histogram init
-    if (tid < 128) qs[tid] = make_uint2(qd->recip[tid >> 6][tid & 63], qd->half[tid >> 6][tid & 63]);
-    else if (tid < 192) qs[tid] = make_uint2(0u, 0u);   // reciprocal 0: every coefficient of a dummy block quantises to 0
+    if (tid < 128) qs[tid] = qd->finv[tid >> 6][tid & 63];
+    else if (tid < 192) qs[tid] = 0.0f;   // reciprocal 0: every coefficient of a dummy block quantises to 0
     if (do_hist)
         for (int i = tid; i < 1024; i += 256) hs[i] = 0;
 
@@ -392,30 +387,33 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             fdct8<true>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
         v[0] -= 8192;  // 64 samples x 128: the only output the -128 level shift changes (exact: multiple of 4)
 
-        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, as an exact reciprocal multiply; the
-        // results are kept as 16-bit pairs in zig-zag order (they live across the CTA scan below); the non-zero AC
-        // coefficients are counted on the way (one token each)
-        const uint2 *qt = qs + ((C::HV > 1 && !real) ? 2 : tbl) * 64;
-        int nnz = 0, zprev = 0, qprev = 0;
+        // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, on the FMA pipes, which the integer
+        // transform leaves idle: with finv = fl32((1 + 2^-20) / d) the single rounding of fma(c, finv, 1.5 * 2^23) lands
+        // on exactly that quotient for every divisor and |c| <= 2^18 (ties of |c|/d go away from zero because finv is a
+        // little large, everything else is further than |c| * 2^-20 from a tie; checked exhaustively on the CPU,
+        // tests/cpp/quant_exhaustive.c). The quotient is the low half of the result's bit pattern; results are kept
+        // as 16-bit pairs in zig-zag order (they live across the CTA scan below); the non-zero AC coefficients are
+        // counted on the way (one token each) as saturate(q * q), also on the FMA pipes.
+        const float4 *qt = reinterpret_cast<const float4 *>(qs + ((C::HV > 1 && !real) ? 2 : tbl) * 64);
+        constexpr float MAGIC = 12582912.0f;   // 1.5 * 2^23
+        float nnzf = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 64; k++) {
-            const int n = zigzag_nat(k);
-            const int x = v[n];
-            const uint2 rq = qt[n];
-            const int s = x >> 31;
-            const uint32_t a = (uint32_t)((x ^ s) - s) + rq.y;
-            const int qa = (int)__umulhi(a, rq.x);
-            const int z = (qa ^ s) - s;
-            if (k == 0) mydc = z;
-            if (k & 1) {
-                pk[k >> 1] = __byte_perm((uint32_t)zprev, (uint32_t)z, 0x5410);
-                nnz += (k == 1 ? 0 : min(qprev, 1)) + min(qa, 1);   // AC only; one three-input add per pair
-            } else {
-                zprev = z;
-                qprev = qa;
+        for (int n4 = 0; n4 < 16; n4++) {
+            const float4 qv = qt[n4];
+            const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int n = n4 * 4 + j;
+                const float xf = __int_as_float(v[n] + 0x4B400000) - MAGIC;   // exact int -> float for |c| < 2^22
+                const float r = fmaf(xf, qq[j], MAGIC);
+                if (n != 0) { const float zf = r - MAGIC; nnzf += __saturatef(zf * zf); }
+                v[n] = __float_as_int(r);
             }
         }
-        ntok = 1 + nnz + ((pk[31] >> 16) == 0u ? 1 : 0);   // DC, one per non-zero AC, EOB iff the last coefficient is zero
+        mydc = v[0] - 0x4B400000;
+#pragma unroll
+        for (int k = 0; k < 64; k += 2) pk[k >> 1] = __byte_perm((uint32_t)v[zigzag_nat(k)], (uint32_t)v[zigzag_nat(k + 1)], 0x5410);
+        ntok = 1 + (int)nnzf + ((pk[31] >> 16) == 0u ? 1 : 0);   // DC, one per non-zero AC, EOB iff the last coefficient is zero
         if constexpr (DUMP) {
 #pragma unroll
             for (int c = 0; c < 8; c++)
@@ -451,13 +449,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         int pb = -1;
         if (isY) pb = bn > 0 ? blk - 1 : (m > 0 ? blk - C::BPM + C::HV - 1 : -1);
         else pb = m > 0 ? blk - C::BPM : -1;
-        if (pb >= 0) {
-            const int diff = mydc - (int)dcs[pb];
-            const int nb = 32 - __clz(diff < 0 ? -diff : diff);
-            t0 = ((uint32_t)(tbl * 2) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
-        } else {
-            t0 = TOK_RAWDC | ((uint32_t)(tbl * 2) << 24) | ((uint32_t)comp << 16) | ((uint32_t)mydc & 0xFFFFu);
-        }
+        if (pb >= 0) t0 = ((uint32_t)(tbl * 2) << 20) | ((uint32_t)(mydc - (int)dcs[pb]) & 0xFFFFu);   // stage C sizes it
+        else t0 = TOK_RAWDC | ((uint32_t)(tbl * 2) << 20) | ((uint32_t)comp << 16) | ((uint32_t)mydc & 0xFFFFu);
     }
 
     // ---- place of every block in the tile's token run: CTA scan of the token counts
@@ -476,13 +469,14 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     if (tid == C::HV + 1) misc[10] = off;
 
     // ---- run-length walk (jchuff.c encode_one_block): one entry per non-zero AC coefficient, straight to its slot:
-    //      TOK_RAWAC | chroma << 24 | zero run << 16 | coefficient. The divergent region is the store and the reset
-    //      of the run counter; sizes, value bits and ZRL counts are derived in stage C with full warps.
+    //      zero run << 22 | AC table << 20 | coefficient -- the run lands in the token's (run & 15, ZRL count) fields as
+    //      it is. The divergent region is the store and the reset of the run counter; sizes and value bits are derived
+    //      in stage C with full warps.
     if (active) {
         uint32_t sa = smem_u32(tok + off);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(t0) : "memory");
         sa += 4;
-        const uint32_t rbase = TOK_RAWAC | ((uint32_t)tbl << 24);
+        const uint32_t rbase = (uint32_t)(tbl * 2 + 1) << 20;
         uint32_t r = rbase;
 #pragma unroll
         for (int k = 1; k < 64; k++) {
@@ -492,11 +486,11 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
                 const uint32_t e = (k & 1) ? __byte_perm(p2, r, 0x7632) : ((p2 & 0xFFFFu) | r);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(e) : "memory");
                 sa += 4;
-                r = rbase - 0x10000u;
+                r = rbase - (1u << 22);
             }
-            r += 0x10000u;
+            r += 1u << 22;
         }
-        if (pk[31] < 0x10000u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"((uint32_t)(tbl * 2 + 1) << 24) : "memory");
+        if (pk[31] < 0x10000u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(rbase) : "memory");   // EOB
     }
     __syncthreads();
     if (tid == 0) {
@@ -523,9 +517,10 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     }
     if (do_hist) {
         __syncthreads();
-        for (int i = tid; i < 1024; i += 256) {
+        for (int i = tid; i < 1024; i += 256) {   // bin = run & 15 << 6 | table << 4 | size
             const uint32_t n = hs[i];
-            if (n) atomicAdd(&ghist[(i >> 8) * 257 + (i & 255)], n);
+            const int t = (i >> 4) & 3;
+            if (n) atomicAdd(&ghist[t * 257 + ((t & 1) ? (((i >> 6) << 4) | (i & 15)) : (i & 15))], n);
         }
     }
 }
@@ -556,7 +551,7 @@ k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restri
         if (do_hist) atomicAdd(&s_h[c ? 1 : 0][nb & 15], 1u);
         if (resolve) {
             const uint32_t p = c == 0 ? 0u : (c == 1 ? r.pos_cb : r.pos_cr);
-            pool[r.base + p] = ((uint32_t)(c ? 2 : 0) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+            pool[r.base + p] = ((uint32_t)(c ? 2 : 0) << 20) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
         }
     }
     if (t < 3) last_dc[t] = recs[ntile - 1].last_dc[t];

@@ -46,7 +46,7 @@ __constant__ uint8_t c_std_ac_val[2][162] = {
 // least, by two warp reductions each (min of frequency, then max of index among the minima); tree membership is a
 // group id per symbol so "increment codesize along the others chain" becomes "increment every member".
 __global__ void __launch_bounds__(128)
-k_tables(const uint32_t *__restrict__ hist, int optimize, HuffDev *__restrict__ huff, const QuantDev *__restrict__ qd,
+k_tables(const uint32_t *hist /* the predecessor's output: no __restrict__, loads must stay behind pdl_wait() */, int optimize, HuffDev *__restrict__ huff, const QuantDev *__restrict__ qd,
          int full_w, int full_h, int hs, int vs, uint8_t *__restrict__ out, int emit_header, uint32_t *__restrict__ err_out) {
     __shared__ uint8_t s_bits[4][17];
     __shared__ uint8_t s_vals[4][256];
@@ -324,20 +324,24 @@ constexpr int PACK_CTAS = 8;                     // resident CTAs per SM (regist
 constexpr int PACK_K = 8;                        // consecutive tokens per lane and step
 constexpr int PACK_STEP = 32 * PACK_K;           // tokens per warp and step
 constexpr uint32_t PACK_DENSE_TOKENS = 7000;     // above this the shares may not fit the warp buffers: two-pass path
-constexpr uint32_t TOK_NULL = 0x00100000u;       // DC0 symbol 0x10 does not exist: code length 0, no value bits
+constexpr uint32_t TOK_NULL = 1u << 22;          // table DC0 with a zero run of 1 does not exist: no code, no value bits
 
 struct PackShared {
     uint32_t buf[WIN_WORDS];
     uint32_t sub[PACK_WARPS][SUB_WORDS + 4];
-    uint32_t enc[1024];
+    uint32_t code[1024];                         // [token bits 25:16] code << size (the value bits are OR-ed below it)
+    uint8_t len[4096];                           // [token bits 27:16] code length + size + ZRL count * length of the ZRL code
     uint32_t wlen[3][PACK_WARPS];                // bit counts of the warps' shares, three tiles deep
     uint32_t bnd[2][PACK_WARPS + 1];             // words shared by two shares (cell b: the word holding the start of share b)
 };
 
 // One lane's contiguous piece of the bit string: bits are appended to a 64-bit accumulator and every completed
-// 32-bit word is OR-ed into the buffer. `cnt` = valid low bits of acc that are not flushed yet (< 32 between calls).
-// WINDOWED: C++ path, words outside [0, WIN_WORDS) are skipped. Otherwise: predicated red.shared (no branch), words
-// at or beyond the byte address `limit` are dropped (the caller notices the overflow from the share's length).
+// 32-bit word goes to the buffer. `cnt` = valid low bits of acc that are not flushed yet (< 32 between calls).
+// WINDOWED (dense tiles, all warps share one window): atomicOr, words outside [0, WIN_WORDS) are skipped.
+// Otherwise (the warp's own buffer): a word is completed by exactly one lane, which stores it whole -- bits that
+// earlier lanes own in it are zero in that store and are OR-ed in afterwards (finish(), after a warp barrier), so
+// the hot path has no atomics and the buffer needs no clearing except the word a share ends in. Words at or beyond
+// the byte address `limit` are dropped (the caller notices the overflow from the share's length).
 template <bool WINDOWED>
 struct LaneEmitter {
     uint64_t acc;
@@ -362,7 +366,7 @@ struct LaneEmitter {
         } else {
             const uint32_t wv = __funnelshift_r((uint32_t)acc, (uint32_t)(acc >> 32), cnt);   // acc >> (cnt - 32) if cnt >= 32
             asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ge.u32 p, %1, 32;\n\tsetp.lt.and.u32 q, %0, %3, p;\n\t"
-                         "@q red.shared.or.b32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t@p sub.u32 %1, %1, 32;\n\t}"
+                         "@q st.shared.b32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t@p sub.u32 %1, %1, 32;\n\t}"
                          : "+r"(addr), "+r"(cnt) : "r"(wv), "r"(limit) : "memory");
         }
     }
@@ -370,7 +374,7 @@ struct LaneEmitter {
         if (cnt) {
             const uint32_t wv = (uint32_t)acc << (32u - cnt);
             if (WINDOWED) { if ((uint32_t)wi < (uint32_t)WIN_WORDS) atomicOr(&buf[wi], wv); }
-            else if (addr < limit) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(wv) : "memory");
+            else if (addr < limit) atomicOr(buf + ((addr - smem_u32(buf)) >> 2), wv);
         }
     }
 };
@@ -392,9 +396,8 @@ __device__ __forceinline__ void load_tokens(const uint4 *tk4, uint32_t v0, uint3
 
 // The warp's share [lo, hi) of the walk, coded into `buf` starting at bit `run`; returns the bit position after it.
 template <bool WINDOWED>
-__device__ __forceinline__ int pack_scatter(const uint32_t *enc, uint32_t *buf, uint32_t nwords, const uint4 *tk4, uint32_t a,
+__device__ __forceinline__ int pack_scatter(const PackShared &sh, uint32_t *buf, uint32_t nwords, const uint4 *tk4, uint32_t a,
                                             uint32_t lo, uint32_t hi, int run, int lane, uint32_t zr_y, uint32_t zr_c) {
-    const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
     for (uint32_t s0 = lo; s0 < hi; s0 += PACK_STEP) {
         const uint32_t v0 = s0 + lane * PACK_K;
         uint32_t w[PACK_K], L[PACK_K], bits[PACK_K];
@@ -406,11 +409,10 @@ __device__ __forceinline__ int pack_scatter(const uint32_t *enc, uint32_t *buf, 
         }
 #pragma unroll
         for (int k = 0; k < PACK_K; k++) {
-            const uint32_t en = enc[(w[k] >> 16) & 0x3FFu];
-            const uint32_t nb = (w[k] >> 16) & 15u;
-            L[k] = (en & 31u) + nb;
-            bits[k] = ((en >> 8) << nb) | (w[k] & 0xFFFFu);
-            Lt += L[k] + (w[k] >> 28) * ((w[k] & (2u << 24)) ? zl_c : zl_y);
+            const uint32_t i12 = (w[k] >> 16) & 0xFFFu;
+            L[k] = sh.len[i12];
+            bits[k] = sh.code[i12 & 0x3FFu] | (w[k] & 0xFFFFu);
+            Lt += L[k];
         }
         uint32_t inc = Lt;
 #pragma unroll
@@ -420,35 +422,41 @@ __device__ __forceinline__ int pack_scatter(const uint32_t *enc, uint32_t *buf, 
         }
         LaneEmitter<WINDOWED> e;
         e.start(buf, run + (int)(inc - Lt), nwords);
+        if (!WINDOWED) {
+            // lane 0 continues the word the previous step ended in: it takes the bits that are already there
+            if (lane == 0 && e.cnt != 0u && e.addr < e.limit) e.acc = (uint64_t)(buf[run >> 5] >> (32u - e.cnt));
+        }
         run += (int)__shfl_sync(0xffffffffu, inc, 31);
 #pragma unroll
         for (int k = 0; k < PACK_K; k++) {
-            const uint32_t nz = w[k] >> 28;
+            uint32_t n = L[k];
+            const uint32_t nz = (w[k] >> 26) & 3u;
             if (nz) {   // ZRL symbols ahead of this coefficient (about one token in sixty)
-                const uint32_t zr = (w[k] & (2u << 24)) ? zr_c : zr_y;
+                const uint32_t zr = (w[k] & (2u << 20)) ? zr_c : zr_y;
+                n -= nz * (zr & 31u);
                 e.put(zr >> 8, zr & 31u);
                 if (nz > 1u) {
                     e.put(zr >> 8, zr & 31u);
                     if (nz > 2u) e.put(zr >> 8, zr & 31u);
                 }
             }
-            e.put(bits[k], L[k]);
+            e.put(bits[k], n);
         }
+        if (!WINDOWED) __syncwarp();   // every whole word of this step is stored: now the pieces that do not fill a word
         e.finish();
+        if (!WINDOWED) __syncwarp();
     }
     return run;
 }
 
 // bits of the warp's share without coding them (two-pass path)
-__device__ __forceinline__ uint32_t pack_length(const uint32_t *enc, const uint4 *tk4, uint32_t a, uint32_t lo, uint32_t hi,
-                                                int lane, uint32_t zl_y, uint32_t zl_c) {
+__device__ __forceinline__ uint32_t pack_length(const PackShared &sh, const uint4 *tk4, uint32_t a, uint32_t lo, uint32_t hi, int lane) {
     uint32_t len = 0;
     for (uint32_t v0 = lo + lane * PACK_K; v0 < hi; v0 += PACK_STEP) {
         uint32_t w[PACK_K];
         load_tokens(tk4, v0, a, hi, w);
 #pragma unroll
-        for (int k = 0; k < PACK_K; k++)
-            len += (enc[(w[k] >> 16) & 0x3FFu] & 31u) + ((w[k] >> 16) & 15u) + (w[k] >> 28) * ((w[k] & (2u << 24)) ? zl_c : zl_y);
+        for (int k = 0; k < PACK_K; k++) len += sh.len[(w[k] >> 16) & 0xFFFu];
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
@@ -478,7 +486,7 @@ __device__ __forceinline__ void pack_flush_shared_words(uint32_t *bnd, const uin
 }
 
 __global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
-k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int ntiles, const HuffDev *__restrict__ huff,
+k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int ntiles, const HuffDev *huff,
        uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits, uint32_t sub_words) {
     __shared__ __align__(16) PackShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -486,10 +494,29 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
     for (int i = tid; i < PACK_WARPS * (SUB_WORDS + 4); i += PACK_THREADS) sh.sub[0][i] = 0;
     if (tid < 2 * (PACK_WARPS + 1)) sh.bnd[0][tid] = 0;
     pdl_wait();   // everything above ran under k_tables
-    for (int i = tid; i < 1024; i += PACK_THREADS) sh.enc[i] = huff->enc[i >> 8][i & 255];
+    // code tables in token-bin order (common.cuh tok_bin): code << size, and the full length per (ZRL count, bin).
+    // The tables are k_tables' output: every load of them must stay behind pdl_wait() (volatile: a load through a
+    // const __restrict__ pointer may be hoisted above the wait).
+    const volatile HuffDev *vh = huff;
+    for (int i = tid; i < 1024; i += PACK_THREADS) {
+        const uint32_t bin = (uint32_t)i, t = (bin >> 4) & 3u, nb = bin & 15u;
+        const bool valid = (t & 1u) || (bin >> 6) == 0u;   // DC bins carry no run
+        const uint32_t sym = (t & 1u) ? (((bin >> 6) << 4) | nb) : nb;
+        const uint32_t en = valid ? vh->enc[t][sym] : 0u;
+        const uint32_t l = en & 0xFFu;
+        sh.code[bin] = l ? ((en >> 8) << nb) : 0u;
+        sh.len[bin] = (uint8_t)(l ? l + nb : 0u);
+    }
     __syncthreads();
-    const uint32_t zr_y = sh.enc[0x1F0], zr_c = sh.enc[0x3F0];   // ZRL (0xF0) codes of the two AC tables
-    const uint32_t zl_y = zr_y & 31u, zl_c = zr_c & 31u;
+    // ZRL (0xF0) codes of the two AC tables: code << 8 | length
+    const uint32_t zr_y = (sh.code[tok_bin(1, 0xF0)] << 8) | sh.len[tok_bin(1, 0xF0)];
+    const uint32_t zr_c = (sh.code[tok_bin(3, 0xF0)] << 8) | sh.len[tok_bin(3, 0xF0)];
+    for (int i = 1024 + tid; i < 4096; i += PACK_THREADS) {   // ZRL counts 1..3 (AC tokens only)
+        const uint32_t bin = (uint32_t)i & 0x3FFu, nz = (uint32_t)i >> 10, l = sh.len[bin];
+        const uint32_t zl = ((bin & 0x20u) ? zr_c : zr_y) & 0xFFu;
+        sh.len[i] = (uint8_t)((l && (bin & 0x10u)) ? l + nz * zl : l);
+    }
+    __syncthreads();
     uint32_t *sub = sh.sub[wid];
 
     bool pend = false;      // the previous tile's shared words are still in their cells
@@ -517,8 +544,8 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
         // ---- 1. code the share into the warp's buffer (or only measure it: dense tiles)
         const bool dense = rec.count > PACK_DENSE_TOKENS;
         uint32_t len;
-        if (!dense) len = (uint32_t)pack_scatter<false>(sh.enc, sub, sub_words, tk4, a, lo, hi, 0, lane, zr_y, zr_c);
-        else len = pack_length(sh.enc, tk4, a, lo, hi, lane, zl_y, zl_c);
+        if (!dense) len = (uint32_t)pack_scatter<false>(sh, sub, sub_words, tk4, a, lo, hi, 0, lane, zr_y, zr_c);
+        else len = pack_length(sh, tk4, a, lo, hi, lane);
         if (lane == 0) sh.wlen[l3][wid] = len;
         __syncthreads();   // ---- 2. also: every warp is done with the previous tile's cells
         if (pend && tid == 0) pack_flush_shared_words(sh.bnd[cur ^ 1], sh.wlen[pl3], pslot);
@@ -556,7 +583,7 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
             }
             const uint32_t nwords = (total + 31u) >> 5;
             for (uint32_t wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
-                pack_scatter<true>(sh.enc, sh.buf, WIN_WORDS, tk4, a, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
+                pack_scatter<true>(sh, sh.buf, WIN_WORDS, tk4, a, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
                 __syncthreads();
                 const uint32_t wn = min((uint32_t)WIN_WORDS, nwords - wbase);
                 for (uint32_t i = tid; i < wn; i += PACK_THREADS) { slot[wbase + i] = sh.buf[i]; sh.buf[i] = 0; }
@@ -575,7 +602,7 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
 // look-back over `desc` (zeroed per encode; chunk ids come from a ticket so predecessors are always running).
 constexpr int SCAN_CHUNK = 4096;
 __global__ void __launch_bounds__(1024)
-k_scan_tiles(const uint32_t *__restrict__ tile_bits, int ntiles, uint64_t *__restrict__ tile_off,
+k_scan_tiles(const uint32_t *tile_bits /* k_pack's output: no __restrict__ (pdl_wait) */, int ntiles, uint64_t *__restrict__ tile_off,
              const uint32_t *__restrict__ slots, uint64_t *__restrict__ strip_bits, uint64_t *__restrict__ desc,
              uint32_t *__restrict__ ticket, uint32_t *__restrict__ chunk_tile, uint32_t nchunk_cap, uint32_t *__restrict__ err) {
     __shared__ uint32_t s_w[32];
@@ -959,7 +986,7 @@ __global__ void k_seam_from_bits(int *seam, const int64_t *__restrict__ bits_all
 // strip's last byte is the head of the next strip's record tokens coded with the (identical) tables.
 __device__ __forceinline__ uint32_t dc_token(int c, int diff) {
     const int nb = 32 - __clz(diff < 0 ? -diff : diff);
-    return ((uint32_t)(c ? 2 : 0) << 24) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+    return ((uint32_t)(c ? 2 : 0) << 20) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
@@ -1066,10 +1093,11 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
                 const int c = (tk >> 16) & 3u;
                 tk = dc_token(c, (int)(int16_t)(tk & 0xFFFFu) - (int)rec[rank].last_dc[c]);
             }
-            const uint32_t tb = (tk >> 24) & 3u, sy = (tk >> 16) & 0xFFu;
+            const uint32_t tb = (tk >> 20) & 3u, nv = (tk >> 16) & 15u;
+            const uint32_t sy = (tb & 1u) ? ((((tk >> 22) & 15u) << 4) | nv) : nv;
             const uint32_t zr = huff->enc[tb][0xF0];
-            for (uint32_t z = 0; z < ((tk >> 28) & 3u); z++) { acc = (acc << (zr & 0xFFu)) | (zr >> 8); n += zr & 0xFFu; }
-            const uint32_t en = huff->enc[tb][sy], nv = (tb & 1u) ? (sy & 15u) : sy;
+            for (uint32_t z = 0; z < ((tk >> 26) & 3u); z++) { acc = (acc << (zr & 0xFFu)) | (zr >> 8); n += zr & 0xFFu; }
+            const uint32_t en = huff->enc[tb][sy];
             acc = (acc << (en & 0xFFu)) | (en >> 8); n += en & 0xFFu;
             acc = (acc << nv) | (tk & 0xFFFFu); n += nv;
             bad |= !(en & 0xFFu);
