@@ -61,9 +61,18 @@ struct XchgArena {
 
 constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)
 constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
-constexpr int STUFF_THREADS = 256;
-constexpr int STUFF_CTAS = 4;                  // resident CTAs per SM: the chunk pipeline is latency bound (ticket, look-back)
-constexpr int STUFF_PIECES = 4;                 // 16-byte pieces per thread and chunk (strided by STUFF_THREADS * 16)
+#ifndef B2J_STUFF_THREADS
+#define B2J_STUFF_THREADS 256
+#endif
+#ifndef B2J_STUFF_CTAS
+#define B2J_STUFF_CTAS 4
+#endif
+#ifndef B2J_STUFF_PIECES
+#define B2J_STUFF_PIECES 4
+#endif
+constexpr int STUFF_THREADS = B2J_STUFF_THREADS;
+constexpr int STUFF_CTAS = B2J_STUFF_CTAS;     // resident CTAs per SM: the chunk pipeline is latency bound (ticket, look-back)
+constexpr int STUFF_PIECES = B2J_STUFF_PIECES;  // 16-byte pieces per thread and chunk (strided by STUFF_THREADS * 16)
 constexpr int STUFF_BPT = 16 * STUFF_PIECES;    // unstuffed bytes per thread and chunk
 constexpr int STUFF_CHUNK = STUFF_THREADS * STUFF_BPT; // unstuffed bytes per stuff chunk
 
