@@ -85,6 +85,9 @@ B2J_API const char *b2j_last_error(const b2j_ctx *ctx);
 B2J_API const char *b2j_version(void);
 
 /* The caller's CUDA stream (cudaStream_t as void*); NULL = the context's own stream. */
+/* Restart markers every `rows` MCU rows of whole-image encodes (0 = none, the default): jchuff.c emit_restart /
+ * jcmarker.c emit_dri with restart_interval = rows * MCUs per row (cv2: IMWRITE_JPEG_RST_INTERVAL). */
+B2J_API int b2j_set_restart_rows(b2j_ctx *ctx, int rows);
 B2J_API int b2j_set_stream(b2j_ctx *ctx, void *cuda_stream);
 
 /* Upper bound of the JPEG size b2j_encode can produce for this context. */

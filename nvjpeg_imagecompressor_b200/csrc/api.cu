@@ -99,6 +99,7 @@ struct b2j_ctx {
     XchgArena **d_peers;           // device array [peer_world] of every rank's arena
     void *peer_opened[XCHG_MAX_WORLD];   // mappings from b2j_peer_open (closed in b2j_destroy)
     int n_opened, peer_rank, peer_world;
+    int rst_rows;                  // restart interval in MCU rows (0: none); b2j_set_restart_rows
     uint32_t xseq;                 // images exchanged so far (identical on every rank)
     unsigned long long peer_timeout_ns;   // bound of the wait for the peers' records (B2J_PEER_TIMEOUT_MS, default 10 s)
 };
@@ -213,7 +214,7 @@ static int enc_alloc(b2j_ctx *ctx) {
     // every buffer is allocated only while its pointer is null: a call that failed half way can be repeated
     if (!ctx->d_pool) CK(cudaMalloc(&ctx->d_pool, (size_t)g.nblocks * 64 * 4 + 64));  // +64: k_pack reads whole 16-byte groups
     int rc = ensure_tiles(ctx, g); if (rc) return rc;
-    ctx->out_cap = (size_t)g.nblocks * 208 + 4096;
+    ctx->out_cap = (size_t)g.nblocks * 208 + 4096 + (size_t)g.mcuy * 3;   // + pad/RSTn bytes of restart intervals
     if (!ctx->d_out) CK(cudaMalloc(&ctx->d_out, ctx->out_cap));
     ctx->ndesc = ctx->out_cap / STUFF_CHUNK + 4;
     // 1024 scan descriptors cover 4M tiles: no geometry within the configured size re-allocates (b2j_strip_state
@@ -288,7 +289,16 @@ int b2j_set_stream(b2j_ctx *ctx, void *s) {
     return B2J_OK;
 }
 
-size_t b2j_encode_bound(const b2j_ctx *ctx) { return ctx ? (size_t)ctx->cap_g.nblocks * 208 + 4096 : 0; }
+size_t b2j_encode_bound(const b2j_ctx *ctx) { return ctx ? (size_t)ctx->cap_g.nblocks * 208 + 4096 + (size_t)ctx->cap_g.mcuy * 3 : 0; }
+
+// Restart markers every `rows` MCU rows (0 = none): DRI = rows * MCUs per row in the header, RSTn between the intervals,
+// DC predictors restart (jchuff.c emit_restart; the stream equals libjpeg-turbo's with restart_interval = rows * mcux).
+// Whole-image encodes only; the interval must fit DRI's 16 bits for the configured width.
+int b2j_set_restart_rows(b2j_ctx *ctx, int rows) {
+    if (!ctx || rows < 0 || (long long)rows * ctx->cap_g.mcux > 65535) return B2J_EINVAL;
+    ctx->rst_rows = rows;
+    return B2J_OK;
+}
 uint64_t b2j_launch_count(const b2j_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int b2j_set_debug(b2j_ctx *ctx, int flags) { if (!ctx) return B2J_EINVAL; ctx->debug = flags; return B2J_OK; }
 int b2j_enable_timing(b2j_ctx *ctx, int on) { if (!ctx) return B2J_EINVAL; ctx->timing = on != 0; return B2J_OK; }
@@ -328,7 +338,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
     rc = enc_reset(ctx); if (rc) return rc;
     tick(ctx, 1);
     CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 0, ctx->d_pool, 0, nullptr, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 0, ctx->d_pool, 0, nullptr, 0, ctx->stream));
     ctx->launches += 2;
     tick(ctx, 2);
     return B2J_OK;
@@ -337,7 +347,7 @@ int b2j_strip_phase1(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width,
 int b2j_strip_phase1b(b2j_ctx *ctx) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, ctx->p.optimize, ctx->d_pool, 1, nullptr, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, ctx->p.optimize, ctx->d_pool, 1, nullptr, ctx->rst_rows * ctx->g.tiles_x, ctx->stream));
     ctx->launches += 1;
     tick(ctx, 3);
     return B2J_OK;
@@ -347,9 +357,13 @@ int b2j_strip_phase2(b2j_ctx *ctx, int full_w, int full_h) {
     if (!ctx || !ctx->enc_ready) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
     // header is always composed; phase3 decides whether it is part of this strip's output (hdr_len is re-set there)
-    CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, &ctx->d_ctrl->huff_err, ctx->stream));
+    CK(launch_tables(ctx->d_ctrl->hist, ctx->p.optimize, ctx->d_huff, ctx->d_quant, full_w, full_h, ctx->g.hs, ctx->g.vs, ctx->d_out, 1, ctx->rst_rows * ctx->g.mcux, &ctx->d_ctrl->huff_err, ctx->stream));
     tick(ctx, 4);
     CK(launch_pack(ctx->d_pool, ctx->d_recs, ctx->g, ctx->d_huff, ctx->d_slots, ctx->d_tile_bits, ctx->debug & 2, ctx->stream));
+    if (ctx->rst_rows) {   // pad every interval to a byte boundary and append its RSTn marker, before the tile scan
+        CK(launch_rst_pad(ctx->d_slots, ctx->d_tile_bits, ctx->g.ntiles, ctx->rst_rows * ctx->g.tiles_x, ctx->stream));
+        ctx->launches += 1;
+    }
     tick(ctx, 5);
     CK(launch_scan_tiles(ctx->d_tile_bits, ctx->g.ntiles, ctx->d_tile_off, ctx->d_slots, ctx->d_ctrl->strip_bits, ctx->d_sdesc,
                          &ctx->d_ctrl->scan_ticket, ctx->d_chunk_tile, (uint32_t)ctx->ndesc, &ctx->d_ctrl->err, ctx->stream));
@@ -365,6 +379,7 @@ static int phase3_launch(b2j_ctx *ctx, int flags, bool hdr_done = false) {
     StuffArgs a;
     a.slots = ctx->d_slots; a.tile_bits = ctx->d_tile_bits; a.tile_off = ctx->d_tile_off; a.ntiles = ctx->g.ntiles;
     a.chunk_tile = ctx->d_chunk_tile;
+    a.rst_tiles = ctx->rst_rows * ctx->g.tiles_x;
     a.seam = ctx->d_ctrl->seam; a.append_eoi = (flags & 2) ? 1 : 0; a.huff = ctx->d_huff;
     a.out = ctx->d_out; a.cap = ctx->out_cap; a.desc = ctx->d_desc; a.ticket = &ctx->d_ctrl->ticket;
     a.out_len = &ctx->d_ctrl->out_len; a.err = &ctx->d_ctrl->err;
@@ -403,7 +418,7 @@ int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width
     // symbol counts are always taken: they also give every strip's bit count once the tables are known
     CK(launch_fdct(d_bgr, step, ctx->g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, 1, 0, ctx->g.mcuy, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
     tick(ctx, 2);
-    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 1, ctx->d_pool, 1, &ctx->d_ctrl->rec, ctx->stream));
+    CK(launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 1, ctx->d_pool, 1, &ctx->d_ctrl->rec, 0, ctx->stream));
     ctx->launches += 2;
     if (ctx->peer_world > 0) {   // connected: the record goes straight into every rank's arena
         ctx->xseq++;

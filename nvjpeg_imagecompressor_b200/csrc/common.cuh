@@ -60,7 +60,7 @@ struct XchgArena {
 };
 
 constexpr int PACK_BLOCKS = 256;               // blocks per pack tile (= fdct tile capacity)
-constexpr int SLOT_WORDS = PACK_BLOCKS * 52;   // worst case 64 coefs * 26 bits = 1664 bits = 52 words per block
+constexpr int SLOT_WORDS = PACK_BLOCKS * 52 + 4; // worst case 64 coefs * 26 bits = 52 words per block, + pad/RSTn bits of an interval end
 #ifndef B2J_STUFF_THREADS
 #define B2J_STUFF_THREADS 256
 #endif

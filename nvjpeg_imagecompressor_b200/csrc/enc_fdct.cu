@@ -533,7 +533,7 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 __global__ void __launch_bounds__(256)
 k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restrict__ pred_in,
                uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist,
-               uint32_t *__restrict__ pool, int resolve, StripRecord *__restrict__ xr) {
+               uint32_t *__restrict__ pool, int resolve, StripRecord *__restrict__ xr, int rst_tiles) {
     __shared__ uint32_t s_h[2][16];   // DC categories 0..11 of the two DC tables, aggregated per CTA
     pdl_trigger();
     pdl_wait();
@@ -545,7 +545,8 @@ k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restri
         const int tile = t / 3, c = t - tile * 3;
         const TileRec r = recs[tile];
         const int dc = r.first_dc[c];
-        const int pd = tile > 0 ? recs[tile - 1].last_dc[c] : pred_in[c];
+        // restart intervals (rst_tiles = tiles per interval, whole MCU rows): predictors return to 0 at an interval start
+        const int pd = tile == 0 ? pred_in[c] : ((rst_tiles && tile % rst_tiles == 0) ? 0 : recs[tile - 1].last_dc[c]);
         const int diff = dc - pd;
         const int nb = nbits_of(diff);
         if (do_hist) atomicAdd(&s_h[c ? 1 : 0][nb & 15], 1u);
@@ -622,9 +623,9 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 }
 
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, cudaStream_t s) {
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, int rst_tiles, cudaStream_t s) {
     const int n = max(64, g.tiles_x * g.mcuy * 3);
-    return launch_pdl(k_dc_edge_hist, dim3((n + 255) / 256), dim3(256), 0, s, recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr);
+    return launch_pdl(k_dc_edge_hist, dim3((n + 255) / 256), dim3(256), 0, s, recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr, rst_tiles);
 }
 
 }  // namespace b2j

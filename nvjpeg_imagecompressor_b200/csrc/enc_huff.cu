@@ -46,8 +46,10 @@ __constant__ uint8_t c_std_ac_val[2][162] = {
 // least, by two warp reductions each (min of frequency, then max of index among the minima); tree membership is a
 // group id per symbol so "increment codesize along the others chain" becomes "increment every member".
 __global__ void __launch_bounds__(128)
-k_tables(const uint32_t *hist /* the predecessor's output: no __restrict__, loads must stay behind pdl_wait() */, int optimize, HuffDev *__restrict__ huff, const QuantDev *__restrict__ qd,
-         int full_w, int full_h, int hs, int vs, uint8_t *__restrict__ out, int emit_header, uint32_t *__restrict__ err_out) {
+k_tables(const uint32_t *hist /* the predecessor's output: no __restrict__, loads must stay behind pdl_wait() */, int optimize,
+         HuffDev *__restrict__ huff, const QuantDev *__restrict__ qd,
+         int full_w, int full_h, int hs, int vs, uint8_t *__restrict__ out, int emit_header, int restart_interval,
+         uint32_t *__restrict__ err_out) {
     __shared__ uint8_t s_bits[4][17];
     __shared__ uint8_t s_vals[4][256];
     __shared__ uint32_t s_enc[4][256];
@@ -243,11 +245,12 @@ k_tables(const uint32_t *hist /* the predecessor's output: no __restrict__, load
 
     // ---- headers (jcmarker.c): SOI, JFIF APP0, 2 x DQT, SOF0, 4 x DHT, SOS -- section offsets by thread 0, bytes by
     //      all threads
-    __shared__ uint32_t s_off[8];   // DQT0, DQT1, SOF0, DHT0..3, SOS
+    __shared__ uint32_t s_off[9];   // DQT0, DQT1, SOF0, DHT0..3, SOS, DRI (jcmarker.c: after the scan's DHTs, before SOS)
     if (threadIdx.x == 0) {
         uint32_t n = 20;
         s_off[0] = n; n += 69; s_off[1] = n; n += 69; s_off[2] = n; n += 19;
         for (int q = 0; q < 4; q++) { s_off[3 + q] = n; n += 21 + s_nsym[q]; }
+        s_off[8] = n; if (restart_interval) n += 6;
         s_off[7] = n; n += 14;
         if (!emit_header) n = 0;
         s_hdr_len = n;
@@ -274,6 +277,10 @@ k_tables(const uint32_t *hist /* the predecessor's output: no __restrict__, load
             const uint8_t sof[19] = {0xFF, 0xC0, 0, 17, 8, (uint8_t)(full_h >> 8), (uint8_t)full_h, (uint8_t)(full_w >> 8), (uint8_t)full_w,
                                      3, 1, (uint8_t)((hs << 4) | vs), 0, 2, 0x11, 1, 3, 0x11, 1};
             for (int i = 0; i < 19; i++) d[i] = sof[i];
+        }
+        if (x == 96 && restart_interval) {
+            uint8_t *d = h + s_off[8];
+            d[0] = 0xFF; d[1] = 0xDD; d[2] = 0; d[3] = 4; d[4] = (uint8_t)(restart_interval >> 8); d[5] = (uint8_t)restart_interval;
         }
         if (x == 64) {
             uint8_t *d = h + s_off[7];
@@ -597,6 +604,29 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_rst_pad (restart intervals, jchuff.c emit_restart): every interval but the last ends with 1-bits up to a byte
+// boundary and the marker 0xFF, 0xD0 + (interval & 7). Intervals are whole MCU rows, i.e. whole tiles, and start byte
+// aligned, so the padding is a function of the interval's own bit count: one thread per interval adds the bits to the
+// interval's last tile (its slot has 4 spare words) before the tile scan runs. k_stuff leaves the marker's 0xFF alone.
+__global__ void __launch_bounds__(128)
+k_rst_pad(uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits, int ntiles, int rst_tiles) {
+    pdl_wait();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long first = (long long)j * rst_tiles, last = first + rst_tiles - 1;
+    if (last >= ntiles - 1) return;   // the last interval: no marker, k_stuff pads the end of the stream
+    uint64_t B = 0;
+    for (long long t = first; t <= last; t++) B += tile_bits[t];
+    const uint32_t pad = (8u - (uint32_t)(B & 7u)) & 7u, n = pad + 16u;
+    const uint64_t v = ((uint64_t)((1u << pad) - 1u) << 16) | 0xFF00u | (0xD0u + ((uint32_t)j & 7u));
+    const uint32_t tb = tile_bits[last], wi = tb >> 5, sh = tb & 31u;
+    const uint64_t acc = (v << (64u - n)) >> sh;   // bits [sh, sh + n) of the two words starting at wi
+    uint32_t *slot = slots + (size_t)last * SLOT_WORDS;
+    slot[wi] = (sh ? (slot[wi] & ~(0xFFFFFFFFu >> sh)) : 0u) | (uint32_t)(acc >> 32);
+    if (sh + n > 32u) slot[wi + 1] = (uint32_t)acc;
+    tile_bits[last] = tb + n;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_scan_tiles: exclusive scan of the per-tile bit counts (ntiles ~ 4e4 for the headline image). One CTA per chunk
 // of 4096 counts (16-byte coalesced loads, 4 counts per thread, warp shuffles), chunks chained by a decoupled
 // look-back over `desc` (zeroed per encode; chunk ids come from a ticket so predecessors are always running).
@@ -731,12 +761,14 @@ __device__ __noinline__ uint32_t stuff_seam_word(const StuffTiles &tl, const uin
 // One 32-bit piece of the stream (w: first byte in bits 31..24) -> its bytes in memory order with a 0x00 after every
 // 0xFF, OR-ed into the zeroed staging buffer at byte offset o (any alignment). Branch-free: the byte expansion is two
 // PRMTs whose selectors come from a 16-entry table indexed by the word's 0xFF mask. Returns the bytes produced.
-__device__ __forceinline__ uint32_t stuff_place_word(uint32_t w, uint32_t o, uint32_t sbase, const uint32_t *s_lut) {
+// `keep`: 0x01 in byte b (memory order) unless byte b is the 0xFF of a restart marker, which takes no 0x00.
+__device__ __forceinline__ uint32_t stuff_place_word(uint32_t w, uint32_t o, uint32_t sbase, const uint32_t *s_lut,
+                                                     uint32_t keep = 0x01010101u) {
     const uint32_t l = __byte_perm(w, 0, 0x0123);
     uint32_t mm = l & (l >> 4) & 0x0F0F0F0Fu;   // a byte is 0xFF iff all eight bits survive the and-fold
     mm &= mm >> 2;
     mm &= mm >> 1;
-    mm &= 0x01010101u;
+    mm &= keep;
     const uint32_t m4 = (mm * 0x01020408u) >> 24;   // bit i: byte i is 0xFF
     const uint32_t sel = s_lut[m4];
     const uint32_t lo = __byte_perm(l, 0, sel & 0xFFFFu), hi = __byte_perm(l, 0, sel >> 16);
@@ -749,6 +781,7 @@ __device__ __forceinline__ uint32_t stuff_place_word(uint32_t w, uint32_t o, uin
     return 4u + __popc(m4);
 }
 
+template <bool RST>
 __global__ void __launch_bounds__(STUFF_THREADS, STUFF_CTAS)
 k_stuff(StuffArgs a) {
     constexpr int NWARP = STUFF_THREADS / 32;
@@ -807,6 +840,7 @@ k_stuff(StuffArgs a) {
         uint32_t w[NP][4];
         int nvalid[NP];
         uint32_t cnt[NP];
+        uint32_t marker[NP];   // RST: bit k set = byte k of the piece is a restart marker's 0xFF (not stuffed)
         int tau = tau0;
 #pragma unroll
         for (int i = 0; i < NP; i++) {
@@ -814,10 +848,21 @@ k_stuff(StuffArgs a) {
             nvalid[i] = jb >= NB ? 0 : (int)min((uint64_t)16, NB - jb);
 #pragma unroll
             for (int q = 0; q < 4; q++) w[i][q] = 0;
+            marker[i] = 0;
             if (nvalid[i] > 0) {
                 uint64_t p = (uint64_t)a_skip + 8 * jb;
                 while (tl.off(tau + 1) <= p) tau++;
                 uint64_t tstart = tl.off(tau), tend = tl.off(tau + 1);
+                if (RST) {   // the markers inside this piece: the one that ends the interval of its first bit, and (tiny
+                             // intervals) the ones that follow while they still begin inside the piece
+                    int iv_last = (tau / a.rst_tiles + 1) * a.rst_tiles - 1;
+                    while (iv_last < a.ntiles - 1) {
+                        const long long m = (long long)(tl.off(iv_last + 1) >> 3) - 2 - (long long)jb;
+                        if (m >= 16) break;
+                        if (m >= 0) marker[i] |= 1u << m;
+                        iv_last += a.rst_tiles;
+                    }
+                }
                 if (p + 128 <= tend) {  // all bits inside one tile
                     const uint32_t qb = (uint32_t)(p - tstart);
                     const uint32_t *slot = a.slots + (size_t)tau * SLOT_WORDS + (qb >> 5);
@@ -860,6 +905,11 @@ k_stuff(StuffArgs a) {
 #pragma unroll
                     for (int bb = 0; bb < 4; bb++)
                         if (4 * q + bb >= nvalid[i]) m &= ~(1u << (24 - 8 * bb));
+                }
+                if (RST) {
+#pragma unroll
+                    for (int bb = 0; bb < 4; bb++)
+                        if ((marker[i] >> (4 * q + bb)) & 1u) m &= ~(1u << (24 - 8 * bb));
                 }
                 nff += __popc(m);
             }
@@ -905,14 +955,21 @@ k_stuff(StuffArgs a) {
             uint32_t o = off[i];
             if (nvalid[i] == 16) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) o += stuff_place_word(w[i][q], o, sbase, s_lut);
+                for (int q = 0; q < 4; q++) {
+                    uint32_t keep = 0x01010101u;
+                    if (RST) {
+                        const uint32_t mk = (marker[i] >> (4 * q)) & 15u;   // bit bb: byte bb of this word (memory order)
+                        keep &= ~((mk & 1u) | ((mk & 2u) << 7) | ((mk & 4u) << 14) | ((mk & 8u) << 21));
+                    }
+                    o += stuff_place_word(w[i][q], o, sbase, s_lut, keep);
+                }
             } else {
                 for (int k = 0; k < nvalid[i]; k++) {
                     uint32_t byte = 0;
 #pragma unroll
                     for (int q = 0; q < 4; q++) if ((k >> 2) == q) byte = (w[i][q] >> (24 - 8 * (k & 3))) & 0xFFu;
                     atomicOr(&s_out32[o >> 2], byte << ((o & 3u) * 8u));
-                    o += byte == 0xFFu ? 2u : 1u;
+                    o += (byte == 0xFFu && !(RST && ((marker[i] >> k) & 1u))) ? 2u : 1u;
                 }
             }
         }
@@ -951,13 +1008,17 @@ k_stuff(StuffArgs a) {
 
 // ------------------------------------------------------------------------------------------------------
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
-                          int hs, int vs, uint8_t *out, int emit_header, uint32_t *err_out, cudaStream_t s) {
-    return launch_pdl(k_tables, dim3(1), dim3(128), 0, s, hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header, err_out);
+                          int hs, int vs, uint8_t *out, int emit_header, int restart_interval, uint32_t *err_out, cudaStream_t s) {
+    return launch_pdl(k_tables, dim3(1), dim3(128), 0, s, hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header, restart_interval, err_out);
 }
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s) {
     const int grid = min(g.ntiles, 148 * PACK_CTAS);
     return launch_pdl(k_pack, dim3(grid), dim3(PACK_THREADS), 0, s, pool, recs, g.ntiles, huff, slots, tile_bits, small_buffers ? 24u : (uint32_t)SUB_WORDS);
+}
+cudaError_t launch_rst_pad(uint32_t *slots, uint32_t *tile_bits, int ntiles, int rst_tiles, cudaStream_t s) {
+    const int nint = (ntiles + rst_tiles - 1) / rst_tiles;
+    return launch_pdl(k_rst_pad, dim3((nint + 127) / 128), dim3(128), 0, s, slots, tile_bits, ntiles, rst_tiles);
 }
 int scan_desc_count(int ntiles) { return (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
 cudaError_t launch_scan_tiles(const uint32_t *tile_bits, int ntiles, uint64_t *tile_off, const uint32_t *slots,
@@ -1132,7 +1193,8 @@ cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, 
     return cudaGetLastError();
 }
 cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s) {
-    return launch_pdl(k_stuff, dim3(grid), dim3(STUFF_THREADS), 0, s, a);
+    return a.rst_tiles ? launch_pdl(k_stuff<true>, dim3(grid), dim3(STUFF_THREADS), 0, s, a)
+                       : launch_pdl(k_stuff<false>, dim3(grid), dim3(STUFF_THREADS), 0, s, a);
 }
 
 }  // namespace b2j

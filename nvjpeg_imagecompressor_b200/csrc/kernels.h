@@ -13,9 +13,14 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 // xr != NULL: one-collective strip exchange (first MCU left to k_strip_merge, record fields filled)
 // resolve != 0: also rewrite each tile's three raw-DC tokens in `pool` as final DC-difference tokens
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, cudaStream_t s);
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, int rst_tiles,
+                                cudaStream_t s);
+// restart_interval != 0: DRI marker (MCUs per interval) between the DHTs and SOS
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
-                          int hs, int vs, uint8_t *out, int emit_header, uint32_t *err_out, cudaStream_t s);
+                          int hs, int vs, uint8_t *out, int emit_header, int restart_interval, uint32_t *err_out, cudaStream_t s);
+// restart intervals of rst_tiles tiles (whole MCU rows): every interval but the last gets 1-padding to a byte boundary
+// and its RSTn marker appended to its last tile's bits (run between k_pack and the tile scan)
+cudaError_t launch_rst_pad(uint32_t *slots, uint32_t *tile_bits, int ntiles, int rst_tiles, cudaStream_t s);
 // small_buffers != 0 (tests): the per-warp bit buffers pretend to hold 24 words, forcing the overflow path
 cudaError_t launch_pack(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff,
                         uint32_t *slots, uint32_t *tile_bits, int small_buffers, cudaStream_t s);
@@ -34,6 +39,7 @@ struct StuffArgs {
     const int *seam;            // device: [0] skip = leading bits owned by the previous strip's last byte,
                                 //         [1] ext ^ 0xFF, ext = next strip's first 8 bits (0xFF: pad with ones)
     int append_eoi;
+    int rst_tiles;              // tiles per restart interval (0: none): the markers' 0xFF bytes are not stuffed
     const HuffDev *huff;        // hdr_len
     uint8_t *out;
     size_t cap;

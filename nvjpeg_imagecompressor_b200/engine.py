@@ -110,6 +110,10 @@ class Engine:
                                        _ptr(recon) if want_recon else None, W * 3, C.byref(ps)))
         return j1[: n1.value], j2[: n2.value], recon, ps.value
 
+    def set_restart_rows(self, rows):
+        """Restart markers every `rows` MCU rows (0 = none); the stream equals cv2's with RST_INTERVAL = rows * mcux."""
+        self._ck(self._L.b2j_set_restart_rows(self._h, int(rows)))
+
     # ---------------------------------------------------------------- device API (pointers from torch tensors)
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._L.b2j_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))

@@ -181,3 +181,21 @@ def test_headline_full_image_digest(P, golden, oracle):
         assert jpg.size == e["jpeg_len"], e
         assert sha(jpg)[:32] == e["jpeg_sha256_128"], e
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,css,q,opt,rows", [(256, 320, 1, 95, 1, 1), (200, 333, 3, 90, 1, 2), (129, 200, 0, 75, 0, 1),
+                                              (96, 250, 2, 95, 1, 3), (160, 64, 4, 100, 1, 1), (8, 40, 0, 95, 1, 1),
+                                              (1040, 600, 1, 95, 1, 5)])
+def test_restart_rows(P, oracle, W, H, css, q, opt, rows):
+    """SURVEY.md 8f N2, encoder half: RSTn every `rows` MCU rows == libjpeg-turbo with restart_interval = rows * mcux."""
+    img = oracle.synth(W, H, 21, 8)
+    g = oracle.geometry(W, H, css)
+    want = oracle.encode(img, css, q, opt, rows * g.mcux)
+    eng = P.Engine(W, H, q, bool(opt), css)
+    eng.set_restart_rows(rows)
+    got = eng.encode(img)
+    assert got.size == want.size and np.array_equal(got, want)
+    eng.set_restart_rows(0)
+    assert np.array_equal(eng.encode(img), oracle.encode(img, css, q, opt))
+    eng.close()
