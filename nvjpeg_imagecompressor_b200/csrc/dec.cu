@@ -19,6 +19,7 @@ struct DecCtrl {
     uint32_t dticket[32];  // one counter per de-stuff launch
     uint32_t err;
     uint32_t changed;
+    uint32_t nmark;      // restart markers found by k_destuff
 };
 
 struct Decoder {
@@ -31,6 +32,8 @@ struct Decoder {
     uint64_t *d_st_in = nullptr, *d_st_out = nullptr;
     uint32_t *d_nblk = nullptr, *d_blk_start = nullptr;
     uint8_t *d_done = nullptr;   // per decoder chunk (256 subsequences): first synchronisation pass has run
+    uint32_t *d_bnd = nullptr;   // restart intervals: start offsets in the unstuffed stream (k_destuff<true>)
+    size_t bnd_cap = 0;
     size_t nsub_cap = 0;
     cudaStream_t up_stream = nullptr;   // uploads of the scan pieces
     cudaEvent_t ev_up[33] = {};
@@ -95,6 +98,7 @@ void dec_destroy(Decoder *d) {
     for (auto &e : d->ev_up) if (e) cudaEventDestroy(e);
     if (d->up_stream) cudaStreamDestroy(d->up_stream);
     cudaFree(d->d_done);
+    cudaFree(d->d_bnd);
     delete d;
 }
 
@@ -103,7 +107,15 @@ void dec_set_spec_launches(Decoder *d, int n) { d->spec_launches = n < 1 ? 1 : n
 
 const void *dec_coef_ptr(Decoder *d, size_t *bytes) { *bytes = (size_t)d->nblocks_cap * 128; return d->d_coef; }
 
-static int ensure(Decoder *d, size_t scan_len, const Geom &g) {
+static int ensure(Decoder *d, size_t scan_len, const Geom &g, int restart_interval) {
+    if (restart_interval > 0) {
+        const size_t need = ((size_t)g.mcux * g.mcuy + restart_interval - 1) / restart_interval + 2;
+        if (need > d->bnd_cap) {
+            cudaFree(d->d_bnd); d->d_bnd = nullptr; d->bnd_cap = 0;
+            DCK(cudaMalloc(&d->d_bnd, (need + need / 4) * 4));
+            d->bnd_cap = need + need / 4;
+        }
+    }
     if (scan_len + 256 > d->scan_cap) {
         cudaFree(d->d_scan); cudaFree(d->d_u); d->d_scan = d->d_u = nullptr; d->scan_cap = 0;
         const size_t cap = scan_len + scan_len / 4 + 4096;
@@ -141,10 +153,11 @@ static int ensure(Decoder *d, size_t scan_len, const Geom &g) {
 
 int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
             cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful) {
-    if (info.restart_interval != 0) { snprintf(d->err, d->errlen, "restart markers (DRI=%d) are not supported yet", info.restart_interval); return B2J_EFORMAT; }
+    const int rst = info.restart_interval;   // MCUs per restart interval (0: none)
+    if (rst && info.scan_len >= 0xFFFFFFF0ull) { snprintf(d->err, d->errlen, "restart-marker scans of 4 GB and more are not supported"); return B2J_EFORMAT; }
     if (g.nblocks > d->nblocks_cap) { snprintf(d->err, d->errlen, "image exceeds the context's size"); return B2J_ESIZE; }
     if (info.scan_offset + info.scan_len > len || info.scan_len == 0) return B2J_EFORMAT;
-    int rc = ensure(d, info.scan_len, g);
+    int rc = ensure(d, info.scan_len, g, rst);
     if (rc) return rc;
     const size_t n = info.scan_len;
     const size_t nsub_max = (n * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS;
@@ -175,7 +188,10 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     // has landed and the first synchronisation pass runs on the decoder chunks whose bytes are complete, so most of
     // that pass hides behind the upload (large scans, speculative mode).
     const int nch = (int)((n + 4095) / 4096);
-    const int npieces = (spec && n >= (16u << 20)) ? 8 : 1;   // fewer, larger pieces: a piece should fill the GPU
+    // restart markers: one piece (a marker's two bytes may straddle pieces: k_destuff looks one byte ahead)
+    const int npieces = (spec && n >= (16u << 20) && !rst) ? 8 : 1;   // fewer, larger pieces: a piece should fill the GPU
+    uint32_t *bnd = rst ? d->d_bnd : nullptr;
+    const uint32_t *nmark = rst ? &d->d_ctrl->nmark : nullptr;
     const size_t piece = ((n + npieces - 1) / npieces + 4095) & ~(size_t)4095;
     DCK(cudaEventRecord(d->ev_up[32], s));                       // the scan buffer is free once earlier work on s is done
     DCK(cudaStreamWaitEvent(d->up_stream, d->ev_up[32], 0));
@@ -194,12 +210,12 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         const int c0 = (int)(b0 / 4096), c1 = j == npieces - 1 ? nch : (int)(b1 / 4096);
         if (c1 > c0) {
             DCK(launch_destuff(d->d_scan, n, d->d_u, d->d_desc, &d->d_ctrl->dticket[j], c0, c1, &d->d_ctrl->u_len, &d->d_ctrl->avail,
-                               &d->d_ctrl->err, s));
+                               bnd, (uint32_t)d->bnd_cap, &d->d_ctrl->nmark, &d->d_ctrl->err, s));
             if (launches) (*launches)++;
         }
         if (npieces > 1 && j < npieces - 1) {
             DCK(launch_dec_sync(d->d_u, &d->d_ctrl->avail, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 1, d->d_done,
-                                &d->d_ctrl->changed, (b1 * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS, s));
+                                &d->d_ctrl->changed, (b1 * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS, bnd, nmark, s));
             if (launches) (*launches)++;
         }
     }
@@ -210,7 +226,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         for (; rounds < nl; rounds++) {
             DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
             DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 0, d->d_done,
-                                &d->d_ctrl->changed, nsub_max, s));
+                                &d->d_ctrl->changed, nsub_max, bnd, nmark, s));
             if (launches) (*launches)++;
         }
         DCK(cudaMemcpyAsync(&d->h_flag[2], &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
@@ -220,7 +236,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
             if (rounds >= 256) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
             DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
             DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 0, d->d_done,
-                                &d->d_ctrl->changed, nsub_max, s));
+                                &d->d_ctrl->changed, nsub_max, bnd, nmark, s));
             if (launches) (*launches)++;
             if (rounds == 0) continue;  // the first launch always moves states
             DCK(cudaMemcpyAsync(d->h_flag, &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
@@ -232,13 +248,13 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     if (tm) cudaEventRecord(d->ev[2], s);
     DCK(launch_scan_u32(d->d_nblk, d->d_blk_start, nsub_max, d->d_desc + d->desc_cap, &d->d_ctrl->ticket[1], &d->d_ctrl->err, s));
     DCK(launch_dec_write(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_out, d->d_blk_start, g.bpm, hv, d->d_coef, d->d_dc, (uint32_t)g.nblocks,
-                         &d->d_ctrl->err, nsub_max, s));
+                         &d->d_ctrl->err, nsub_max, bnd, nmark, s));
     DCK(launch_dc_scan(d->d_dc, g, d->d_desc + 2 * d->desc_cap, &d->d_ctrl->ticket[2], d->desc_cap, &d->d_ctrl->err, s));
     if (tm) cudaEventRecord(d->ev[3], s);
     uint8_t *py = d->d_planes;
     uint8_t *pcb = py + (((size_t)g.mcux * 8 * g.hs * g.mcuy * 8 * g.vs + 63) & ~(size_t)63);
     uint8_t *pcr = pcb + (((size_t)g.mcux * 8 * g.mcuy * 8 + 63) & ~(size_t)63);
-    DCK(launch_idct(d->d_coef, d->d_dc, g, d->d_tb, py, pcb, pcr, s));
+    DCK(launch_idct(d->d_coef, d->d_dc, g, d->d_tb, py, pcb, pcr, rst, s));
     if (tm) cudaEventRecord(d->ev[4], s);
     DCK(launch_upcolor(py, pcb, pcr, g, d_bgr, step, s));
     if (tm) cudaEventRecord(d->ev[5], s);

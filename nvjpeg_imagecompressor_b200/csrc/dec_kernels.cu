@@ -22,10 +22,15 @@ namespace b2j {
 // One launch handles the 4 KB chunks [c0, c1) of the scan (the bytes before them are already there: a byte only looks
 // at its predecessor), so the scan can be de-stuffed piece by piece while it is still being uploaded; look-back
 // descriptors carry over, `ticket` is a fresh counter per launch, *avail = bytes produced up to the end of the launch.
+// RST (streams with restart markers, jdmarker.c read_restart_marker): the two bytes of every FF Dn are dropped as well
+// and the output offset where the next interval begins goes to bnd[j], j = ordinal of the marker (the look-back
+// carries the marker count in the upper bits of its sums); bnd[number of markers] = 0xFFFFFFFF closes the list.
+constexpr int DS_MK_SHIFT = 38;   // look-back value: kept bytes | markers << 38
+template <bool RST>
 __global__ void __launch_bounds__(256)
 k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint64_t *__restrict__ desc,
           uint32_t *__restrict__ ticket, int c0, int c1, uint64_t *__restrict__ out_len, uint64_t *__restrict__ avail,
-          uint32_t *__restrict__ err) {
+          uint32_t *__restrict__ bnd, uint32_t bnd_cap, uint32_t *__restrict__ nmark, uint32_t *__restrict__ err) {
     __shared__ int s_chunk;
     __shared__ uint32_t s_warp[8];
     __shared__ uint64_t s_goff;
@@ -38,15 +43,25 @@ k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, u
         const int ch = s_chunk;
         if (ch >= c1) break;
         const size_t base = (size_t)ch * 4096 + (size_t)tid * 16;
-        uint8_t b[17];
+        uint8_t b[18];
         b[0] = base > 0 && base <= n ? in[base - 1] : 0;
 #pragma unroll
         for (int i = 0; i < 16; i++) b[i + 1] = base + i < n ? in[base + i] : 0;
-        uint32_t keep = 0;
+        b[17] = (RST && base + 16 < n) ? in[base + 16] : 0;
+        uint32_t keep = 0, mark = 0;   // mark: bit i = byte i is the second byte of a restart marker
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-            if (base + i < n && !(b[i + 1] == 0 && b[i] == 0xFF)) keep |= 1u << i;
-        const uint32_t cnt = __popc(keep);
+        for (int i = 0; i < 16; i++) {
+            if (base + i >= n) continue;
+            bool k = !(b[i + 1] == 0 && b[i] == 0xFF);
+            if (RST) {
+                const bool second = b[i] == 0xFF && (b[i + 1] & 0xF8) == 0xD0;
+                const bool first = b[i + 1] == 0xFF && (b[i + 2] & 0xF8) == 0xD0 && base + i + 1 < n;
+                if (second) mark |= 1u << i;
+                k = k && !second && !first;
+            }
+            if (k) keep |= 1u << i;
+        }
+        const uint32_t cnt = __popc(keep) | (RST ? (uint32_t)__popc(mark) << 16 : 0u);   // kept bytes | markers << 16
         uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -62,21 +77,44 @@ k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, u
             if (i < wid) wbase += x;
             total += x;
         }
-        uint32_t o = wbase + inc - cnt;
+        const uint32_t ex = wbase + inc - cnt;   // exclusive: kept bytes | markers << 16 before this thread
+        uint32_t o = ex & 0xFFFFu;
+        const uint32_t o0 = o;
 #pragma unroll
         for (int i = 0; i < 16; i++)
             if (keep & (1u << i)) s_out[o++] = b[i + 1];
         if (wid == 0) {
-            const uint64_t pre = lookback_exclusive(desc, ch, total, err);
+            const uint64_t local = (uint64_t)(total & 0xFFFFu) | ((uint64_t)(total >> 16) << DS_MK_SHIFT);
+            const uint64_t pre = lookback_exclusive(desc, ch, local, err);
             if (lane == 0) s_goff = pre;
         }
         __syncthreads();
-        uint8_t *dst = out + s_goff;
-        for (uint32_t i = tid; i < total; i += 256) dst[i] = s_out[i];
-        if (ch == c1 - 1 && tid == 0) *avail = s_goff + total;
+        const uint64_t goff = s_goff & ((1ull << DS_MK_SHIFT) - 1);
+        const uint32_t tkept = total & 0xFFFFu;
+        uint8_t *dst = out + goff;
+        for (uint32_t i = tid; i < tkept; i += 256) dst[i] = s_out[i];
+        if (RST && mark) {   // the interval after marker j begins at the output offset of the first byte kept after it
+            uint32_t j = (uint32_t)(s_goff >> DS_MK_SHIFT) + (ex >> 16), oo = o0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (mark & (1u << i)) {
+                    if (j < bnd_cap) bnd[j] = (uint32_t)(goff + oo); else atomicOr(err, 16u);
+                    j++;
+                }
+                if (keep & (1u << i)) oo++;
+            }
+        }
+        if (ch == c1 - 1 && tid == 0) *avail = goff + tkept;
         if (ch == nchunks - 1) {
-            if (tid < 64) dst[total + tid] = 0xFF;  // padding the bit reader may peek into
-            if (tid == 0) *out_len = s_goff + total;
+            if (tid < 64) dst[tkept + tid] = 0xFF;  // padding the bit reader may peek into
+            if (tid == 0) {
+                *out_len = goff + tkept;
+                if (RST) {
+                    const uint32_t nm = (uint32_t)(s_goff >> DS_MK_SHIFT) + (total >> 16);
+                    *nmark = nm;
+                    if (nm < bnd_cap) bnd[nm] = 0xFFFFFFFFu; else atomicOr(err, 16u);
+                }
+            }
         }
         __syncthreads();
     }
@@ -135,13 +173,41 @@ __device__ __noinline__ uint32_t huff_sym_long(const SH &sh, uint32_t t, uint32_
     return 0xFFFFu;  // invalid: skip one bit and keep going
 }
 
+// Restart intervals (jdhuff.c process_restart): bnd[j] = byte offset in the unstuffed stream where interval j + 1
+// begins (k_destuff<true>), closed by 0xFFFFFFFF. At such a position the decoder is at the start of an MCU with
+// nothing pending; the bits before it that do not hold a whole symbol are the 1-padding of the interval's last byte
+// (no code is all ones, so a symbol read from the padding always runs across the boundary). A decoder that is not
+// synchronised yet obeys the same two rules, which is what makes every boundary a synchronisation point.
+struct RstTrack {
+    const uint32_t *bnd;
+    uint32_t j, lim;   // next boundary: index, and position in bits relative to the chunk (0xFFFFFFFF: none in reach)
+    uint64_t chunk_bit0;
+    __device__ __forceinline__ void load() {
+        const uint32_t b = bnd[j];
+        const uint64_t rel = (uint64_t)b * 8 - chunk_bit0;
+        lim = (b == 0xFFFFFFFFu || rel > 0x7FFFFFFFull) ? 0xFFFFFFFFu : (uint32_t)rel;
+    }
+    __device__ __forceinline__ void init(const uint32_t *b, uint32_t nmark, uint64_t cb0, uint32_t q) {
+        bnd = b; chunk_bit0 = cb0;
+        const uint64_t pos = cb0 + q;
+        uint32_t lo = 0, hi = nmark;   // smallest j with bnd[j] * 8 >= pos (bnd[nmark] is the sentinel)
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t)b[mid] * 8 >= pos) hi = mid; else lo = mid + 1;
+        }
+        j = lo;
+        load();
+    }
+    __device__ __forceinline__ void next() { j++; load(); }
+};
+
 // Decodes from `start_state` up to `end_bit` (jdhuff.c decode_mcu, one symbol per iteration). Positions are kept
 // relative to the chunk (32-bit); the block state machine (DC / coefficient / ZRL / EOB) is branch-free.
-template <bool WRITE>
+template <bool WRITE, bool RST>
 __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t chunk_bit0, uint64_t start_state,
                                                  uint64_t end_bit, uint64_t total_bits, int bpm, int hv,
                                                  uint32_t &nblk_out, int16_t *__restrict__ coef, uint32_t blk_base,
-                                                 uint32_t nblocks) {
+                                                 uint32_t nblocks, const uint32_t *__restrict__ bnd, uint32_t nmark) {
     uint32_t q = (uint32_t)((start_state >> 16) - chunk_bit0);
     int c = (int)((start_state >> 8) & 0xFF), k = (int)(start_state & 0xFF);
     uint32_t nblk = 0;
@@ -149,7 +215,10 @@ __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t c
     const uint32_t tot = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;          // end of the stream, clamped
     const uint32_t stop = min((uint32_t)(end_bit - chunk_bit0), tot);
     const uint16_t *lut = &sh.lut[0][0];
+    RstTrack rt;
+    if (RST) rt.init(bnd, nmark, chunk_bit0, q);
     while (q < stop) {
+        if (RST && q >= rt.lim) { c = 0; k = 0; rt.next(); }   // an interval begins here
         const uint32_t g = q >> 5, o = q & 31u;
         const uint32_t w0 = sh.words[(g & 31u) * (DEC_THREADS + 1) + (g >> 5)];
         const uint32_t g1 = g + 1;
@@ -159,8 +228,13 @@ __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t c
         const uint32_t t = (c < hv ? 0u : 2u) + (dc ? 0u : 1u);
         uint32_t e = lut[(t << DEC_LUT_BITS) + (win >> (32 - DEC_LUT_BITS))];
         if (e == 0) e = huff_sym_long(sh, t, win >> 16);
-        if (e == 0xFFFFu) { q += 1; continue; }            // invalid code
+        if (e == 0xFFFFu) {                                  // invalid code
+            if (RST && q + 16 > rt.lim) { q = rt.lim; c = 0; k = 0; rt.next(); continue; }   // ... in the padding of an interval
+            q += 1;
+            continue;
+        }
         const uint32_t len = e >> 8, s = e & 15u, r = (e >> 4) & 15u;
+        if (RST && q + len + s > rt.lim) { q = rt.lim; c = 0; k = 0; rt.next(); continue; }   // padding before a restart marker
         if (q + len + s > tot) { q = tot; break; }         // padding bits at the very end
         int val = 0;
         if (s) {
@@ -207,10 +281,12 @@ __device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__r
 // produced it. `changed` is raised when a CTA did not converge or its last end state moved.
 // From the third round on only a few subsequences still see a new start state: every round first compacts the
 // subsequences that need decoding into a list, and the threads take list entries, so the warps stay full.
+template <bool RST>
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
            uint64_t *__restrict__ st_in, uint64_t *__restrict__ st_out, uint32_t *__restrict__ nblk, int bpm, int hv,
-           int inner, int mode, uint8_t *__restrict__ done, uint32_t *__restrict__ changed) {
+           int inner, int mode, uint8_t *__restrict__ done, uint32_t *__restrict__ changed,
+           const uint32_t *__restrict__ bnd, const uint32_t *__restrict__ nmark_p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -228,6 +304,7 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
     }
     const uint64_t total_bits = nbytes * 8;
     if (chunk_bit0 >= total_bits) return;
+    const uint32_t nmark = RST ? *nmark_p : 0u;
     dec_load_chunk(sh, u, mode == 1 ? *u_len & ~(uint64_t)3 : (nbytes + 64) & ~(uint64_t)3, cta, tb);
     const size_t i = cta * DEC_THREADS + tid;
     const uint64_t my_bit0 = chunk_bit0 + (uint64_t)tid * SUB_BITS;
@@ -261,7 +338,7 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
             t = sh.list[tid];
             in = sh.state[t];
             const uint64_t t_end = chunk_bit0 + (uint64_t)(t + 1) * SUB_BITS;
-            outst = decode_range<false>(sh, chunk_bit0, in, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0);
+            outst = decode_range<false, RST>(sh, chunk_bit0, in, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0, bnd, nmark);
         }
         __syncthreads();
         if (t >= 0) {
@@ -301,10 +378,12 @@ struct DecWriteShared {
     uint32_t blk[DEC_THREADS][32];                   // word w of thread t's block at [t][w ^ (t & 31)]
 };
 
+template <bool RST>
 __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
             const uint64_t *__restrict__ st_out, const uint32_t *__restrict__ blk_start, int bpm, int hv,
-            int16_t *__restrict__ coef, int16_t *__restrict__ dcarr, uint32_t nblocks, uint32_t *__restrict__ err) {
+            int16_t *__restrict__ coef, int16_t *__restrict__ dcarr, uint32_t nblocks, uint32_t *__restrict__ err,
+            const uint32_t *__restrict__ bnd, const uint32_t *__restrict__ nmark_p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecWriteShared &sh = *reinterpret_cast<DecWriteShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -346,9 +425,12 @@ k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, c
     uint64_t end_state = in;
     const uint16_t *lut = &sh.lut[0][0];
     uint32_t *cell = sh.blk[tid];
+    RstTrack rt;
+    if (RST) rt.init(bnd, *nmark_p, chunk_bit0, q);
     while (__any_sync(0xffffffffu, active)) {
         bool flush = false;
         if (active) {
+            if (RST && q >= rt.lim) { c = 0; k = 0; rt.next(); }   // an interval begins here (states are synchronised: nothing pending)
             const uint32_t g = q >> 5, o = q & 31u;
             const uint32_t w0 = sh.words[(g & 31u) * WR_STRIDE + (g >> 5)];
             const uint32_t g1 = g + 1;
@@ -359,7 +441,13 @@ k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, c
             uint32_t e = lut[(t << DEC_LUT_BITS) + (win >> (32 - DEC_LUT_BITS))];
             if (e == 0) e = huff_sym_long(sh, t, win >> 16);
             const uint32_t len = e >> 8, s = e & 15u, r = (e >> 4) & 15u;
-            if (e == 0xFFFFu || q + len + s > tot) {   // cannot happen on synchronised states except in the final padding
+            if (RST && ((e == 0xFFFFu && q + 16 > rt.lim) || (e != 0xFFFFu && q + len + s > rt.lim))) {
+                // the 1-padding before a restart marker: the next interval (and block) begins at the boundary
+                q = rt.lim; c = 0; k = 0;
+                rt.next();
+                owning = true;
+                if (q >= stop) active = false;   // blocks that start at or past my last bit are not mine
+            } else if (e == 0xFFFFu || q + len + s > tot) {   // cannot happen on synchronised states except in the final padding
                 q = tot;
                 active = false;
             } else {
@@ -552,7 +640,7 @@ __device__ __forceinline__ void idct8(int &i0, int &i1, int &i2, int &i3, int &i
 
 __global__ void __launch_bounds__(256, 2)
 k_idct(const int16_t *__restrict__ coef, const int16_t *__restrict__ dcarr, Geom g, const DecTables *__restrict__ tb,
-       uint8_t *__restrict__ py, uint8_t *__restrict__ pcb, uint8_t *__restrict__ pcr) {
+       uint8_t *__restrict__ py, uint8_t *__restrict__ pcb, uint8_t *__restrict__ pcr, int rst_mcus) {
     __shared__ __align__(16) uint4 s_c[256 * 8];
     __shared__ uint16_t s_q[2][64];
     const int tid = threadIdx.x;
@@ -584,7 +672,14 @@ k_idct(const int16_t *__restrict__ coef, const int16_t *__restrict__ dcarr, Geom
             v[n] = cv * (int)q[n];
         }
     }
-    v[0] = (int)dcarr[b] * (int)q[0];   // the un-differenced DC (the coefficient array holds the difference)
+    // the un-differenced DC (the coefficient array holds the difference): k_dc_scan's running sum, taken from the start
+    // of the block's restart interval (predictors return to 0 there; 16-bit modular differences are exact)
+    int dcv = dcarr[b];
+    if (rst_mcus > 0 && m >= rst_mcus) {
+        const int pm = (m / rst_mcus) * rst_mcus - 1;   // last MCU of the previous interval
+        dcv = (int16_t)(dcv - (int)dcarr[pm * g.bpm + (isY ? hv - 1 : bn)]);
+    }
+    v[0] = dcv * (int)q[0];
 #pragma unroll
     for (int c = 0; c < 8; c++) idct8<11>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
     uint8_t *dst;
@@ -752,9 +847,11 @@ k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const
 size_t dec_sync_smem() { return sizeof(DecShared); }
 
 cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,
-                           uint64_t *out_len, uint64_t *avail, uint32_t *err, cudaStream_t s) {
+                           uint64_t *out_len, uint64_t *avail, uint32_t *bnd, uint32_t bnd_cap, uint32_t *nmark, uint32_t *err,
+                           cudaStream_t s) {
     const int grid = std::max(1, std::min(148 * 6, c1 - c0));
-    k_destuff<<<grid, 256, 0, s>>>(in, n, out, desc, ticket, c0, c1, out_len, avail, err);
+    if (bnd) k_destuff<true><<<grid, 256, 0, s>>>(in, n, out, desc, ticket, c0, c1, out_len, avail, bnd, bnd_cap, nmark, err);
+    else k_destuff<false><<<grid, 256, 0, s>>>(in, n, out, desc, ticket, c0, c1, out_len, avail, nullptr, 0, nullptr, err);
     return cudaGetLastError();
 }
 
@@ -765,9 +862,13 @@ static cudaError_t dec_attr() {
     if (e != cudaSuccess) return e;
     const uint64_t bit = 1ull << (dev & 63);
     if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
-    e = cudaFuncSetAttribute(k_dec_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    e = cudaFuncSetAttribute(k_dec_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_dec_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWriteShared));
+    e = cudaFuncSetAttribute(k_dec_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dec_write<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWriteShared));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dec_write<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecWriteShared));
     if (e != cudaSuccess) return e;
     done.fetch_or(bit, std::memory_order_release);
     return cudaSuccess;
@@ -775,24 +876,28 @@ static cudaError_t dec_attr() {
 
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
                             uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
-                            size_t nsub, cudaStream_t s) {
+                            size_t nsub, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s) {
     cudaError_t e = dec_attr();
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((nsub + DEC_THREADS - 1) / DEC_THREADS);
     if (grid == 0) return cudaSuccess;
-    k_dec_sync<<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv, inner,
-                                                            mode, done, changed);
+    if (bnd) k_dec_sync<true><<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv,
+                                                                        inner, mode, done, changed, bnd, nmark);
+    else k_dec_sync<false><<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv,
+                                                                     inner, mode, done, changed, nullptr, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
                              const uint32_t *blk_start, int bpm, int hv, int16_t *coef, int16_t *dcarr, uint32_t nblocks,
-                             uint32_t *err, size_t nsub_max, cudaStream_t s) {
+                             uint32_t *err, size_t nsub_max, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s) {
     cudaError_t e = dec_attr();
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((nsub_max + DEC_THREADS - 1) / DEC_THREADS);
-    k_dec_write<<<grid, DEC_THREADS, sizeof(DecWriteShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm, hv, coef,
-                                                                  dcarr, nblocks, err);
+    if (bnd) k_dec_write<true><<<grid, DEC_THREADS, sizeof(DecWriteShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm,
+                                                                              hv, coef, dcarr, nblocks, err, bnd, nmark);
+    else k_dec_write<false><<<grid, DEC_THREADS, sizeof(DecWriteShared), s>>>(u, u_len, (const DecTables *)tb, st_out, blk_start, bpm,
+                                                                           hv, coef, dcarr, nblocks, err, nullptr, nullptr);
     return cudaGetLastError();
 }
 
@@ -810,8 +915,8 @@ cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_
 }
 
 cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb,
-                        uint8_t *pcr, cudaStream_t s) {
-    k_idct<<<g.ntiles, 256, 0, s>>>(coef, dcarr, g, (const DecTables *)tb, py, pcb, pcr);
+                        uint8_t *pcr, int rst_mcus, cudaStream_t s) {
+    k_idct<<<g.ntiles, 256, 0, s>>>(coef, dcarr, g, (const DecTables *)tb, py, pcb, pcr, rst_mcus);
     return cudaGetLastError();
 }
 

@@ -20,23 +20,27 @@ size_t dec_tables_size();
 int dec_build_tables(const JpegInfo &info, void *dst_host);
 
 // 4 KB chunks [c0, c1) of the n-byte scan; `ticket`: a zeroed counter per launch; *avail = bytes produced so far
+// bnd != NULL (restart markers): FF Dn pairs are dropped too; bnd[j] = output offset where interval j + 1 begins,
+// bnd[*nmark] = 0xFFFFFFFF (bnd_cap entries available)
 cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,
-                           uint64_t *out_len, uint64_t *avail, uint32_t *err, cudaStream_t s);
+                           uint64_t *out_len, uint64_t *avail, uint32_t *bnd, uint32_t bnd_cap, uint32_t *nmark, uint32_t *err,
+                           cudaStream_t s);
 // mode 0: whole stream present (*u_len final); mode 1: stream still arriving (*u_len = bytes so far), first pass of the
 // complete chunks only. done[chunk] (zeroed per decode) marks chunks whose first pass has run. nsub: subsequences covered.
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
                             uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
-                            size_t nsub, cudaStream_t s);
+                            size_t nsub, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s);
 cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
                              const uint32_t *blk_start, int bpm, int hv, int16_t *coef, int16_t *dcarr, uint32_t nblocks,
-                             uint32_t *err, size_t nsub_max, cudaStream_t s);
+                             uint32_t *err, size_t nsub_max, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s);
 cudaError_t launch_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint64_t *desc, uint32_t *ticket, uint32_t *err,
                             cudaStream_t s);
 // coef here = the compact DC array (one int16 per block)
 cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_t *ticket, size_t desc_stride, uint32_t *err,
                            cudaStream_t s);
+// rst_mcus: restart interval in MCUs (0: none): DC predictors return to 0 at every interval start
 cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb,
-                        uint8_t *pcr, cudaStream_t s);
+                        uint8_t *pcr, int rst_mcus, cudaStream_t s);
 cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr, size_t step,
                            cudaStream_t s);
 

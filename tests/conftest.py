@@ -24,3 +24,10 @@ def oracle():
     import oracle as O
     O.build()
     return O
+
+
+@pytest.fixture(scope="session")
+def golden_rst():
+    """cv2-written streams WITH restart markers (tests/golden/make_golden_rst.py)"""
+    with open(os.path.join(ROOT, "tests", "golden", "golden_rst.json")) as f:
+        return json.load(f)

@@ -268,3 +268,40 @@ def test_against_reference_nvjpeg_output(P):
     assert psnr_mine >= psnr_ref - 0.05, (psnr_mine, psnr_ref)
     print(f"size {mine.size} vs nvJPEG {ref_jpg.size} ({100.0 * (mine.size - ref_jpg.size) / ref_jpg.size:+.2f} %), "
           f"PSNR {psnr_mine:.3f} vs {psnr_ref:.3f} dB")
+
+
+def test_restart_interval_streams(P, oracle, golden_rst):
+    """SURVEY.md 8f N2, decoder half: streams with DRI / RSTn markers (every interval is a known synchronisation point;
+    DC predictors restart) decode to cv2.imdecode's pixels -- the 200 committed cv2 IMWRITE_JPEG_RST_INTERVAL digests
+    (1 MCU, ragged, one and two MCU rows, longer than the image; five subsamplings), regenerated through the checker
+    whose byte-identity with cv2 tests/test_oracle_golden.py establishes."""
+    eng = P.Engine(640, 360, 95, True, "444")
+    n = 0
+    for c in golden_rst["cases"]:
+        img = oracle.synth(c["W"], c["H"], c["seed"], c["amp"])
+        jpg = oracle.encode(img, c["css"], c["quality"], c["optimize"], c["restart_interval"])
+        assert jpg.size == c["jpeg_len"] and sha(jpg)[:32] == c["jpeg_sha256_128"], c
+        out = eng.decode(jpg)
+        assert sha(out)[:32] == c["decoded_sha256_128"], c
+        n += 1
+    assert n == 200
+    eng.close()
+
+
+def test_restart_round_trip_large(P, oracle):
+    """Own restart streams (b2j_set_restart_rows) decode to the same pixels as the stream without markers, over
+    several decoder chunks and the three synchronisation schedules; q100 included (long synchronisation distances)."""
+    W, H = 1600, 640
+    img = oracle.synth(W, H, 5, 8)
+    for css, q, rows in ((1, 95, 1), (3, 100, 2), (0, 100, 1)):
+        eng = P.Engine(W, H, q, True, css)
+        plain = eng.encode(img)
+        want = eng.decode(plain)
+        eng.set_restart_rows(rows)
+        jpg = eng.encode(img)
+        assert jpg.size != plain.size
+        for dbg in (0, 4):
+            eng.set_debug(dbg)
+            assert np.array_equal(eng.decode(jpg), want), (css, q, rows, dbg)
+        eng.set_debug(0)
+        eng.close()

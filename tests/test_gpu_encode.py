@@ -199,3 +199,21 @@ def test_restart_rows(P, oracle, W, H, css, q, opt, rows):
     eng.set_restart_rows(0)
     assert np.array_equal(eng.encode(img), oracle.encode(img, css, q, opt))
     eng.close()
+
+
+def test_restart_rows_golden_digests(P, oracle, golden_rst):
+    """Row-aligned intervals of the committed cv2 IMWRITE_JPEG_RST_INTERVAL digests (all five subsamplings)."""
+    n = 0
+    for c in golden_rst["cases"]:
+        g = oracle.geometry(c["W"], c["H"], c["css"])
+        ri = c["restart_interval"]
+        if ri % g.mcux or ri // g.mcux == 0 or ri > 65535:
+            continue
+        img = oracle.synth(c["W"], c["H"], c["seed"], c["amp"])
+        eng = P.Engine(c["W"], c["H"], c["quality"], bool(c["optimize"]), c["css"])
+        eng.set_restart_rows(ri // g.mcux)
+        jpg = eng.encode(img)
+        assert jpg.size == c["jpeg_len"] and sha(jpg)[:32] == c["jpeg_sha256_128"], c
+        eng.close()
+        n += 1
+    assert n >= 40
