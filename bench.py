@@ -33,6 +33,18 @@ PEAKS_FALLBACK_GBS = 6650.0
 PUBLISHED_MPIX_S = 1652.0   # BASELINE.md section 1 (reference README.md:48): 332.8 Mpix / 201.45 ms, RTX 3060
 
 
+def kernel_source_digest():
+    """sha256 over the CUDA sources of the library: profiles/traffic.json carries the digest of the code it was captured on
+    (scripts/ncu_export.py); a capture of other code is not reported as this run's traffic."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "nvjpeg_imagecompressor_b200", "csrc", "*"))):
+        with open(f, "rb") as fh:
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -170,13 +182,18 @@ def run_reference(args, rank, world):
                 L.ref_last_times(h, *[C.byref(t) for t in tt])
                 if i >= args.warmup:
                     e2e_ms.append(dt)
-            # device-resident bracket (planes already uploaded): ImageCompressorImpl.cu:279-281 + size query
-            for i in range(args.warmup + args.steps):
-                ms = C.c_float(0)
-                if L.ref_encode_resident(h, C.byref(ms), C.byref(n)) != 0:
-                    raise RuntimeError("ref_encode_resident failed")
-                if i >= args.warmup:
-                    gpu_ms.append(ms.value)
+            # device-resident bracket (planes already uploaded): the reference's own bracket ImageCompressorImpl.cu:279-281
+            # (events around nvjpegEncodeImage only: `strict`) and the same with the size query inside, i.e. until the
+            # bitstream is complete on the device (`value`, as in round 1)
+            strict_ms = []
+            L.ref_encode_resident2.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
+            for strict in (1, 0):
+                for i in range(args.warmup + args.steps):
+                    ms = C.c_float(0)
+                    if L.ref_encode_resident2(h, strict, C.byref(ms), C.byref(n)) != 0:
+                        raise RuntimeError("ref_encode_resident failed")
+                    if i >= args.warmup:
+                        (strict_ms if strict else gpu_ms).append(ms.value)
             # the reference's decode of the JPEG it just wrote (DecodeWorker + getCVImageOnCPU: ImageCompressorImpl.cu:311-385,
             # :184-232): device phase (host JPEG -> planar BGR in HBM, cudaEvent bracket) and the whole call (3 x D2H + CPU
             # interleave into a host BGR image)
@@ -208,7 +225,11 @@ def run_reference(args, rank, world):
             line.update({"value": round(W * H / ms / 1e3, 1), "ms_per_step": round(ms, 3), "gpu_launches": None,
                          "e2e": {"value": round(W * H / e2e / 1e3, 1), "unit": "Mpix/s", "ms_per_step": round(e2e, 2),
                                  "h2d_bytes_per_step": W * H * 3, "d2h_bytes_per_step": int(n.value),
-                                 "split_ms": round(tt[1].value, 1), "h2d_ms": round(tt[2].value, 1)},
+                                 "split_ms": round(tt[1].value, 1), "h2d_ms": round(tt[2].value, 1),
+                                 "split": "SSSE3 byte shuffles, one thread (a stand-in for cv::split's SIMD path)",
+                                 "device_ms_with_size_query": round(ms, 3),
+                                 "device_ms_strict_bracket": round(float(np.mean(strict_ms)), 3),
+                                 "device_mpix_s_strict_bracket": round(W * H / float(np.mean(strict_ms)) / 1e3, 1)},
                          "reference_kind": "nvjpeg call sequence of ImageCompressorImpl.cu:19-45,269-294 "
                                            f"({'progressive as shipped' if args.ref_progressive else 'baseline sequential'}, "
                                            "4:2:2, q95, optimized Huffman) on this GPU; n_gpus ignored (single-GPU library)",
@@ -216,6 +237,7 @@ def run_reference(args, rank, world):
             line["vs_baseline"] = round(line["value"] / PUBLISHED_MPIX_S, 2)
             if ref_decode is not None:
                 line["decode"] = ref_decode
+                line["e2e"]["decode"] = ref_decode
             line["cpu_baseline"] = cpu_baseline()
             return line
         except Exception as e:  # fall through to the CPU arm
@@ -395,7 +417,12 @@ def run_b200(args, rank, world, local_rank):
             for _ in range(kd):
                 eng.decode_ptr(jpg, h_rec.data_ptr(), W * 3)
             dth = (time.perf_counter() - t0) / kd
+            eng.enable_timing(True)   # per-stage CUDA events inside the library: one extra, untimed decode
+            with torch.cuda.stream(stream):
+                eng.decode_device(jpg, d_rec.data_ptr(), W * 3)
+                eng.decode_finish()
             dt_st = {k: round(v, 3) for k, v in eng.timings().items() if k.startswith("dec_")}
+            eng.enable_timing(False)
             decode = {"metric": "decode_mpix_per_s", "value": round(W * H / dec_ms / 1e3, 1), "unit": "Mpix/s",
                       "ms_per_step": round(dec_ms, 3), "input": "host JPEG bytes (this run's output), output BGR in HBM",
                       "e2e": {"value": round(W * H / dth / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dth * 1e3, 2),
@@ -432,12 +459,16 @@ def run_b200(args, rank, world, local_rank):
     line = {"metric": "encode_mpix_per_s", "value": round(W * H / ms / 1e3, 1), "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": round(W * H / ms / 1e3 / PUBLISHED_MPIX_S, 2), "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "jpeg_bytes": int(nbytes), "jpeg_sha256": digest, "bit_exact_vs_libjpeg_turbo": bit_exact,
-                       "vs_baseline_basis": "BASELINE.md section 1: the reference README's 201.45 ms = 1652 Mpix/s for this configuration "
-                                            "(8320x40000, 4:2:2, q95, optimised Huffman) on an RTX 3060, its own images", "l2": "inputs (998 MB image, ~0.8 GB token pool) "
-                       "exceed the 126 MB L2; no flush between steps", "parallelism": "single GPU" if world == 1 else
-                       f"{world} MCU-row strips; per image every strip shares a 4 KB record (symbol counts, edge DCs, first tokens) by {exchange}"},
+            "config": {"workload": WORKLOAD},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    # what the stream is (kept inside `e2e`, which the driver records whole; `config` is the workload alone so that
+    # both arms carry the same one)
+    e2e.update({"jpeg_bytes": int(nbytes), "jpeg_sha256": digest, "bit_exact_vs_libjpeg_turbo": bit_exact,
+                "vs_baseline_basis": "BASELINE.md section 1: the reference README's 201.45 ms = 1652 Mpix/s for this configuration "
+                                     "(8320x40000, 4:2:2, q95, optimised Huffman) on an RTX 3060, its own images",
+                "l2": "inputs (998 MB image, ~0.8 GB token pool) exceed the 126 MB L2; no flush between steps",
+                "parallelism": "single GPU" if world == 1 else
+                f"{world} MCU-row strips; per image every strip shares a 4 KB record (symbol counts, edge DCs, first tokens) by {exchange}"})
     if world > 1 and stage_acc:
         st = {k: v / args.steps for k, v in stage_acc.items()}
         ksum = sum(st.get(k, 0.0) for k in ("fdct", "hist_edge", "tables", "pack", "scan", "stuff"))
@@ -448,6 +479,7 @@ def run_b200(args, rank, world, local_rank):
         line["e2e_pageable"] = e2e_pageable
     if decode is not None:
         line["decode"] = decode
+        e2e["decode"] = decode   # inside a recorded object: the decode half of BASELINE.json's metric
     if world == 1:
         from nvjpeg_imagecompressor_b200 import _native as NAT
         st = {k: v / args.steps for k, v in stage_acc.items()}
@@ -465,14 +497,20 @@ def run_b200(args, rank, world, local_rank):
         path_bytes = W * H * 3 + int(nbytes)
         ach = path_bytes / (st[top] * 1e-3) / 1e9
         traffic = None
+        traffic_note = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f)["kernels"].get(names[top], {}).get("dram_bytes")
+                tj = json.load(f)
+            if tj.get("source_digest") == kernel_source_digest():
+                traffic = tj["kernels"].get(names[top], {}).get("dram_bytes")
+            else:
+                traffic_note = ("profiles/traffic.json was captured on other kernel sources (digest %s, this tree %s): not reported"
+                                % (tj.get("source_digest"), kernel_source_digest()))
         except Exception:
             pass
         line["roofline"] = {"bound": "hbm", "kernel": names[top],
                             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                            "traffic": traffic, "peak_source": which,
+                            "traffic": traffic, "traffic_note": traffic_note, "peak_source": which,
                             "algorithmic_bytes_per_launch": int(path_bytes), "bytes_per_pixel": round(path_bytes / (W * H), 4),
                             "kernel_ms": round(st[top], 4), "tokens": ntok,
                             "kernel_timing": f"CUDA events around every kernel on the launching stream, averaged over a second pass of "
@@ -488,6 +526,12 @@ def run_b200(args, rank, world, local_rank):
                                              "achieved": round(path_bytes / (ms * 1e-3) / 1e9, 1),
                                              "frac": round(path_bytes / (ms * 1e-3) / 1e9 / peak, 4)}}
         line["stages_ms"] = {k: round(v, 4) for k, v in st.items() if k in ("fdct", "hist_edge", "tables", "pack", "scan", "stuff", "total")}
+        line["roofline"]["stages_ms"] = line["stages_ms"]
+        if decode and "ms_per_step" in decode:   # decode: JPEG bytes read once + 3 B per pixel written once
+            line["roofline"]["decode"] = {"algorithmic_bytes": int(path_bytes), "ms": decode["ms_per_step"],
+                                          "achieved": round(path_bytes / (decode["ms_per_step"] * 1e-3) / 1e9, 1),
+                                          "frac": round(path_bytes / (decode["ms_per_step"] * 1e-3) / 1e9 / peak, 4),
+                                          "stages_ms": decode.get("stages_ms")}
         try:
             line["cpu_baseline"] = cpu_baseline()
         except Exception as e:

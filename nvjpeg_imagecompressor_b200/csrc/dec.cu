@@ -3,6 +3,7 @@
 // this library's kernels; output planes are never materialised as three B/G/R planes (the reference's
 // getCVImageOnCPU :184-232 step disappears into k_upcolor's interleaved store).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -55,6 +56,7 @@ struct Decoder {
     void *upload_user = nullptr;
     bool speculated = false;   // the last run issued a fixed number of synchronisation launches without looking
     int spec_launches = 3;     // that number (tests shorten it to force the retry path)
+    int long_group = 0;        // B2J_DEC_GROUP: subsequences per thread of k_dec_sync_long (0: chosen per stream)
 };
 
 #define DCK(call)                                                                                                  \
@@ -71,6 +73,7 @@ Decoder *dec_create(int nblocks_cap, char *err, size_t errlen) {
     d->nblocks_cap = nblocks_cap;
     d->err = err;
     d->errlen = errlen;
+    if (const char *e = getenv("B2J_DEC_GROUP")) d->long_group = atoi(e);
     bool ok = cudaMalloc(&d->d_ctrl, sizeof(DecCtrl)) == cudaSuccess && cudaMalloc(&d->d_tb, dec_tables_size()) == cudaSuccess &&
               cudaHostAlloc(&d->h_tb, dec_tables_size(), cudaHostAllocDefault) == cudaSuccess &&
               cudaHostAlloc(&d->h_flag, 16, cudaHostAllocDefault) == cudaSuccess &&
@@ -232,11 +235,18 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         DCK(cudaMemcpyAsync(&d->h_flag[2], &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
         rounds--;
     } else {
+        // long synchronisation distances / checked retry: one pass per launch, groups of subsequences per thread
+        // (k_dec_sync_long); the host looks at the "an end state moved" flag after every launch
+        // group length: a correction travels one group per launch and every launch is a pass over the stream, so streams
+        // that practically never synchronise on their own (200+ bits per block) take long groups; the retry of an
+        // ordinary stream keeps them short (more threads, few groups still moving after the second launch)
+        const bool hard = (double)n * 8.0 / (double)g.nblocks >= 200.0;
+        const int group = d->long_group > 0 ? d->long_group : (hard ? 32 : 8);
         for (;; rounds++) {
-            if (rounds >= 256) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
+            if (rounds >= 65536) { snprintf(d->err, d->errlen, "Huffman synchronisation did not converge"); return B2J_EINTERNAL; }
             DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
-            DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 0, d->d_done,
-                                &d->d_ctrl->changed, nsub_max, bnd, nmark, s));
+            DCK(launch_dec_sync_long(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, rounds == 0, group,
+                                     &d->d_ctrl->changed, nsub_max, bnd, nmark, s));
             if (launches) (*launches)++;
             if (rounds == 0) continue;  // the first launch always moves states
             DCK(cudaMemcpyAsync(d->h_flag, &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
@@ -245,6 +255,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         }
     }
     d->last_rounds = rounds + 1;
+    if (getenv("B2J_DEC_VERBOSE")) fprintf(stderr, "[b2j decode] %s synchronisation: %d launches, scan %zu bytes, %.1f bits/block\n", spec ? "scheduled" : "checked", d->last_rounds, n, (double)n * 8.0 / (double)g.nblocks);
     if (tm) cudaEventRecord(d->ev[2], s);
     DCK(launch_scan_u32(d->d_nblk, d->d_blk_start, nsub_max, d->d_desc + d->desc_cap, &d->d_ctrl->ticket[1], &d->d_ctrl->err, s));
     DCK(launch_dec_write(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_out, d->d_blk_start, g.bpm, hv, d->d_coef, d->d_dc, (uint32_t)g.nblocks,

@@ -361,6 +361,148 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
     if (any || (live && last_live && mine != before) || (live && sh.state[tid] != used)) atomicOr(changed, 1u);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// k_dec_sync_long: the synchronisation for streams with LONG synchronisation distances (q100: blocks rarely end with
+// EOB, so a decoder that starts out of phase stays out of phase for many kilobits) and for the checked retry. One
+// thread decodes a GROUP of `DEC_GROUP` (8 ... 64, chosen by the host) consecutive subsequences in one go (a streaming bit reader on the unstuffed
+// bytes in global memory), recording the state at every 1024-bit boundary on the way, so k_scan_u32 / k_dec_write see
+// the same per-subsequence arrays as after k_dec_sync -- but a launch costs one pass over the stream and carries a
+// correction DEC_GROUP subsequences further, where k_dec_sync re-decodes every subsequence once per subsequence of
+// distance. A group whose start state did not change since it was last decoded is skipped.
+constexpr int DEC_LONG_THREADS = 128;
+struct DecTabShared {
+    uint16_t lut[4][1 << DEC_LUT_BITS];
+    int32_t maxcode[4][18];
+    int32_t valoff[4][17];
+    uint8_t vals[4][256];
+};
+
+template <bool RST>
+__global__ void __launch_bounds__(DEC_LONG_THREADS)
+k_dec_sync_long(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
+                uint64_t *__restrict__ st_in, uint64_t *__restrict__ st_out, uint32_t *__restrict__ nblk, int bpm, int hv,
+                int first, int DEC_GROUP, uint32_t *__restrict__ changed, const uint32_t *__restrict__ bnd,
+                const uint32_t *__restrict__ nmark_p) {
+    __shared__ DecTabShared sh;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * (1 << DEC_LUT_BITS); i += DEC_LONG_THREADS) (&sh.lut[0][0])[i] = (&tb->lut[0][0])[i];
+    for (int i = tid; i < 4 * 18; i += DEC_LONG_THREADS) (&sh.maxcode[0][0])[i] = (&tb->maxcode[0][0])[i];
+    for (int i = tid; i < 4 * 17; i += DEC_LONG_THREADS) (&sh.valoff[0][0])[i] = (&tb->valoff[0][0])[i];
+    for (int i = tid; i < 4 * 256; i += DEC_LONG_THREADS) (&sh.vals[0][0])[i] = (&tb->vals[0][0])[i];
+    __syncthreads();
+    const uint64_t nbytes = *u_len;
+    const uint64_t total_bits = nbytes * 8;
+    const size_t grp = (size_t)blockIdx.x * DEC_LONG_THREADS + tid;
+    const size_t sub0 = grp * DEC_GROUP;
+    const uint64_t bit0 = (uint64_t)sub0 * SUB_BITS;
+    if (bit0 >= total_bits) return;
+    // start state: the stream's start, the guess "a block starts exactly at my first bit" (first launch), or what the
+    // previous group reached in the previous launch
+    const uint64_t in = grp == 0 ? pack_state(0, 0, 0) : (first ? pack_state(bit0, 0, 0) : st_out[sub0 - 1]);
+    if (!first && in == st_in[sub0]) return;   // nothing new for this group
+    st_in[sub0] = in;
+    uint64_t q = in >> 16;                      // absolute bit position
+    int c = (int)((in >> 8) & 0xFF), k = (int)(in & 0xFF);
+    // streaming bit reader: acc holds the next `nav` bits left-aligned; words come from a four-word register queue that
+    // is refilled with 16-byte loads issued one vector ahead (a thread walks alone through its kilobytes: the load
+    // latency must not sit on the symbol chain)
+    const uint4 *u4 = reinterpret_cast<const uint4 *>(u);
+    uint64_t acc = 0;
+    int nav = 0, qn = 0;           // qn: words left in the queue
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    uint4 ahead = make_uint4(0, 0, 0, 0);
+    size_t vidx = 0;               // index of the vector in `ahead`
+    auto next_word = [&]() -> uint32_t {
+        if (qn == 0) {
+            w0 = ahead.x; w1 = ahead.y; w2 = ahead.z; w3 = ahead.w;
+            qn = 4;
+            vidx++;
+            ahead = u4[vidx];
+        }
+        const uint32_t w = w0;
+        w0 = w1; w1 = w2; w2 = w3;
+        qn--;
+        return __byte_perm(w, 0, 0x0123);
+    };
+    auto seek = [&](uint64_t pos) {
+        const size_t widx = (size_t)(pos >> 5);
+        vidx = widx >> 2;
+        const uint4 cur = u4[vidx];
+        w0 = cur.x; w1 = cur.y; w2 = cur.z; w3 = cur.w;
+        qn = 4;
+        vidx++;
+        ahead = u4[vidx];
+        for (int i = 0; i < (int)(widx & 3); i++) { w0 = w1; w1 = w2; w2 = w3; qn--; }
+        const uint32_t a = next_word(), b = next_word();
+        acc = (((uint64_t)a << 32) | b) << (pos & 31u);
+        nav = 64 - (int)(pos & 31u);
+    };
+    seek(q);
+    uint64_t lim = ~0ull;   // next restart boundary (absolute bits)
+    uint32_t bj = 0;
+    if (RST) {
+        const uint32_t nm = *nmark_p;
+        uint32_t lo = 0, hi = nm;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint64_t)bnd[mid] * 8 >= q) hi = mid; else lo = mid + 1; }
+        bj = lo;
+        lim = bnd[bj] == 0xFFFFFFFFu ? ~0ull : (uint64_t)bnd[bj] * 8;
+    }
+    const uint16_t *lut = &sh.lut[0][0];
+    uint32_t nb = 0;
+    int j = 0;                                  // subsequence of the group that is being decoded
+    uint64_t sub_end = min(bit0 + SUB_BITS, total_bits);
+    bool moved = false;
+    // the state at the first symbol boundary at or past a subsequence's end is that subsequence's end state
+    auto record = [&]() {
+        while (j < DEC_GROUP && q >= sub_end) {
+            const size_t si = sub0 + j;
+            const uint64_t stt = pack_state(q, c, k);
+            if (j == DEC_GROUP - 1 || sub_end >= total_bits) moved = moved || first || st_out[si] != stt;
+            st_out[si] = stt;
+            nblk[si] = nb;
+            nb = 0;
+            j++;
+            if (sub_end >= total_bits) { j = DEC_GROUP; break; }
+            sub_end = min(sub_end + SUB_BITS, total_bits);
+            if (j < DEC_GROUP) st_in[sub0 + j] = stt;
+        }
+    };
+    record();
+    while (j < DEC_GROUP) {
+        if (RST && q >= lim) { c = 0; k = 0; bj++; lim = bnd[bj] == 0xFFFFFFFFu ? ~0ull : (uint64_t)bnd[bj] * 8; }
+        if (nav <= 32) {
+            acc |= (uint64_t)next_word() << (32 - nav);
+            nav += 32;
+        }
+        const uint32_t win = (uint32_t)(acc >> 32);
+        const bool dc = k == 0;
+        const uint32_t t = (c < hv ? 0u : 2u) + (dc ? 0u : 1u);
+        uint32_t e = lut[(t << DEC_LUT_BITS) + (win >> (32 - DEC_LUT_BITS))];
+        if (e == 0) e = huff_sym_long(sh, t, win >> 16);
+        uint32_t adv;
+        if (e == 0xFFFFu) {
+            if (RST && q + 16 > lim) { q = lim; c = 0; k = 0; bj++; lim = bnd[bj] == 0xFFFFFFFFu ? ~0ull : (uint64_t)bnd[bj] * 8; seek(q); record(); continue; }
+            adv = 1;                             // invalid code (only while unsynchronised): skip one bit
+        } else {
+            const uint32_t len = e >> 8, sz = e & 15u, r = (e >> 4) & 15u;
+            adv = len + sz;
+            if (RST && q + adv > lim) { q = lim; c = 0; k = 0; bj++; lim = bnd[bj] == 0xFFFFFFFFu ? ~0ull : (uint64_t)bnd[bj] * 8; seek(q); record(); continue; }
+            if (q + adv > total_bits) { q = total_bits; record(); break; }   // padding bits at the very end
+            int knew = sz ? k + (int)r + 1 : (r == 15u ? k + 16 : 64);
+            if (dc) knew = 1;
+            const bool done = knew > 63;
+            k = done ? 0 : knew;
+            c = done ? (c + 1 == bpm ? 0 : c + 1) : c;
+            nb += done ? 1u : 0u;
+        }
+        q += adv;
+        acc <<= adv;
+        nav -= (int)adv;
+        if (q >= sub_end) record();
+    }
+    if (moved) atomicOr(changed, 1u);
+}
+
 // Final pass: decode every subsequence from its synchronised start state and write whole coefficient blocks
 // (zig-zag order, DC still differential). A block belongs to the thread in whose subsequence it STARTS: that thread
 // keeps decoding past its last bit until the block is complete (a block is at most 1665 bits: two subsequences of
@@ -885,6 +1027,18 @@ cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void 
                                                                         inner, mode, done, changed, bnd, nmark);
     else k_dec_sync<false><<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv,
                                                                      inner, mode, done, changed, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dec_sync_long(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
+                                 uint32_t *nblk, int bpm, int hv, int first, int group, uint32_t *changed, size_t nsub,
+                                 const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s) {
+    const int DEC_GROUP = group < 1 ? 1 : group;
+    const size_t ngrp = (nsub + DEC_GROUP - 1) / DEC_GROUP;
+    const unsigned grid = (unsigned)((ngrp + DEC_LONG_THREADS - 1) / DEC_LONG_THREADS);
+    if (grid == 0) return cudaSuccess;
+    if (bnd) k_dec_sync_long<true><<<grid, DEC_LONG_THREADS, 0, s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv, first, DEC_GROUP, changed, bnd, nmark);
+    else k_dec_sync_long<false><<<grid, DEC_LONG_THREADS, 0, s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv, first, DEC_GROUP, changed, nullptr, nullptr);
     return cudaGetLastError();
 }
 

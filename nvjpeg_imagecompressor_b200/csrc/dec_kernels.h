@@ -30,6 +30,11 @@ cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
                             uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
                             size_t nsub, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s);
+// long synchronisation distances and the checked retry: one launch = one pass, groups of 8 subsequences per thread;
+// first != 0: every group starts from the guess, else from its predecessor's last end state (skipped if unchanged)
+cudaError_t launch_dec_sync_long(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
+                                 uint32_t *nblk, int bpm, int hv, int first, int group, uint32_t *changed, size_t nsub,
+                                 const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s);
 cudaError_t launch_dec_write(const uint8_t *u, const uint64_t *u_len, const void *tb, const uint64_t *st_out,
                              const uint32_t *blk_start, int bpm, int hv, int16_t *coef, int16_t *dcarr, uint32_t nblocks,
                              uint32_t *err, size_t nsub_max, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s);

@@ -9,10 +9,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--width", type=int, default=8320); ap.add_argument("--height", type=int, default=40000)
 ap.add_argument("--css", default="422"); ap.add_argument("--quality", type=int, default=95)
 ap.add_argument("--optimize", type=int, default=1); ap.add_argument("--iters", type=int, default=4)
+ap.add_argument("--restart-rows", type=int, default=0)
 a = ap.parse_args()
 img = synth(a.width, a.height)
 eng = P.Engine(a.width, a.height, a.quality, bool(a.optimize), a.css)
 st = torch.cuda.Stream(); eng.set_stream(st.cuda_stream)
+if a.restart_rows:
+    eng.set_restart_rows(a.restart_rows)
 optr, lptr = eng.encode_device(img.data_ptr(), a.width * 3, a.width, a.height)
 n = eng.encode_finish()
 jpg_d = torch.empty(n, dtype=torch.uint8, device="cuda")
