@@ -125,8 +125,22 @@ B2J_API int b2j_psnr(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n,
 B2J_API int b2j_diff_psnr_device(b2j_ctx *ctx, const uint8_t *d_a, const uint8_t *d_b, size_t n, int mode,
                                  uint8_t *d_out, const uint64_t **d_ssd);
 
-/* Secondary compression: encode -> reconstruct -> difference map -> encode(diff), plus PSNR(orig, recon),
- * device resident between the steps. Any output pointer may be NULL. */
+/* Reconstruction without an entropy decode: the pixels every decoder produces from the LAST encode of this context,
+ * from the quantised coefficients the encoder kept (set B2J_DEBUG_COEF before that encode): de-quantise + IDCT +
+ * upsample + colour conversion. Device pointer, asynchronous on the context's stream. */
+B2J_API int b2j_reconstruct_device(b2j_ctx *ctx, uint8_t *d_bgr, size_t step);
+
+/* Secondary compression, device resident (README.md:8): encode -> reconstruct (from the encoder's coefficients, no
+ * Huffman decode, no host round trip) -> difference map + SSD -> encode(difference). d_bgr: device pointer, contiguous
+ * rows (step == width * 3). Asynchronous; the returned pointers are context-owned device buffers (primary JPEG,
+ * secondary JPEG, reconstruction, difference map; any may be NULL). b2j_secondary_finish waits, validates both
+ * encodes and returns the two lengths, PSNR(orig, recon) and the exact SSD. */
+B2J_API int b2j_secondary_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int height, int diff_mode,
+                                 const uint8_t **d_jpg1, const uint8_t **d_jpg2, const uint8_t **d_recon,
+                                 const uint8_t **d_diff);
+B2J_API int b2j_secondary_finish(b2j_ctx *ctx, size_t *len1, size_t *len2, double *psnr, uint64_t *ssd);
+
+/* The same from and to host memory (upload, b2j_secondary_device, downloads). Any output pointer may be NULL. */
 B2J_API int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, int diff_mode,
                           uint8_t *jpg1, size_t cap1, size_t *len1, uint8_t *jpg2, size_t cap2, size_t *len2,
                           uint8_t *recon, size_t recon_step, double *psnr);

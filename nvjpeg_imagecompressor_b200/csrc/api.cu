@@ -13,6 +13,7 @@
 #include "../../include/b2jpeg.h"
 #include "common.cuh"
 #include "dec.h"
+#include "dec_kernels.h"
 #include "hostpipe.h"
 #include "kernels.h"
 
@@ -94,12 +95,15 @@ struct b2j_ctx {
     size_t last_len, last_step;
     uint8_t *last_bgr;
     b2j_ctx *second;  // encoder for the difference image (secondary compression)
+    uint8_t *d_rplanes; size_t rplanes_bytes;   // reconstruction from the encoder's coefficients: sample planes
+    void *d_rtb;                                // ... and de-quantisation tables (a DecTables with q filled)
     // peer-memory exchange of the strip records (multi-GPU encode without a collective)
     XchgArena *d_arena;            // this rank's arena (peers store into it)
     XchgArena **d_peers;           // device array [peer_world] of every rank's arena
     void *peer_opened[XCHG_MAX_WORLD];   // mappings from b2j_peer_open (closed in b2j_destroy)
     int n_opened, peer_rank, peer_world;
     int rst_rows;                  // restart interval in MCU rows (0: none); b2j_set_restart_rows
+    size_t sec_pixels;             // b2j_secondary_device: samples of the image in flight (PSNR denominator)
     uint32_t xseq;                 // images exchanged so far (identical on every rank)
     unsigned long long peer_timeout_ns;   // bound of the wait for the peers' records (B2J_PEER_TIMEOUT_MS, default 10 s)
 };
@@ -275,6 +279,7 @@ void b2j_destroy(b2j_ctx *ctx) {
     cudaFree(ctx->d_chunk_tile);
     cudaFree(ctx->d_tile_off); cudaFree(ctx->d_ctrl);   // d_pred_in, d_sdesc, d_desc live in d_ctrl's allocation
     cudaFree(ctx->d_huff); cudaFree(ctx->d_quant); cudaFree(ctx->d_out); cudaFree(ctx->d_recon); cudaFree(ctx->d_diff);
+    cudaFree(ctx->d_rplanes); cudaFree(ctx->d_rtb);
     if (ctx->h_ret) cudaFreeHost(ctx->h_ret);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_copy) if (ev) cudaEventDestroy(ev);
@@ -844,65 +849,106 @@ int b2j_psnr(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, double 
     return diff_psnr_host(ctx, a, b, n, 0, nullptr, psnr, ssd);
 }
 
+// Reconstruction without an entropy decode: the pixels every decoder will produce from the LAST encode of this
+// context, from the quantised coefficients k_fdct kept (B2J_DEBUG_COEF set before that encode): de-quantise + islow
+// IDCT + fancy upsampling + YCbCr->BGR, the decoder's own kernels. Asynchronous on the context's stream.
+int b2j_reconstruct_device(b2j_ctx *ctx, uint8_t *d_bgr, size_t step) {
+    if (!ctx || !d_bgr) return B2J_EINVAL;
+    if (!ctx->enc_ready || !(ctx->debug & 1) || !ctx->d_coef) { snprintf(ctx->err, sizeof(ctx->err), "b2j_reconstruct_device needs an encode with B2J_DEBUG_COEF set"); return B2J_EINVAL; }
+    const Geom &g = ctx->g;
+    if (step < (size_t)g.W * 3) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t ysz = ((size_t)g.mcux * 8 * g.hs * g.mcuy * 8 * g.vs + 63) & ~(size_t)63;
+    const size_t csz = ((size_t)g.mcux * 8 * g.mcuy * 8 + 63) & ~(size_t)63;
+    if (ctx->rplanes_bytes < ysz + 2 * csz + 256) {
+        cudaFree(ctx->d_rplanes); ctx->d_rplanes = nullptr; ctx->rplanes_bytes = 0;
+        CK(cudaMalloc(&ctx->d_rplanes, ysz + 2 * csz + 256));
+        ctx->rplanes_bytes = ysz + 2 * csz + 256;
+    }
+    if (!ctx->d_rtb) {
+        std::vector<uint8_t> h(dec_tables_size(), 0);
+        DecTables *t = reinterpret_cast<DecTables *>(h.data());
+        memcpy(t->q, ctx->hq.q, sizeof(t->q));
+        CK(cudaMalloc(&ctx->d_rtb, dec_tables_size()));
+        CK(cudaMemcpy(ctx->d_rtb, h.data(), h.size(), cudaMemcpyHostToDevice));
+    }
+    uint8_t *py = ctx->d_rplanes, *pcb = py + ysz, *pcr = pcb + csz;
+    CK(launch_idct(ctx->d_coef, nullptr, g, ctx->d_rtb, py, pcb, pcr, 0, ctx->stream));
+    CK(launch_upcolor(py, pcb, pcr, g, d_bgr, step, ctx->stream));
+    ctx->launches += 2;
+    return B2J_OK;
+}
+
+// Secondary compression, device resident and asynchronous: encode -> reconstruct from the encoder's own coefficients
+// -> difference map + SSD -> encode(difference). Nothing leaves the device, nothing is entropy-decoded, the host is
+// not waited for; b2j_secondary_finish returns the two lengths and the PSNR.
+int b2j_secondary_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int height, int diff_mode,
+                         const uint8_t **d_jpg1, const uint8_t **d_jpg2, const uint8_t **d_recon, const uint8_t **d_diff) {
+    if (!ctx || !d_bgr || step != (size_t)width * 3 || (diff_mode != 0 && diff_mode != 1)) return B2J_EINVAL;   // contiguous rows
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)width * 3 * height;
+    if (ctx->d_recon_bytes < bytes) { cudaFree(ctx->d_recon); ctx->d_recon = nullptr; ctx->d_recon_bytes = 0; CK(cudaMalloc(&ctx->d_recon, bytes)); ctx->d_recon_bytes = bytes; }
+    if (ctx->d_diff_bytes < bytes) { cudaFree(ctx->d_diff); ctx->d_diff = nullptr; ctx->d_diff_bytes = 0; CK(cudaMalloc(&ctx->d_diff, bytes)); ctx->d_diff_bytes = bytes; }
+    if (!ctx->second) {
+        b2j_params p2 = ctx->p; p2.flags = 0; p2.device = ctx->device;
+        int rc2 = b2j_create(&p2, &ctx->second); if (rc2) return rc2;
+    }
+    b2j_set_stream(ctx->second, ctx->stream);
+    const int dbg = ctx->debug;
+    ctx->debug |= 1;
+    int rc = ensure_debug(ctx);
+    const uint8_t *o1 = nullptr, *o2 = nullptr; const uint64_t *l1, *l2;
+    if (!rc) rc = b2j_encode_device(ctx, d_bgr, step, width, height, &o1, &l1);
+    if (!rc) rc = b2j_reconstruct_device(ctx, ctx->d_recon, (size_t)width * 3);
+    ctx->debug = dbg;
+    if (rc) return rc;
+    rc = b2j_diff_psnr_device(ctx, d_bgr, ctx->d_recon, bytes, diff_mode, ctx->d_diff, nullptr); if (rc) return rc;
+    rc = b2j_encode_device(ctx->second, ctx->d_diff, (size_t)width * 3, width, height, &o2, &l2);
+    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "secondary encode: %s", ctx->second->err); return rc; }
+    if (d_jpg1) *d_jpg1 = o1;
+    if (d_jpg2) *d_jpg2 = o2;
+    if (d_recon) *d_recon = ctx->d_recon;
+    if (d_diff) *d_diff = ctx->d_diff;
+    ctx->sec_pixels = (size_t)width * height * 3;
+    return B2J_OK;
+}
+
+int b2j_secondary_finish(b2j_ctx *ctx, size_t *len1, size_t *len2, double *psnr, uint64_t *ssd) {
+    if (!ctx || !ctx->second) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    // the SSD lives in the first encoder's control block: b2j_diff_psnr_device ran after its encode was queued, and
+    // fetch_ret copies the block (length, checks, SSD) in one go
+    int rc = fetch_ret(ctx); if (rc) return rc;
+    if (len1) *len1 = (size_t)ctx->h_ret->out_len;
+    if (ssd) *ssd = ctx->h_ret->ssd;
+    if (psnr) *psnr = psnr_from_ssd(ctx->h_ret->ssd, ctx->sec_pixels);
+    size_t n2 = 0;
+    rc = b2j_encode_finish(ctx->second, &n2);
+    if (rc) { snprintf(ctx->err, sizeof(ctx->err), "secondary encode: %s", ctx->second->err); return rc; }
+    if (len2) *len2 = n2;
+    return B2J_OK;
+}
+
 int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, int diff_mode, uint8_t *jpg1,
                   size_t cap1, size_t *len1, uint8_t *jpg2, size_t cap2, size_t *len2, uint8_t *recon, size_t recon_step,
                   double *psnr) {
     if (!ctx || !bgr || step < (size_t)width * 3 || (diff_mode != 0 && diff_mode != 1)) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
-    // 1. encode (keeps the uploaded image in d_img and the JPEG in d_out)
-    std::vector<uint8_t> tmp;
-    uint8_t *o1 = jpg1; size_t c1 = cap1;
-    if (!o1) { tmp.resize(b2j_encode_bound(ctx) < ((size_t)width * height * 3 + 4096) ? b2j_encode_bound(ctx) : (size_t)width * height * 3 + 4096); o1 = tmp.data(); c1 = tmp.size(); }
-    size_t n1 = 0;
-    int rc = b2j_encode(ctx, bgr, step, width, height, o1, c1, &n1); if (rc) return rc;
+    int rc = enc_alloc(ctx); if (rc) return rc;
+    // host pixels -> device (contiguous rows), then everything stays there: b2j_secondary_device
+    const size_t row = (size_t)width * 3;
+    rc = ensure_img(ctx, row * height); if (rc) return rc;
+    rc = upload_2d(ctx, ctx->d_img, row, bgr, step, row, height, ctx->stream); if (rc) return rc;
+    const uint8_t *dj1 = nullptr, *dj2 = nullptr, *drec = nullptr;
+    rc = b2j_secondary_device(ctx, ctx->d_img, row, width, height, diff_mode, &dj1, &dj2, &drec, nullptr); if (rc) return rc;
+    size_t n1 = 0, n2 = 0;
+    rc = b2j_secondary_finish(ctx, &n1, &n2, psnr, nullptr); if (rc) return rc;
+    for (int i = 0; i < StageRing::N; i++) ctx->ring.busy[i] = false;   // every upload has completed
     if (len1) *len1 = n1;
-    // 2. reconstruct on the device from the host JPEG bytes (the decoder parses headers on the host)
-    const size_t dstep = ((size_t)width * 3 + 15) & ~(size_t)15;
-    const size_t bytes = dstep * height;
-    if (ctx->d_recon_bytes < bytes) {
-        cudaFree(ctx->d_recon); ctx->d_recon = nullptr; ctx->d_recon_bytes = 0;
-        CK(cudaMalloc(&ctx->d_recon, bytes)); ctx->d_recon_bytes = bytes;
-    }
-    if (ctx->d_diff_bytes < bytes) {   // grow-only, like the other per-context buffers
-        cudaFree(ctx->d_diff); ctx->d_diff = nullptr; ctx->d_diff_bytes = 0;
-        CK(cudaMalloc(&ctx->d_diff, bytes));
-        ctx->d_diff_bytes = bytes;
-    }
-    {
-        JpegInfo info;
-        rc = parse_for(ctx, o1, n1, &info, nullptr, nullptr); if (rc) return rc;
-        rc = decode_parsed(ctx, o1, n1, info, ctx->d_recon, dstep, true); if (rc) return rc;
-    }
-    // 3. difference map + SSD; the pitch padding of both device images is zero-filled so it adds nothing
-    if (dstep != (size_t)width * 3) {
-        CK(cudaMemset2DAsync(ctx->d_img + (size_t)width * 3, dstep, 0, dstep - (size_t)width * 3, height, ctx->stream));
-        CK(cudaMemset2DAsync(ctx->d_recon + (size_t)width * 3, dstep, 0, dstep - (size_t)width * 3, height, ctx->stream));
-    }
-    rc = b2j_diff_psnr_device(ctx, ctx->d_img, ctx->d_recon, bytes, diff_mode, ctx->d_diff, nullptr); if (rc) return rc;
-    CK(cudaMemcpyAsync(&ctx->h_ret->ssd, &ctx->d_ctrl->ssd, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (recon) CK(cudaMemcpy2DAsync(recon, recon_step, ctx->d_recon, dstep, (size_t)width * 3, height, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err)); if (rc) return rc;
-    if (psnr) *psnr = psnr_from_ssd(ctx->h_ret->ssd, (size_t)width * height * 3);
-    // 4. encode the difference image with the same parameters (second encoder state, same stream)
-    if (jpg2 || len2) {
-        if (!ctx->second) {
-            b2j_params p2 = ctx->p; p2.flags = 0; p2.device = ctx->device;
-            rc = b2j_create(&p2, &ctx->second); if (rc) return rc;
-        }
-        b2j_set_stream(ctx->second, ctx->stream);
-        const uint8_t *dj; const uint64_t *dl;
-        rc = b2j_encode_device(ctx->second, ctx->d_diff, dstep, width, height, &dj, &dl);
-        size_t n2 = 0;
-        if (!rc) rc = b2j_encode_finish(ctx->second, &n2);
-        if (rc) { snprintf(ctx->err, sizeof(ctx->err), "secondary encode: %s", ctx->second->err); return rc; }
-        if (len2) *len2 = n2;
-        if (jpg2) {
-            if (n2 > cap2) return B2J_ECAPACITY;
-            CK(cudaMemcpyAsync(jpg2, dj, n2, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-        }
-    }
+    if (len2) *len2 = n2;
+    if (jpg1) { if (n1 > cap1) return B2J_ECAPACITY; rc = download_linear(ctx, jpg1, dj1, n1, ctx->stream); if (rc) return rc; }
+    if (jpg2) { if (n2 > cap2) return B2J_ECAPACITY; rc = download_linear(ctx, jpg2, dj2, n2, ctx->stream); if (rc) return rc; }
+    if (recon) { rc = download_2d(ctx, recon, recon_step, drec, row, row, height, ctx->stream); if (rc) return rc; }
     return B2J_OK;
 }
 

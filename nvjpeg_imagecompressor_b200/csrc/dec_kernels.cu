@@ -816,8 +816,9 @@ k_idct(const int16_t *__restrict__ coef, const int16_t *__restrict__ dcarr, Geom
     }
     // the un-differenced DC (the coefficient array holds the difference): k_dc_scan's running sum, taken from the start
     // of the block's restart interval (predictors return to 0 there; 16-bit modular differences are exact)
-    int dcv = dcarr[b];
-    if (rst_mcus > 0 && m >= rst_mcus) {
+    // (dcarr == NULL: the blocks come from the encoder and hold the quantised DC itself -- b2j_reconstruct_device)
+    int dcv = dcarr ? (int)dcarr[b] : (int)(int16_t)(s_c[tid * 8 + (0 ^ (tid & 7))].x & 0xFFFFu);
+    if (dcarr && rst_mcus > 0 && m >= rst_mcus) {
         const int pm = (m / rst_mcus) * rst_mcus - 1;   // last MCU of the previous interval
         dcv = (int16_t)(dcv - (int)dcarr[pm * g.bpm + (isY ? hv - 1 : bn)]);
     }

@@ -16,7 +16,9 @@
 //   stage C: the whole CTA walks the run in output order: entry -> (ZRL count | table | run/size symbol | value
 //            bits), symbol statistics with full-warp shared atomics, coalesced stores to the token pool
 // The entropy coder (enc_huff.cu k_pack) then works token-parallel: uniform work per lane instead of a divergent
-// per-coefficient branch. With DUMP the quantised coefficients are also written (parity tests only).
+// per-coefficient branch. With DUMP the quantised coefficients are also written (16-byte stores straight from the
+// registers): the parity tests read them, and the secondary-compression path reconstructs the image from them
+// (b2j_reconstruct_device: de-quantise + IDCT + upsample, no entropy decode).
 #include <atomic>
 
 #include "common.cuh"
@@ -34,7 +36,6 @@ struct K1 {
     static constexpr int RAW_STRIDE = TILE_PX * 3;  // multiple of 16 for all five modes
     static constexpr int RAW_BYTES = RAW_STRIDE * MCU_H;
     static constexpr int TOK_BYTES = 64 * 256 * 4 + 256;    // the tile's token run: <= 64 tokens per block
-    static constexpr int STAGE_BYTES = 256 * 128;           // DUMP only
     static constexpr int Y_STRIDE = TILE_PX;
     static constexpr int Y_BYTES = Y_STRIDE * MCU_H;
     static constexpr int C_STRIDE = TM_MAX * 8;
@@ -49,9 +50,7 @@ struct K1 {
     static constexpr int OFF_DC = OFF_HIST + 4096;       // int16[256]
     static constexpr int OFF_MISC = OFF_DC + 512;        // warp totals[8], pool base, chroma DC token offsets
     static constexpr int OFF_BAR = OFF_MISC + 64;        // mbarrier
-    static constexpr int OFF_STAGE = OFF_BAR + 16;       // DUMP only
-    static constexpr int SMEM = OFF_STAGE;
-    static constexpr int SMEM_DUMP = OFF_STAGE + STAGE_BYTES;
+    static constexpr int SMEM = OFF_BAR + 16;
     static_assert(OFF_CR + C_BYTES <= TOK_BYTES, "planes must fit inside the token area");
     static_assert(SMEM <= 75 * 1024, "three CTAs per SM");
     static_assert(RAW_BYTES <= TOK_BYTES, "raw tile must fit in the token area");
@@ -211,7 +210,6 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     int16_t *dcs = reinterpret_cast<int16_t *>(smem + C::OFF_DC);
     uint32_t *misc = reinterpret_cast<uint32_t *>(smem + C::OFF_MISC);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-    uint4 *stage = reinterpret_cast<uint4 *>(smem + C::OFF_STAGE);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int my = blockIdx.y + my0;
@@ -414,10 +412,12 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 #pragma unroll
         for (int k = 0; k < 64; k += 2) pk[k >> 1] = __byte_perm((uint32_t)v[zigzag_nat(k)], (uint32_t)v[zigzag_nat(k + 1)], 0x5410);
         ntok = 1 + (int)nnzf + ((pk[31] >> 16) == 0u ? 1 : 0);   // DC, one per non-zero AC, EOB iff the last coefficient is zero
-        if constexpr (DUMP) {
+        if constexpr (DUMP) {   // quantised coefficients, scan order, zig-zag inside the block
+            uint4 *cdst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM + blk) * 64);
+            if (real || C::HV == 1) {
 #pragma unroll
-            for (int c = 0; c < 8; c++)
-                stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                for (int c = 0; c < 8; c++) cdst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
         }
         if (real) dcs[blk] = (int16_t)mydc;
     }
@@ -435,8 +435,9 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         if (active && !real) {
             dcs[blk] = (int16_t)mydc;
             if constexpr (DUMP) {
+                uint4 *cdst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM + blk) * 64);
 #pragma unroll
-                for (int c = 0; c < 8; c++) stage[blk * 8 + (c ^ (blk & 7))] = make_uint4(c == 0 ? ((uint32_t)mydc & 0xFFFFu) : 0u, 0u, 0u, 0u);
+                for (int c = 0; c < 8; c++) cdst[c] = make_uint4(c == 0 ? ((uint32_t)mydc & 0xFFFFu) : 0u, 0u, 0u, 0u);
             }
         }
         __syncthreads();
@@ -508,13 +509,6 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     if (do_hist) stage_c<true>(tok, pool + (size_t)misc[8], total, hs, tid);
     else stage_c<false>(tok, pool + (size_t)misc[8], total, hs, tid);
 
-    if constexpr (DUMP) {  // quantised coefficients, scan order (parity tests)
-        uint4 *cdst = reinterpret_cast<uint4 *>(coef + ((size_t)((size_t)my * g.mcux + mx0) * C::BPM) * 64);
-        for (int i = tid; i < nblk * 8; i += 256) {
-            const int b = i >> 3, c = i & 7;
-            cdst[i] = stage[b * 8 + (c ^ (b & 7))];
-        }
-    }
     if (do_hist) {
         __syncthreads();
         for (int i = tid; i < 1024; i += 256) {   // bin = run & 15 << 6 | table << 4 | size
@@ -576,7 +570,7 @@ static cudaError_t launch_one2(const uint8_t *img, size_t step, const Geom &g, c
                                uint32_t *pool_count, TileRec *recs, uint32_t *hist, int do_hist, int my0, int nrows,
                                int16_t *coef, cudaStream_t s) {
     using C = K1<HS, VS>;
-    constexpr int SM = DUMP ? C::SMEM_DUMP : C::SMEM;
+    constexpr int SM = C::SMEM;
     // the attribute is per device: one bit per device ordinal (a process may hold contexts on several GPUs)
     static std::atomic<uint64_t> attr_done{0};
     int dev = 0;

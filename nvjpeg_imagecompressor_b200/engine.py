@@ -115,6 +115,22 @@ class Engine:
         self._ck(self._L.b2j_set_restart_rows(self._h, int(rows)))
 
     # ---------------------------------------------------------------- device API (pointers from torch tensors)
+    def reconstruct_device(self, d_bgr_ptr, step):
+        """Pixels of the last encode (made with set_debug(1)) from its quantised coefficients; asynchronous."""
+        self._ck(self._L.b2j_reconstruct_device(self._h, C.c_void_p(d_bgr_ptr), step))
+
+    def secondary_device(self, d_ptr, step, W, H, diff_mode=1):
+        """Device-resident secondary compression, asynchronous -> device pointers (jpg1, jpg2, recon, diff)."""
+        p = [C.c_void_p() for _ in range(4)]
+        self._ck(self._L.b2j_secondary_device(self._h, C.c_void_p(d_ptr), step, W, H, int(diff_mode), *[C.byref(x) for x in p]))
+        return tuple(x.value for x in p)
+
+    def secondary_finish(self):
+        """-> (len1, len2, psnr, ssd) of the last secondary_device"""
+        n1, n2, ps, ssd = C.c_size_t(0), C.c_size_t(0), C.c_double(0), C.c_uint64(0)
+        self._ck(self._L.b2j_secondary_finish(self._h, C.byref(n1), C.byref(n2), C.byref(ps), C.byref(ssd)))
+        return n1.value, n2.value, ps.value, ssd.value
+
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._L.b2j_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -239,10 +239,11 @@ class StripSecondary:
     encode(difference) + PSNR, every step on the rank's own MCU-row strip; both JPEG streams are stitched single-image
     streams (two StripEncoders), the PSNR comes from an all_reduce of the strips' exact integer SSDs.
 
-    Reconstruction needs no exchange when the sampling has no vertical subsampling (444 / 422 / 411): quantisation,
-    IDCT and the horizontal triangle upsampling never look across an MCU row, so the strip encoded and decoded as an
-    image of its own gives exactly the rows the whole image's decode would give (tests/test_gpu_strips.py). 420 / 440
-    upsample vertically across strip borders and are refused for world > 1.
+    The strip is reconstructed from the quantised coefficients its own encoder produced (b2j_reconstruct_device), which
+    needs no exchange when the sampling has no vertical subsampling (444 / 422 / 411): quantisation, IDCT and the
+    horizontal triangle upsampling never look across an MCU row, so the strip gives exactly the rows the whole image's
+    decode would give (tests/test_gpu_strips.py). 420 / 440 upsample vertically across strip borders and are refused
+    for world > 1.
     """
 
     def __init__(self, W, H, quality=95, optimize=True, css="422", diff_mode=1, rank=None, world=None, device=None,
@@ -258,15 +259,14 @@ class StripSecondary:
         self.y0, self.y1 = self.enc1.y0, self.enc1.y1
         rows_max = max(b - a for a, b in self.enc1.rows)
         dev = self.enc1.b.device
-        self.solo = Engine(W, rows_max, quality, optimize, css_id, device=dev.index)
         self.recon = torch.empty((rows_max, W, 3), dtype=torch.uint8, device=dev)
         self.diff = torch.empty((rows_max, W, 3), dtype=torch.uint8, device=dev)
-        self._host = torch.empty(rows_max * W * 3 // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)
         self._ssd = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._solo_out = self.solo.strip_state().d_out
-        # one stream for the three encoder states, the decoder and torch's copies / collectives
+        # the primary encoder keeps its quantised coefficients: the strip is reconstructed from them (no entropy decode)
+        self.enc1.b.eng.set_debug(1)
+        # one stream for the two encoder states and torch's copies / collectives
         self.stream = torch.cuda.Stream(device=dev)
-        for e in (self.enc1.b.eng, self.enc2.b.eng, self.solo):
+        for e in (self.enc1.b.eng, self.enc2.b.eng):
             e.set_stream(self.stream.cuda_stream)
 
     def run(self, d_ptr, step):
@@ -280,14 +280,10 @@ class StripSecondary:
     def _run(self, d_ptr, step):
         rows, W = self.y1 - self.y0, self.W
         n1 = self.enc1.encode_strip(d_ptr, step)
-        # the strip as an image of its own -> its pixels as every decoder will reconstruct them
-        self.solo.encode_device(d_ptr, step, W, rows)
-        n = self.solo.encode_finish()
-        self._host[:n].copy_(_view(self._solo_out, (n,), "|u1", self.recon.device), non_blocking=True)
-        self.stream.synchronize()
-        self.solo.decode_device(self._host[:n].numpy(), self.recon.data_ptr(), W * 3)
-        self.solo.decode_finish()
-        ssd_ptr = self.solo.diff_psnr_device(d_ptr, self.recon.data_ptr(), rows * W * 3, self.mode, self.diff.data_ptr())
+        # the strip's pixels as every decoder will reconstruct them: de-quantise + IDCT + upsample of the coefficients
+        # the encoder just produced (b2j_reconstruct_device) -- nothing is encoded twice, decoded or sent to the host
+        self.enc1.b.eng.reconstruct_device(self.recon.data_ptr(), W * 3)
+        ssd_ptr = self.enc2.b.eng.diff_psnr_device(d_ptr, self.recon.data_ptr(), rows * W * 3, self.mode, self.diff.data_ptr())
         self._ssd.copy_(_view(ssd_ptr, (1,), "<i8", self.recon.device))
         if self.world > 1:
             dist.all_reduce(self._ssd, op=dist.ReduceOp.SUM, group=self.group)

@@ -142,6 +142,32 @@ def test_secondary_compression(P, oracle):
         eng.close()
 
 
+def test_reconstruct_from_coefficients_and_device_secondary(P, oracle):
+    """b2j_reconstruct_device (de-quantise + IDCT + upsample of the encoder's own coefficients, no entropy decode) gives
+    exactly the decoder's pixels for every subsampling and ragged sizes; b2j_secondary_device / _finish == the checker."""
+    import torch
+    for (W, H) in ((333, 222), (64, 48), (17, 33), (640, 360)):
+        img = oracle.synth(W, H, 3, 8)
+        d_img = torch.from_numpy(img).cuda()
+        for css in range(5):
+            eng = P.Engine(W, H, 92, True, css)
+            eng.set_debug(1)
+            jpg = eng.encode(img)
+            rec = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+            eng.reconstruct_device(rec.data_ptr(), W * 3)
+            torch.cuda.synchronize()
+            eng.set_debug(0)
+            want = oracle.decode(jpg)
+            assert np.array_equal(rec.cpu().numpy(), want), (W, H, css)
+            for mode in (0, 1):
+                eng.secondary_device(d_img.data_ptr(), W * 3, W, H, mode)
+                n1, n2, ps, ssd = eng.secondary_finish()
+                assert n1 == jpg.size and ssd == oracle.ssd(img, want), (W, H, css, mode)
+                assert abs(ps - oracle.psnr(img, want)) < 1e-12
+                assert n2 == oracle.encode(oracle.diff(img, want, mode), css, 92, 1).size
+            eng.close()
+
+
 def test_runner_facade_demo_sequence(P, oracle, tmp_path):
     """The reference demo's call order (src/ImageCompressor/main.cpp:24-78) through the Python facade."""
     r = P.NvjpegCompressRunner(640, 360, 95, True, verbose=False)
