@@ -726,11 +726,48 @@ static int dec_ensure(b2j_ctx *ctx) {
 int b2j_peek(const uint8_t *jpg, size_t len, int *width, int *height, int *css) {
     JpegInfo info;
     int rc = parse_jpeg(jpg, len, &info);
-    if (rc) return rc;
+    if (rc) {   // progressive (SOF2) files are decoded too
+        ProgInfo pi;
+        if (parse_progressive(jpg, len, &pi) != B2J_OK) return rc;
+        if (width) *width = pi.W;
+        if (height) *height = pi.H;
+        if (css) *css = pi.css;
+        prog_free(&pi);
+        return B2J_OK;
+    }
     if (width) *width = info.W;
     if (height) *height = info.H;
     if (css) *css = info.css;
     return B2J_OK;
+}
+
+// progressive (SOF2) files: parsed and decoded scan by scan (dec_prog.cu); returns B2J_EFORMAT if it is not one
+static int decode_progressive_to(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_bgr, size_t step, bool alloc_recon,
+                                 int *width, int *height) {
+    ProgInfo pi;
+    int rc = parse_progressive(jpg, len, &pi);
+    if (rc) return rc;
+    if (width) *width = pi.W;
+    if (height) *height = pi.H;
+    Geom g;
+    rc = make_geom(pi.W, pi.H, pi.css, &g);
+    if (!rc && (d_bgr || alloc_recon)) {
+        size_t dstep = step;
+        if (alloc_recon) {
+            dstep = ((size_t)pi.W * 3 + 15) & ~(size_t)15;
+            if (ctx->d_recon_bytes < dstep * pi.H) {
+                cudaFree(ctx->d_recon); ctx->d_recon = nullptr; ctx->d_recon_bytes = 0;
+                if (cudaMalloc(&ctx->d_recon, dstep * pi.H) != cudaSuccess) { prog_free(&pi); return B2J_ECUDA; }
+                ctx->d_recon_bytes = dstep * pi.H;
+            }
+            d_bgr = ctx->d_recon;
+        }
+        if (dstep < (size_t)pi.W * 3) rc = B2J_EINVAL;
+        if (!rc) rc = dec_ensure(ctx);
+        if (!rc) rc = dec_run_progressive(ctx->dec, jpg, len, pi, g, d_bgr, dstep, ctx->stream, &ctx->launches);
+    }
+    prog_free(&pi);
+    return rc;
 }
 
 static int decode_parsed(b2j_ctx *ctx, const uint8_t *jpg, size_t len, const JpegInfo &info, uint8_t *d_bgr, size_t step, bool careful) {
@@ -753,7 +790,13 @@ int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_b
     if (!ctx || !jpg) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
     JpegInfo info;
-    int rc = parse_for(ctx, jpg, len, &info, width, height); if (rc) return rc;
+    int rc = parse_for(ctx, jpg, len, &info, width, height);
+    if (rc == B2J_EFORMAT) {   // not a baseline file: progressive? (decoded synchronously, nothing left for b2j_decode_finish)
+        if (ctx->last_jpg) { const int rf = b2j_decode_finish(ctx); if (rf) return rf; }
+        const int rp = decode_progressive_to(ctx, jpg, len, d_bgr, step, false, width, height);
+        if (rp != B2J_EFORMAT) return rp;
+    }
+    if (rc) return rc;
     if (!d_bgr) return B2J_OK;
     // one decode in flight per context: an unfinished predecessor is finished (validated, retried if needed) first
     if (ctx->last_jpg) { rc = b2j_decode_finish(ctx); if (rc) return rc; }
@@ -781,7 +824,20 @@ int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bgr, size_
     if (!ctx || !jpg) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
     JpegInfo info;
-    int rc = parse_for(ctx, jpg, len, &info, width, height); if (rc) return rc;
+    int rc = parse_for(ctx, jpg, len, &info, width, height);
+    if (rc == B2J_EFORMAT) {   // not a baseline file: progressive?
+        int pw = 0, ph = 0;
+        const int rp = decode_progressive_to(ctx, jpg, len, nullptr, 0, bgr != nullptr, &pw, &ph);
+        if (rp != B2J_EFORMAT) {
+            if (width) *width = pw;
+            if (height) *height = ph;
+            if (rp || !bgr) return rp;
+            if (step < (size_t)pw * 3) return B2J_EINVAL;
+            const size_t dstep = ((size_t)pw * 3 + 15) & ~(size_t)15;
+            return download_2d(ctx, bgr, step, ctx->d_recon, dstep, (size_t)pw * 3, ph, ctx->stream);
+        }
+    }
+    if (rc) return rc;
     if (!bgr) return B2J_OK;
     if (step < (size_t)info.W * 3) return B2J_EINVAL;
     const size_t dstep = ((size_t)info.W * 3 + 15) & ~(size_t)15;

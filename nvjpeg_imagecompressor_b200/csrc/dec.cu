@@ -282,6 +282,18 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     return B2J_OK;
 }
 
+int dec_run_progressive(Decoder *d, const uint8_t *jpg, size_t len, const ProgInfo &info, const Geom &g, uint8_t *d_bgr,
+                        size_t step, cudaStream_t s, uint64_t *launches) {
+    if (g.nblocks > d->nblocks_cap) { snprintf(d->err, d->errlen, "image exceeds the context's size"); return B2J_ESIZE; }
+    int rc = ensure(d, 4096, g, 0);
+    if (rc) return rc;
+    if (d->in_flight) { DCK(cudaStreamSynchronize(d->last_stream)); d->in_flight = false; }
+    d->speculated = false;
+    d->last_stream = s;
+    DCK(cudaMemsetAsync(&d->d_ctrl->err, 0, 4, s));
+    return dec_progressive(jpg, len, info, g, d->d_coef, d->d_tb, d->d_planes, d_bgr, step, s, launches, d->err, d->errlen);
+}
+
 int dec_check(Decoder *d, char *err, size_t errlen) {
     if (!d) return B2J_OK;
     if (cudaMemcpyAsync(&d->h_flag[1], &d->d_ctrl->err, 4, cudaMemcpyDeviceToHost, d->last_stream) != cudaSuccess ||

@@ -36,3 +36,29 @@ void dec_set_spec_launches(Decoder *d, int n);   // speculative synchronisation 
 const void *dec_coef_ptr(Decoder *d, size_t *bytes);
 
 }  // namespace b2j
+
+namespace b2j {
+
+// ---- progressive (SOF2) streams: what the reference as shipped writes (ImageCompressorImpl.cu:28) -------------------
+struct ProgScan {
+    int ncomp, comp[3];            // components of the scan (indices 0 Y, 1 Cb, 2 Cr)
+    int Ss, Se, Ah, Al;            // spectral selection, successive approximation
+    int restart_interval;          // MCUs (interleaved) or blocks (one component) per interval, 0 = none
+    size_t seg_off, seg_len;       // entropy-coded segment in the file (stuffed bytes, RSTn markers inside)
+    uint8_t bits[2][3][17];        // [0 DC | 1 AC][component of the scan]: the tables in force at this SOS
+    uint8_t vals[2][3][256];
+};
+struct ProgInfo {
+    int W, H, css, hs, vs;
+    uint16_t qt[2][64];            // natural order: luma, chroma
+    int nscans;
+    ProgScan *scans;               // nscans entries (malloc'ed by parse_progressive, freed by prog_free)
+};
+// jdmarker.c for SOF2 files with three components, chroma 1x1; B2J_EFORMAT for anything else
+int parse_progressive(const uint8_t *jpg, size_t len, ProgInfo *info);
+void prog_free(ProgInfo *info);
+// every scan is absorbed into the coefficient array in file order, then the baseline back end runs
+int dec_run_progressive(Decoder *d, const uint8_t *jpg, size_t len, const ProgInfo &info, const Geom &g, uint8_t *d_bgr,
+                        size_t step, cudaStream_t s, uint64_t *launches);
+
+}  // namespace b2j

@@ -42,6 +42,15 @@ int main(int argc, char **argv) {
             free(tb);
             if (info.W <= 0 || info.H <= 0 || info.css < 0 || info.css > 4) { printf("BAD INFO it=%d\n", it); return 2; }
         }
+        {   // the progressive parser on the same bytes
+            b2j::ProgInfo pi;
+            if (b2j::parse_progressive(heap, s.size(), &pi) == 0) {
+                ok++;
+                for (int i = 0; i < pi.nscans; i++)
+                    if (pi.scans[i].seg_off + pi.scans[i].seg_len > s.size() || pi.scans[i].ncomp < 1 || pi.scans[i].ncomp > 3) { printf("BAD SCAN it=%d\n", it); return 2; }
+                b2j::prog_free(&pi);
+            }
+        }
         total++;
         free(heap);
     }

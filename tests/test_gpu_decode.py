@@ -194,11 +194,13 @@ def test_runner_facade_demo_sequence(P, oracle, tmp_path):
 def test_rejects_unsupported(P, oracle):
     cv2 = pytest.importorskip("cv2")
     img = oracle.synth(64, 64, 1, 8)
-    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    ok, gray = cv2.imencode(".jpg", img[:, :, 0])   # one component: outside the three-component interface of the reference
     eng = P.Engine(64, 64)
     with pytest.raises(P.B2JError) as ei:
-        eng.decode(prog.ravel())
+        eng.decode(gray.ravel())
     assert ei.value.rc == -5
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])   # progressive files are decoded (row N4)
+    assert np.array_equal(eng.decode(prog.ravel()), cv2.imdecode(prog, cv2.IMREAD_COLOR))
     with pytest.raises(P.B2JError):
         eng.decode(np.zeros(1000, np.uint8))
     eng.close()
@@ -331,3 +333,59 @@ def test_restart_round_trip_large(P, oracle):
             assert np.array_equal(eng.decode(jpg), want), (css, q, rows, dbg)
         eng.set_debug(0)
         eng.close()
+
+
+def test_progressive_streams(P, oracle):
+    """progressive (SOF2) files -- the format the reference as shipped writes (ImageCompressorImpl.cu:28)
+    -- decode to libjpeg-turbo's pixels: the committed cv2-written files (with and without restart markers) and
+    jpeg_simple_progression streams for every subsampling / ragged sizes (the checker's progressive encoder, byte-identical
+    to cv2.imencode(IMWRITE_JPEG_PROGRESSIVE): tests/test_oracle_golden.py)."""
+    import json
+    with open(os.path.join(HERE, "golden", "golden_prog.json")) as f:
+        files = json.load(f)["files"]
+    eng = P.Engine(640, 360, 95, True, "444")
+    for c in files:
+        jpg = np.fromfile(os.path.join(HERE, "golden", c["file"]), np.uint8)
+        assert P.Engine.peek(jpg) == (c["W"], c["H"], c["css"])
+        out = eng.decode(jpg)
+        assert out.shape == (c["H"], c["W"], 3) and sha(out) == c["decoded_sha256"], c
+    rng = np.random.default_rng(4)
+    for (W, H) in ((50, 70), (8, 8), (1, 1), (135, 121), (257, 63), (640, 360)):
+        for img in (oracle.synth(W, H, 6, 8), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)):
+            for css in range(5):
+                for q in (50, 95, 100):
+                    jpg = oracle.encode_progressive(img, css, q)
+                    assert np.array_equal(eng.decode(jpg), oracle.decode(jpg)), (W, H, css, q)
+    eng.close()
+
+
+def test_decode_reference_progressive_nvjpeg_streams(P):
+    """The unmodified reference encodes PROGRESSIVE 4:4:4 (ImageCompressorImpl.cu:28,31): the streams its nvJPEG call
+    sequence writes with that setting decode to cv2.imdecode's pixels."""
+    import ctypes as C
+    cv2 = pytest.importorskip("cv2")
+    lib = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "libref_nvjpeg.so")
+    if not os.path.exists(lib):
+        pytest.skip("nvJPEG harness not built")
+    L = C.CDLL(lib)
+    from nvjpeg_imagecompressor_b200.synth import synth
+    W, H = 1024, 768
+    img = synth(W, H, 3).cpu().numpy()
+    eng = P.Engine(W, H, 95, True, "444")
+    for css in (0, 1, 3):
+        h = C.c_void_p()
+        assert L.ref_create(W, H, 95, 1, css, 1, C.byref(h)) == 0   # progressive = 1
+        if L.ref_build_compress_env(h) != 0:
+            pytest.skip("nvJPEG cannot run here")
+        out = np.empty(W * H * 3, np.uint8)
+        n = C.c_size_t(0)
+        rc = L.ref_compress(h, C.c_void_p(img.ctypes.data), C.c_size_t(W * 3), C.c_void_p(out.ctypes.data), C.c_size_t(out.size), C.byref(n))
+        assert rc == 0
+        jpg = out[: n.value].copy()
+        L.ref_destroy(h)
+        assert 0xC2 in jpg[:1024].tolist()   # a progressive frame header
+        want = cv2.imdecode(jpg, cv2.IMREAD_COLOR)
+        assert want is not None and want.shape == (H, W, 3)
+        got = eng.decode(jpg)
+        assert np.array_equal(got, want), f"css {css}: {np.count_nonzero(got != want)} values differ"
+    eng.close()
