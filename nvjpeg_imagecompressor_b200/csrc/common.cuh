@@ -22,15 +22,29 @@ struct Geom {
 
 // One token per coded coefficient / EOB / DC difference:
 //   [27:26] number of ZRL (0xF0) symbols that precede it (zero run >> 4)   [25:22] zero run & 15
-//   [21:20] table (0 DC0, 1 AC0, 2 DC1, 3 AC1)                            [19:16] size (bits of |value|)
+//   [21:18] size (bits of |value|)      [17:16] (tcode + zero run) & 3, tcode: 0 AC luma, 1 AC chroma, 2 DC luma, 3 DC chroma
 //   [15:0]  value bits (already masked to `size` bits)
-// Bits [25:16] index the symbol (TOK_SYM: the histogram bins of k_fdct and the code table of k_pack use this order).
-// TOK_RAWDC: DC of a block whose predecessor lives in the previous tile; [21:20] table, [17:16] component, [15:0] the
+// Bits [25:16] index the symbol: k_fdct's histogram bins and k_pack's code tables use this order. It is chosen for
+// the shared-memory banks of those tables (32 lanes look up 32 different tokens): the bank is (size & 7) << 2 |
+// (tcode + run) & 3, so the common symbols -- sizes 0..7 of runs 0..3 of one table -- sit in 32 different banks. The run
+// enters the table field for free: the run counter of k_fdct's walk advances both fields with one add (tcode <= 1 for
+// the AC tables and runs <= 62 keep that sum inside bits [21:16]; stage C masks the size field).
+// Huffman tables elsewhere are numbered 0 DC0, 1 AC0, 2 DC1, 3 AC1 (HuffDev, histograms).
+// TOK_RAWDC: DC of a block whose predecessor lives in the previous tile; [17:16] tcode, [19:18] component, [15:0] the
 // quantised DC itself (k_dc_edge_hist rewrites it as a difference token).
 constexpr uint32_t TOK_RAWDC = 1u << 28;
-__host__ __device__ constexpr uint32_t tok_bin(uint32_t table, uint32_t sym) {   // bin of (table, JPEG symbol)
-    return (table & 1u) ? (((sym >> 4) << 6) | (table << 4) | (sym & 15u)) : ((table << 4) | (sym & 15u));
+constexpr uint32_t TOK_RUN_STEP = (1u << 22) + (1u << 16);   // one more zero coefficient: run field and table field
+__host__ __device__ constexpr uint32_t tcode_of(uint32_t table) { return (table & 1u) ? (table >> 1) : 2u + (table >> 1); }
+__host__ __device__ constexpr uint32_t table_of(uint32_t tcode) { return tcode < 2u ? 2u * tcode + 1u : 2u * (tcode - 2u); }
+__host__ __device__ constexpr uint32_t tok_bin(uint32_t table, uint32_t sym) {   // bin of (Huffman table, JPEG symbol)
+    return (table & 1u) ? ((((sym >> 4) & 15u) << 6) | ((sym & 15u) << 2) | ((tcode_of(table) + (sym >> 4)) & 3u))
+                        : (((sym & 15u) << 2) | tcode_of(table));
 }
+__host__ __device__ constexpr uint32_t bin_table(uint32_t bin) { return table_of(((bin & 3u) - (bin >> 6)) & 3u); }
+__host__ __device__ constexpr uint32_t bin_symbol(uint32_t bin) {   // JPEG symbol of a bin (DC bins carry no run)
+    return (bin_table(bin) & 1u) ? (((bin >> 6) << 4) | ((bin >> 2) & 15u)) : ((bin >> 2) & 15u);
+}
+__host__ __device__ constexpr uint32_t tok_dc(uint32_t table, uint32_t size, uint32_t vbits) { return (tcode_of(table) << 16) | (size << 18) | vbits; }
 struct TileRec {                               // one per fdct tile (<= 256 blocks, one MCU-row segment)
     uint32_t base, count;                      // token run in the pool
     int16_t first_dc[3], last_dc[3];           // DCs of the tile's first / last MCU (last Y block, Cb, Cr)

@@ -169,30 +169,31 @@ __device__ __forceinline__ void ycc(int b, int g, int r, int &y, int &cb, int &c
 
 __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : v); }
 
-// Stage C of k_fdct: entries (run << 22 | table << 20 | coefficient, DC difference or 0 for EOB) become final tokens
-// (common.cuh: ZRL count | run & 15 | table | size | value bits) with ONE formula for DC, AC and EOB entries: the
-// size is the bit length of |value|, the value bits are jchuff.c's (value, or value - 1 if negative, masked). Raw-DC
-// tokens (first MCU of the tile) pass through. Every token counts one symbol in the bin given by its bits [25:16];
-// the three raw-DC tokens land in bins 0x000 / 0x021 / 0x022 and are taken out again by thread 0 (k_dc_edge_hist
-// counts their real symbols).
+// Stage C of k_fdct: entries (run and table fields as in the final token | coefficient, DC difference or 0 for EOB)
+// become final tokens (common.cuh) with ONE formula for DC, AC and EOB entries: the size is the bit length of |value|,
+// the value bits are jchuff.c's (value, or value - 1 if negative, masked). Raw-DC tokens (first MCU of the tile) pass
+// through. Every token counts one symbol in the bin given by its bits [25:16]; the three raw-DC tokens land in bins
+// 2 / 7 / 11 and are taken out again by thread 0 (k_dc_edge_hist counts their real symbols).
 template <bool HIST>
 __device__ __forceinline__ void stage_c(const uint32_t *tok, uint32_t *__restrict__ dst, uint32_t total, uint32_t *hs, int tid) {
 #pragma unroll 4
     for (uint32_t i = tid; i < total; i += 256) {
         const uint32_t e = tok[i];
         const int z = (int)(int16_t)(e & 0xFFFFu);
-        const uint32_t nb = 32u - (uint32_t)__clz(abs(z));
+        uint32_t msb;
+        asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"((uint32_t)abs(z)));
+        const uint32_t nb = msb + 1u;           // bfind(0) = -1
         const uint32_t vb = (uint32_t)(z + (z >> 31)) & ((1u << nb) - 1u);
-        const uint32_t conv = (e & 0xFFF00000u) | (nb << 16) | vb;
+        const uint32_t conv = (e & 0x0FC30000u) | (nb << 18) | vb;   // the walk's carries into the size field go away here
         const uint32_t tk = (e & TOK_RAWDC) ? e : conv;
         dst[i] = tk;
         if (HIST) {
             atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
             const uint32_t nz = (tk >> 26) & 3u;        // ZRL (0xF0) symbols ahead of this coefficient: about one token in sixty
-            if (nz) atomicAdd(&hs[(15u << 6) | (tk >> 16 & 0x30u)], nz);
+            if (nz) atomicAdd(&hs[tok_bin(bin_table((tk >> 16) & 0x3FFu), 0xF0u)], nz);
         }
     }
-    if (HIST && tid == 0) { atomicSub(&hs[0x000], 1u); atomicSub(&hs[0x021], 1u); atomicSub(&hs[0x022], 1u); }
+    if (HIST && tid == 0) { atomicSub(&hs[2], 1u); atomicSub(&hs[7], 1u); atomicSub(&hs[11], 1u); }   // tcode 2 / 3 | component << 2
 }
 
 template <int HS, int VS, bool DUMP>
@@ -450,8 +451,8 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         int pb = -1;
         if (isY) pb = bn > 0 ? blk - 1 : (m > 0 ? blk - C::BPM + C::HV - 1 : -1);
         else pb = m > 0 ? blk - C::BPM : -1;
-        if (pb >= 0) t0 = ((uint32_t)(tbl * 2) << 20) | ((uint32_t)(mydc - (int)dcs[pb]) & 0xFFFFu);   // stage C sizes it
-        else t0 = TOK_RAWDC | ((uint32_t)(tbl * 2) << 20) | ((uint32_t)comp << 16) | ((uint32_t)mydc & 0xFFFFu);
+        if (pb >= 0) t0 = ((uint32_t)(2 + tbl) << 16) | ((uint32_t)(mydc - (int)dcs[pb]) & 0xFFFFu);   // stage C sizes it
+        else t0 = TOK_RAWDC | ((uint32_t)(2 + tbl) << 16) | ((uint32_t)comp << 18) | ((uint32_t)mydc & 0xFFFFu);
     }
 
     // ---- place of every block in the tile's token run: CTA scan of the token counts
@@ -470,14 +471,14 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
     if (tid == C::HV + 1) misc[10] = off;
 
     // ---- run-length walk (jchuff.c encode_one_block): one entry per non-zero AC coefficient, straight to its slot:
-    //      zero run << 22 | AC table << 20 | coefficient -- the run lands in the token's (run & 15, ZRL count) fields as
-    //      it is. The divergent region is the store and the reset of the run counter; sizes and value bits are derived
-    //      in stage C with full warps.
+    //      the token's run / ZRL-count and table fields | coefficient: the run counter advances by TOK_RUN_STEP, which
+    //      puts the run where the token wants it and adds it to the table field (common.cuh). The divergent region is the
+    //      store and the reset of the run counter; sizes and value bits are derived in stage C with full warps.
     if (active) {
         uint32_t sa = smem_u32(tok + off);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(t0) : "memory");
         sa += 4;
-        const uint32_t rbase = (uint32_t)(tbl * 2 + 1) << 20;
+        const uint32_t rbase = (uint32_t)tbl << 16;   // tcode of the block's AC table
         uint32_t r = rbase;
 #pragma unroll
         for (int k = 1; k < 64; k++) {
@@ -487,9 +488,9 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
                 const uint32_t e = (k & 1) ? __byte_perm(p2, r, 0x7632) : ((p2 & 0xFFFFu) | r);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(e) : "memory");
                 sa += 4;
-                r = rbase - (1u << 22);
+                r = rbase - TOK_RUN_STEP;
             }
-            r += 1u << 22;
+            r += TOK_RUN_STEP;
         }
         if (pk[31] < 0x10000u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(rbase) : "memory");   // EOB
     }
@@ -511,10 +512,9 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 
     if (do_hist) {
         __syncthreads();
-        for (int i = tid; i < 1024; i += 256) {   // bin = run & 15 << 6 | table << 4 | size
+        for (int i = tid; i < 1024; i += 256) {   // token bins (common.cuh) -> (table, symbol)
             const uint32_t n = hs[i];
-            const int t = (i >> 4) & 3;
-            if (n) atomicAdd(&ghist[t * 257 + ((t & 1) ? (((i >> 6) << 4) | (i & 15)) : (i & 15))], n);
+            if (n) atomicAdd(&ghist[bin_table(i) * 257 + bin_symbol(i)], n);
         }
     }
 }
@@ -546,7 +546,7 @@ k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restri
         if (do_hist) atomicAdd(&s_h[c ? 1 : 0][nb & 15], 1u);
         if (resolve) {
             const uint32_t p = c == 0 ? 0u : (c == 1 ? r.pos_cb : r.pos_cr);
-            pool[r.base + p] = ((uint32_t)(c ? 2 : 0) << 20) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+            pool[r.base + p] = tok_dc(c ? 2u : 0u, (uint32_t)nb, (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
         }
     }
     if (t < 3) last_dc[t] = recs[ntile - 1].last_dc[t];

@@ -331,7 +331,8 @@ constexpr int PACK_CTAS = 8;                     // resident CTAs per SM (regist
 constexpr int PACK_K = 8;                        // consecutive tokens per lane and step
 constexpr int PACK_STEP = 32 * PACK_K;           // tokens per warp and step
 constexpr uint32_t PACK_DENSE_TOKENS = 7000;     // above this the shares may not fit the warp buffers: two-pass path
-constexpr uint32_t TOK_NULL = 1u << 22;          // table DC0 with a zero run of 1 does not exist: no code, no value bits
+constexpr uint32_t TOK_NULL = ((1u << 6) | 3u) << 16;   // bin (run 1, size 0, tcode 2 = DC luma): no such symbol -> no code, no bits
+static_assert(bin_table(TOK_NULL >> 16) == 0u, "TOK_NULL must name a DC table with a run");
 
 struct PackShared {
     uint32_t buf[WIN_WORDS];
@@ -439,7 +440,7 @@ __device__ __forceinline__ int pack_scatter(const PackShared &sh, uint32_t *buf,
             uint32_t n = L[k];
             const uint32_t nz = (w[k] >> 26) & 3u;
             if (nz) {   // ZRL symbols ahead of this coefficient (about one token in sixty)
-                const uint32_t zr = (w[k] & (2u << 20)) ? zr_c : zr_y;
+                const uint32_t zr = (bin_table((w[k] >> 16) & 0x3FFu) & 2u) ? zr_c : zr_y;
                 n -= nz * (zr & 31u);
                 e.put(zr >> 8, zr & 31u);
                 if (nz > 1u) {
@@ -506,9 +507,9 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
     // const __restrict__ pointer may be hoisted above the wait).
     const volatile HuffDev *vh = huff;
     for (int i = tid; i < 1024; i += PACK_THREADS) {
-        const uint32_t bin = (uint32_t)i, t = (bin >> 4) & 3u, nb = bin & 15u;
+        const uint32_t bin = (uint32_t)i, t = bin_table(bin), nb = (bin >> 2) & 15u;
         const bool valid = (t & 1u) || (bin >> 6) == 0u;   // DC bins carry no run
-        const uint32_t sym = (t & 1u) ? (((bin >> 6) << 4) | nb) : nb;
+        const uint32_t sym = bin_symbol(bin);
         const uint32_t en = valid ? vh->enc[t][sym] : 0u;
         const uint32_t l = en & 0xFFu;
         sh.code[bin] = l ? ((en >> 8) << nb) : 0u;
@@ -520,8 +521,9 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
     const uint32_t zr_c = (sh.code[tok_bin(3, 0xF0)] << 8) | sh.len[tok_bin(3, 0xF0)];
     for (int i = 1024 + tid; i < 4096; i += PACK_THREADS) {   // ZRL counts 1..3 (AC tokens only)
         const uint32_t bin = (uint32_t)i & 0x3FFu, nz = (uint32_t)i >> 10, l = sh.len[bin];
-        const uint32_t zl = ((bin & 0x20u) ? zr_c : zr_y) & 0xFFu;
-        sh.len[i] = (uint8_t)((l && (bin & 0x10u)) ? l + nz * zl : l);
+        const uint32_t t = bin_table(bin);
+        const uint32_t zl = ((t & 2u) ? zr_c : zr_y) & 0xFFu;
+        sh.len[i] = (uint8_t)((l && (t & 1u)) ? l + nz * zl : l);
     }
     __syncthreads();
     uint32_t *sub = sh.sub[wid];
@@ -1047,7 +1049,7 @@ __global__ void k_seam_from_bits(int *seam, const int64_t *__restrict__ bits_all
 // strip's last byte is the head of the next strip's record tokens coded with the (identical) tables.
 __device__ __forceinline__ uint32_t dc_token(int c, int diff) {
     const int nb = 32 - __clz(diff < 0 ? -diff : diff);
-    return ((uint32_t)(c ? 2 : 0) << 20) | ((uint32_t)nb << 16) | ((uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
+    return tok_dc(c ? 2u : 0u, (uint32_t)nb, (uint32_t)(diff + (diff >> 31)) & ((1u << nb) - 1u));
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
@@ -1101,7 +1103,7 @@ k_strip_merge(const StripRecord *rec, int rank, int world, uint32_t *__restrict_
         const int k = tid / 3, c = tid - k * 3;
         const int diff = (int)rec[k].first_dc[c] - (k ? (int)rec[k - 1].last_dc[c] : 0);
         const uint32_t tk = dc_token(c, diff);
-        atomicAdd(&hist[(c ? 2 : 0) * 257 + ((tk >> 16) & 15u)], 1u);
+        atomicAdd(&hist[(c ? 2 : 0) * 257 + ((tk >> 18) & 15u)], 1u);
         if (k == rank) {   // this strip's own first MCU: the raw-DC tokens k_dc_edge_hist left alone
             const TileRec r = recs[0];
             pool[r.base + (c == 0 ? 0u : (c == 1 ? r.pos_cb : r.pos_cr))] = tk;
@@ -1128,7 +1130,7 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
     if (tid <= rank * 3 + 2) {               // DC symbols at the strip starts 0..rank
         const int k = tid / 3, c = tid - k * 3;
         const uint32_t tk = dc_token(c, (int)rec[k].first_dc[c] - (k ? (int)rec[k - 1].last_dc[c] : 0));
-        const uint32_t nb = (tk >> 16) & 15u, l = huff->enc[c ? 2 : 0][nb] & 0xFFu;
+        const uint32_t nb = (tk >> 18) & 15u, l = huff->enc[c ? 2 : 0][nb] & 0xFFu;
         bad |= !l;
         if (k < rank) before += l + nb; else own += l + nb;
     }
@@ -1151,11 +1153,11 @@ k_strip_seam(const StripRecord *__restrict__ rec, int rank, int world, HuffDev *
         for (uint32_t j = 0; j < nx.ntok && n < 8; j++) {
             uint32_t tk = nx.tok[j];
             if (tk & TOK_RAWDC) {
-                const int c = (tk >> 16) & 3u;
+                const int c = (tk >> 18) & 3u;
                 tk = dc_token(c, (int)(int16_t)(tk & 0xFFFFu) - (int)rec[rank].last_dc[c]);
             }
-            const uint32_t tb = (tk >> 20) & 3u, nv = (tk >> 16) & 15u;
-            const uint32_t sy = (tb & 1u) ? ((((tk >> 22) & 15u) << 4) | nv) : nv;
+            const uint32_t bin = (tk >> 16) & 0x3FFu, tb = bin_table(bin), nv = (bin >> 2) & 15u;
+            const uint32_t sy = bin_symbol(bin);
             const uint32_t zr = huff->enc[tb][0xF0];
             for (uint32_t z = 0; z < ((tk >> 26) & 3u); z++) { acc = (acc << (zr & 0xFFu)) | (zr >> 8); n += zr & 0xFFu; }
             const uint32_t en = huff->enc[tb][sy];
