@@ -13,6 +13,8 @@ class NvjpegCompressRunnerImpl {
 public:
     b2j_params p;
     b2j_ctx *enc = nullptr, *dec = nullptr;
+    int ngpus = 1, restart_rows = 0;
+    b2j_multi *multi = nullptr;   // compress() over several GPUs (ngpus > 1)
     static bool quiet() { return getenv("B2J_QUIET") != nullptr; }
     int ensure(b2j_ctx **c) {
         if (*c) return 0;
@@ -37,8 +39,9 @@ static int css_of(int sampling) {
     }
 }
 
-NvjpegCompressRunner::NvjpegCompressRunner(int width, int height, int quality, bool optimize, int sampling) {
+NvjpegCompressRunner::NvjpegCompressRunner(int width, int height, int quality, bool optimize, int sampling, int ngpus) {
     compressor = new NvjpegCompressRunnerImpl();
+    compressor->ngpus = ngpus < 1 ? 1 : ngpus;
     b2j_default_params(&compressor->p);
     compressor->p.width = width; compressor->p.height = height; compressor->p.quality = quality;
     compressor->p.optimize = optimize ? 1 : 0; compressor->p.css = css_of(sampling);
@@ -53,11 +56,31 @@ NvjpegCompressRunner::~NvjpegCompressRunner() {
 
 void NvjpegCompressRunner::buildCompressEnv() {
     if (compressor->ensure(&compressor->enc) != 0) std::cerr << "[ERROR] buildCompressEnv: no CUDA device / out of memory" << std::endl;
+    else b2j_set_restart_rows(compressor->enc, compressor->restart_rows);
+    if (compressor->ngpus > 1 && !compressor->multi) {
+        int ids[16], n = 0;
+        if (const char *e = getenv("B2J_MULTI_DEVICES")) {   // e.g. "0,1,2,3" (tests: "0,0" = two contexts on one GPU)
+            for (const char *q = e; *q && n < 16;) { ids[n++] = atoi(q); while (*q && *q != ',') q++; if (*q == ',') q++; }
+        } else {
+            for (; n < compressor->ngpus && n < 16; n++) ids[n] = n;
+        }
+        if (b2j_multi_create(&compressor->p, n, ids, &compressor->multi) != 0) {
+            std::cerr << "[ERROR] buildCompressEnv: cannot set up " << n << " GPUs, using one" << std::endl;
+            compressor->multi = nullptr;
+        }
+    }
+}
+void NvjpegCompressRunner::setRestartRows(int mcu_rows) {
+    compressor->restart_rows = mcu_rows < 0 ? 0 : mcu_rows;
+    if (compressor->enc) b2j_set_restart_rows(compressor->enc, compressor->restart_rows);
 }
 void NvjpegCompressRunner::buildDecodeEnv() {
     if (compressor->ensure(&compressor->dec) != 0) std::cerr << "[ERROR] buildDecodeEnv: no CUDA device / out of memory" << std::endl;
 }
-void NvjpegCompressRunner::deleteCompressEnv() { compressor->drop(&compressor->enc, compressor->dec); }
+void NvjpegCompressRunner::deleteCompressEnv() {
+    if (compressor->multi) { b2j_multi_destroy(compressor->multi); compressor->multi = nullptr; }
+    compressor->drop(&compressor->enc, compressor->dec);
+}
 void NvjpegCompressRunner::deleteDecodeEnv() { compressor->drop(&compressor->dec, compressor->enc); }
 
 std::vector<unsigned char> NvjpegCompressRunner::compress(cv::Mat image, int *run_state) {
@@ -65,16 +88,25 @@ std::vector<unsigned char> NvjpegCompressRunner::compress(cv::Mat image, int *ru
     std::vector<unsigned char> obuffer;
     b2j_ctx *c = compressor->enc;
     if (c && !image.empty() && image.type() == CV_8UC3) {
-        // the JPEG is rarely larger than a third of the pixels; grow once if the engine says so
-        size_t cap = (size_t)image.rows * image.cols + 65536, n = 0;
-        obuffer.resize(cap);
-        int rc = b2j_encode(c, image.data, image.step, image.cols, image.rows, obuffer.data(), cap, &n);
-        if (rc == B2J_ECAPACITY) {
-            cap = b2j_encode_bound(c);
+        size_t n = 0;
+        int rc;
+        if (compressor->multi && compressor->restart_rows == 0) {
+            // strips over several GPUs: the bytes land in place, so the buffer is sized before the encode
+            size_t cap = (size_t)image.rows * image.cols + 65536;
             obuffer.resize(cap);
-            rc = b2j_encode(c, image.data, image.step, image.cols, image.rows, obuffer.data(), cap, &n);
+            rc = b2j_multi_encode(compressor->multi, image.data, image.step, image.cols, image.rows, obuffer.data(), cap, &n);
+            if (rc == B2J_ECAPACITY) {
+                cap = b2j_encode_bound(c);
+                obuffer.resize(cap);
+                rc = b2j_multi_encode(compressor->multi, image.data, image.step, image.cols, image.rows, obuffer.data(), cap, &n);
+            }
+            if (rc != B2J_OK) { std::cerr << "[ERROR] compress: " << b2j_multi_last_error(compressor->multi) << std::endl; n = 0; }
+        } else {
+            // encode first, then size the vector to the JPEG (no zero-filled worst-case buffer), then fetch the bytes
+            rc = b2j_encode_begin(c, image.data, image.step, image.cols, image.rows, &n);
+            if (rc == B2J_OK) { obuffer.resize(n); rc = b2j_encode_fetch(c, obuffer.data(), n); }
+            if (rc != B2J_OK) { std::cerr << "[ERROR] compress: " << b2j_last_error(c) << std::endl; n = 0; }
         }
-        if (rc != B2J_OK) { std::cerr << "[ERROR] compress: " << b2j_last_error(c) << std::endl; n = 0; }
         obuffer.resize(n);
     }
     if (run_state) *run_state = obuffer.empty() ? 0 : 1;
@@ -159,19 +191,24 @@ std::vector<unsigned char> NvjpegCompressRunner::secondaryCompress(cv::Mat image
     std::vector<unsigned char> j1, j2;
     b2j_ctx *c = compressor->enc;
     if (c && !image.empty() && image.type() == CV_8UC3) {
-        const size_t cap = (size_t)image.rows * image.cols * 3 + 65536;
-        j1.resize(cap);
-        j2.resize(cap);
+        // device resident: upload once, both encodes and the reconstruction stay in HBM; the host vectors are sized to
+        // the two streams after the fact (b2j_secondary_device / _finish), the pixels come down only if asked for
+        std::vector<unsigned char> none;
         size_t n1 = 0, n2 = 0;
-        cv::Mat rec(image.rows, image.cols, CV_8UC3);
         double ps = 0;
-        const int rc = b2j_secondary(c, image.data, image.step, image.cols, image.rows, offset128 ? B2J_DIFF_OFFSET128 : B2J_DIFF_ABS, j1.data(), cap,
-                                     &n1, j2.data(), cap, &n2, rec.data, rec.step, &ps);
-        if (rc != B2J_OK) { std::cerr << "[ERROR] secondaryCompress: " << b2j_last_error(c) << std::endl; n1 = n2 = 0; }
-        j1.resize(n1);
-        j2.resize(n2);
+        const size_t row = (size_t)image.cols * 3;
+        int rc = b2j_secondary(c, image.data, image.step, image.cols, image.rows, offset128 ? B2J_DIFF_OFFSET128 : B2J_DIFF_ABS, nullptr, 0, &n1,
+                               nullptr, 0, &n2, nullptr, 0, &ps);
+        if (rc == B2J_OK) {
+            j1.resize(n1);
+            j2.resize(n2);
+            cv::Mat rec;
+            if (reconstruction) rec.create(image.rows, image.cols, CV_8UC3);
+            rc = b2j_secondary_fetch(c, j1.data(), n1, j2.data(), n2, reconstruction ? rec.data : nullptr, reconstruction ? (size_t)rec.step : row);
+            if (rc == B2J_OK && reconstruction) *reconstruction = rec;
+        }
+        if (rc != B2J_OK) { std::cerr << "[ERROR] secondaryCompress: " << b2j_last_error(c) << std::endl; j1.clear(); j2.clear(); }
         if (diff_jpeg) *diff_jpeg = j2;
-        if (reconstruction && n1) *reconstruction = rec;
         if (psnr_db) *psnr_db = ps;
     }
     if (run_state) *run_state = j1.empty() ? 0 : 1;

@@ -8,6 +8,7 @@
 //     (README default 4:2:2) and the stream is baseline sequential, not progressive (ImageCompressorImpl.cu:28)
 //   * CUDA failures never exit(1) (ImageCompressorImpl.cuh:16-34); they produce the documented failure signal
 //   * reconstruct / differenceMap / psnr / secondaryCompress implement the README's feature bullet (README.md:8)
+//   * a defaulted 6th constructor argument spreads compress() over several GPUs; setRestartRows() turns DRI/RSTn on
 #ifndef IMAGECOMPRESSOR_H_
 #define IMAGECOMPRESSOR_H_
 
@@ -38,8 +39,11 @@ private:
     NvjpegCompressRunnerImpl *compressor;
 
 public:
-    // sampling: 444, 422, 440, 420 or 411
-    NvjpegCompressRunner(int width = 8320, int height = 40000, int quality = 95, bool optimize = true, int sampling = 422);
+    // sampling: 444, 422, 440, 420 or 411. ngpus > 1: compress() cuts the image into MCU-row strips over that many GPUs of
+    // this node (devices 0 .. ngpus-1, or the comma-separated list in B2J_MULTI_DEVICES) from this one process
+    // (b2j_multi_*); the bytes are the single-GPU bytes.
+    NvjpegCompressRunner(int width = 8320, int height = 40000, int quality = 95, bool optimize = true, int sampling = 422,
+                         int ngpus = 1);
     ~NvjpegCompressRunner();
 
     NvjpegCompressRunner(const NvjpegCompressRunner &) = delete;
@@ -64,6 +68,11 @@ public:
     void buildDecodeEnv();
     void deleteCompressEnv();
     void deleteDecodeEnv();
+
+    // Restart markers every `mcu_rows` MCU rows in what compress() writes (0 = none, the default; single-GPU path):
+    // nvjpegEncoderParamsSetRestartInterval / cv2 IMWRITE_JPEG_RST_INTERVAL at the reference's parameter site
+    // (ImageCompressorImpl.cu:28-31). decode() / reconstruct() accept any restart interval and progressive files.
+    void setRestartRows(int mcu_rows);
 
     // README.md:8 -- reconstruction, difference map, secondary compression, PSNR
     cv::Mat reconstruct(const std::vector<unsigned char> &obuffer, int *run_state);

@@ -97,6 +97,12 @@ B2J_API size_t b2j_encode_bound(const b2j_ctx *ctx);
 B2J_API int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out,
                        size_t cap, size_t *len);
 
+/* The same in two steps, for callers that size their output after the encode (the C++ facade's std::vector):
+ * b2j_encode_begin uploads and encodes (the JPEG stays in the context's device buffer) and returns its length,
+ * b2j_encode_fetch copies it to host memory. */
+B2J_API int b2j_encode_begin(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, size_t *len);
+B2J_API int b2j_encode_fetch(b2j_ctx *ctx, uint8_t *out, size_t cap);
+
 /* Device -> device, asynchronous on the context's stream. d_bgr: device pointer. On return *d_out points at
  * the context-owned device buffer that will hold the complete JPEG; its length is written to the device word
  * *d_len (uint64). b2j_encode_finish synchronises and returns the length. */
@@ -139,6 +145,10 @@ B2J_API int b2j_secondary_device(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step
                                  const uint8_t **d_jpg1, const uint8_t **d_jpg2, const uint8_t **d_recon,
                                  const uint8_t **d_diff);
 B2J_API int b2j_secondary_finish(b2j_ctx *ctx, size_t *len1, size_t *len2, double *psnr, uint64_t *ssd);
+
+/* Results of the last b2j_secondary_device + _finish (or b2j_secondary) -> host memory; any pointer may be NULL. */
+B2J_API int b2j_secondary_fetch(b2j_ctx *ctx, uint8_t *jpg1, size_t cap1, uint8_t *jpg2, size_t cap2, uint8_t *recon,
+                                size_t recon_step);
 
 /* The same from and to host memory (upload, b2j_secondary_device, downloads). Any output pointer may be NULL. */
 B2J_API int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, int diff_mode,
@@ -199,6 +209,18 @@ B2J_API int b2j_peer_connect(b2j_ctx *ctx, int rank, int world, void *const *d_a
 B2J_API int b2j_strip_phase1x(b2j_ctx *ctx, const uint8_t *d_bgr, size_t step, int width, int rows);
 B2J_API int b2j_strip_phase2x(b2j_ctx *ctx, const void *d_records_all, int rank, int world, int full_width,
                               int full_height, int flags);
+
+/* ---- several GPUs of one node from ONE process and one host thread (ngpus / device_ids) -------------
+ * One image is cut into MCU-row strips, one per GPU; the strips exchange their 4 KB records through peer memory
+ * (NVLink stores + flags, no collective), every strip's rows go up over its own GPU's link in groups with the fdct of
+ * a group behind it, every strip's bytes come down straight to their place in `out`. The stream is byte for byte the
+ * single-GPU stream. device_ids == NULL: devices 0 .. ngpus-1 (at most 16). */
+typedef struct b2j_multi b2j_multi;
+B2J_API int b2j_multi_create(const b2j_params *p, int ngpus, const int *device_ids, b2j_multi **out);
+B2J_API void b2j_multi_destroy(b2j_multi *m);
+B2J_API int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out,
+                             size_t cap, size_t *len);
+B2J_API const char *b2j_multi_last_error(const b2j_multi *m);
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */
 enum { B2J_DBG_COEF = 0, B2J_DBG_HIST = 1, B2J_DBG_TABLES = 2, B2J_DBG_TILE_BITS = 3, B2J_DBG_DEC_COEF = 4,

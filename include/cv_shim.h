@@ -5,6 +5,7 @@
 #define B2J_CV_SHIM_H_
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -28,8 +29,9 @@ public:
     }
     void create(int r, int c, int type) {
         rows = r; cols = c; type_ = type; step = (size_t)c * channels();
-        store_ = std::shared_ptr<std::vector<unsigned char>>(new std::vector<unsigned char>(step * (size_t)r));
-        data = store_->data();
+        // like cv::Mat::create (fastMalloc): uninitialised memory -- the pages are first touched by whoever fills them
+        store_ = std::shared_ptr<unsigned char>((unsigned char *)malloc(step * (size_t)r + 64), free);
+        data = store_.get();
     }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return type_; }
@@ -42,7 +44,7 @@ public:
     Mat clone() const { Mat m(rows, cols, type_); for (int r = 0; r < rows; r++) memcpy(m.ptr(r), ptr(r), (size_t)cols * channels()); return m; }
 private:
     int type_ = CV_8UC3;
-    std::shared_ptr<std::vector<unsigned char>> store_;
+    std::shared_ptr<unsigned char> store_;
 };
 }  // namespace cv
 #endif

@@ -6,5 +6,5 @@ runner.py   NvjpegCompressRunner, the reference's facade (ImageCompressor.h) in 
 strips.py   multi-GPU MCU-row strip encoder over torch.distributed
 """
 from ._native import CSS, build, lib  # noqa: F401
-from .engine import B2JError, Engine  # noqa: F401
+from .engine import B2JError, Engine, MultiEngine  # noqa: F401
 from .runner import NvjpegCompressRunner  # noqa: F401

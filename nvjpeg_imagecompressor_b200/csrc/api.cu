@@ -661,8 +661,46 @@ static int upload_linear(void *user, uint8_t *d_dst, const uint8_t *src, size_t 
     return rc;
 }
 
-int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
-    if (!ctx || !bgr || !out || !len || step < (size_t)width * 3) return B2J_EINVAL;
+// Rows of a host image (pinned or pageable) -> ctx->d_img in MCU-row groups on the copy stream; the fdct of a group
+// starts as soon as its rows have landed. One call issues group `gi` (of `ngroups`): callers that drive several
+// contexts interleave the groups of their strips so that every GPU's link is busy. Geometry must be set (ctx->g).
+static int upload_fdct_group(b2j_ctx *ctx, const uint8_t *bgr, size_t step, size_t dstep, int gi, int ngroups, int do_hist, bool pageable_in) {
+    const Geom &g = ctx->g;
+    const int rows_per = (g.mcuy + ngroups - 1) / ngroups;
+    const int my0 = gi * rows_per;
+    if (my0 >= g.mcuy) return B2J_OK;
+    const int mcu_h = 8 * g.vs, width = g.W, height = g.H;
+    const int nr = std::min(rows_per, g.mcuy - my0);
+    const int y0 = my0 * mcu_h, y1 = std::min(height, (my0 + nr) * mcu_h);
+    if (gi == 0) {
+        CK(cudaEventRecord(ctx->ev_copy[63], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[63], 0));
+    }
+    if (pageable_in) {   // copy threads -> pinned ring -> DMA: the group goes up while the next one is being staged
+        StageRing &r = ctx->ring;
+        const int slot = gi % StageRing::N;
+        if (r.busy[slot]) CK(cudaEventSynchronize(r.ev[slot]));
+        ctx->pool->copy2d(r.buf[slot], (size_t)width * 3, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0);
+        CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, r.buf[slot], (size_t)width * 3, (size_t)width * 3, y1 - y0,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(r.ev[slot], ctx->copy_stream));
+        r.busy[slot] = true;
+    } else {
+        CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    CK(cudaEventRecord(ctx->ev_copy[gi], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[gi], 0));
+    CK(launch_fdct(ctx->d_img, dstep, g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, do_hist, my0, nr, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
+    ctx->launches += 1;
+    return B2J_OK;
+}
+
+static int upload_groups_of(const Geom &g) { return std::max(1, std::min(32, g.mcuy / 64)); }
+
+// host pixels -> complete JPEG in the context's device buffer; *len = its size (waits for the encode)
+int b2j_encode_begin(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, size_t *len) {
+    if (!ctx || !bgr || !len || step < (size_t)width * 3) return B2J_EINVAL;
     CK(cudaSetDevice(ctx->device));
     int rc = enc_alloc(ctx); if (rc) return rc;
     rc = set_strip_geom(ctx, width, height); if (rc) return rc;
@@ -672,44 +710,180 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
     tick(ctx, 0);
     rc = enc_reset(ctx); if (rc) return rc;
     // upload in MCU-row groups on the copy stream; the fdct of a group starts as soon as its rows have landed
-    const int ngroups = std::max(1, std::min(32, g.mcuy / 64));
-    const int rows_per = (g.mcuy + ngroups - 1) / ngroups;
+    const int ngroups = upload_groups_of(g);
     const bool pageable_in = is_pageable_host(bgr);
-    if (pageable_in) { rc = ensure_hostpipe(ctx, (size_t)rows_per * 8 * g.vs * (size_t)width * 3); if (rc) return rc; }
-    CK(cudaEventRecord(ctx->ev_copy[63], ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[63], 0));
-    const int mcu_h = 8 * g.vs;
+    if (pageable_in) { rc = ensure_hostpipe(ctx, (size_t)((g.mcuy + ngroups - 1) / ngroups) * 8 * g.vs * (size_t)width * 3); if (rc) return rc; }
     tick(ctx, 1);
-    for (int gi = 0, my0 = 0; my0 < g.mcuy; gi++, my0 += rows_per) {
-        const int nr = std::min(rows_per, g.mcuy - my0);
-        const int y0 = my0 * mcu_h, y1 = std::min(height, (my0 + nr) * mcu_h);
-        if (pageable_in) {   // copy threads -> pinned ring -> DMA: the group goes up while the next one is being staged
-            StageRing &r = ctx->ring;
-            const int slot = gi % StageRing::N;
-            if (r.busy[slot]) CK(cudaEventSynchronize(r.ev[slot]));
-            ctx->pool->copy2d(r.buf[slot], (size_t)width * 3, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0);
-            CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, r.buf[slot], (size_t)width * 3, (size_t)width * 3, y1 - y0,
-                                 cudaMemcpyHostToDevice, ctx->copy_stream));
-            CK(cudaEventRecord(r.ev[slot], ctx->copy_stream));
-            r.busy[slot] = true;
-        } else {
-            CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)y0 * dstep, dstep, bgr + (size_t)y0 * step, step, (size_t)width * 3, y1 - y0,
-                                 cudaMemcpyHostToDevice, ctx->copy_stream));
-        }
-        CK(cudaEventRecord(ctx->ev_copy[gi], ctx->copy_stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[gi], 0));
-        CK(launch_fdct(ctx->d_img, dstep, g, ctx->d_quant, ctx->d_pool, &ctx->d_ctrl->pool_count, ctx->d_recs, ctx->d_ctrl->hist, ctx->p.optimize, my0, nr, (ctx->debug & 1) ? ctx->d_coef : nullptr, ctx->stream));
-        ctx->launches += 1;
-    }
+    for (int gi = 0; gi < ngroups; gi++) { rc = upload_fdct_group(ctx, bgr, step, dstep, gi, ngroups, ctx->p.optimize, pageable_in); if (rc) return rc; }
     tick(ctx, 2);
     rc = enc_tail(ctx, width, height); if (rc) return rc;
     rc = fetch_ret(ctx); if (rc) return rc;
     collect_timings(ctx);
+    for (int i = 0; i < StageRing::N; i++) ctx->ring.busy[i] = false;   // every upload has completed (fetch_ret synchronised)
+    *len = (size_t)ctx->h_ret->out_len;
+    return B2J_OK;
+}
+
+// the JPEG of the last b2j_encode_begin -> host memory (pinned or pageable)
+int b2j_encode_fetch(b2j_ctx *ctx, uint8_t *out, size_t cap) {
+    if (!ctx || !out || !ctx->enc_ready) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->h_ret->out_len;
     if (n > cap) { snprintf(ctx->err, sizeof(ctx->err), "output needs %zu bytes, buffer has %zu", n, cap); return B2J_ECAPACITY; }
-    for (int i = 0; i < StageRing::N; i++) ctx->ring.busy[i] = false;   // every upload has completed (fetch_ret synchronised)
-    rc = download_linear(ctx, out, ctx->d_out, n, ctx->stream); if (rc) return rc;
+    return download_linear(ctx, out, ctx->d_out, n, ctx->stream);
+}
+
+int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
+    if (!out || !len) return B2J_EINVAL;
+    size_t n = 0;
+    int rc = b2j_encode_begin(ctx, bgr, step, width, height, &n); if (rc) return rc;
+    rc = b2j_encode_fetch(ctx, out, cap); if (rc) return rc;
     *len = n;
+    return B2J_OK;
+}
+
+// ------------------------------------------------------------------------------------------ several GPUs, one process
+// One image over the GPUs of one node from a single host thread: MCU-row strips, one context per GPU, the strips'
+// records exchanged through peer memory (b2j_peer_*), every strip's rows uploaded in groups over its own GPU's link
+// with the fdct of a group behind it, every strip's bytes downloaded straight to their place in the caller's buffer.
+struct b2j_multi {
+    int n;
+    bool shared_device;   // two contexts on one GPU (tests): the host then separates the pushes from the waits
+    b2j_ctx *ctx[XCHG_MAX_WORLD];
+    char err[256];
+};
+
+void b2j_multi_destroy(b2j_multi *m) {
+    if (!m) return;
+    for (int k = 0; k < m->n; k++) {
+        if (m->ctx[k] && k > 0) m->ctx[k]->pool = nullptr;   // the copy threads belong to context 0
+        b2j_destroy(m->ctx[k]);
+    }
+    delete m;
+}
+
+const char *b2j_multi_last_error(const b2j_multi *m) { return m ? m->err : "null"; }
+
+int b2j_multi_create(const b2j_params *p, int ngpus, const int *device_ids, b2j_multi **out) {
+    if (!p || !out || ngpus < 1 || ngpus > XCHG_MAX_WORLD) return B2J_EINVAL;
+    b2j_multi *m = new (std::nothrow) b2j_multi();
+    if (!m) return B2J_ENOMEM;
+    memset(m, 0, sizeof(*m));
+    m->n = ngpus;
+    void *arenas[XCHG_MAX_WORLD] = {};
+    int rc = B2J_OK;
+    for (int k = 0; k < ngpus && !rc; k++) {
+        b2j_params pk = *p;
+        pk.device = device_ids ? device_ids[k] : k;
+        pk.flags |= B2J_FLAG_ENCODE;
+        rc = b2j_create(&pk, &m->ctx[k]);
+        if (!rc) rc = b2j_peer_export(m->ctx[k], nullptr, &arenas[k]);
+    }
+    for (int k = 0; k < ngpus && !rc; k++) {   // every GPU stores into every other GPU's arena
+        cudaSetDevice(m->ctx[k]->device);
+        for (int j = 0; j < ngpus; j++) {
+            if (j == k) continue;
+            if (m->ctx[j]->device == m->ctx[k]->device) continue;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(m->ctx[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { snprintf(m->err, sizeof(m->err), "no peer access %d -> %d: %s", m->ctx[k]->device, m->ctx[j]->device, cudaGetErrorString(e)); rc = B2J_ECUDA; break; }
+            cudaGetLastError();
+        }
+    }
+    for (int k = 0; k < ngpus && !rc; k++) rc = b2j_peer_connect(m->ctx[k], k, ngpus, arenas);
+    for (int k = 0; k < ngpus && !rc; k++)
+        for (int j = 0; j < k; j++) if (m->ctx[j]->device == m->ctx[k]->device) m->shared_device = true;
+    if (rc) {
+        if (!m->err[0]) snprintf(m->err, sizeof(m->err), "context set-up failed (rc=%d)", rc);
+        for (int k = 0; k < ngpus; k++) if (m->ctx[k] && m->ctx[k]->err[0]) fprintf(stderr, "[b2jpeg] b2j_multi_create: context %d: %s\n", k, m->ctx[k]->err);
+        fprintf(stderr, "[b2jpeg] b2j_multi_create: %s\n", m->err);
+        b2j_multi_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return B2J_OK;
+}
+
+int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
+    if (!m || !bgr || !out || !len || step < (size_t)width * 3) return B2J_EINVAL;
+    Geom gw;
+    int rc = make_geom(width, height, m->ctx[0]->p.css, &gw); if (rc) return rc;
+    const int n = std::min(m->n, gw.mcuy);
+    if (n <= 1 || n != m->n) {   // one strip (or fewer MCU rows than GPUs): the single-context path
+        rc = b2j_encode(m->ctx[0], bgr, step, width, height, out, cap, len);
+        if (rc) snprintf(m->err, sizeof(m->err), "%s", m->ctx[0]->err);
+        return rc;
+    }
+#define MCK(k, call) do { rc = (call); if (rc) { snprintf(m->err, sizeof(m->err), "gpu %d: %s", (k), m->ctx[k]->err); return rc; } } while (0)
+    const int mcu_h = 8 * gw.vs;
+    int y0[XCHG_MAX_WORLD + 1];
+    for (int k = 0, my = 0; k <= n; k++) { y0[k] = std::min(height, my * mcu_h); my += gw.mcuy / n + (k < gw.mcuy % n ? 1 : 0); }
+    const size_t dstep = ((size_t)width * 3 + 15) & ~(size_t)15;
+    const bool pageable_in = is_pageable_host(bgr);
+    int ngroups = 1;
+    for (int k = 0; k < n; k++) {
+        b2j_ctx *ctx = m->ctx[k];
+        cudaSetDevice(ctx->device);
+        MCK(k, enc_alloc(ctx));
+        MCK(k, set_strip_geom(ctx, width, y0[k + 1] - y0[k]));
+        MCK(k, ensure_img(ctx, dstep * (size_t)(y0[k + 1] - y0[k])));
+        MCK(k, enc_reset(ctx));
+        ngroups = std::max(ngroups, std::max(1, std::min(16, ctx->g.mcuy / 32)));
+    }
+    if (pageable_in) {   // one set of copy threads feeds every GPU's staging ring
+        for (int k = 0; k < n; k++) {
+            b2j_ctx *ctx = m->ctx[k];
+            cudaSetDevice(ctx->device);
+            if (k > 0 && !ctx->pool) ctx->pool = m->ctx[0]->pool;
+            MCK(k, ensure_hostpipe(ctx, (size_t)((ctx->g.mcuy + ngroups - 1) / ngroups) * mcu_h * (size_t)width * 3));
+            if (k == 0) for (int j = 1; j < n; j++) if (!m->ctx[j]->pool) m->ctx[j]->pool = ctx->pool;
+        }
+    }
+    // 1. uploads and fdct, group by group across the GPUs (symbol counts are always taken: the strips' bit phases come from them)
+    for (int gi = 0; gi < ngroups; gi++)
+        for (int k = 0; k < n; k++) {
+            cudaSetDevice(m->ctx[k]->device);
+            MCK(k, upload_fdct_group(m->ctx[k], bgr + (size_t)y0[k] * step, step, dstep, gi, ngroups, 1, pageable_in));
+        }
+    // 2. the strips' records into every GPU's arena
+    for (int k = 0; k < n; k++) {
+        b2j_ctx *ctx = m->ctx[k];
+        cudaSetDevice(ctx->device);
+        rc = launch_dc_edge_hist(ctx->d_recs, ctx->g, ctx->d_pred_in, ctx->d_ctrl->hist, ctx->d_ctrl->rec.last_dc, 1, ctx->d_pool, 1, &ctx->d_ctrl->rec, 0, ctx->stream) == cudaSuccess ? B2J_OK : B2J_ECUDA;
+        if (!rc) { ctx->xseq++; rc = launch_strip_push(&ctx->d_ctrl->rec, ctx->d_peers, ctx->peer_rank, ctx->peer_world, ctx->xseq, ctx->stream) == cudaSuccess ? B2J_OK : B2J_ECUDA; }
+        ctx->launches += 2;
+        if (rc) { snprintf(m->err, sizeof(m->err), "gpu %d: launch failed", k); return rc; }
+    }
+    if (m->shared_device)   // kernels that wait on one another must not share a GPU: every record is in place first
+        for (int k = 0; k < n; k++) { cudaSetDevice(m->ctx[k]->device); cudaStreamSynchronize(m->ctx[k]->stream); }
+    // 3. tables, entropy coding, seam, byte stuffing of every strip (each waits on the device for the others' records)
+    for (int k = 0; k < n; k++) {
+        cudaSetDevice(m->ctx[k]->device);
+        MCK(k, b2j_strip_phase2x(m->ctx[k], nullptr, k, n, width, height, (k == 0 ? 1 : 0) | (k == n - 1 ? 2 : 0)));
+    }
+    // 4. lengths, then every strip's bytes straight to their place
+    size_t off[XCHG_MAX_WORLD + 1];
+    off[0] = 0;
+    for (int k = 0; k < n; k++) {
+        cudaSetDevice(m->ctx[k]->device);
+        MCK(k, fetch_ret(m->ctx[k]));
+        for (int i = 0; i < StageRing::N; i++) m->ctx[k]->ring.busy[i] = false;
+        off[k + 1] = off[k] + (size_t)m->ctx[k]->h_ret->out_len;
+    }
+    if (off[n] > cap) { snprintf(m->err, sizeof(m->err), "output needs %zu bytes, buffer has %zu", off[n], cap); return B2J_ECAPACITY; }
+    const bool pageable_out = is_pageable_host(out);
+    for (int k = 0; k < n; k++) {
+        b2j_ctx *ctx = m->ctx[k];
+        cudaSetDevice(ctx->device);
+        if (pageable_out) MCK(k, download_linear(ctx, out + off[k], ctx->d_out, off[k + 1] - off[k], ctx->stream));
+        else if (cudaMemcpyAsync(out + off[k], ctx->d_out, off[k + 1] - off[k], cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { snprintf(m->err, sizeof(m->err), "gpu %d: download failed", k); return B2J_ECUDA; }
+    }
+    if (!pageable_out)
+        for (int k = 0; k < n; k++) {
+            cudaSetDevice(m->ctx[k]->device);
+            if (cudaStreamSynchronize(m->ctx[k]->stream) != cudaSuccess) { snprintf(m->err, sizeof(m->err), "gpu %d: %s", k, cudaGetErrorString(cudaGetLastError())); return B2J_ECUDA; }
+        }
+#undef MCK
+    *len = off[n];
     return B2J_OK;
 }
 
@@ -1006,6 +1180,22 @@ int b2j_secondary(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int 
     if (jpg2) { if (n2 > cap2) return B2J_ECAPACITY; rc = download_linear(ctx, jpg2, dj2, n2, ctx->stream); if (rc) return rc; }
     if (recon) { rc = download_2d(ctx, recon, recon_step, drec, row, row, height, ctx->stream); if (rc) return rc; }
     return B2J_OK;
+}
+
+// the results of the last b2j_secondary / b2j_secondary_device (+ _finish) -> host memory; any pointer may be NULL
+int b2j_secondary_fetch(b2j_ctx *ctx, uint8_t *jpg1, size_t cap1, uint8_t *jpg2, size_t cap2, uint8_t *recon, size_t recon_step) {
+    if (!ctx || !ctx->second || !ctx->enc_ready) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n1 = (size_t)ctx->h_ret->out_len, n2 = (size_t)ctx->second->h_ret->out_len;
+    int rc = B2J_OK;
+    if (jpg1) { if (n1 > cap1) return B2J_ECAPACITY; rc = download_linear(ctx, jpg1, ctx->d_out, n1, ctx->stream); if (rc) return rc; }
+    if (jpg2) { if (n2 > cap2) return B2J_ECAPACITY; rc = download_linear(ctx, jpg2, ctx->second->d_out, n2, ctx->stream); if (rc) return rc; }
+    if (recon) {
+        const size_t row = (size_t)ctx->g.W * 3;
+        if (recon_step < row) return B2J_EINVAL;
+        rc = download_2d(ctx, recon, recon_step, ctx->d_recon, row, row, ctx->g.H, ctx->stream);
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------ introspection

@@ -1,7 +1,7 @@
 // dec_prog.cu -- progressive (SOF2) decode: what the reference as shipped writes (NVJPEG_ENCODING_PROGRESSIVE_DCT_HUFFMAN,
 // ImageCompressorImpl.cu:28) and nvJPEG's decoder accepts (:361-366). Every scan is absorbed into the coefficient
-// array in file order (jdphuff.c decode_mcu_DC_first / DC_refine / AC_first / AC_refine as restated in
-// oracle/jpeg_oracle.c orc_decode_progressive, pinned to cv2.imdecode), then the baseline back end runs (k_idct on the
+// array in file order (jdphuff.c decode_mcu_DC_first / DC_refine / AC_first / AC_refine; tests compare the pixels with
+// the CPU checker and cv2.imdecode), then the baseline back end runs (k_idct on the
 // coefficients' own DCs, k_upcolor). Parallelism: restart intervals of a scan are independent (one thread each); a
 // scan without restart markers is ONE sequential chain -- refinement scans read the coefficients' history, so the
 // self-synchronising scheme of the baseline decoder does not carry over. Correct for every stream the parser accepts,

@@ -235,3 +235,50 @@ class Engine:
 
     def launch_count(self):
         return int(self._L.b2j_launch_count(self._h))
+
+
+class MultiEngine:
+    """One image over several GPUs from ONE process (b2j_multi_*): MCU-row strips, records exchanged through peer
+    memory, every strip uploaded over its own GPU's link. encode() returns the single-GPU stream byte for byte."""
+
+    def __init__(self, width, height, quality=95, optimize=True, css="422", devices=(0,)):
+        self._L = N.lib()
+        p = N.Params()
+        self._L.b2j_default_params(C.byref(p))
+        p.width, p.height, p.quality, p.optimize = int(width), int(height), int(quality), int(bool(optimize))
+        p.css = N.CSS[css] if isinstance(css, str) else int(css)
+        self._h = C.c_void_p()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self._L.b2j_multi_create(C.byref(p), len(devices), ids, C.byref(self._h))
+        if rc:
+            raise B2JError(rc, "b2j_multi_create failed")
+        self.W, self.H = int(width), int(height)
+
+    def encode(self, img, out=None):
+        img = np.asarray(img)
+        H, W = img.shape[:2]
+        if out is None:
+            out = np.empty(W * H * 3 // 2 + 65536, np.uint8)
+        n = C.c_size_t(0)
+        rc = self._L.b2j_multi_encode(self._h, _ptr(img), img.strides[0], W, H, _ptr(out), out.size, C.byref(n))
+        if rc:
+            raise B2JError(rc, self._L.b2j_multi_last_error(self._h).decode())
+        return out[: n.value]
+
+    def encode_ptr(self, src_ptr, step, W, H, out_ptr, cap):
+        n = C.c_size_t(0)
+        rc = self._L.b2j_multi_encode(self._h, C.c_void_p(src_ptr), step, W, H, C.c_void_p(out_ptr), cap, C.byref(n))
+        if rc:
+            raise B2JError(rc, self._L.b2j_multi_last_error(self._h).decode())
+        return n.value
+
+    def close(self):
+        if self._h:
+            self._L.b2j_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

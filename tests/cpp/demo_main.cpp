@@ -1,7 +1,8 @@
 // demo_main.cpp -- the reference demo's call order (src/ImageCompressor/main.cpp:16-82) against the drop-in facade:
 // construct -> buildCompressEnv -> compress x2 -> deleteCompressEnv -> buildDecodeEnv -> save x2 -> decode x2 ->
 // deleteDecodeEnv -> delete. Images come from raw BGR files written by the test (no imread in this image).
-// usage: demo W H in1.bgr in2.bgr outdir      exit code 0 = every run_state was 1
+// usage: demo W H in1.bgr in2.bgr outdir [ngpus]     exit code 0 = every run_state was 1
+// ngpus > 1: compress() runs as MCU-row strips over that many contexts of this one process (B2J_MULTI_DEVICES picks the GPUs)
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -23,7 +24,8 @@ int main(int argc, char *argv[]) {
     const int W = atoi(argv[1]), H = atoi(argv[2]);
     const std::string outdir = argv[5];
     int bad = 0;
-    NvjpegCompressRunner *compressor = new NvjpegCompressRunner(W, H, 95, true);
+    const int ngpus = argc > 6 ? atoi(argv[6]) : 1;
+    NvjpegCompressRunner *compressor = new NvjpegCompressRunner(W, H, 95, true, 422, ngpus);
     int compress_run_state, decode_run_state;
     compressor->buildCompressEnv();
     cv::Mat image1 = load(argv[3], W, H);

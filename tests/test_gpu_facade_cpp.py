@@ -24,7 +24,10 @@ def test_facade_compiles_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cpp_demo_sequence(tmp_path, oracle):
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_cpp_demo_sequence(tmp_path, oracle, ngpus):
+    """ngpus = 2: the same demo with compress() spread over two contexts of the one process (b2j_multi_*; both on this
+    GPU here, B2J_MULTI_DEVICES=0,0 -- on a multi-GPU box the facade takes devices 0 .. ngpus-1)."""
     from nvjpeg_imagecompressor_b200 import _native as N
     N.lib()
     exe = _build(str(tmp_path))
@@ -32,7 +35,9 @@ def test_cpp_demo_sequence(tmp_path, oracle):
     a, b = oracle.synth(W, H, 1, 8), oracle.synth(W, H, 2, 8)
     a.tofile(tmp_path / "a.bgr")
     b.tofile(tmp_path / "b.bgr")
-    r = subprocess.run([exe, str(W), str(H), str(tmp_path / "a.bgr"), str(tmp_path / "b.bgr"), str(tmp_path)], capture_output=True, text=True)
+    env = dict(os.environ, B2J_MULTI_DEVICES="0,0")
+    r = subprocess.run([exe, str(W), str(H), str(tmp_path / "a.bgr"), str(tmp_path / "b.bgr"), str(tmp_path), str(ngpus)],
+                       capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("[INFO] Successful.") == 4
     for name, img in (("1", a), ("2", b)):

@@ -188,3 +188,23 @@ def test_strip_secondary_world1_equals_b2j_secondary(oracle):
     assert abs(ps - psnr) < 1e-9
     assert np.array_equal(sec.recon[:H].cpu().numpy(), recon)
     eng.close()
+
+
+@pytest.mark.parametrize("W,H,css,q,opt,n", [(256, 320, 1, 95, 1, 2), (200, 333, 3, 90, 1, 4), (129, 200, 0, 75, 0, 3),
+                                           (1040, 2600, 1, 95, 1, 8), (64, 16, 1, 95, 1, 4)])
+def test_multi_context_one_process(oracle, W, H, css, q, opt, n):
+    """b2j_multi_*: several contexts driven by ONE process and one host thread (here all on this GPU; on a multi-GPU
+    box one per GPU), host image in -> host JPEG out, the records exchanged through peer memory: the bytes are the
+    single-stream bytes, with pageable and with pinned host buffers, several images in a row."""
+    import nvjpeg_imagecompressor_b200 as P
+    img = oracle.synth(W, H, 4, 8)
+    want = oracle.encode(img, css, q, opt)
+    m = P.MultiEngine(W, H, q, bool(opt), css, devices=[0] * n)
+    for it in range(3):
+        got = m.encode(img)                                   # pageable numpy memory
+        assert got.size == want.size and np.array_equal(got, want), (it, "pageable")
+    h_img = torch.from_numpy(img).pin_memory()
+    h_out = torch.empty(W * H * 3 + 65536, dtype=torch.uint8).pin_memory()
+    nb = m.encode_ptr(h_img.data_ptr(), W * 3, W, H, h_out.data_ptr(), h_out.numel())
+    assert nb == want.size and np.array_equal(h_out[:nb].numpy(), want), "pinned"
+    m.close()
