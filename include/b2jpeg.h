@@ -119,6 +119,12 @@ B2J_API int b2j_decode(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *bg
 /* Host JPEG bytes -> device BGR (d_bgr: device pointer, pitch step); asynchronous after the header parse. */
 B2J_API int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_bgr, size_t step,
                               int *width, int *height);
+/* A baseline JPEG whose entropy-coded segment is already in DEVICE memory: hdr = the file's bytes from SOI up to and
+ * including the SOS header (host, a few hundred bytes), d_scan = the stuffed scan bytes up to the terminating marker
+ * (device). height_override > 0 replaces the frame height: whole restart intervals of whole MCU rows decode as an image
+ * of their own (one image decoded by several GPUs: strips.StripDecoder). Synchronous and validated. */
+B2J_API int b2j_decode_scan_device(b2j_ctx *ctx, const uint8_t *hdr, size_t hdr_len, const uint8_t *d_scan, size_t scan_len,
+                                   int height_override, uint8_t *d_bgr, size_t step, int *width, int *height);
 /* Completes the last b2j_decode_device: waits for it and validates it. The decode runs a fixed schedule of Huffman
  * synchronisation launches without asking the host; in the rare case that was too short the image is decoded again
  * here with the checked schedule. `jpg` of the b2j_decode_device call must stay valid until this returns. */

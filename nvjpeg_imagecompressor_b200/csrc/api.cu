@@ -944,12 +944,13 @@ static int decode_progressive_to(b2j_ctx *ctx, const uint8_t *jpg, size_t len, u
     return rc;
 }
 
-static int decode_parsed(b2j_ctx *ctx, const uint8_t *jpg, size_t len, const JpegInfo &info, uint8_t *d_bgr, size_t step, bool careful) {
+static int decode_parsed(b2j_ctx *ctx, const uint8_t *jpg, size_t len, const JpegInfo &info, uint8_t *d_bgr, size_t step, bool careful,
+                         const uint8_t *d_scan_src = nullptr) {
     if (step < (size_t)info.W * 3) return B2J_EINVAL;
     int rc = dec_ensure(ctx); if (rc) return rc;
     Geom g; rc = make_geom(info.W, info.H, info.css, &g); if (rc) return rc;
     dec_set_spec_launches(ctx->dec, (ctx->debug & 4) ? 1 : 3);
-    return dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches, careful);
+    return dec_run(ctx->dec, jpg, len, info, g, d_bgr, step, ctx->stream, ctx->timing ? &ctx->tm : nullptr, &ctx->launches, careful, d_scan_src);
 }
 
 static int parse_for(b2j_ctx *ctx, const uint8_t *jpg, size_t len, JpegInfo *info, int *width, int *height) {
@@ -977,6 +978,32 @@ int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint8_t *d_b
     // remembered for b2j_decode_finish: the caller keeps `jpg` alive until then
     ctx->last_jpg = jpg; ctx->last_len = len; ctx->last_bgr = d_bgr; ctx->last_step = step;
     return decode_parsed(ctx, jpg, len, info, d_bgr, step, false);
+}
+
+// A baseline JPEG whose entropy-coded segment is already in DEVICE memory (the output of b2j_encode_device, a slice
+// of a stream with restart intervals, ...): `hdr` = the file's bytes from SOI up to and including the SOS header (host
+// memory, a few hundred bytes), d_scan = the stuffed scan bytes up to the terminating marker. height_override > 0
+// replaces the frame height: whole restart intervals of whole MCU rows decode as an image of their own (multi-GPU
+// decode of one image, strips.StripDecoder). Synchronous: validated (and redone with the checked schedule if needed)
+// before it returns.
+int b2j_decode_scan_device(b2j_ctx *ctx, const uint8_t *hdr, size_t hdr_len, const uint8_t *d_scan, size_t scan_len,
+                           int height_override, uint8_t *d_bgr, size_t step, int *width, int *height) {
+    if (!ctx || !hdr || !d_scan || !d_bgr || scan_len == 0) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->last_jpg) { int rf = b2j_decode_finish(ctx); if (rf) return rf; }
+    JpegInfo info;
+    int rc = parse_for(ctx, hdr, hdr_len, &info, nullptr, nullptr); if (rc) return rc;
+    if (info.scan_offset != hdr_len) { snprintf(ctx->err, sizeof(ctx->err), "hdr must end with the SOS header"); return B2J_EINVAL; }
+    if (height_override > 0) info.H = height_override;
+    info.scan_offset = 0; info.scan_len = scan_len;
+    if (width) *width = info.W;
+    if (height) *height = info.H;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        rc = decode_parsed(ctx, hdr, hdr_len, info, d_bgr, step, attempt == 1, d_scan); if (rc) return rc;
+        rc = dec_check(ctx->dec, ctx->err, sizeof(ctx->err));
+        if (rc != DEC_RETRY) break;
+    }
+    return rc;
 }
 
 int b2j_decode_finish(b2j_ctx *ctx) {

@@ -155,11 +155,11 @@ static int ensure(Decoder *d, size_t scan_len, const Geom &g, int restart_interv
 }
 
 int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
-            cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful) {
+            cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful, const uint8_t *d_scan_src) {
     const int rst = info.restart_interval;   // MCUs per restart interval (0: none)
     if (rst && info.scan_len >= 0xFFFFFFF0ull) { snprintf(d->err, d->errlen, "restart-marker scans of 4 GB and more are not supported"); return B2J_EFORMAT; }
     if (g.nblocks > d->nblocks_cap) { snprintf(d->err, d->errlen, "image exceeds the context's size"); return B2J_ESIZE; }
-    if (info.scan_offset + info.scan_len > len || info.scan_len == 0) return B2J_EFORMAT;
+    if ((!d_scan_src && info.scan_offset + info.scan_len > len) || info.scan_len == 0) return B2J_EFORMAT;
     int rc = ensure(d, info.scan_len, g, rst);
     if (rc) return rc;
     const size_t n = info.scan_len;
@@ -192,7 +192,8 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     // that pass hides behind the upload (large scans, speculative mode).
     const int nch = (int)((n + 4095) / 4096);
     // restart markers: one piece (a marker's two bytes may straddle pieces: k_destuff looks one byte ahead)
-    const int npieces = (spec && n >= (16u << 20) && !rst) ? 8 : 1;   // fewer, larger pieces: a piece should fill the GPU
+    const int npieces = (spec && n >= (16u << 20) && !rst && !d_scan_src) ? 8 : 1;   // fewer, larger pieces: a piece should fill the GPU
+    const uint8_t *scan_in = d_scan_src ? d_scan_src : d->d_scan;
     uint32_t *bnd = rst ? d->d_bnd : nullptr;
     const uint32_t *nmark = rst ? &d->d_ctrl->nmark : nullptr;
     const size_t piece = ((n + npieces - 1) / npieces + 4095) & ~(size_t)4095;
@@ -200,7 +201,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     DCK(cudaStreamWaitEvent(d->up_stream, d->ev_up[32], 0));
     for (int j = 0; j < npieces; j++) {
         const size_t b0 = std::min(n, (size_t)j * piece), b1 = std::min(n, b0 + piece);
-        if (b1 > b0) {
+        if (b1 > b0 && !d_scan_src) {
             if (d->upload) {
                 const int urc = d->upload(d->upload_user, d->d_scan + b0, jpg + info.scan_offset + b0, b1 - b0, d->up_stream);
                 if (urc) return urc;
@@ -212,7 +213,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         DCK(cudaStreamWaitEvent(s, d->ev_up[j], 0));
         const int c0 = (int)(b0 / 4096), c1 = j == npieces - 1 ? nch : (int)(b1 / 4096);
         if (c1 > c0) {
-            DCK(launch_destuff(d->d_scan, n, d->d_u, d->d_desc, &d->d_ctrl->dticket[j], c0, c1, &d->d_ctrl->u_len, &d->d_ctrl->avail,
+            DCK(launch_destuff(scan_in, n, d->d_u, d->d_desc, &d->d_ctrl->dticket[j], c0, c1, &d->d_ctrl->u_len, &d->d_ctrl->avail,
                                bnd, (uint32_t)d->bnd_cap, &d->d_ctrl->nmark, &d->d_ctrl->err, s));
             if (launches) (*launches)++;
         }

@@ -24,8 +24,9 @@ struct Decoder;
 Decoder *dec_create(int nblocks_cap, char *err, size_t errlen);
 void dec_destroy(Decoder *d);
 // careful = false: no host synchronisation inside (dec_check may then answer DEC_RETRY: run again with careful = true)
+// d_scan_src != NULL: the scan's stuffed bytes are already in device memory (info.scan_len of them): nothing is uploaded
 int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, const Geom &g, uint8_t *d_bgr, size_t step,
-            cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful);
+            cudaStream_t s, b2j_timings *tm, uint64_t *launches, bool careful, const uint8_t *d_scan_src = nullptr);
 constexpr int DEC_RETRY = 1;
 int dec_check(Decoder *d, char *err, size_t errlen);   // synchronises the decode's stream
 // optional: how host bytes reach the device (the API layer stages pageable memory through pinned buffers); the

@@ -115,6 +115,14 @@ class Engine:
         self._ck(self._L.b2j_set_restart_rows(self._h, int(rows)))
 
     # ---------------------------------------------------------------- device API (pointers from torch tensors)
+    def decode_scan_device(self, hdr, d_scan_ptr, scan_len, d_bgr_ptr, step, height_override=0):
+        """Baseline JPEG with its scan bytes already in device memory (hdr: host bytes SOI .. SOS header) -> (W, H)."""
+        hdr = np.ascontiguousarray(hdr, np.uint8)
+        W, H = C.c_int(0), C.c_int(0)
+        self._ck(self._L.b2j_decode_scan_device(self._h, _ptr(hdr), hdr.size, C.c_void_p(d_scan_ptr), int(scan_len), int(height_override),
+                                                C.c_void_p(d_bgr_ptr), step, C.byref(W), C.byref(H)))
+        return W.value, H.value
+
     def reconstruct_device(self, d_bgr_ptr, step):
         """Pixels of the last encode (made with set_debug(1)) from its quantised coefficients; asynchronous."""
         self._ck(self._L.b2j_reconstruct_device(self._h, C.c_void_p(d_bgr_ptr), step))

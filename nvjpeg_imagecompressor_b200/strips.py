@@ -291,3 +291,112 @@ class StripSecondary:
         ssd = int(self._ssd.item())
         psnr = 20.0 * np.log10(255.0 / (np.sqrt(ssd / (self.W * self.H * 3)) + 2.220446049250313e-16))   # cv::PSNR
         return n1, n2, float(psnr)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# One image decoded by N GPUs. A stream whose restart intervals are whole MCU rows shards without
+# any data-path collective: every interval starts byte aligned at a known state with zero DC predictors, so a run of
+# intervals is a baseline scan of its own. Rank k takes the k-th N-th of the scan's BYTES, finds the RSTn markers in
+# it on the GPU, learns from one all_gather of the marker counts which MCU row its first interval is, and decodes
+# its intervals (plus one interval above and below: the vertical chroma filter of 4:2:0 / 4:4:0 looks one chroma row
+# across) through b2j_decode_scan_device with the frame height replaced by its rows. Streams without restart markers
+# do not shard (the synchronisation chain spans the scan): replicas only, as DESIGN.md says.
+def parse_baseline_header(jpg):
+    """-> dict(W, H, css, dri, scan_off, scan_end, hs, vs) of a baseline JPEG (host bytes)."""
+    b = np.asarray(jpg, np.uint8)
+    p, n = 2, b.size
+    out = {"dri": 0}
+    while p + 4 <= n:
+        if b[p] != 0xFF:
+            raise ValueError("not a marker")
+        m = int(b[p + 1])
+        if m == 0xFF:
+            p += 1
+            continue
+        p += 2
+        if m == 0x01 or 0xD0 <= m <= 0xD8:
+            continue
+        L = (int(b[p]) << 8) | int(b[p + 1])
+        if m in (0xC0, 0xC1):
+            out["H"], out["W"] = (int(b[p + 3]) << 8) | int(b[p + 4]), (int(b[p + 5]) << 8) | int(b[p + 6])
+            out["hs"], out["vs"] = int(b[p + 9]) >> 4, int(b[p + 9]) & 15
+            out["sof_height_pos"] = p + 3
+        elif m == 0xDD:
+            out["dri"] = (int(b[p + 2]) << 8) | int(b[p + 3])
+        elif m == 0xDA:
+            out["scan_off"] = p + L
+            end = n - 2 if (b[n - 2] == 0xFF and b[n - 1] == 0xD9) else n
+            out["scan_end"] = end
+            return out
+        p += L
+    raise ValueError("no SOS")
+
+
+class StripDecoder:
+    """One rank of an N-rank decode of ONE image: count_markers() -> int (all-gather it over the ranks), then
+    decode(counts_of_all_ranks) -> (first row, device tensor with this rank's rows)."""
+
+    def __init__(self, jpg, rank, world, device=None):
+        from .engine import Engine
+        self.jpg = np.ascontiguousarray(jpg, np.uint8)
+        self.rank, self.world = int(rank), int(world)
+        h = parse_baseline_header(self.jpg)
+        self.h = h
+        W, H, hs, vs = h["W"], h["H"], h["hs"], h["vs"]
+        self.mcu_h = 8 * vs
+        mcux = -(-W // (8 * hs))
+        self.mcuy = -(-H // self.mcu_h)
+        if h["dri"] == 0 or h["dri"] % mcux:
+            raise ValueError("single-image decode over several GPUs needs restart intervals of whole MCU rows (replicas otherwise)")
+        self.rpi = h["dri"] // mcux                      # MCU rows per interval
+        self.nint = -(-self.mcuy // self.rpi)
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        css = {(1, 1): 0, (2, 1): 1, (1, 2): 2, (2, 2): 3, (4, 1): 4}[(hs, vs)]
+        # the split is by bytes, so a rank's share of the rows depends on the content: twice the fair share, plus the halo
+        rows_cap = min(H, (2 * -(-self.nint // self.world) + 8) * self.rpi * self.mcu_h)
+        self.eng = Engine(W, rows_cap, 95, True, css, device=self.dev.index)
+        self.margin = 1 << 20                            # bytes read beyond the own range on both sides (halo intervals)
+
+    def count_markers(self):
+        h, jpg = self.h, self.jpg
+        s0, s1 = h["scan_off"], h["scan_end"]
+        n = s1 - s0
+        self.lo_own, self.hi_own = s0 + n * self.rank // self.world, s0 + n * (self.rank + 1) // self.world
+        self.lo, self.hi = max(s0, self.lo_own - self.margin), min(s1, self.hi_own + self.margin)
+        self.d = torch.from_numpy(jpg[self.lo:self.hi]).to(self.dev)
+        d = self.d
+        mk = ((d[:-1] == 0xFF) & ((d[1:] & 0xF8) == 0xD0)).nonzero().flatten()
+        self.mk = mk.cpu().numpy().astype(np.int64) + self.lo          # file offsets of the FF of every RSTn in the window
+        self.base = int(np.searchsorted(self.mk, self.lo_own))         # markers in the lower margin come first
+        self.nown = int(np.searchsorted(self.mk, self.hi_own)) - self.base
+        return self.nown
+
+    def decode(self, counts):
+        h, jpg = self.h, self.jpg
+        s0, s1 = h["scan_off"], h["scan_end"]
+        before = int(sum(counts[: self.rank]))            # markers before my byte range = ordinal of my first marker
+        # interval 0 belongs to rank 0, interval j >= 1 to the rank whose byte range holds marker j - 1
+        i0 = 0 if self.rank == 0 else before + 1
+        i1 = min(self.nint, before + self.nown + 1)       # exclusive
+        if i1 <= i0:
+            return 0, torch.empty((0, h["W"], 3), dtype=torch.uint8, device=self.dev)
+        j0, j1 = max(0, i0 - 1), min(self.nint, i1 + 1)   # with one interval of halo on either side
+
+        def start_of(j):                                  # first byte of interval j: after marker j - 1
+            if j == 0:
+                return s0
+            idx = self.base + (j - 1 - before)
+            if idx < 0 or idx >= self.mk.size:
+                raise RuntimeError("a restart interval is larger than the margin read around the rank's byte range")
+            return int(self.mk[idx]) + 2
+
+        b0 = start_of(j0)
+        b1 = s1 if j1 >= self.nint else start_of(j1) - 2
+        rows0, rows1 = j0 * self.rpi * self.mcu_h, min(h["H"], j1 * self.rpi * self.mcu_h)
+        sub = torch.empty((rows1 - rows0, h["W"], 3), dtype=torch.uint8, device=self.dev)
+        self.eng.decode_scan_device(jpg[: s0], self.d.data_ptr() + (b0 - self.lo), b1 - b0, sub.data_ptr(), h["W"] * 3, rows1 - rows0)
+        y0, y1 = i0 * self.rpi * self.mcu_h, min(h["H"], i1 * self.rpi * self.mcu_h)
+        return y0, sub[y0 - rows0: y1 - rows0]
+
+    def close(self):
+        self.eng.close()

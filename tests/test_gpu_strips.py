@@ -208,3 +208,30 @@ def test_multi_context_one_process(oracle, W, H, css, q, opt, n):
     nb = m.encode_ptr(h_img.data_ptr(), W * 3, W, H, h_out.data_ptr(), h_out.numel())
     assert nb == want.size and np.array_equal(h_out[:nb].numpy(), want), "pinned"
     m.close()
+
+
+@pytest.mark.parametrize("W,H,css,q,rows,n", [(640, 720, 1, 95, 1, 2), (640, 720, 3, 90, 1, 4), (333, 500, 2, 95, 2, 3),
+                                            (1040, 2000, 1, 100, 1, 8), (200, 900, 0, 75, 3, 5), (64, 64, 3, 95, 1, 4)])
+def test_single_image_decode_over_strips(oracle, W, H, css, q, rows, n):
+    """one image with restart intervals of whole MCU rows decoded by N ranks (here N decoders in one
+    process; scripts/decode_multi.py runs them as N processes on N GPUs): every rank takes a byte range of the scan,
+    finds its RSTn markers on the GPU, the ranks share only their marker counts, each decodes its intervals plus a
+    halo interval; the rows put together are libjpeg-turbo's pixels (4:2:0 / 4:4:0 included: vertical chroma filter)."""
+    import nvjpeg_imagecompressor_b200 as P
+    from nvjpeg_imagecompressor_b200.strips import StripDecoder
+    img = oracle.synth(W, H, 9, 8)
+    g = oracle.geometry(W, H, css)
+    jpg = oracle.encode(img, css, q, 1, rows * g.mcux)
+    want = oracle.decode(jpg)
+    decs = [StripDecoder(jpg, r, n) for r in range(n)]
+    counts = [d.count_markers() for d in decs]           # what one all_gather of an int per rank gives every rank
+    assert sum(counts) == -(-g.mcuy // rows) - 1
+    out = np.zeros_like(want)
+    covered = 0
+    for d in decs:
+        y0, t = d.decode(counts)
+        out[y0:y0 + t.shape[0]] = t.cpu().numpy()
+        covered += t.shape[0]
+        d.close()
+    assert covered == H
+    assert np.array_equal(out, want)
