@@ -411,6 +411,20 @@ def run_b200(args, rank, world, local_rank):
                 d1.record(stream)
                 stream.synchronize()
             dec_ms = d0.elapsed_time(d1) / kd
+            # the same with the JPEG bytes already in HBM when the timed region starts (b2j_decode_scan_device)
+            from nvjpeg_imagecompressor_b200.strips import parse_baseline_header
+            hd = parse_baseline_header(jpg)
+            d_jpg = torch.from_numpy(jpg).to(dev)
+            scan_len = hd["scan_end"] - hd["scan_off"]
+            with torch.cuda.stream(stream):
+                eng.decode_scan_device(jpg[:hd["scan_off"]], d_jpg.data_ptr() + hd["scan_off"], scan_len, d_rec.data_ptr(), W * 3)
+                d0.record(stream)
+                for _ in range(kd):
+                    eng.decode_scan_device(jpg[:hd["scan_off"]], d_jpg.data_ptr() + hd["scan_off"], scan_len, d_rec.data_ptr(), W * 3)
+                d1.record(stream)
+                stream.synchronize()
+            dec_res_ms = d0.elapsed_time(d1) / kd
+            del d_jpg
             h_rec = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
             eng.decode_ptr(jpg, h_rec.data_ptr(), W * 3)
             t0 = time.perf_counter()
@@ -423,8 +437,10 @@ def run_b200(args, rank, world, local_rank):
                 eng.decode_finish()
             dt_st = {k: round(v, 3) for k, v in eng.timings().items() if k.startswith("dec_")}
             eng.enable_timing(False)
-            decode = {"metric": "decode_mpix_per_s", "value": round(W * H / dec_ms / 1e3, 1), "unit": "Mpix/s",
-                      "ms_per_step": round(dec_ms, 3), "input": "host JPEG bytes (this run's output), output BGR in HBM",
+            decode = {"metric": "decode_mpix_per_s", "value": round(W * H / dec_res_ms / 1e3, 1), "unit": "Mpix/s",
+                      "ms_per_step": round(dec_res_ms, 3), "input": "this run's JPEG, bytes resident in HBM (b2j_decode_scan_device), output BGR in HBM",
+                      "from_host_bytes": {"value": round(W * H / dec_ms / 1e3, 1), "unit": "Mpix/s", "ms_per_step": round(dec_ms, 3),
+                                          "api": "b2j_decode_device + b2j_decode_finish (pinned host JPEG -> BGR in HBM, upload inside)"},
                       "e2e": {"value": round(W * H / dth / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dth * 1e3, 2),
                               "h2d_bytes_per_step": int(n2), "d2h_bytes_per_step": W * H * 3,
                               "api": "b2j_decode (host JPEG -> host BGR), pinned output"},

@@ -91,15 +91,9 @@ std::vector<unsigned char> NvjpegCompressRunner::compress(cv::Mat image, int *ru
         size_t n = 0;
         int rc;
         if (compressor->multi && compressor->restart_rows == 0) {
-            // strips over several GPUs: the bytes land in place, so the buffer is sized before the encode
-            size_t cap = (size_t)image.rows * image.cols + 65536;
-            obuffer.resize(cap);
-            rc = b2j_multi_encode(compressor->multi, image.data, image.step, image.cols, image.rows, obuffer.data(), cap, &n);
-            if (rc == B2J_ECAPACITY) {
-                cap = b2j_encode_bound(c);
-                obuffer.resize(cap);
-                rc = b2j_multi_encode(compressor->multi, image.data, image.step, image.cols, image.rows, obuffer.data(), cap, &n);
-            }
+            // strips over several GPUs: encode, size the vector to the stitched stream, fetch every strip's bytes into place
+            rc = b2j_multi_encode_begin(compressor->multi, image.data, image.step, image.cols, image.rows, &n);
+            if (rc == B2J_OK) { obuffer.resize(n); rc = b2j_multi_encode_fetch(compressor->multi, obuffer.data(), n); }
             if (rc != B2J_OK) { std::cerr << "[ERROR] compress: " << b2j_multi_last_error(compressor->multi) << std::endl; n = 0; }
         } else {
             // encode first, then size the vector to the JPEG (no zero-filled worst-case buffer), then fetch the bytes

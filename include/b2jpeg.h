@@ -226,6 +226,9 @@ B2J_API int b2j_multi_create(const b2j_params *p, int ngpus, const int *device_i
 B2J_API void b2j_multi_destroy(b2j_multi *m);
 B2J_API int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out,
                              size_t cap, size_t *len);
+/* in two steps (the caller sizes its buffer to the stream): encode on every GPU, then fetch the strips' bytes */
+B2J_API int b2j_multi_encode_begin(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, size_t *len);
+B2J_API int b2j_multi_encode_fetch(b2j_multi *m, uint8_t *out, size_t cap);
 B2J_API const char *b2j_multi_last_error(const b2j_multi *m);
 
 /* ---- introspection used by the parity tests (device -> host copies of intermediate state) ------------- */

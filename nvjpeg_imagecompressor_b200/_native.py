@@ -44,7 +44,8 @@ SYMBOLS = ["b2j_default_params", "b2j_create", "b2j_destroy", "b2j_last_error", 
            "b2j_encode_bound", "b2j_encode", "b2j_encode_device", "b2j_encode_finish", "b2j_peek", "b2j_decode",
            "b2j_decode_device", "b2j_decode_finish", "b2j_decode_scan_device", "b2j_diff", "b2j_psnr", "b2j_diff_psnr_device", "b2j_secondary",
            "b2j_reconstruct_device", "b2j_secondary_device", "b2j_secondary_finish", "b2j_secondary_fetch", "b2j_encode_begin", "b2j_encode_fetch",
-           "b2j_multi_create", "b2j_multi_destroy", "b2j_multi_encode", "b2j_multi_last_error",
+           "b2j_multi_create", "b2j_multi_destroy", "b2j_multi_encode", "b2j_multi_encode_begin", "b2j_multi_encode_fetch",
+           "b2j_multi_last_error",
            "b2j_strip_state_get", "b2j_strip_phase1", "b2j_strip_phase1b", "b2j_strip_phase2", "b2j_strip_phase3", "b2j_strip_phase3_dev", "b2j_strip_phase1x", "b2j_strip_phase2x", "b2j_peer_export", "b2j_peer_open", "b2j_peer_connect", "b2j_set_restart_rows",
            "b2j_debug_read", "b2j_set_debug", "b2j_last_timings", "b2j_enable_timing", "b2j_launch_count", "b2j_host_alloc",
            "b2j_host_free"]

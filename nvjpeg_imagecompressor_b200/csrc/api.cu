@@ -748,6 +748,8 @@ int b2j_encode(b2j_ctx *ctx, const uint8_t *bgr, size_t step, int width, int hei
 // with the fdct of a group behind it, every strip's bytes downloaded straight to their place in the caller's buffer.
 struct b2j_multi {
     int n;
+    int last_n;                       // strips of the last encode
+    size_t off[XCHG_MAX_WORLD + 1];   // byte offsets of the strips' bytes in the stitched stream
     bool shared_device;   // two contexts on one GPU (tests): the host then separates the pushes from the waits
     b2j_ctx *ctx[XCHG_MAX_WORLD];
     char err[256];
@@ -803,14 +805,16 @@ int b2j_multi_create(const b2j_params *p, int ngpus, const int *device_ids, b2j_
     return B2J_OK;
 }
 
-int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
-    if (!m || !bgr || !out || !len || step < (size_t)width * 3) return B2J_EINVAL;
+// upload + encode on every GPU; *len = size of the stitched stream (the strips' bytes stay in HBM until b2j_multi_encode_fetch)
+int b2j_multi_encode_begin(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, size_t *len) {
+    if (!m || !bgr || !len || step < (size_t)width * 3) return B2J_EINVAL;
     Geom gw;
     int rc = make_geom(width, height, m->ctx[0]->p.css, &gw); if (rc) return rc;
     const int n = std::min(m->n, gw.mcuy);
     if (n <= 1 || n != m->n) {   // one strip (or fewer MCU rows than GPUs): the single-context path
-        rc = b2j_encode(m->ctx[0], bgr, step, width, height, out, cap, len);
+        rc = b2j_encode_begin(m->ctx[0], bgr, step, width, height, len);
         if (rc) snprintf(m->err, sizeof(m->err), "%s", m->ctx[0]->err);
+        m->last_n = 1; m->off[0] = 0; m->off[1] = rc ? 0 : *len;
         return rc;
     }
 #define MCK(k, call) do { rc = (call); if (rc) { snprintf(m->err, sizeof(m->err), "gpu %d: %s", (k), m->ctx[k]->err); return rc; } } while (0)
@@ -860,8 +864,8 @@ int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, i
         cudaSetDevice(m->ctx[k]->device);
         MCK(k, b2j_strip_phase2x(m->ctx[k], nullptr, k, n, width, height, (k == 0 ? 1 : 0) | (k == n - 1 ? 2 : 0)));
     }
-    // 4. lengths, then every strip's bytes straight to their place
-    size_t off[XCHG_MAX_WORLD + 1];
+    // 4. lengths
+    size_t *off = m->off;
     off[0] = 0;
     for (int k = 0; k < n; k++) {
         cudaSetDevice(m->ctx[k]->device);
@@ -869,7 +873,25 @@ int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, i
         for (int i = 0; i < StageRing::N; i++) m->ctx[k]->ring.busy[i] = false;
         off[k + 1] = off[k] + (size_t)m->ctx[k]->h_ret->out_len;
     }
+    m->last_n = n;
+    *len = off[n];
+    return B2J_OK;
+#undef MCK
+}
+
+// every strip's bytes straight to their place in `out`
+int b2j_multi_encode_fetch(b2j_multi *m, uint8_t *out, size_t cap) {
+    if (!m || !out || m->last_n < 1) return B2J_EINVAL;
+    int rc = B2J_OK;
+    const int n = m->last_n;
+    const size_t *off = m->off;
+#define MCK(k, call) do { rc = (call); if (rc) { snprintf(m->err, sizeof(m->err), "gpu %d: %s", (k), m->ctx[k]->err); return rc; } } while (0)
     if (off[n] > cap) { snprintf(m->err, sizeof(m->err), "output needs %zu bytes, buffer has %zu", off[n], cap); return B2J_ECAPACITY; }
+    if (n == 1) {
+        rc = b2j_encode_fetch(m->ctx[0], out, cap);
+        if (rc) snprintf(m->err, sizeof(m->err), "%s", m->ctx[0]->err);
+        return rc;
+    }
     const bool pageable_out = is_pageable_host(out);
     for (int k = 0; k < n; k++) {
         b2j_ctx *ctx = m->ctx[k];
@@ -883,7 +905,15 @@ int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, i
             if (cudaStreamSynchronize(m->ctx[k]->stream) != cudaSuccess) { snprintf(m->err, sizeof(m->err), "gpu %d: %s", k, cudaGetErrorString(cudaGetLastError())); return B2J_ECUDA; }
         }
 #undef MCK
-    *len = off[n];
+    return B2J_OK;
+}
+
+int b2j_multi_encode(b2j_multi *m, const uint8_t *bgr, size_t step, int width, int height, uint8_t *out, size_t cap, size_t *len) {
+    if (!out || !len) return B2J_EINVAL;
+    size_t n = 0;
+    int rc = b2j_multi_encode_begin(m, bgr, step, width, height, &n); if (rc) return rc;
+    rc = b2j_multi_encode_fetch(m, out, cap); if (rc) return rc;
+    *len = n;
     return B2J_OK;
 }
 

@@ -338,7 +338,9 @@ class StripDecoder:
 
     def __init__(self, jpg, rank, world, device=None):
         from .engine import Engine
-        self.jpg = np.ascontiguousarray(jpg, np.uint8)
+        # a (pinned) torch tensor keeps its memory kind for the uploads; numpy input is wrapped
+        self.jt = jpg if torch.is_tensor(jpg) else torch.from_numpy(np.ascontiguousarray(jpg, np.uint8))
+        self.jpg = self.jt.numpy()
         self.rank, self.world = int(rank), int(world)
         h = parse_baseline_header(self.jpg)
         self.h = h
@@ -363,7 +365,7 @@ class StripDecoder:
         n = s1 - s0
         self.lo_own, self.hi_own = s0 + n * self.rank // self.world, s0 + n * (self.rank + 1) // self.world
         self.lo, self.hi = max(s0, self.lo_own - self.margin), min(s1, self.hi_own + self.margin)
-        self.d = torch.from_numpy(jpg[self.lo:self.hi]).to(self.dev)
+        self.d = self.jt[self.lo:self.hi].to(self.dev, non_blocking=True)
         d = self.d
         mk = ((d[:-1] == 0xFF) & ((d[1:] & 0xF8) == 0xD0)).nonzero().flatten()
         self.mk = mk.cpu().numpy().astype(np.int64) + self.lo          # file offsets of the FF of every RSTn in the window

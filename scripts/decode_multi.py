@@ -32,7 +32,9 @@ img = synth(W, H)
 optr, _ = eng.encode_device(img.data_ptr(), W * 3, W, H)
 n = eng.encode_finish()
 from nvjpeg_imagecompressor_b200.strips import _view
-jpg = _view(optr, (n,), "|u1", dev).cpu().numpy().copy()
+jt = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+jt.copy_(_view(optr, (n,), "|u1", dev)); torch.cuda.synchronize()
+jpg = jt.numpy()
 want_sha = None
 if rank == 0:
     full = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
@@ -43,7 +45,7 @@ if rank == 0:
     torch.cuda.synchronize()
     one_gpu_ms = (time.perf_counter() - t0) * 1e3
 eng.close(); del img
-dec = StripDecoder(jpg, rank, world, device=lr)
+dec = StripDecoder(jt, rank, world, device=lr)
 cnt = torch.zeros(world, dtype=torch.int64, device=dev)
 def run():
     c = dec.count_markers()
