@@ -4,7 +4,7 @@
 # CPU box with scripts/ncu_export.py. Every profiled command first runs plain and must exit 0.
 #   encode   : --set full of one launch of every encode kernel, headline config (8320x40000 4:2:2 q95 optimised)
 #   decode   : --set full of one decode of the headline JPEG
-#   metrics  : --set full of k_diff_psnr (difference map + SSD)
+#   metrics  : --set full of k_diff_psnr (difference map + SSD), k_idct and k_upcolor on the secondary-compression path
 #   launches : per-launch device times of bench.py (gpu__time_duration only)
 set -e
 TAG=${1:-r02}
@@ -20,13 +20,13 @@ encode)
     ;;
 decode)
     python scripts/decode_times.py > $OUT/${TAG}_decode_times.jsonl
-    $NCU --set full --import-source on -k regex:"k_destuff|k_dec_|k_scan_u32|k_dc_scan|k_idct|k_upcolor" -c 40 \
+    $NCU --set full --import-source on -k regex:"k_destuff|k_dec_|k_scan_u32|k_dc_scan|k_idct|k_upcolor" -s 23 -c 23 \
         -f -o $OUT/prof_${TAG}_decode python scripts/decode_times.py > $OUT/${TAG}_decode_ncu.log 2>&1
     ;;
 metrics)
-    python scripts/sweep.py --only-secondary > $OUT/${TAG}_secondary.jsonl
-    $NCU --set full --import-source on -k regex:"k_diff_psnr|k_recon" -c 4 \
-        -f -o $OUT/prof_${TAG}_metrics python scripts/sweep.py --only-secondary > $OUT/${TAG}_metrics_ncu.log 2>&1
+    python scripts/secondary_multi.py --iters 1 > $OUT/${TAG}_secondary.jsonl
+    $NCU --set full --import-source on -k regex:"k_diff_psnr|k_idct|k_upcolor" -s 3 -c 3 \
+        -f -o $OUT/prof_${TAG}_metrics python scripts/secondary_multi.py --iters 1 > $OUT/${TAG}_metrics_ncu.log 2>&1
     ;;
 launches)
     python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_bench_plain.json

@@ -20,6 +20,7 @@ struct DecCtrl {
     uint32_t dticket[32];  // one counter per de-stuff launch
     uint32_t err;
     uint32_t changed;
+    uint32_t changed_alt;   // the launches of the fixed schedule alternate between the two flags
     uint32_t nmark;      // restart markers found by k_destuff
 };
 
@@ -219,7 +220,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         }
         if (npieces > 1 && j < npieces - 1) {
             DCK(launch_dec_sync(d->d_u, &d->d_ctrl->avail, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 1, d->d_done,
-                                &d->d_ctrl->changed, (b1 * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS, bnd, nmark, s));
+                                &d->d_ctrl->changed, (b1 * 8 + DEC_SUB_BITS - 1) / DEC_SUB_BITS, bnd, nmark, nullptr, s));
             if (launches) (*launches)++;
         }
     }
@@ -227,13 +228,17 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     int rounds = 0;
     if (spec) {
         const int nl = npieces > 1 ? std::max(1, DEC_SPEC_LAUNCHES - 1) : DEC_SPEC_LAUNCHES;
+        uint32_t *flag = &d->d_ctrl->changed, *prev = nullptr;
         for (; rounds < nl; rounds++) {
-            DCK(cudaMemsetAsync(&d->d_ctrl->changed, 0, 4, s));
+            // a launch whose predecessor in this loop moved nothing returns at once (its own flag stays 0)
+            flag = (rounds & 1) ? &d->d_ctrl->changed_alt : &d->d_ctrl->changed;
+            DCK(cudaMemsetAsync(flag, 0, 4, s));
             DCK(launch_dec_sync(d->d_u, &d->d_ctrl->u_len, d->d_tb, d->d_st_in, d->d_st_out, d->d_nblk, g.bpm, hv, 8, 0, d->d_done,
-                                &d->d_ctrl->changed, nsub_max, bnd, nmark, s));
+                                flag, nsub_max, bnd, nmark, prev, s));
+            prev = flag;
             if (launches) (*launches)++;
         }
-        DCK(cudaMemcpyAsync(&d->h_flag[2], &d->d_ctrl->changed, 4, cudaMemcpyDeviceToHost, s));
+        DCK(cudaMemcpyAsync(&d->h_flag[2], flag, 4, cudaMemcpyDeviceToHost, s));
         rounds--;
     } else {
         // long synchronisation distances / checked retry: one pass per launch, groups of subsequences per thread

@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(DEC_THREADS)
 k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, const DecTables *__restrict__ tb,
            uint64_t *__restrict__ st_in, uint64_t *__restrict__ st_out, uint32_t *__restrict__ nblk, int bpm, int hv,
            int inner, int mode, uint8_t *__restrict__ done, uint32_t *__restrict__ changed,
-           const uint32_t *__restrict__ bnd, const uint32_t *__restrict__ nmark_p) {
+           const uint32_t *__restrict__ bnd, const uint32_t *__restrict__ nmark_p, const uint32_t *skip_if_zero) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    if (skip_if_zero && *skip_if_zero == 0u) return;   // the previous launch of the schedule found a fixed point: nothing can move
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t cta = blockIdx.x;
     const uint64_t chunk_bit0 = (uint64_t)cta * SUB_BITS * DEC_THREADS;
@@ -1019,15 +1020,15 @@ static cudaError_t dec_attr() {
 
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
                             uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
-                            size_t nsub, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s) {
+                            size_t nsub, const uint32_t *bnd, const uint32_t *nmark, const uint32_t *skip_if_zero, cudaStream_t s) {
     cudaError_t e = dec_attr();
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((nsub + DEC_THREADS - 1) / DEC_THREADS);
     if (grid == 0) return cudaSuccess;
     if (bnd) k_dec_sync<true><<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv,
-                                                                        inner, mode, done, changed, bnd, nmark);
+                                                                        inner, mode, done, changed, bnd, nmark, skip_if_zero);
     else k_dec_sync<false><<<grid, DEC_THREADS, sizeof(DecShared), s>>>(u, u_len, (const DecTables *)tb, st_in, st_out, nblk, bpm, hv,
-                                                                     inner, mode, done, changed, nullptr, nullptr);
+                                                                     inner, mode, done, changed, nullptr, nullptr, skip_if_zero);
     return cudaGetLastError();
 }
 

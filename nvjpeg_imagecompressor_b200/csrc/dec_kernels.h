@@ -29,7 +29,7 @@ cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *
 // complete chunks only. done[chunk] (zeroed per decode) marks chunks whose first pass has run. nsub: subsequences covered.
 cudaError_t launch_dec_sync(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,
                             uint32_t *nblk, int bpm, int hv, int inner, int mode, uint8_t *done, uint32_t *changed,
-                            size_t nsub, const uint32_t *bnd, const uint32_t *nmark, cudaStream_t s);
+                            size_t nsub, const uint32_t *bnd, const uint32_t *nmark, const uint32_t *skip_if_zero, cudaStream_t s);
 // long synchronisation distances and the checked retry: one launch = one pass, groups of 8 subsequences per thread;
 // first != 0: every group starts from the guess, else from its predecessor's last end state (skipped if unchanged)
 cudaError_t launch_dec_sync_long(const uint8_t *u, const uint64_t *u_len, const void *tb, uint64_t *st_in, uint64_t *st_out,

@@ -190,7 +190,8 @@ __device__ __forceinline__ void stage_c(const uint32_t *tok, uint32_t *__restric
         if (HIST) {
             atomicAdd(&hs[(tk >> 16) & 0x3FFu], 1u);
             const uint32_t nz = (tk >> 26) & 3u;        // ZRL (0xF0) symbols ahead of this coefficient: about one token in sixty
-            if (nz) atomicAdd(&hs[tok_bin(bin_table((tk >> 16) & 0x3FFu), 0xF0u)], nz);
+            // bin of the ZRL symbol of this token's AC table: run 15, size 0, table field (tcode + 15) & 3 = (field - run - 1) & 3
+            if (nz) atomicAdd(&hs[(15u << 6) | (((tk >> 16) - (tk >> 22) - 1u) & 3u)], nz);
         }
     }
     if (HIST && tid == 0) { atomicSub(&hs[2], 1u); atomicSub(&hs[7], 1u); atomicSub(&hs[11], 1u); }   // tcode 2 / 3 | component << 2
