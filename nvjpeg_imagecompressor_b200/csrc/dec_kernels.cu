@@ -144,6 +144,7 @@ __device__ __forceinline__ uint32_t huff_sym(const uint16_t *lut, const int32_t 
 constexpr int SUB_BITS = 1024;                 // subsequence length
 constexpr int SUB_WORDS = SUB_BITS / 32;
 constexpr int DEC_THREADS = 256;               // subsequences per CTA
+constexpr int DEC_FIRST_SKIP = 512;            // bits of every subsequence the first synchronisation pass does not decode
 constexpr int DEC_SMEM_WORDS = SUB_WORDS * (DEC_THREADS + 1);
 
 struct DecShared {
@@ -339,7 +340,15 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
             t = sh.list[tid];
             in = sh.state[t];
             const uint64_t t_end = chunk_bit0 + (uint64_t)(t + 1) * SUB_BITS;
-            outst = decode_range<false, RST>(sh, chunk_bit0, in, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0, bnd, nmark);
+            uint64_t from = in;
+            // The very first pass only looks for a synchronisation point: every start state is a guess and the block
+            // counts are thrown away (the next round decodes again from the real states), so it decodes the second half
+            // of the subsequence only -- a decoder is in step after one or two hundred bits on ordinary streams.
+            if (first_launch && round == 0 && !(cta == 0 && t == 0)) {
+                from = pack_state(chunk_bit0 + (uint64_t)t * SUB_BITS + DEC_FIRST_SKIP, 0, 0);
+                in = ~0ull;
+            }
+            outst = decode_range<false, RST>(sh, chunk_bit0, from, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0, bnd, nmark);
         }
         __syncthreads();
         if (t >= 0) {
