@@ -141,6 +141,17 @@ B2J_API int b2j_diff_psnr_device(b2j_ctx *ctx, const uint8_t *d_a, const uint8_t
  * from the quantised coefficients the encoder kept (set B2J_DEBUG_COEF before that encode): de-quantise + IDCT +
  * upsample + colour conversion. Device pointer, asynchronous on the context's stream. */
 B2J_API int b2j_reconstruct_device(b2j_ctx *ctx, uint8_t *d_bgr, size_t step);
+/* The same in two halves, for a strip of a larger image (one strip per GPU): planes first, then -- after one chroma row
+ * from each neighbour strip has been copied into this strip's halo rows (row_bytes bytes each: the upper neighbour's
+ * *_last rows into *_halo_top, the lower neighbour's *_first rows into *_halo_bottom) -- upsampling and colour
+ * conversion; the vertical chroma filter of 4:2:0 / 4:4:0 then gives the whole image's pixels at the strip borders. */
+typedef struct b2j_recon_planes {
+    size_t row_bytes;                               /* true chroma width in samples */
+    uint8_t *cb_first, *cr_first, *cb_last, *cr_last;            /* this strip's first / last chroma rows (device) */
+    uint8_t *cb_halo_top, *cr_halo_top, *cb_halo_bottom, *cr_halo_bottom;   /* where the neighbours' rows go */
+} b2j_recon_planes;
+B2J_API int b2j_reconstruct_planes(b2j_ctx *ctx, b2j_recon_planes *out);
+B2J_API int b2j_reconstruct_color(b2j_ctx *ctx, uint8_t *d_bgr, size_t step, int halo_top, int halo_bottom);
 
 /* Secondary compression, device resident (README.md:8): encode -> reconstruct (from the encoder's coefficients, no
  * Huffman decode, no host round trip) -> difference map + SSD -> encode(difference). d_bgr: device pointer, contiguous

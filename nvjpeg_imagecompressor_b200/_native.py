@@ -26,6 +26,11 @@ class StripState(C.Structure):
                 ("d_record", C.c_void_p)]
 
 
+class ReconPlanes(C.Structure):
+    _fields_ = [("row_bytes", C.c_size_t)] + [(n, C.c_void_p) for n in ("cb_first", "cr_first", "cb_last", "cr_last", "cb_halo_top",
+                                                                         "cr_halo_top", "cb_halo_bottom", "cr_halo_bottom")]
+
+
 STRIP_RECORD_BYTES = 4176
 
 
@@ -43,7 +48,7 @@ class HuffDev(C.Structure):
 SYMBOLS = ["b2j_default_params", "b2j_create", "b2j_destroy", "b2j_last_error", "b2j_version", "b2j_set_stream",
            "b2j_encode_bound", "b2j_encode", "b2j_encode_device", "b2j_encode_finish", "b2j_peek", "b2j_decode",
            "b2j_decode_device", "b2j_decode_finish", "b2j_decode_scan_device", "b2j_diff", "b2j_psnr", "b2j_diff_psnr_device", "b2j_secondary",
-           "b2j_reconstruct_device", "b2j_secondary_device", "b2j_secondary_finish", "b2j_secondary_fetch", "b2j_encode_begin", "b2j_encode_fetch",
+           "b2j_reconstruct_device", "b2j_reconstruct_planes", "b2j_reconstruct_color", "b2j_secondary_device", "b2j_secondary_finish", "b2j_secondary_fetch", "b2j_encode_begin", "b2j_encode_fetch",
            "b2j_multi_create", "b2j_multi_destroy", "b2j_multi_encode", "b2j_multi_encode_begin", "b2j_multi_encode_fetch",
            "b2j_multi_last_error",
            "b2j_strip_state_get", "b2j_strip_phase1", "b2j_strip_phase1b", "b2j_strip_phase2", "b2j_strip_phase3", "b2j_strip_phase3_dev", "b2j_strip_phase1x", "b2j_strip_phase2x", "b2j_peer_export", "b2j_peer_open", "b2j_peer_connect", "b2j_set_restart_rows",
@@ -106,6 +111,8 @@ def lib():
     L.b2j_decode_scan_device.argtypes = [vp, u8p, sz, vp, sz, i, vp, sz, C.POINTER(i), C.POINTER(i)]
     L.b2j_secondary_fetch.argtypes = [vp, u8p, sz, u8p, sz, u8p, sz]
     L.b2j_reconstruct_device.argtypes = [vp, vp, sz]
+    L.b2j_reconstruct_planes.argtypes = [vp, C.POINTER(ReconPlanes)]
+    L.b2j_reconstruct_color.argtypes = [vp, vp, sz, i, i]
     L.b2j_secondary_device.argtypes = [vp, vp, sz, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.b2j_secondary_finish.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.b2j_strip_state_get.argtypes = [vp, C.POINTER(StripState)]

@@ -1139,19 +1139,30 @@ int b2j_psnr(b2j_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, double 
 // Reconstruction without an entropy decode: the pixels every decoder will produce from the LAST encode of this
 // context, from the quantised coefficients k_fdct kept (B2J_DEBUG_COEF set before that encode): de-quantise + islow
 // IDCT + fancy upsampling + YCbCr->BGR, the decoder's own kernels. Asynchronous on the context's stream.
-int b2j_reconstruct_device(b2j_ctx *ctx, uint8_t *d_bgr, size_t step) {
-    if (!ctx || !d_bgr) return B2J_EINVAL;
-    if (!ctx->enc_ready || !(ctx->debug & 1) || !ctx->d_coef) { snprintf(ctx->err, sizeof(ctx->err), "b2j_reconstruct_device needs an encode with B2J_DEBUG_COEF set"); return B2J_EINVAL; }
+static int recon_layout(b2j_ctx *ctx, uint8_t **py, uint8_t **pcb, uint8_t **pcr) {
     const Geom &g = ctx->g;
-    if (step < (size_t)g.W * 3) return B2J_EINVAL;
-    CK(cudaSetDevice(ctx->device));
+    const size_t cs = (size_t)g.mcux * 8;   // chroma row pitch; one spare row above and below every chroma plane (halos)
     const size_t ysz = ((size_t)g.mcux * 8 * g.hs * g.mcuy * 8 * g.vs + 63) & ~(size_t)63;
-    const size_t csz = ((size_t)g.mcux * 8 * g.mcuy * 8 + 63) & ~(size_t)63;
+    const size_t csz = (cs * ((size_t)g.mcuy * 8 + 2) + 63) & ~(size_t)63;
     if (ctx->rplanes_bytes < ysz + 2 * csz + 256) {
         cudaFree(ctx->d_rplanes); ctx->d_rplanes = nullptr; ctx->rplanes_bytes = 0;
         CK(cudaMalloc(&ctx->d_rplanes, ysz + 2 * csz + 256));
         ctx->rplanes_bytes = ysz + 2 * csz + 256;
     }
+    *py = ctx->d_rplanes; *pcb = *py + ysz + cs; *pcr = *pcb + csz;
+    return B2J_OK;
+}
+
+// First half of the reconstruction: de-quantise + IDCT of the coefficients the last encode kept -> sample planes.
+// A strip of a larger image (several GPUs) then fetches one chroma row from each neighbour strip into its halo rows
+// before b2j_reconstruct_color: the vertical chroma filter of 4:2:0 / 4:4:0 looks one row across the border.
+int b2j_reconstruct_planes(b2j_ctx *ctx, b2j_recon_planes *out) {
+    if (!ctx) return B2J_EINVAL;
+    if (!ctx->enc_ready || !(ctx->debug & 1) || !ctx->d_coef) { snprintf(ctx->err, sizeof(ctx->err), "b2j_reconstruct_* needs an encode with B2J_DEBUG_COEF set"); return B2J_EINVAL; }
+    const Geom &g = ctx->g;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *py, *pcb, *pcr;
+    int rc = recon_layout(ctx, &py, &pcb, &pcr); if (rc) return rc;
     if (!ctx->d_rtb) {
         std::vector<uint8_t> h(dec_tables_size(), 0);
         DecTables *t = reinterpret_cast<DecTables *>(h.data());
@@ -1159,11 +1170,37 @@ int b2j_reconstruct_device(b2j_ctx *ctx, uint8_t *d_bgr, size_t step) {
         CK(cudaMalloc(&ctx->d_rtb, dec_tables_size()));
         CK(cudaMemcpy(ctx->d_rtb, h.data(), h.size(), cudaMemcpyHostToDevice));
     }
-    uint8_t *py = ctx->d_rplanes, *pcb = py + ysz, *pcr = pcb + csz;
     CK(launch_idct(ctx->d_coef, nullptr, g, ctx->d_rtb, py, pcb, pcr, 0, ctx->stream));
-    CK(launch_upcolor(py, pcb, pcr, g, d_bgr, step, ctx->stream));
-    ctx->launches += 2;
+    ctx->launches += 1;
+    if (out) {
+        const size_t cs = (size_t)g.mcux * 8;
+        const int dh = g.dh[1];
+        out->row_bytes = (size_t)g.dw[1];
+        out->cb_first = pcb; out->cr_first = pcr;
+        out->cb_last = pcb + (size_t)(dh - 1) * cs; out->cr_last = pcr + (size_t)(dh - 1) * cs;
+        out->cb_halo_top = pcb - cs; out->cr_halo_top = pcr - cs;
+        out->cb_halo_bottom = pcb + (size_t)dh * cs; out->cr_halo_bottom = pcr + (size_t)dh * cs;
+    }
     return B2J_OK;
+}
+
+// Second half: upsampling + colour conversion of the planes. halo_top / halo_bottom != 0: the halo rows are filled.
+int b2j_reconstruct_color(b2j_ctx *ctx, uint8_t *d_bgr, size_t step, int halo_top, int halo_bottom) {
+    if (!ctx || !d_bgr || !ctx->d_rplanes) return B2J_EINVAL;
+    const Geom &g = ctx->g;
+    if (step < (size_t)g.W * 3) return B2J_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *py, *pcb, *pcr;
+    int rc = recon_layout(ctx, &py, &pcb, &pcr); if (rc) return rc;
+    CK(launch_upcolor(py, pcb, pcr, g, d_bgr, step, ctx->stream, halo_top, halo_bottom));
+    ctx->launches += 1;
+    return B2J_OK;
+}
+
+int b2j_reconstruct_device(b2j_ctx *ctx, uint8_t *d_bgr, size_t step) {
+    if (!ctx || !d_bgr) return B2J_EINVAL;
+    int rc = b2j_reconstruct_planes(ctx, nullptr); if (rc) return rc;
+    return b2j_reconstruct_color(ctx, d_bgr, step, 0, 0);
 }
 
 // Secondary compression, device resident and asynchronous: encode -> reconstruct from the encoder's own coefficients

@@ -862,7 +862,7 @@ k_idct(const int16_t *__restrict__ coef, const int16_t *__restrict__ dcarr, Geom
 // k_upcolor: jdsample.c fancy upsampling (h2v1 / h2v2 / h1v2 triangle filters, h4v1 replication) on the TRUE
 // downsampled size + jdcolor.c YCbCr->RGB, 8 pixels per thread, stored interleaved B,G,R (cv::Mat CV_8UC3).
 template <int HS, int VS>
-__device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, size_t stride, int dw, int dh, int x, int y) {
+__device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, size_t stride, int dw, int rlo, int rhi, int x, int y) {
     if (HS == 1 && VS == 1) return p[(size_t)y * stride + x];
     if (HS == 4) return p[(size_t)y * stride + (x >> 2)];
     if (HS == 2 && VS == 1) {
@@ -874,13 +874,13 @@ __device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, size_t s
     }
     if (HS == 1 && VS == 2) {
         const int r = y >> 1;
-        const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+        const int rn = (y & 1) ? min(r + 1, rhi) : max(r - 1, rlo);
         return (3 * p[(size_t)r * stride + x] + p[(size_t)rn * stride + x] + ((y & 1) ? 2 : 1)) >> 2;
     }
     // h2v2
     const int r = y >> 1, i = x >> 1;
     if (dw <= 2) return p[(size_t)r * stride + i];
-    const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+    const int rn = (y & 1) ? min(r + 1, rhi) : max(r - 1, rlo);
     const uint8_t *r0 = p + (size_t)r * stride, *r1 = p + (size_t)rn * stride;
     const int s = 3 * r0[i] + r1[i];
     if (x & 1) return i < dw - 1 ? (3 * s + 3 * r0[i + 1] + r1[i + 1] + 7) >> 4 : (4 * s + 7) >> 4;
@@ -889,7 +889,7 @@ __device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, size_t s
 
 // the same eight upsampled chroma samples for an INTERIOR group (every neighbour exists): word loads, no edge tests
 template <int HS, int VS>
-__device__ __forceinline__ void chroma8_interior(const uint8_t *__restrict__ p, size_t stride, int dh, int x0, int y, int (&c)[8]) {
+__device__ __forceinline__ void chroma8_interior(const uint8_t *__restrict__ p, size_t stride, int rlo, int rhi, int x0, int y, int (&c)[8]) {
     auto six = [](const uint8_t *row, int i0, int (&s)[6]) {   // samples i0 - 1 .. i0 + 4 (i0 % 4 == 0)
         const uint32_t w = *reinterpret_cast<const uint32_t *>(row + i0);
         s[0] = row[i0 - 1];
@@ -915,7 +915,7 @@ __device__ __forceinline__ void chroma8_interior(const uint8_t *__restrict__ p, 
         }
     } else if (HS == 1 && VS == 2) {
         const int r = y >> 1;
-        const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+        const int rn = (y & 1) ? min(r + 1, rhi) : max(r - 1, rlo);
         const uint2 a = *reinterpret_cast<const uint2 *>(p + (size_t)r * stride + x0);
         const uint2 bq = *reinterpret_cast<const uint2 *>(p + (size_t)rn * stride + x0);
         const int bias = (y & 1) ? 2 : 1;
@@ -926,7 +926,7 @@ __device__ __forceinline__ void chroma8_interior(const uint8_t *__restrict__ p, 
         }
     } else {   // h2v2
         const int r = y >> 1;
-        const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+        const int rn = (y & 1) ? min(r + 1, rhi) : max(r - 1, rlo);
         int s0[6], s1[6], t[6];
         six(p + (size_t)r * stride, x0 >> 1, s0);
         six(p + (size_t)rn * stride, x0 >> 1, s1);
@@ -943,21 +943,21 @@ __device__ __forceinline__ void chroma8_interior(const uint8_t *__restrict__ p, 
 template <int HS, int VS>
 __global__ void __launch_bounds__(256)
 k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const uint8_t *__restrict__ pcr, Geom g,
-          uint8_t *__restrict__ bgr, size_t step) {
+          uint8_t *__restrict__ bgr, size_t step, int rlo, int rhi) {   // rlo / rhi: first / last chroma row the vertical filter may read
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 pixels
     const int y = blockIdx.y;
     const int x0 = gx * 8;
     if (x0 >= g.W) return;
     const size_t ys = (size_t)g.mcux * 8 * HS, cs = (size_t)g.mcux * 8;
-    const int dw = g.dw[1], dh = g.dh[1];
+    const int dw = g.dw[1];
     uint8_t *dst = bgr + (size_t)y * step + (size_t)x0 * 3;
     uint8_t o[24];
     // interior groups (all neighbours of all eight pixels exist, 8-byte aligned destination): vector loads and stores
     if (x0 >= 8 && x0 + 16 <= g.W && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         const uint2 yw = *reinterpret_cast<const uint2 *>(py + (size_t)y * ys + x0);
         int cbv[8], crv[8];
-        chroma8_interior<HS, VS>(pcb, cs, dh, x0, y, cbv);
-        chroma8_interior<HS, VS>(pcr, cs, dh, x0, y, crv);
+        chroma8_interior<HS, VS>(pcb, cs, rlo, rhi, x0, y, cbv);
+        chroma8_interior<HS, VS>(pcr, cs, rlo, rhi, x0, y, crv);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int Y = (int)(((i < 4 ? yw.x : yw.y) >> (8 * (i & 3))) & 0xFF);
@@ -983,8 +983,8 @@ k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const
     for (int i = 0; i < 8; i++) {
         const int x = min(x0 + i, g.W - 1);
         const int Y = py[(size_t)y * ys + x];
-        const int cb = chroma_at<HS, VS>(pcb, cs, dw, dh, x, y) - 128;
-        const int cr = chroma_at<HS, VS>(pcr, cs, dw, dh, x, y) - 128;
+        const int cb = chroma_at<HS, VS>(pcb, cs, dw, rlo, rhi, x, y) - 128;
+        const int cr = chroma_at<HS, VS>(pcr, cs, dw, rlo, rhi, x, y) - 128;
         const int r = Y + ((91881 * cr + 32768) >> 16);
         const int b = Y + ((116130 * cb + 32768) >> 16);
         const int gg = Y + ((-22554 * cb - 46802 * cr + 32768) >> 16);
@@ -1087,19 +1087,19 @@ cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g
 
 template <int HS, int VS>
 static cudaError_t upcolor_one(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr,
-                               size_t step, cudaStream_t s) {
+                               size_t step, int halo_top, int halo_bottom, cudaStream_t s) {
     dim3 grid(((g.W + 7) / 8 + 255) / 256, g.H);
-    k_upcolor<HS, VS><<<grid, 256, 0, s>>>(py, pcb, pcr, g, bgr, step);
+    k_upcolor<HS, VS><<<grid, 256, 0, s>>>(py, pcb, pcr, g, bgr, step, halo_top ? -1 : 0, halo_bottom ? g.dh[1] : g.dh[1] - 1);
     return cudaGetLastError();
 }
 
 cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr, size_t step,
-                           cudaStream_t s) {
-    if (g.hs == 1 && g.vs == 1) return upcolor_one<1, 1>(py, pcb, pcr, g, bgr, step, s);
-    if (g.hs == 2 && g.vs == 1) return upcolor_one<2, 1>(py, pcb, pcr, g, bgr, step, s);
-    if (g.hs == 1 && g.vs == 2) return upcolor_one<1, 2>(py, pcb, pcr, g, bgr, step, s);
-    if (g.hs == 2 && g.vs == 2) return upcolor_one<2, 2>(py, pcb, pcr, g, bgr, step, s);
-    if (g.hs == 4 && g.vs == 1) return upcolor_one<4, 1>(py, pcb, pcr, g, bgr, step, s);
+                           cudaStream_t s, int halo_top, int halo_bottom) {
+    if (g.hs == 1 && g.vs == 1) return upcolor_one<1, 1>(py, pcb, pcr, g, bgr, step, halo_top, halo_bottom, s);
+    if (g.hs == 2 && g.vs == 1) return upcolor_one<2, 1>(py, pcb, pcr, g, bgr, step, halo_top, halo_bottom, s);
+    if (g.hs == 1 && g.vs == 2) return upcolor_one<1, 2>(py, pcb, pcr, g, bgr, step, halo_top, halo_bottom, s);
+    if (g.hs == 2 && g.vs == 2) return upcolor_one<2, 2>(py, pcb, pcr, g, bgr, step, halo_top, halo_bottom, s);
+    if (g.hs == 4 && g.vs == 1) return upcolor_one<4, 1>(py, pcb, pcr, g, bgr, step, halo_top, halo_bottom, s);
     return cudaErrorInvalidValue;
 }
 

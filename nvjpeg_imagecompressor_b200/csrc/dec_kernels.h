@@ -46,8 +46,10 @@ cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_
 // rst_mcus: restart interval in MCUs (0: none): DC predictors return to 0 at every interval start
 cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb,
                         uint8_t *pcr, int rst_mcus, cudaStream_t s);
+// halo_top / halo_bottom: the chroma planes hold one valid row above row 0 / below the last row (a strip of a larger
+// image: the vertical filter of 4:2:0 / 4:4:0 then reads the neighbour strip's row instead of replicating the edge)
 cudaError_t launch_upcolor(const uint8_t *py, const uint8_t *pcb, const uint8_t *pcr, const Geom &g, uint8_t *bgr, size_t step,
-                           cudaStream_t s);
+                           cudaStream_t s, int halo_top = 0, int halo_bottom = 0);
 
 // progressive files (dec_prog.cu): all scans into d_coef, then IDCT + upsampling; synchronises the stream before returning
 int dec_progressive(const uint8_t *jpg, size_t len, const ProgInfo &info, const Geom &g, int16_t *d_coef, void *d_tb,

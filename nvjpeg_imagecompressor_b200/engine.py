@@ -127,6 +127,15 @@ class Engine:
         """Pixels of the last encode (made with set_debug(1)) from its quantised coefficients; asynchronous."""
         self._ck(self._L.b2j_reconstruct_device(self._h, C.c_void_p(d_bgr_ptr), step))
 
+    def reconstruct_planes(self):
+        """First half of reconstruct_device (de-quantise + IDCT); -> N.ReconPlanes (device pointers of the edge / halo rows)."""
+        rp = N.ReconPlanes()
+        self._ck(self._L.b2j_reconstruct_planes(self._h, C.byref(rp)))
+        return rp
+
+    def reconstruct_color(self, d_bgr_ptr, step, halo_top=False, halo_bottom=False):
+        self._ck(self._L.b2j_reconstruct_color(self._h, C.c_void_p(d_bgr_ptr), step, int(halo_top), int(halo_bottom)))
+
     def secondary_device(self, d_ptr, step, W, H, diff_mode=1):
         """Device-resident secondary compression, asynchronous -> device pointers (jpg1, jpg2, recon, diff)."""
         p = [C.c_void_p() for _ in range(4)]

@@ -239,11 +239,12 @@ class StripSecondary:
     encode(difference) + PSNR, every step on the rank's own MCU-row strip; both JPEG streams are stitched single-image
     streams (two StripEncoders), the PSNR comes from an all_reduce of the strips' exact integer SSDs.
 
-    The strip is reconstructed from the quantised coefficients its own encoder produced (b2j_reconstruct_device), which
-    needs no exchange when the sampling has no vertical subsampling (444 / 422 / 411): quantisation, IDCT and the
+    The strip is reconstructed from the quantised coefficients its own encoder produced (b2j_reconstruct_planes /
+    _color). Without vertical subsampling (444 / 422 / 411) that needs no exchange: quantisation, IDCT and the
     horizontal triangle upsampling never look across an MCU row, so the strip gives exactly the rows the whole image's
-    decode would give (tests/test_gpu_strips.py). 420 / 440 upsample vertically across strip borders and are refused
-    for world > 1.
+    decode would give (tests/test_gpu_strips.py). 420 / 440 upsample vertically with a filter that looks one chroma row
+    across the strip border: neighbouring ranks swap that one Cb and one Cr row (a point-to-point exchange of
+    2 * ceil(W / hs) bytes per border, dist.batch_isend_irecv) between the IDCT and the colour step.
     """
 
     def __init__(self, W, H, quality=95, optimize=True, css="422", diff_mode=1, rank=None, world=None, device=None,
@@ -254,9 +255,12 @@ class StripSecondary:
         self.enc1 = StripEncoder(W, H, quality, optimize, css_id, rank, world, None, device, group)
         self.enc2 = StripEncoder(W, H, quality, optimize, css_id, rank, world, None, device, group)
         self.rank, self.world = self.enc1.rank, self.enc1.world
-        if self.world > 1 and _VS[css_id] != 1:
-            raise ValueError("secondary compression over strips needs a sampling without vertical subsampling")
         self.y0, self.y1 = self.enc1.y0, self.enc1.y1
+        # halo exchange partners: only for a vertical chroma filter; ranks without rows (world > MCU rows) sit at the tail
+        rows = self.enc1.rows
+        vert = _VS[css_id] != 1 and self.y1 > self.y0
+        self.halo_top = vert and self.rank > 0
+        self.halo_bottom = vert and self.rank + 1 < self.world and rows[self.rank + 1][1] > rows[self.rank + 1][0]
         rows_max = max(b - a for a, b in self.enc1.rows)
         dev = self.enc1.b.device
         self.recon = torch.empty((rows_max, W, 3), dtype=torch.uint8, device=dev)
@@ -282,7 +286,11 @@ class StripSecondary:
         n1 = self.enc1.encode_strip(d_ptr, step)
         # the strip's pixels as every decoder will reconstruct them: de-quantise + IDCT + upsample of the coefficients
         # the encoder just produced (b2j_reconstruct_device) -- nothing is encoded twice, decoded or sent to the host
-        self.enc1.b.eng.reconstruct_device(self.recon.data_ptr(), W * 3)
+        eng = self.enc1.b.eng
+        rp = eng.reconstruct_planes()
+        if self.halo_top or self.halo_bottom:
+            self._swap_halos(rp)
+        eng.reconstruct_color(self.recon.data_ptr(), W * 3, self.halo_top, self.halo_bottom)
         ssd_ptr = self.enc2.b.eng.diff_psnr_device(d_ptr, self.recon.data_ptr(), rows * W * 3, self.mode, self.diff.data_ptr())
         self._ssd.copy_(_view(ssd_ptr, (1,), "<i8", self.recon.device))
         if self.world > 1:
@@ -291,6 +299,24 @@ class StripSecondary:
         ssd = int(self._ssd.item())
         psnr = 20.0 * np.log10(255.0 / (np.sqrt(ssd / (self.W * self.H * 3)) + 2.220446049250313e-16))   # cv::PSNR
         return n1, n2, float(psnr)
+
+
+    def _swap_halos(self, rp):
+        """One chroma row each way across every strip border this rank has (Cb then Cr, the same order on both sides)."""
+        dev, n = self.recon.device, int(rp.row_bytes)
+        v = lambda p: _view(p, (n,), "|u1", dev)
+        peer = lambda r: dist.get_global_rank(self.group, r) if self.group is not None else r
+        ops = []
+        if self.halo_top:
+            up = peer(self.rank - 1)
+            ops += [dist.P2POp(dist.isend, v(rp.cb_first), up, self.group), dist.P2POp(dist.isend, v(rp.cr_first), up, self.group),
+                    dist.P2POp(dist.irecv, v(rp.cb_halo_top), up, self.group), dist.P2POp(dist.irecv, v(rp.cr_halo_top), up, self.group)]
+        if self.halo_bottom:
+            dn = peer(self.rank + 1)
+            ops += [dist.P2POp(dist.isend, v(rp.cb_last), dn, self.group), dist.P2POp(dist.isend, v(rp.cr_last), dn, self.group),
+                    dist.P2POp(dist.irecv, v(rp.cb_halo_bottom), dn, self.group), dist.P2POp(dist.irecv, v(rp.cr_halo_bottom), dn, self.group)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
 
 
 # ---------------------------------------------------------------------------------------------------------------

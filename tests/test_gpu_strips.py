@@ -171,6 +171,40 @@ def test_strip_decodes_alone_to_the_images_rows(oracle, css):
     full.close()
 
 
+@pytest.mark.parametrize("css,W,H,n", [("420", 200, 160, 3), ("440", 131, 203, 4), ("420", 64, 250, 8), ("422", 96, 64, 2)])
+def test_strips_reconstruct_with_chroma_halos(oracle, css, W, H, n):
+    """Vertical subsampling: the strips' planes + one chroma row swapped across every border (what StripSecondary sends
+    between ranks) + the colour step = the whole image's decode, bit for bit."""
+    import nvjpeg_imagecompressor_b200 as P
+    from nvjpeg_imagecompressor_b200 import _native as N
+    from nvjpeg_imagecompressor_b200.strips import _view, strip_rows
+    img = oracle.synth(W, H, 11, 8)
+    whole = oracle.decode(oracle.encode(img, N.CSS[css], 90, 1))
+    d = torch.from_numpy(img).cuda()
+    rows = [r for r in strip_rows(H, N.CSS[css], n) if r[1] > r[0]]
+    engs, rps = [], []
+    for y0, y1 in rows:
+        e = P.Engine(W, y1 - y0, 90, True, css)
+        e.set_debug(1)
+        e.encode_device(d[y0:y1].data_ptr(), W * 3, W, y1 - y0)
+        engs.append(e)
+        rps.append(e.reconstruct_planes())
+    torch.cuda.synchronize()
+    v = lambda p, rp: _view(p, (int(rp.row_bytes),), "|u1", d.device)
+    for k in range(len(rows) - 1):
+        a, b = rps[k], rps[k + 1]
+        v(a.cb_halo_bottom, a).copy_(v(b.cb_first, b)); v(a.cr_halo_bottom, a).copy_(v(b.cr_first, b))
+        v(b.cb_halo_top, b).copy_(v(a.cb_last, a)); v(b.cr_halo_top, b).copy_(v(a.cr_last, a))
+    torch.cuda.synchronize()
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=d.device)
+    for k, (e, (y0, y1)) in enumerate(zip(engs, rows)):
+        e.reconstruct_color(out[y0:y1].data_ptr(), W * 3, k > 0, k + 1 < len(rows))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), whole)
+    for e in engs:
+        e.close()
+
+
 def test_strip_secondary_world1_equals_b2j_secondary(oracle):
     import nvjpeg_imagecompressor_b200 as P
     from nvjpeg_imagecompressor_b200.strips import StripSecondary
