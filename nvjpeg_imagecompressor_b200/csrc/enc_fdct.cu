@@ -528,12 +528,18 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
 __global__ void __launch_bounds__(256)
 k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restrict__ pred_in,
                uint32_t *__restrict__ ghist, int16_t *__restrict__ last_dc, int do_hist,
-               uint32_t *__restrict__ pool, int resolve, StripRecord *__restrict__ xr, int rst_tiles) {
+               uint32_t *__restrict__ pool, int resolve, StripRecord *__restrict__ xr, int rst_tiles,
+               uint32_t *__restrict__ fuse_zero) {
     __shared__ uint32_t s_h[2][16];   // DC categories 0..11 of the two DC tables, aggregated per CTA
     pdl_trigger();
     pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ntile = g.tiles_x * g.mcuy;
+    // k_pack_stuff's per-tile look-back state (two descriptors + the tail word: 5 words per tile), cleared on the way
+    if (fuse_zero && t < ntile * 3) {
+        if (2 * t < 5 * ntile) fuse_zero[2 * t] = 0;
+        if (2 * t + 1 < 5 * ntile) fuse_zero[2 * t + 1] = 0;
+    }
     if (threadIdx.x < 32) s_h[threadIdx.x >> 4][threadIdx.x & 15] = 0;
     __syncthreads();
     if (t < ntile * 3 && (do_hist || resolve) && !(xr && t < 3)) {
@@ -618,9 +624,10 @@ cudaError_t launch_fdct(const uint8_t *img, size_t step, const Geom &g, const Qu
 }
 
 cudaError_t launch_dc_edge_hist(const TileRec *recs, const Geom &g, const int16_t *pred_in, uint32_t *hist,
-                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, int rst_tiles, cudaStream_t s) {
+                                int16_t *last_dc, int do_hist, uint32_t *pool, int resolve, StripRecord *xr, int rst_tiles, cudaStream_t s,
+                                uint32_t *fuse_zero) {
     const int n = max(64, g.tiles_x * g.mcuy * 3);
-    return launch_pdl(k_dc_edge_hist, dim3((n + 255) / 256), dim3(256), 0, s, recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr, rst_tiles);
+    return launch_pdl(k_dc_edge_hist, dim3((n + 255) / 256), dim3(256), 0, s, recs, g, pred_in, hist, last_dc, do_hist, pool, resolve, xr, rst_tiles, fuse_zero);
 }
 
 }  // namespace b2j

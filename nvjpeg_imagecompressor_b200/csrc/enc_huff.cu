@@ -403,8 +403,8 @@ __device__ __forceinline__ void load_tokens(const uint4 *tk4, uint32_t v0, uint3
 }
 
 // The warp's share [lo, hi) of the walk, coded into `buf` starting at bit `run`; returns the bit position after it.
-template <bool WINDOWED>
-__device__ __forceinline__ int pack_scatter(const PackShared &sh, uint32_t *buf, uint32_t nwords, const uint4 *tk4, uint32_t a,
+template <bool WINDOWED, class SH>
+__device__ __forceinline__ int pack_scatter(const SH &sh, uint32_t *buf, uint32_t nwords, const uint4 *tk4, uint32_t a,
                                             uint32_t lo, uint32_t hi, int run, int lane, uint32_t zr_y, uint32_t zr_c) {
     for (uint32_t s0 = lo; s0 < hi; s0 += PACK_STEP) {
         const uint32_t v0 = s0 + lane * PACK_K;
@@ -458,7 +458,8 @@ __device__ __forceinline__ int pack_scatter(const PackShared &sh, uint32_t *buf,
 }
 
 // bits of the warp's share without coding them (two-pass path)
-__device__ __forceinline__ uint32_t pack_length(const PackShared &sh, const uint4 *tk4, uint32_t a, uint32_t lo, uint32_t hi, int lane) {
+template <class SH>
+__device__ __forceinline__ uint32_t pack_length(const SH &sh, const uint4 *tk4, uint32_t a, uint32_t lo, uint32_t hi, int lane) {
     uint32_t len = 0;
     for (uint32_t v0 = lo + lane * PACK_K; v0 < hi; v0 += PACK_STEP) {
         uint32_t w[PACK_K];
@@ -493,18 +494,11 @@ __device__ __forceinline__ void pack_flush_shared_words(uint32_t *bnd, const uin
     if (last != 0xffffffffu) slot[last] = acc;
 }
 
-__global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
-k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int ntiles, const HuffDev *huff,
-       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits, uint32_t sub_words) {
-    __shared__ __align__(16) PackShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < WIN_WORDS; i += PACK_THREADS) sh.buf[i] = 0;
-    for (int i = tid; i < PACK_WARPS * (SUB_WORDS + 4); i += PACK_THREADS) sh.sub[0][i] = 0;
-    if (tid < 2 * (PACK_WARPS + 1)) sh.bnd[0][tid] = 0;
-    pdl_wait();   // everything above ran under k_tables
-    // code tables in token-bin order (common.cuh tok_bin): code << size, and the full length per (ZRL count, bin).
-    // The tables are k_tables' output: every load of them must stay behind pdl_wait() (volatile: a load through a
-    // const __restrict__ pointer may be hoisted above the wait).
+// Code tables in token-bin order (common.cuh tok_bin): code << size, and the full length per (ZRL count, bin); -> the
+// ZRL (0xF0) codes of the two AC tables as code << 8 | length. The tables are k_tables' output: every load of them must
+// stay behind pdl_wait() (volatile: a load through a const __restrict__ pointer may be hoisted above the wait).
+template <class SH>
+__device__ __forceinline__ void pack_build_tables(SH &sh, const HuffDev *huff, int tid, uint32_t &zr_y, uint32_t &zr_c) {
     const volatile HuffDev *vh = huff;
     for (int i = tid; i < 1024; i += PACK_THREADS) {
         const uint32_t bin = (uint32_t)i, t = bin_table(bin), nb = (bin >> 2) & 15u;
@@ -516,9 +510,8 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
         sh.len[bin] = (uint8_t)(l ? l + nb : 0u);
     }
     __syncthreads();
-    // ZRL (0xF0) codes of the two AC tables: code << 8 | length
-    const uint32_t zr_y = (sh.code[tok_bin(1, 0xF0)] << 8) | sh.len[tok_bin(1, 0xF0)];
-    const uint32_t zr_c = (sh.code[tok_bin(3, 0xF0)] << 8) | sh.len[tok_bin(3, 0xF0)];
+    zr_y = (sh.code[tok_bin(1, 0xF0)] << 8) | sh.len[tok_bin(1, 0xF0)];
+    zr_c = (sh.code[tok_bin(3, 0xF0)] << 8) | sh.len[tok_bin(3, 0xF0)];
     for (int i = 1024 + tid; i < 4096; i += PACK_THREADS) {   // ZRL counts 1..3 (AC tokens only)
         const uint32_t bin = (uint32_t)i & 0x3FFu, nz = (uint32_t)i >> 10, l = sh.len[bin];
         const uint32_t t = bin_table(bin);
@@ -526,6 +519,19 @@ k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int 
         sh.len[i] = (uint8_t)((l && (t & 1u)) ? l + nz * zl : l);
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
+k_pack(const uint32_t *__restrict__ pool, const TileRec *__restrict__ recs, int ntiles, const HuffDev *huff,
+       uint32_t *__restrict__ slots, uint32_t *__restrict__ tile_bits, uint32_t sub_words) {
+    __shared__ __align__(16) PackShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < WIN_WORDS; i += PACK_THREADS) sh.buf[i] = 0;
+    for (int i = tid; i < PACK_WARPS * (SUB_WORDS + 4); i += PACK_THREADS) sh.sub[0][i] = 0;
+    if (tid < 2 * (PACK_WARPS + 1)) sh.bnd[0][tid] = 0;
+    pdl_wait();   // everything above ran under k_tables
+    uint32_t zr_y, zr_c;
+    pack_build_tables(sh, huff, tid, zr_y, zr_c);
     uint32_t *sub = sh.sub[wid];
 
     bool pend = false;      // the previous tile's shared words are still in their cells
@@ -1009,6 +1015,411 @@ k_stuff(StuffArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_pack_stuff: k_pack, the tile scan and k_stuff in ONE kernel for whole-image encodes without restart markers -- the
+// tile slots never travel through HBM and the second kernel's latency chain is gone. Tiles are handed out by a ticket
+// (so every predecessor of a tile is running or done) and go through
+//   1. k_pack's coding of the warps' shares into their own bit buffers (same code)
+//   2. decoupled look-back #1 over the tiles' BIT counts -> G = the tile's bit offset in the entropy-coded segment.
+//      The tile owns the stream bytes that END inside it: the first one starts with the G & 7 last bits of the tile
+//      before (published per tile next to the descriptor: `tail`), the bits after its last whole byte go to the next.
+//   3. the shares are shifted into one tile-wide bit string in shared memory (word 0: the predecessor's tail bits)
+//   4. 16-byte pieces of that string (one per thread and round, FUSE_NP rounds): 0xFF count -> CTA scan -> the tile's
+//      stuffed size -> decoupled look-back #2 over the BYTE counts -> the tile's place in the output
+//   5. round by round: bytes staged with their 0x00s at tile-local offsets (the warp buffers' memory, two halves),
+//      copied out as 16-byte vectors (k_stuff's code)
+// Dense tiles (bits that do not fit the shared buffers) are rare: their bit string goes window by window into the
+// tile's slot in global memory as in k_pack and is stuffed from there, 8 KB at a time, after a counting pass.
+constexpr int FUSE_BUF_WORDS = WIN_WORDS + 16;          // word 0 = lead, bits from word 1, zero words behind
+constexpr int FUSE_ROUND = PACK_THREADS * 16;           // unstuffed bytes per round: one 16-byte piece per thread
+constexpr int FUSE_NP = 4;                              // rounds per span: 8 KB = the most a shared-memory tile holds
+constexpr int FUSE_SPAN = FUSE_NP * FUSE_ROUND;
+constexpr int FUSE_STAGE_WORDS = (2 * FUSE_ROUND + 64) / 4;
+constexpr int FUSE_SUB_PAD = 20;
+static_assert(PACK_WARPS * (SUB_WORDS + FUSE_SUB_PAD) >= 2 * FUSE_STAGE_WORDS, "the warp buffers double as two staging halves");
+static_assert(FUSE_SPAN * 8 >= WIN_WORDS * 32, "a shared-memory tile is one span");
+
+struct FusedShared {
+    uint32_t buf[FUSE_BUF_WORDS];
+    uint32_t sub[PACK_WARPS][SUB_WORDS + FUSE_SUB_PAD];
+    uint32_t code[1024];
+    uint8_t len[4096];
+    uint32_t wlen[PACK_WARPS];
+    uint32_t wtail[PACK_WARPS];                   // the last min(8, length) bits of every share
+    uint32_t s_warp[FUSE_NP][PACK_WARPS];
+    uint32_t lut[16];
+    uint64_t G, goff;
+    int tile;
+};
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// the last 8 bits of the stream up to the end of tile t (published by the tile's CTA as soon as it has coded them)
+__device__ __forceinline__ uint32_t fuse_wait_tail(const uint32_t *tail, int t, uint32_t *err) {
+    uint32_t v = ld_volatile_u32(&tail[t]);
+    unsigned spins = 0;
+    while (!(v >> 31)) {
+        __nanosleep(20);
+        v = ld_volatile_u32(&tail[t]);
+        if (++spins > (1u << 22)) { *err = 1; break; }   // never hang the GPU
+    }
+    return v & 0xFFu;
+}
+
+// 16 bytes of the byte string that starts at bit (32 * w0 - s') of src, s' = (32 - s) & 31: piece j, MSB first
+__device__ __forceinline__ void fuse_load_piece(const uint32_t *src, uint32_t w0, uint32_t s, uint32_t j, uint32_t (&w)[4]) {
+    const uint32_t *p = src + w0 + 4u * j;
+    uint32_t x[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) x[q] = p[q];
+#pragma unroll
+    for (int q = 0; q < 4; q++) w[q] = __funnelshift_l(x[q + 1], x[q], s);
+}
+// 0xFF bytes among the first nvalid bytes of a piece
+__device__ __forceinline__ uint32_t fuse_count_ff(const uint32_t (&w)[4], int nvalid) {
+    uint32_t nff = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t m = w[q] & (w[q] >> 4) & 0x0F0F0F0Fu;
+        m &= m >> 2;
+        m &= m >> 1;
+        m &= 0x01010101u;
+        if (nvalid < 16) {
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+                if (4 * q + bb >= nvalid) m &= ~(1u << (24 - 8 * bb));
+        }
+        nff += __popc(m);
+    }
+    return nff;
+}
+
+struct FuseArgs {
+    const uint32_t *pool;
+    const TileRec *recs;
+    int ntiles;
+    const HuffDev *huff;
+    uint32_t *slots;
+    uint32_t *tile_bits;
+    uint32_t sub_words;
+    uint64_t *desc_bits, *desc_bytes;   // look-back descriptors, one per tile (zeroed)
+    uint32_t *tail;                     // per tile: 1 << 31 | its last 8 bits (zeroed)
+    uint32_t *ticket;                   // zeroed
+    uint8_t *out;
+    size_t cap;
+    uint64_t *out_len;
+    uint32_t *err;
+};
+
+// Bytes [0, nb) (nb <= FUSE_SPAN) of the byte string at (src, w0, s): stuffed and written to a.out. LOOKBACK: the span
+// is the whole tile -- its stuffed size goes through look-back #2 and gives the place; otherwise `goff` is the place.
+// Returns the stuffed size. Every thread of the CTA calls it; the staging halves must be zero and are zero afterwards.
+template <bool LOOKBACK>
+__device__ __forceinline__ uint32_t fuse_stuff_span(FusedShared &sh, const FuseArgs &a, const uint32_t *src, uint32_t w0, uint32_t s,
+                                                    uint32_t nb, uint64_t goff, int t, uint32_t hdr, bool last_span) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t *stage = &sh.sub[0][0];
+    uint32_t cnt[FUSE_NP], inc[FUSE_NP];
+#pragma unroll
+    for (int i = 0; i < FUSE_NP; i++) {
+        const uint32_t jb = (uint32_t)i * FUSE_ROUND + (uint32_t)tid * 16u;
+        cnt[i] = 0;
+        if ((uint32_t)i * FUSE_ROUND < nb && jb < nb) {
+            const int nvalid = (int)min(16u, nb - jb);
+            uint32_t w[4];
+            fuse_load_piece(src, w0, s, jb >> 4, w);
+            cnt[i] = (uint32_t)nvalid + fuse_count_ff(w, nvalid);
+        }
+        inc[i] = cnt[i];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < FUSE_NP; i++) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc[i], o);
+            if (lane >= o) inc[i] += y;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int i = 0; i < FUSE_NP; i++) sh.s_warp[i][wid] = inc[i];
+    }
+    __syncthreads();
+    uint32_t off[FUSE_NP], rstart[FUSE_NP], rtotal[FUSE_NP], total = 0;
+#pragma unroll
+    for (int i = 0; i < FUSE_NP; i++) {
+        uint32_t wb = 0, tt = 0;
+#pragma unroll
+        for (int k = 0; k < PACK_WARPS; k++) {
+            const uint32_t x = sh.s_warp[i][k];
+            if (k < wid) wb += x;
+            tt += x;
+        }
+        rstart[i] = total;
+        rtotal[i] = tt;
+        off[i] = wb + inc[i] - cnt[i];   // inside the round
+        total += tt;
+    }
+    if (LOOKBACK) {
+        if (wid == 0) {   // the other warps stage round 0 meanwhile
+            const uint64_t pre = lookback_exclusive(a.desc_bytes, t, total, a.err);
+            if (lane == 0) sh.goff = pre;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FUSE_NP; i++) {
+        if ((uint32_t)i * FUSE_ROUND < nb) {   // uniform
+            uint32_t *half = stage + (i & 1) * FUSE_STAGE_WORDS;
+            const uint32_t sbase = smem_u32(half);
+            const uint32_t jb = (uint32_t)i * FUSE_ROUND + (uint32_t)tid * 16u;
+            if (jb < nb) {
+                const int nvalid = (int)min(16u, nb - jb);
+                uint32_t w[4];
+                fuse_load_piece(src, w0, s, jb >> 4, w);
+                uint32_t o = off[i];
+                if (nvalid == 16) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) o += stuff_place_word(w[q], o, sbase, sh.lut);
+                } else {
+                    for (int k = 0; k < nvalid; k++) {
+                        uint32_t byte = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if ((k >> 2) == q) byte = (w[q] >> (24 - 8 * (k & 3))) & 0xFFu;
+                        atomicOr(&half[o >> 2], byte << ((o & 3u) * 8u));
+                        o += byte == 0xFFu ? 2u : 1u;
+                    }
+                }
+            }
+            __syncthreads();
+            if (LOOKBACK) goff = sh.goff;
+            const uint64_t g0 = (uint64_t)hdr + goff + rstart[i];
+            const uint32_t rt = rtotal[i];
+            if (g0 + rt + (last_span ? 2u : 0u) > a.cap) {
+                if (tid == 0) *a.err = 3;
+            } else {
+                uint8_t *dst = a.out + g0;
+                const uint8_t *s_out = reinterpret_cast<const uint8_t *>(half);
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+                for (uint32_t v = tid; 16 * v < rt + mis; v += PACK_THREADS) {
+                    const int k0 = (int)(16 * v) - (int)mis;
+                    if (k0 >= 0 && (uint32_t)k0 + 16 <= rt) {
+                        const uint32_t wi = (uint32_t)k0 >> 2, bs = ((uint32_t)k0 & 3u) * 8u;
+                        const uint32_t x0 = half[wi], x1 = half[wi + 1], x2 = half[wi + 2], x3 = half[wi + 3], x4 = half[wi + 4];
+                        uint4 o4;
+                        o4.x = __funnelshift_r(x0, x1, bs); o4.y = __funnelshift_r(x1, x2, bs);
+                        o4.z = __funnelshift_r(x2, x3, bs); o4.w = __funnelshift_r(x3, x4, bs);
+                        *reinterpret_cast<uint4 *>(dst + k0) = o4;
+                    } else {
+                        for (int k = max(k0, 0); k < min(k0 + 16, (int)rt); k++) dst[k] = s_out[k];
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t v = tid; v * 16 < rt + 20; v += PACK_THREADS) reinterpret_cast<uint4 *>(half)[v] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
+k_pack_stuff(FuseArgs a) {
+    __shared__ __align__(16) FusedShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < FUSE_BUF_WORDS; i += PACK_THREADS) sh.buf[i] = 0;
+    for (int i = tid; i < PACK_WARPS * (SUB_WORDS + FUSE_SUB_PAD); i += PACK_THREADS) sh.sub[0][i] = 0;
+    if (tid < 16) {   // PRMT selectors of stuff_place_word
+        uint32_t sel = 0;
+        int n = 0;
+        for (int i = 0; i < 4; i++) {
+            sel |= (uint32_t)i << (4 * n++);
+            if (tid & (1 << i)) sel |= 4u << (4 * n++);
+        }
+        for (; n < 8; n++) sel |= 4u << (4 * n);
+        sh.lut[tid] = sel;
+    }
+    pdl_wait();   // everything above ran under k_tables
+    uint32_t zr_y, zr_c;
+    pack_build_tables(sh, a.huff, tid, zr_y, zr_c);
+    const uint32_t hdr = reinterpret_cast<const volatile HuffDev *>(a.huff)->hdr_len;
+    uint32_t *sub = sh.sub[wid];
+    const uint32_t sub_words = a.sub_words;
+
+    for (;;) {
+        if (tid == 0) sh.tile = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int t = sh.tile;
+        if (t >= a.ntiles) break;
+        const bool last_tile = t == a.ntiles - 1;
+        const TileRec rec = a.recs[t];
+        const uint32_t al = rec.base & 3u;
+        const uint32_t vend = al + rec.count;
+        const uint4 *tk4 = reinterpret_cast<const uint4 *>(a.pool + (rec.base - al));
+        const uint32_t per = (((vend + PACK_WARPS - 1u) / PACK_WARPS) + PACK_STEP - 1u) & ~(uint32_t)(PACK_STEP - 1);
+        const uint32_t lo = min(vend, (uint32_t)wid * per), hi = min(vend, lo + per);
+        if (t + (int)gridDim.x < a.ntiles) {   // a tile some CTA takes about one tile time from now: on its way into L2
+            const TileRec nx = a.recs[t + gridDim.x];
+            const char *p0 = reinterpret_cast<const char *>(a.pool + (nx.base & ~31u));
+            const uint32_t nbytes = ((nx.base & 31u) + nx.count) * 4u;
+            for (uint32_t o = tid * 128u; o < nbytes; o += PACK_THREADS * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+        }
+
+        // ---- 1. code the share into the warp's buffer (or only measure it: dense tiles)
+        const bool dense = rec.count > PACK_DENSE_TOKENS;
+        uint32_t len;
+        if (!dense) len = (uint32_t)pack_scatter<false>(sh, sub, sub_words, tk4, al, lo, hi, 0, lane, zr_y, zr_c);
+        else len = pack_length(sh, tk4, al, lo, hi, lane);
+        if (lane == 0) {
+            sh.wlen[wid] = len;
+            uint32_t wt = 0;
+            if (!dense && len != 0u && len <= sub_words * 32u) {
+                const uint32_t take = min(8u, len), pos = len - take;
+                wt = __funnelshift_l(sub[(pos >> 5) + 1], sub[pos >> 5], pos & 31u) >> (32u - take);
+            }
+            sh.wtail[wid] = wt;
+        }
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+        bool two_pass = dense;
+#pragma unroll
+        for (int w = 0; w < PACK_WARPS; w++) {
+            const uint32_t x = sh.wlen[w];
+            if (w < wid) base += x;
+            total += x;
+            if (x > sub_words * 32u) two_pass = true;
+        }
+        if (total > (uint32_t)WIN_WORDS * 32u - 64u) two_pass = true;
+        if (tid == 0) a.tile_bits[t] = total;
+
+        // ---- 2. the tile's tail bits and look-back #1 (warp 0; the other warps go on)
+        uint32_t pred_tail = 0xFFFFFFFFu;   // thread 0: the stream's last 8 bits before this tile, once it was needed
+        if (wid == 0) {
+            if (!two_pass && lane == 0) {   // the stream's last 8 bits up to the end of this tile
+                uint32_t acc = 0, got = 0;
+#pragma unroll
+                for (int w = PACK_WARPS - 1; w >= 0; w--) {
+                    const uint32_t l = sh.wlen[w];
+                    if (l && got < 8u) {
+                        const uint32_t take = min(8u - got, l);
+                        acc |= (sh.wtail[w] & ((1u << take) - 1u)) << got;
+                        got += take;
+                    }
+                }
+                if (got < 8u) {   // a tile of fewer than 8 bits (flat image, one MCU): the rest comes from before
+                    pred_tail = t ? fuse_wait_tail(a.tail, t - 1, a.err) : 0u;
+                    acc = ((pred_tail << got) | acc) & 0xFFu;
+                }
+                st_volatile_u32(&a.tail[t], 0x80000000u | acc);
+            }
+            const uint64_t G = lookback_exclusive(a.desc_bits, t, total, a.err);
+            if (lane == 0) sh.G = G;
+        }
+        uint32_t *slot = a.slots + (size_t)t * SLOT_WORDS;
+        if (!two_pass) {
+            // ---- 3. shift the share into the tile's bit string (bit 32 + base); clear the buffer behind
+            const uint32_t shv = base & 31u, fw = 1u + (base >> 5);
+            const uint32_t nV = (shv + len + 31u) >> 5;
+            const uint32_t tailbits = (shv + len) & 31u;
+            for (uint32_t i = lane; i < nV; i += 32) {
+                const uint32_t hi_w = i ? sub[i - 1] : 0u, lo_w = sub[i];
+                const uint32_t v = __funnelshift_r(lo_w, hi_w, shv);
+                if ((i == 0 && shv != 0u) || (i == nV - 1 && tailbits != 0u)) atomicOr(&sh.buf[fw + i], v);
+                else sh.buf[fw + i] = v;
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < nV + 1; i += 32) sub[i] = 0;
+        } else {
+            if (!dense) {
+                for (uint32_t i = lane; i < (uint32_t)SUB_WORDS + FUSE_SUB_PAD; i += 32) sub[i] = 0;
+            }
+            const uint32_t nwords = (total + 31u) >> 5;
+            for (uint32_t wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
+                pack_scatter<true>(sh, sh.buf, WIN_WORDS, tk4, al, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
+                __syncthreads();
+                const uint32_t wn = min((uint32_t)WIN_WORDS, nwords - wbase);
+                for (uint32_t i = tid; i < wn; i += PACK_THREADS) { slot[1u + wbase + i] = sh.buf[i]; sh.buf[i] = 0; }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                slot[1u + nwords] = 0; slot[2u + nwords] = 0;   // the pieces read a little past the end
+                const uint32_t pos = total - 8u;                // a tile has at least 12 bits
+                const uint32_t v = __funnelshift_l(slot[1u + (pos >> 5) + 1u], slot[1u + (pos >> 5)], pos & 31u) >> 24;
+                st_volatile_u32(&a.tail[t], 0x80000000u | v);
+            }
+        }
+        __syncthreads();   // bit string complete, G known
+        const uint64_t G = sh.G;
+        const uint32_t phi = (uint32_t)G & 7u;
+        const uint64_t nbytes64 = ((G + total + (last_tile ? 7u : 0u)) >> 3) - (G >> 3);
+        if (tid == 0) {
+            uint32_t *wsrc = two_pass ? slot : sh.buf;
+            uint32_t lead = 0;
+            if (phi) {   // the first byte starts with the last phi bits of the stream before this tile (phi != 0: t > 0)
+                if (pred_tail == 0xFFFFFFFFu) pred_tail = fuse_wait_tail(a.tail, t - 1, a.err);
+                lead = pred_tail & ((1u << phi) - 1u);
+            }
+            wsrc[0] = lead;
+            if (last_tile) {   // jchuff.c flush_bits: the last byte is filled with 1-bits
+                const uint32_t pad = (8u - ((phi + total) & 7u)) & 7u;
+                if (pad) {
+                    const uint32_t pos = 32u + total, wi = pos >> 5, sb = pos & 31u;
+                    const uint64_t v = ((uint64_t)((1u << pad) - 1u) << (64u - pad)) >> sb;
+                    wsrc[wi] |= (uint32_t)(v >> 32);
+                    if ((uint32_t)v) wsrc[wi + 1] |= (uint32_t)v;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t w0 = phi ? 0u : 1u, s = (32u - phi) & 31u;
+        uint64_t end;
+        if (!two_pass) {
+            const uint32_t st = fuse_stuff_span<true>(sh, a, sh.buf, w0, s, (uint32_t)nbytes64, 0, t, hdr, last_tile);
+            end = (uint64_t)hdr + sh.goff + st;
+            for (uint32_t i = tid; i < ((32u + total + 31u) >> 5) + 6u; i += PACK_THREADS) sh.buf[i] = 0;
+        } else {
+            // counting pass, then look-back #2, then span by span
+            uint32_t c = 0;
+            for (uint64_t jb = (uint64_t)tid * 16u; jb < nbytes64; jb += FUSE_ROUND) {
+                const int nvalid = (int)min((uint64_t)16, nbytes64 - jb);
+                uint32_t w[4];
+                fuse_load_piece(slot, w0, s, (uint32_t)(jb >> 4), w);
+                c += (uint32_t)nvalid + fuse_count_ff(w, nvalid);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) sh.s_warp[0][wid] = c;
+            __syncthreads();
+            uint32_t stot = 0;
+#pragma unroll
+            for (int k = 0; k < PACK_WARPS; k++) stot += sh.s_warp[0][k];
+            __syncthreads();   // s_warp is reused by the spans
+            if (wid == 0) {
+                const uint64_t pre = lookback_exclusive(a.desc_bytes, t, stot, a.err);
+                if (lane == 0) sh.goff = pre;
+            }
+            __syncthreads();
+            uint64_t goff = sh.goff;
+            for (uint64_t b0 = 0; b0 < nbytes64; b0 += FUSE_SPAN) {
+                const uint32_t nb = (uint32_t)min((uint64_t)FUSE_SPAN, nbytes64 - b0);
+                goff += fuse_stuff_span<false>(sh, a, slot + (b0 >> 2), w0, s, nb, goff, t, hdr, last_tile && b0 + FUSE_SPAN >= nbytes64);
+                __syncthreads();
+            }
+            end = (uint64_t)hdr + goff;
+        }
+        if (last_tile && tid == 0) {
+            if (end + 2 <= a.cap) { a.out[end] = 0xFF; a.out[end + 1] = 0xD9; }
+            *a.out_len = end + 2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 cudaError_t launch_tables(const uint32_t *hist, int optimize, HuffDev *huff, const QuantDev *qd, int full_w, int full_h,
                           int hs, int vs, uint8_t *out, int emit_header, int restart_interval, uint32_t *err_out, cudaStream_t s) {
     return launch_pdl(k_tables, dim3(1), dim3(128), 0, s, hist, optimize, huff, qd, full_w, full_h, hs, vs, out, emit_header, restart_interval, err_out);
@@ -1194,6 +1605,18 @@ cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, 
     k_seam_from_bits<<<1, 1, 0, s>>>(seam, bits_all, rank, world);
     return cudaGetLastError();
 }
+cudaError_t launch_pack_stuff(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff, uint32_t *slots,
+                              uint32_t *tile_bits, int force_overflow, uint64_t *desc_bits, uint64_t *desc_bytes, uint32_t *tail,
+                              uint32_t *ticket, uint8_t *out, size_t cap, uint64_t *out_len, uint32_t *err, cudaStream_t s) {
+    FuseArgs a;
+    a.pool = pool; a.recs = recs; a.ntiles = g.ntiles; a.huff = huff; a.slots = slots; a.tile_bits = tile_bits;
+    a.sub_words = force_overflow ? 24u : (uint32_t)SUB_WORDS;
+    a.desc_bits = desc_bits; a.desc_bytes = desc_bytes; a.tail = tail; a.ticket = ticket; a.out = out; a.cap = cap;
+    a.out_len = out_len; a.err = err;
+    const int grid = std::min(g.ntiles, 148 * PACK_CTAS);
+    return launch_pdl(k_pack_stuff, dim3(grid), dim3(PACK_THREADS), 0, s, a);
+}
+
 cudaError_t launch_stuff(const StuffArgs &a, int grid, cudaStream_t s) {
     return a.rst_tiles ? launch_pdl(k_stuff<true>, dim3(grid), dim3(STUFF_THREADS), 0, s, a)
                        : launch_pdl(k_stuff<false>, dim3(grid), dim3(STUFF_THREADS), 0, s, a);

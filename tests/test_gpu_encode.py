@@ -87,11 +87,31 @@ def test_pack_buffer_regimes(P, oracle):
                 eng = P.Engine(W, H, q, bool(opt), css)
                 for name, img in (("noise", noise), ("soft", soft)):
                     want = oracle.encode(img, css, q, opt)
-                    for dbg in (0, 2):   # 2 = B2J_DEBUG_SMALL_PACK_BUFFERS: every warp buffer overflows -> recovery path
+                    # 2 = B2J_DEBUG_SMALL_PACK_BUFFERS: every warp buffer overflows -> recovery path; 8 = B2J_DEBUG_UNFUSED:
+                    # k_pack + k_scan_tiles + k_stuff (the strips' kernels) instead of the fused k_pack_stuff
+                    for dbg in (0, 2, 8, 10):
                         eng.set_debug(dbg)
                         jpg = eng.encode(img)
                         assert jpg.size == want.size and np.array_equal(jpg, want), f"{name} css{css} q{q} opt{opt} dbg{dbg}"
                 eng.close()
+
+
+def test_tiny_tiles(P, oracle):
+    """Flat and narrow images: tiles of one MCU whose codes are 1-2 bits each (a tile shorter than a byte: the fused
+    entropy kernel chains the tail bits through several tiles), and single-tile images."""
+    rng = np.random.default_rng(5)
+    for css in range(5):
+        for W, H in ((8, 8), (8, 200), (16, 64), (24, 40), (40, 16), (2000, 8)):
+            for kind in ("flat", "noise"):
+                img = np.full((H, W, 3), 131, np.uint8) if kind == "flat" else rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+                for q, opt in ((95, 1), (50, 0)):
+                    eng = P.Engine(W, H, q, bool(opt), css)
+                    for dbg in (0, 8):
+                        eng.set_debug(dbg)
+                        jpg = eng.encode(img)
+                        want = oracle.encode(img, css, q, opt)
+                        assert jpg.size == want.size and np.array_equal(jpg, want), (css, W, H, kind, q, opt, dbg)
+                    eng.close()
 
 
 def test_golden_cases(P, golden, oracle):
