@@ -535,10 +535,11 @@ k_dc_edge_hist(const TileRec *__restrict__ recs, Geom g, const int16_t *__restri
     pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ntile = g.tiles_x * g.mcuy;
-    // k_pack_stuff's per-tile look-back state (two descriptors + the tail word: 5 words per tile), cleared on the way
+    // k_pack_stuff's look-back state (two items per tile: two descriptors + the tail word each), cleared on the way
     if (fuse_zero && t < ntile * 3) {
-        if (2 * t < 5 * ntile) fuse_zero[2 * t] = 0;
-        if (2 * t + 1 < 5 * ntile) fuse_zero[2 * t + 1] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (4 * t + k < 10 * ntile) fuse_zero[4 * t + k] = 0;
     }
     if (threadIdx.x < 32) s_h[threadIdx.x >> 4][threadIdx.x & 15] = 0;
     __syncthreads();

@@ -345,7 +345,7 @@ struct PackShared {
 
 // One lane's contiguous piece of the bit string: bits are appended to a 64-bit accumulator and every completed
 // 32-bit word goes to the buffer. `cnt` = valid low bits of acc that are not flushed yet (< 32 between calls).
-// WINDOWED (dense tiles, all warps share one window): atomicOr, words outside [0, WIN_WORDS) are skipped.
+// WINDOWED (dense tiles, the warps share one window): atomicOr, words outside the window [0, nwords) are skipped.
 // Otherwise (the warp's own buffer): a word is completed by exactly one lane, which stores it whole -- bits that
 // earlier lanes own in it are zero in that store and are OR-ed in afterwards (finish(), after a warp barrier), so
 // the hot path has no atomics and the buffer needs no clearing except the word a share ends in. Words at or beyond
@@ -356,9 +356,10 @@ struct LaneEmitter {
     uint32_t cnt;
     uint32_t addr, limit;   // fast: shared byte address of the current word / end of the buffer
     int wi;                 // windowed: word index relative to the window
+    uint32_t win;           // windowed: words in the window
     uint32_t *buf;
     __device__ __forceinline__ void start(uint32_t *b, int pos, uint32_t nwords) {
-        buf = b; acc = 0; cnt = (uint32_t)pos & 31u; wi = pos >> 5;
+        buf = b; acc = 0; cnt = (uint32_t)pos & 31u; wi = pos >> 5; win = nwords;
         addr = smem_u32(b) + (uint32_t)(pos >> 5) * 4u;
         limit = smem_u32(b) + nwords * 4u;
     }
@@ -368,7 +369,7 @@ struct LaneEmitter {
         if (WINDOWED) {
             if (cnt >= 32u) {
                 cnt -= 32u;
-                if ((uint32_t)wi < (uint32_t)WIN_WORDS) atomicOr(&buf[wi], (uint32_t)(acc >> cnt));
+                if ((uint32_t)wi < win) atomicOr(&buf[wi], (uint32_t)(acc >> cnt));
                 wi++;
             }
         } else {
@@ -381,7 +382,7 @@ struct LaneEmitter {
     __device__ __forceinline__ void finish() {
         if (cnt) {
             const uint32_t wv = (uint32_t)acc << (32u - cnt);
-            if (WINDOWED) { if ((uint32_t)wi < (uint32_t)WIN_WORDS) atomicOr(&buf[wi], wv); }
+            if (WINDOWED) { if ((uint32_t)wi < win) atomicOr(&buf[wi], wv); }
             else if (addr < limit) atomicOr(buf + ((addr - smem_u32(buf)) >> 2), wv);
         }
     }
@@ -1015,40 +1016,39 @@ k_stuff(StuffArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_pack_stuff: k_pack, the tile scan and k_stuff in ONE kernel for whole-image encodes without restart markers -- the
-// tile slots never travel through HBM and the second kernel's latency chain is gone. Tiles are handed out by a ticket
-// (so every predecessor of a tile is running or done) and go through
-//   1. k_pack's coding of the warps' shares into their own bit buffers (same code)
-//   2. decoupled look-back #1 over the tiles' BIT counts -> G = the tile's bit offset in the entropy-coded segment.
-//      The tile owns the stream bytes that END inside it: the first one starts with the G & 7 last bits of the tile
-//      before (published per tile next to the descriptor: `tail`), the bits after its last whole byte go to the next.
-//   3. the shares are shifted into one tile-wide bit string in shared memory (word 0: the predecessor's tail bits)
-//   4. 16-byte pieces of that string (one per thread and round, FUSE_NP rounds): 0xFF count -> CTA scan -> the tile's
-//      stuffed size -> decoupled look-back #2 over the BYTE counts -> the tile's place in the output
-//   5. round by round: bytes staged with their 0x00s at tile-local offsets (the warp buffers' memory, two halves),
-//      copied out as 16-byte vectors (k_stuff's code)
-// Dense tiles (bits that do not fit the shared buffers) are rare: their bit string goes window by window into the
-// tile's slot in global memory as in k_pack and is stuffed from there, 8 KB at a time, after a counting pass.
-constexpr int FUSE_BUF_WORDS = WIN_WORDS + 16;          // word 0 = lead, bits from word 1, zero words behind
-constexpr int FUSE_ROUND = PACK_THREADS * 16;           // unstuffed bytes per round: one 16-byte piece per thread
-constexpr int FUSE_NP = 4;                              // rounds per span: 8 KB = the most a shared-memory tile holds
-constexpr int FUSE_SPAN = FUSE_NP * FUSE_ROUND;
+// k_pack_stuff: k_pack, the tile scan and k_stuff in ONE kernel for whole-image encodes without restart markers: the
+// coded bits never travel through HBM and there is no second kernel with its own latency chain. The unit of work is
+// an ITEM = one of FUSE_PARTS consecutive parts of an fdct tile's token run, and one WARP does everything for its
+// item on its own -- the CTA only shares the code tables, so the item loop has no CTA barrier at all and the
+// latencies of the look-backs are covered by the other warps of the SM. Items are handed out by a ticket (every
+// predecessor of an item is running or done):
+//   1. k_pack's coding of the item's tokens into the warp's bit buffer, from bit 32 (word 0 is the lead word)
+//   2. the stream's last 8 bits up to the item's end are published (`tail`); decoupled look-back #1 over the items'
+//      BIT counts -> G = the item's bit offset in the entropy-coded segment. The item owns the stream bytes that END
+//      inside it: the first one starts with the G & 7 last bits before the item (the predecessor's tail -> lead
+//      word), the bits after its last whole byte go to the next item; the image's last item pads with 1-bits.
+//   3. 16-byte pieces of that byte string (one per lane and round, straight from the bit buffer with a funnel shift
+//      by the phase): 0xFF count -> warp scan -> the item's stuffed size -> decoupled look-back #2 over the BYTE
+//      counts -> the item's place in the output
+//   4. round by round: the pieces' bytes staged with their 0x00s (k_stuff's PRMT expansion), copied out as 16-byte
+//      vectors
+// Items whose bits do not fit the warp's buffer (q ~ 100) are coded window by window into global memory (the slot
+// area of the unfused path) and stuffed from there after a counting pass.
+constexpr int FUSE_PARTS = 2;                           // items per fdct tile
+constexpr int FUSE_BITS_WORDS = 1024;                   // bit buffer per warp: 32 kbit (a typical item is ~13 kbit)
+constexpr int FUSE_BUF_WORDS = FUSE_BITS_WORDS + 16;    // + lead word and zero words behind
+constexpr int FUSE_ROUND = 32 * 16;                     // unstuffed bytes per round: one 16-byte piece per lane
 constexpr int FUSE_STAGE_WORDS = (2 * FUSE_ROUND + 64) / 4;
-constexpr int FUSE_SUB_PAD = 20;
-static_assert(PACK_WARPS * (SUB_WORDS + FUSE_SUB_PAD) >= 2 * FUSE_STAGE_WORDS, "the warp buffers double as two staging halves");
-static_assert(FUSE_SPAN * 8 >= WIN_WORDS * 32, "a shared-memory tile is one span");
+constexpr int FUSE_CTAS = 7;                            // resident CTAs per SM (shared memory)
+constexpr uint32_t FUSE_DENSE_TOKENS = 3500;            // above this the item may not fit the buffer: coded through global memory
+constexpr int FUSE_SLOT_WORDS = SLOT_WORDS / FUSE_PARTS;
 
 struct FusedShared {
-    uint32_t buf[FUSE_BUF_WORDS];
-    uint32_t sub[PACK_WARPS][SUB_WORDS + FUSE_SUB_PAD];
     uint32_t code[1024];
     uint8_t len[4096];
-    uint32_t wlen[PACK_WARPS];
-    uint32_t wtail[PACK_WARPS];                   // the last min(8, length) bits of every share
-    uint32_t s_warp[FUSE_NP][PACK_WARPS];
     uint32_t lut[16];
-    uint64_t G, goff;
-    int tile;
+    uint32_t buf[PACK_WARPS][FUSE_BUF_WORDS];
+    uint32_t stage[PACK_WARPS][FUSE_STAGE_WORDS];
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
@@ -1060,19 +1060,19 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// the last 8 bits of the stream up to the end of tile t (published by the tile's CTA as soon as it has coded them)
+// the last 8 bits of the stream up to the end of item t (published by the item's warp as soon as it has coded them)
 __device__ __forceinline__ uint32_t fuse_wait_tail(const uint32_t *tail, int t, uint32_t *err) {
     uint32_t v = ld_volatile_u32(&tail[t]);
     unsigned spins = 0;
     while (!(v >> 31)) {
-        __nanosleep(20);
+        __nanosleep(100);
         v = ld_volatile_u32(&tail[t]);
-        if (++spins > (1u << 22)) { *err = 1; break; }   // never hang the GPU
+        if (++spins > (1u << 20)) { *err = 1; break; }   // never hang the GPU
     }
     return v & 0xFFu;
 }
 
-// 16 bytes of the byte string that starts at bit (32 * w0 - s') of src, s' = (32 - s) & 31: piece j, MSB first
+// 16 bytes of the byte string whose bytes are the bits of src from bit 32 * w0 + ((32 - s) & 31) on: piece j, MSB first
 __device__ __forceinline__ void fuse_load_piece(const uint32_t *src, uint32_t w0, uint32_t s, uint32_t j, uint32_t (&w)[4]) {
     const uint32_t *p = src + w0 + 4u * j;
     uint32_t x[5];
@@ -1106,10 +1106,9 @@ struct FuseArgs {
     int ntiles;
     const HuffDev *huff;
     uint32_t *slots;
-    uint32_t *tile_bits;
-    uint32_t sub_words;
-    uint64_t *desc_bits, *desc_bytes;   // look-back descriptors, one per tile (zeroed)
-    uint32_t *tail;                     // per tile: 1 << 31 | its last 8 bits (zeroed)
+    uint32_t buf_words;                 // bit buffer words the coder may fill (tests: small -> the global-memory path)
+    uint64_t *desc_bits, *desc_bytes;   // look-back descriptors, one per item (zeroed)
+    uint32_t *tail;                     // per item: 1 << 31 | the stream's last 8 bits up to its end (zeroed)
     uint32_t *ticket;                   // zeroed
     uint8_t *out;
     size_t cap;
@@ -1117,122 +1116,95 @@ struct FuseArgs {
     uint32_t *err;
 };
 
-// Bytes [0, nb) (nb <= FUSE_SPAN) of the byte string at (src, w0, s): stuffed and written to a.out. LOOKBACK: the span
-// is the whole tile -- its stuffed size goes through look-back #2 and gives the place; otherwise `goff` is the place.
-// Returns the stuffed size. Every thread of the CTA calls it; the staging halves must be zero and are zero afterwards.
-template <bool LOOKBACK>
-__device__ __forceinline__ uint32_t fuse_stuff_span(FusedShared &sh, const FuseArgs &a, const uint32_t *src, uint32_t w0, uint32_t s,
-                                                    uint32_t nb, uint64_t goff, int t, uint32_t hdr, bool last_span) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t *stage = &sh.sub[0][0];
-    uint32_t cnt[FUSE_NP], inc[FUSE_NP];
-#pragma unroll
-    for (int i = 0; i < FUSE_NP; i++) {
-        const uint32_t jb = (uint32_t)i * FUSE_ROUND + (uint32_t)tid * 16u;
-        cnt[i] = 0;
-        if ((uint32_t)i * FUSE_ROUND < nb && jb < nb) {
-            const int nvalid = (int)min(16u, nb - jb);
-            uint32_t w[4];
-            fuse_load_piece(src, w0, s, jb >> 4, w);
-            cnt[i] = (uint32_t)nvalid + fuse_count_ff(w, nvalid);
-        }
-        inc[i] = cnt[i];
+// stuffed size of bytes [0, nb) of the byte string at (src, w0, s); one warp, result in every lane
+__device__ __forceinline__ uint32_t fuse_count_span(const uint32_t *src, uint32_t w0, uint32_t s, uint64_t nb) {
+    const int lane = threadIdx.x & 31;
+    uint32_t c = 0;
+#pragma unroll 1
+    for (uint64_t jb = (uint64_t)lane * 16u; jb < nb; jb += FUSE_ROUND) {
+        const int nvalid = (int)min((uint64_t)16, nb - jb);
+        uint32_t w[4];
+        fuse_load_piece(src, w0, s, (uint32_t)(jb >> 4), w);
+        c += (uint32_t)nvalid + fuse_count_ff(w, nvalid);
     }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-        for (int i = 0; i < FUSE_NP; i++) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, inc[i], o);
-            if (lane >= o) inc[i] += y;
-        }
-    }
-    if (lane == 31) {
-#pragma unroll
-        for (int i = 0; i < FUSE_NP; i++) sh.s_warp[i][wid] = inc[i];
-    }
-    __syncthreads();
-    uint32_t off[FUSE_NP], rstart[FUSE_NP], rtotal[FUSE_NP], total = 0;
-#pragma unroll
-    for (int i = 0; i < FUSE_NP; i++) {
-        uint32_t wb = 0, tt = 0;
-#pragma unroll
-        for (int k = 0; k < PACK_WARPS; k++) {
-            const uint32_t x = sh.s_warp[i][k];
-            if (k < wid) wb += x;
-            tt += x;
-        }
-        rstart[i] = total;
-        rtotal[i] = tt;
-        off[i] = wb + inc[i] - cnt[i];   // inside the round
-        total += tt;
-    }
-    if (LOOKBACK) {
-        if (wid == 0) {   // the other warps stage round 0 meanwhile
-            const uint64_t pre = lookback_exclusive(a.desc_bytes, t, total, a.err);
-            if (lane == 0) sh.goff = pre;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < FUSE_NP; i++) {
-        if ((uint32_t)i * FUSE_ROUND < nb) {   // uniform
-            uint32_t *half = stage + (i & 1) * FUSE_STAGE_WORDS;
-            const uint32_t sbase = smem_u32(half);
-            const uint32_t jb = (uint32_t)i * FUSE_ROUND + (uint32_t)tid * 16u;
-            if (jb < nb) {
-                const int nvalid = (int)min(16u, nb - jb);
-                uint32_t w[4];
-                fuse_load_piece(src, w0, s, jb >> 4, w);
-                uint32_t o = off[i];
-                if (nvalid == 16) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) o += stuff_place_word(w[q], o, sbase, sh.lut);
-                } else {
-                    for (int k = 0; k < nvalid; k++) {
-                        uint32_t byte = 0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) if ((k >> 2) == q) byte = (w[q] >> (24 - 8 * (k & 3))) & 0xFFu;
-                        atomicOr(&half[o >> 2], byte << ((o & 3u) * 8u));
-                        o += byte == 0xFFu ? 2u : 1u;
-                    }
-                }
-            }
-            __syncthreads();
-            if (LOOKBACK) goff = sh.goff;
-            const uint64_t g0 = (uint64_t)hdr + goff + rstart[i];
-            const uint32_t rt = rtotal[i];
-            if (g0 + rt + (last_span ? 2u : 0u) > a.cap) {
-                if (tid == 0) *a.err = 3;
-            } else {
-                uint8_t *dst = a.out + g0;
-                const uint8_t *s_out = reinterpret_cast<const uint8_t *>(half);
-                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
-                for (uint32_t v = tid; 16 * v < rt + mis; v += PACK_THREADS) {
-                    const int k0 = (int)(16 * v) - (int)mis;
-                    if (k0 >= 0 && (uint32_t)k0 + 16 <= rt) {
-                        const uint32_t wi = (uint32_t)k0 >> 2, bs = ((uint32_t)k0 & 3u) * 8u;
-                        const uint32_t x0 = half[wi], x1 = half[wi + 1], x2 = half[wi + 2], x3 = half[wi + 3], x4 = half[wi + 4];
-                        uint4 o4;
-                        o4.x = __funnelshift_r(x0, x1, bs); o4.y = __funnelshift_r(x1, x2, bs);
-                        o4.z = __funnelshift_r(x2, x3, bs); o4.w = __funnelshift_r(x3, x4, bs);
-                        *reinterpret_cast<uint4 *>(dst + k0) = o4;
-                    } else {
-                        for (int k = max(k0, 0); k < min(k0 + 16, (int)rt); k++) dst[k] = s_out[k];
-                    }
-                }
-            }
-            __syncthreads();
-            for (uint32_t v = tid; v * 16 < rt + 20; v += PACK_THREADS) reinterpret_cast<uint4 *>(half)[v] = make_uint4(0, 0, 0, 0);
-        }
-    }
-    return total;
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
 }
 
-__global__ void __launch_bounds__(PACK_THREADS, PACK_CTAS)
+// Bytes [0, nb) of the byte string at (src, w0, s) -> stuffed -> a.out + hdr + goff, round by round (32 pieces of 16
+// bytes: offsets from a warp scan, bytes staged with their 0x00s, copied out as 16-byte vectors). One warp; `stage`
+// must be zero and is zero afterwards. Returns the stuffed size.
+__device__ __forceinline__ uint32_t fuse_stuff_span(uint32_t *stage, const uint32_t *lut, const FuseArgs &a, const uint32_t *src, uint32_t w0,
+                                                    uint32_t s, uint64_t nb, uint64_t goff, uint32_t hdr, bool last_span) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(stage);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint64_t r0 = 0; r0 < nb; r0 += FUSE_ROUND) {
+        const uint64_t jb = r0 + (uint64_t)lane * 16u;
+        const int nvalid = jb < nb ? (int)min((uint64_t)16, nb - jb) : 0;
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint32_t cnt = 0;
+        if (nvalid) {
+            fuse_load_piece(src, w0, s, (uint32_t)(jb >> 4), w);
+            cnt = (uint32_t)nvalid + fuse_count_ff(w, nvalid);
+        }
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const uint32_t rt = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t o = inc - cnt;
+        if (nvalid == 16) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) o += stuff_place_word(w[q], o, sbase, lut);
+        } else {
+            for (int k = 0; k < nvalid; k++) {
+                const uint32_t wq = (k >> 2) == 0 ? w[0] : ((k >> 2) == 1 ? w[1] : ((k >> 2) == 2 ? w[2] : w[3]));
+                const uint32_t byte = (wq >> (24 - 8 * (k & 3))) & 0xFFu;
+                atomicOr(&stage[o >> 2], byte << ((o & 3u) * 8u));
+                o += byte == 0xFFu ? 2u : 1u;
+            }
+        }
+        __syncwarp();
+        const uint64_t g0 = (uint64_t)hdr + goff + done;
+        if (g0 + rt + (last_span ? 2u : 0u) > a.cap) {
+            if (lane == 0) *a.err = 3;
+        } else {
+            uint8_t *dst = a.out + g0;
+            const uint8_t *s_out = reinterpret_cast<const uint8_t *>(stage);
+            // bytes up to the first 16-byte boundary of the output and behind the last one: one byte per lane
+            const uint32_t head = min(rt, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+            const uint32_t nvec = (rt - head) >> 4, tail0 = head + 16u * nvec;
+            if ((uint32_t)lane < head) dst[lane] = s_out[lane];
+            if (tail0 + (uint32_t)lane < rt) dst[tail0 + lane] = s_out[tail0 + lane];
+            for (uint32_t v = lane; v < nvec; v += 32) {
+                const uint32_t k0 = head + 16u * v;
+                const uint32_t wi = k0 >> 2, bs = (k0 & 3u) * 8u;
+                const uint32_t x0 = stage[wi], x1 = stage[wi + 1], x2 = stage[wi + 2], x3 = stage[wi + 3], x4 = stage[wi + 4];
+                uint4 o4;
+                o4.x = __funnelshift_r(x0, x1, bs); o4.y = __funnelshift_r(x1, x2, bs);
+                o4.z = __funnelshift_r(x2, x3, bs); o4.w = __funnelshift_r(x3, x4, bs);
+                *reinterpret_cast<uint4 *>(dst + k0) = o4;
+            }
+        }
+        __syncwarp();
+        for (uint32_t v = lane; v * 16 < rt + 20; v += 32) reinterpret_cast<uint4 *>(stage)[v] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        done += rt;
+    }
+    return done;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS, FUSE_CTAS)
 k_pack_stuff(FuseArgs a) {
     __shared__ __align__(16) FusedShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < FUSE_BUF_WORDS; i += PACK_THREADS) sh.buf[i] = 0;
-    for (int i = tid; i < PACK_WARPS * (SUB_WORDS + FUSE_SUB_PAD); i += PACK_THREADS) sh.sub[0][i] = 0;
+    for (int i = tid; i < PACK_WARPS * FUSE_BUF_WORDS; i += PACK_THREADS) sh.buf[0][i] = 0;
+    for (int i = tid; i < PACK_WARPS * FUSE_STAGE_WORDS; i += PACK_THREADS) sh.stage[0][i] = 0;
     if (tid < 16) {   // PRMT selectors of stuff_place_word
         uint32_t sel = 0;
         int n = 0;
@@ -1245,174 +1217,110 @@ k_pack_stuff(FuseArgs a) {
     }
     pdl_wait();   // everything above ran under k_tables
     uint32_t zr_y, zr_c;
-    pack_build_tables(sh, a.huff, tid, zr_y, zr_c);
+    pack_build_tables(sh, a.huff, tid, zr_y, zr_c);   // ends with a CTA barrier: the last one of this kernel
     const uint32_t hdr = reinterpret_cast<const volatile HuffDev *>(a.huff)->hdr_len;
-    uint32_t *sub = sh.sub[wid];
-    const uint32_t sub_words = a.sub_words;
+    uint32_t *buf = sh.buf[wid], *stage = sh.stage[wid];
+    const int nitems = a.ntiles * FUSE_PARTS;
+    const int nwarps = (int)gridDim.x * PACK_WARPS;
 
     for (;;) {
-        if (tid == 0) sh.tile = (int)atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const int t = sh.tile;
-        if (t >= a.ntiles) break;
-        const bool last_tile = t == a.ntiles - 1;
+        int it = 0;
+        if (lane == 0) it = (int)atomicAdd(a.ticket, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= nitems) break;
+        const bool last_item = it == nitems - 1;
+        const int t = it / FUSE_PARTS, part = it - t * FUSE_PARTS;
         const TileRec rec = a.recs[t];
         const uint32_t al = rec.base & 3u;
-        const uint32_t vend = al + rec.count;
         const uint4 *tk4 = reinterpret_cast<const uint4 *>(a.pool + (rec.base - al));
-        const uint32_t per = (((vend + PACK_WARPS - 1u) / PACK_WARPS) + PACK_STEP - 1u) & ~(uint32_t)(PACK_STEP - 1);
-        const uint32_t lo = min(vend, (uint32_t)wid * per), hi = min(vend, lo + per);
-        if (t + (int)gridDim.x < a.ntiles) {   // a tile some CTA takes about one tile time from now: on its way into L2
-            const TileRec nx = a.recs[t + gridDim.x];
+        const uint32_t c0 = (uint32_t)(((uint64_t)rec.count * part) / FUSE_PARTS), c1 = (uint32_t)(((uint64_t)rec.count * (part + 1)) / FUSE_PARTS);
+        const uint32_t first = al + c0, hi = al + c1, lo = first & ~(uint32_t)(PACK_K - 1);
+        if (part == 0 && it + nwarps < nitems) {   // the tile some warp takes about one item time from now: on its way into L2
+            const TileRec nx = a.recs[(it + nwarps) / FUSE_PARTS];
             const char *p0 = reinterpret_cast<const char *>(a.pool + (nx.base & ~31u));
             const uint32_t nbytes = ((nx.base & 31u) + nx.count) * 4u;
-            for (uint32_t o = tid * 128u; o < nbytes; o += PACK_THREADS * 128u)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+            for (uint32_t o = lane * 128u; o < nbytes; o += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         }
 
-        // ---- 1. code the share into the warp's buffer (or only measure it: dense tiles)
-        const bool dense = rec.count > PACK_DENSE_TOKENS;
+        // ---- 1. code the item into the warp's buffer from bit 32 (or only measure it: dense items)
+        const bool dense = c1 - c0 > FUSE_DENSE_TOKENS;
         uint32_t len;
-        if (!dense) len = (uint32_t)pack_scatter<false>(sh, sub, sub_words, tk4, al, lo, hi, 0, lane, zr_y, zr_c);
-        else len = pack_length(sh, tk4, al, lo, hi, lane);
-        if (lane == 0) {
-            sh.wlen[wid] = len;
-            uint32_t wt = 0;
-            if (!dense && len != 0u && len <= sub_words * 32u) {
-                const uint32_t take = min(8u, len), pos = len - take;
-                wt = __funnelshift_l(sub[(pos >> 5) + 1], sub[pos >> 5], pos & 31u) >> (32u - take);
-            }
-            sh.wtail[wid] = wt;
-        }
-        __syncthreads();
-        uint32_t base = 0, total = 0;
-        bool two_pass = dense;
-#pragma unroll
-        for (int w = 0; w < PACK_WARPS; w++) {
-            const uint32_t x = sh.wlen[w];
-            if (w < wid) base += x;
-            total += x;
-            if (x > sub_words * 32u) two_pass = true;
-        }
-        if (total > (uint32_t)WIN_WORDS * 32u - 64u) two_pass = true;
-        if (tid == 0) a.tile_bits[t] = total;
+        if (!dense) len = (uint32_t)pack_scatter<false>(sh, buf, 1u + a.buf_words, tk4, first, lo, hi, 32, lane, zr_y, zr_c) - 32u;
+        else len = pack_length(sh, tk4, first, lo, hi, lane);
+        const bool two_pass = dense || len > a.buf_words * 32u - 64u;
 
-        // ---- 2. the tile's tail bits and look-back #1 (warp 0; the other warps go on)
-        uint32_t pred_tail = 0xFFFFFFFFu;   // thread 0: the stream's last 8 bits before this tile, once it was needed
-        if (wid == 0) {
-            if (!two_pass && lane == 0) {   // the stream's last 8 bits up to the end of this tile
-                uint32_t acc = 0, got = 0;
-#pragma unroll
-                for (int w = PACK_WARPS - 1; w >= 0; w--) {
-                    const uint32_t l = sh.wlen[w];
-                    if (l && got < 8u) {
-                        const uint32_t take = min(8u - got, l);
-                        acc |= (sh.wtail[w] & ((1u << take) - 1u)) << got;
-                        got += take;
-                    }
-                }
-                if (got < 8u) {   // a tile of fewer than 8 bits (flat image, one MCU): the rest comes from before
-                    pred_tail = t ? fuse_wait_tail(a.tail, t - 1, a.err) : 0u;
-                    acc = ((pred_tail << got) | acc) & 0xFFu;
-                }
-                st_volatile_u32(&a.tail[t], 0x80000000u | acc);
+        // ---- 2. the stream's last 8 bits up to the end of this item; look-back #1
+        uint32_t pred_tail = 0xFFFFFFFFu;   // lane 0: the stream's last 8 bits before this item, once they were needed
+        if (!two_pass && lane == 0) {
+            const uint32_t take = min(8u, len), pos = 32u + len - take;
+            uint32_t acc = take ? __funnelshift_l(buf[(pos >> 5) + 1], buf[pos >> 5], pos & 31u) >> (32u - take) : 0u;
+            if (take < 8u) {   // an item of fewer than 8 bits (flat image, one MCU): the rest comes from before
+                pred_tail = it ? fuse_wait_tail(a.tail, it - 1, a.err) : 0u;
+                acc = ((pred_tail << take) | acc) & 0xFFu;
             }
-            const uint64_t G = lookback_exclusive(a.desc_bits, t, total, a.err);
-            if (lane == 0) sh.G = G;
+            st_volatile_u32(&a.tail[it], 0x80000000u | acc);
         }
-        uint32_t *slot = a.slots + (size_t)t * SLOT_WORDS;
-        if (!two_pass) {
-            // ---- 3. shift the share into the tile's bit string (bit 32 + base); clear the buffer behind
-            const uint32_t shv = base & 31u, fw = 1u + (base >> 5);
-            const uint32_t nV = (shv + len + 31u) >> 5;
-            const uint32_t tailbits = (shv + len) & 31u;
-            for (uint32_t i = lane; i < nV; i += 32) {
-                const uint32_t hi_w = i ? sub[i - 1] : 0u, lo_w = sub[i];
-                const uint32_t v = __funnelshift_r(lo_w, hi_w, shv);
-                if ((i == 0 && shv != 0u) || (i == nV - 1 && tailbits != 0u)) atomicOr(&sh.buf[fw + i], v);
-                else sh.buf[fw + i] = v;
+        const uint64_t G = lookback_exclusive<true>(a.desc_bits, it, len, a.err);
+        uint32_t *slot = a.slots + (size_t)it * FUSE_SLOT_WORDS;
+        if (two_pass) {
+            if (!dense) {   // the buffer holds a prefix of the item
+                for (uint32_t i = lane; i < (uint32_t)FUSE_BUF_WORDS; i += 32) buf[i] = 0;
+                __syncwarp();
             }
-            __syncwarp();
-            for (uint32_t i = lane; i < nV + 1; i += 32) sub[i] = 0;
-        } else {
-            if (!dense) {
-                for (uint32_t i = lane; i < (uint32_t)SUB_WORDS + FUSE_SUB_PAD; i += 32) sub[i] = 0;
+            const uint32_t nwords = (len + 31u) >> 5;
+            if (nwords + 4u > (uint32_t)FUSE_SLOT_WORDS) { if (lane == 0) *a.err = 4; continue; }   // beyond any real code table
+            for (uint32_t wbase = 0; wbase < nwords; wbase += FUSE_BITS_WORDS) {
+                pack_scatter<true>(sh, buf, FUSE_BITS_WORDS, tk4, first, lo, hi, -(int)(wbase * 32u), lane, zr_y, zr_c);
+                __syncwarp();
+                const uint32_t wn = min((uint32_t)FUSE_BITS_WORDS, nwords - wbase);
+                for (uint32_t i = lane; i < wn; i += 32) { slot[1u + wbase + i] = buf[i]; buf[i] = 0; }
+                __syncwarp();
             }
-            const uint32_t nwords = (total + 31u) >> 5;
-            for (uint32_t wbase = 0; wbase < nwords; wbase += WIN_WORDS) {
-                pack_scatter<true>(sh, sh.buf, WIN_WORDS, tk4, al, lo, hi, (int)base - (int)(wbase * 32u), lane, zr_y, zr_c);
-                __syncthreads();
-                const uint32_t wn = min((uint32_t)WIN_WORDS, nwords - wbase);
-                for (uint32_t i = tid; i < wn; i += PACK_THREADS) { slot[1u + wbase + i] = sh.buf[i]; sh.buf[i] = 0; }
-                __syncthreads();
-            }
-            if (tid == 0) {
+            if (lane == 0) {
                 slot[1u + nwords] = 0; slot[2u + nwords] = 0;   // the pieces read a little past the end
-                const uint32_t pos = total - 8u;                // a tile has at least 12 bits
+                const uint32_t pos = len - 8u;                  // a dense item has thousands of bits
                 const uint32_t v = __funnelshift_l(slot[1u + (pos >> 5) + 1u], slot[1u + (pos >> 5)], pos & 31u) >> 24;
-                st_volatile_u32(&a.tail[t], 0x80000000u | v);
+                st_volatile_u32(&a.tail[it], 0x80000000u | v);
             }
         }
-        __syncthreads();   // bit string complete, G known
-        const uint64_t G = sh.G;
         const uint32_t phi = (uint32_t)G & 7u;
-        const uint64_t nbytes64 = ((G + total + (last_tile ? 7u : 0u)) >> 3) - (G >> 3);
-        if (tid == 0) {
-            uint32_t *wsrc = two_pass ? slot : sh.buf;
+        const uint64_t nbytes64 = ((G + len + (last_item ? 7u : 0u)) >> 3) - (G >> 3);
+        if (lane == 0) {
+            uint32_t *wsrc = two_pass ? slot : buf;
             uint32_t lead = 0;
-            if (phi) {   // the first byte starts with the last phi bits of the stream before this tile (phi != 0: t > 0)
-                if (pred_tail == 0xFFFFFFFFu) pred_tail = fuse_wait_tail(a.tail, t - 1, a.err);
+            if (phi) {   // the first byte starts with the last phi bits of the stream before this item (phi != 0: it > 0)
+                if (pred_tail == 0xFFFFFFFFu) pred_tail = fuse_wait_tail(a.tail, it - 1, a.err);
                 lead = pred_tail & ((1u << phi) - 1u);
             }
             wsrc[0] = lead;
-            if (last_tile) {   // jchuff.c flush_bits: the last byte is filled with 1-bits
-                const uint32_t pad = (8u - ((phi + total) & 7u)) & 7u;
+            if (last_item) {   // jchuff.c flush_bits: the last byte is filled with 1-bits
+                const uint32_t pad = (8u - ((phi + len) & 7u)) & 7u;
                 if (pad) {
-                    const uint32_t pos = 32u + total, wi = pos >> 5, sb = pos & 31u;
+                    const uint32_t pos = 32u + len, wi = pos >> 5, sb = pos & 31u;
                     const uint64_t v = ((uint64_t)((1u << pad) - 1u) << (64u - pad)) >> sb;
                     wsrc[wi] |= (uint32_t)(v >> 32);
                     if ((uint32_t)v) wsrc[wi + 1] |= (uint32_t)v;
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
         const uint32_t w0 = phi ? 0u : 1u, s = (32u - phi) & 31u;
+        // ---- 3. + 4. (the same code for both homes of the bit string; separate calls keep the address spaces apart)
         uint64_t end;
         if (!two_pass) {
-            const uint32_t st = fuse_stuff_span<true>(sh, a, sh.buf, w0, s, (uint32_t)nbytes64, 0, t, hdr, last_tile);
-            end = (uint64_t)hdr + sh.goff + st;
-            for (uint32_t i = tid; i < ((32u + total + 31u) >> 5) + 6u; i += PACK_THREADS) sh.buf[i] = 0;
+            const uint32_t st = fuse_count_span(buf, w0, s, nbytes64);
+            const uint64_t goff = lookback_exclusive<true>(a.desc_bytes, it, st, a.err);
+            fuse_stuff_span(stage, sh.lut, a, buf, w0, s, nbytes64, goff, hdr, last_item);
+            end = (uint64_t)hdr + goff + st;
+            for (uint32_t i = lane; i < ((32u + len + 31u) >> 5) + 2u; i += 32) buf[i] = 0;
+            __syncwarp();
         } else {
-            // counting pass, then look-back #2, then span by span
-            uint32_t c = 0;
-            for (uint64_t jb = (uint64_t)tid * 16u; jb < nbytes64; jb += FUSE_ROUND) {
-                const int nvalid = (int)min((uint64_t)16, nbytes64 - jb);
-                uint32_t w[4];
-                fuse_load_piece(slot, w0, s, (uint32_t)(jb >> 4), w);
-                c += (uint32_t)nvalid + fuse_count_ff(w, nvalid);
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) sh.s_warp[0][wid] = c;
-            __syncthreads();
-            uint32_t stot = 0;
-#pragma unroll
-            for (int k = 0; k < PACK_WARPS; k++) stot += sh.s_warp[0][k];
-            __syncthreads();   // s_warp is reused by the spans
-            if (wid == 0) {
-                const uint64_t pre = lookback_exclusive(a.desc_bytes, t, stot, a.err);
-                if (lane == 0) sh.goff = pre;
-            }
-            __syncthreads();
-            uint64_t goff = sh.goff;
-            for (uint64_t b0 = 0; b0 < nbytes64; b0 += FUSE_SPAN) {
-                const uint32_t nb = (uint32_t)min((uint64_t)FUSE_SPAN, nbytes64 - b0);
-                goff += fuse_stuff_span<false>(sh, a, slot + (b0 >> 2), w0, s, nb, goff, t, hdr, last_tile && b0 + FUSE_SPAN >= nbytes64);
-                __syncthreads();
-            }
-            end = (uint64_t)hdr + goff;
+            const uint32_t st = fuse_count_span(slot, w0, s, nbytes64);
+            const uint64_t goff = lookback_exclusive<true>(a.desc_bytes, it, st, a.err);
+            fuse_stuff_span(stage, sh.lut, a, slot, w0, s, nbytes64, goff, hdr, last_item);
+            end = (uint64_t)hdr + goff + st;
         }
-        if (last_tile && tid == 0) {
+        if (last_item && lane == 0) {
             if (end + 2 <= a.cap) { a.out[end] = 0xFF; a.out[end + 1] = 0xD9; }
             *a.out_len = end + 2;
         }
@@ -1605,15 +1513,16 @@ cudaError_t launch_seam_from_bits(int *seam, const int64_t *bits_all, int rank, 
     k_seam_from_bits<<<1, 1, 0, s>>>(seam, bits_all, rank, world);
     return cudaGetLastError();
 }
+int fuse_items(int ntiles) { return ntiles * FUSE_PARTS; }
 cudaError_t launch_pack_stuff(const uint32_t *pool, const TileRec *recs, const Geom &g, const HuffDev *huff, uint32_t *slots,
-                              uint32_t *tile_bits, int force_overflow, uint64_t *desc_bits, uint64_t *desc_bytes, uint32_t *tail,
+                              int small_buffers, uint64_t *desc_bits, uint64_t *desc_bytes, uint32_t *tail,
                               uint32_t *ticket, uint8_t *out, size_t cap, uint64_t *out_len, uint32_t *err, cudaStream_t s) {
     FuseArgs a;
-    a.pool = pool; a.recs = recs; a.ntiles = g.ntiles; a.huff = huff; a.slots = slots; a.tile_bits = tile_bits;
-    a.sub_words = force_overflow ? 24u : (uint32_t)SUB_WORDS;
+    a.pool = pool; a.recs = recs; a.ntiles = g.ntiles; a.huff = huff; a.slots = slots;
+    a.buf_words = small_buffers ? 48u : (uint32_t)FUSE_BITS_WORDS;
     a.desc_bits = desc_bits; a.desc_bytes = desc_bytes; a.tail = tail; a.ticket = ticket; a.out = out; a.cap = cap;
     a.out_len = out_len; a.err = err;
-    const int grid = std::min(g.ntiles, 148 * PACK_CTAS);
+    const int grid = std::min((g.ntiles * FUSE_PARTS + PACK_WARPS - 1) / PACK_WARPS, 148 * FUSE_CTAS);
     return launch_pdl(k_pack_stuff, dim3(grid), dim3(PACK_THREADS), 0, s, a);
 }
 
