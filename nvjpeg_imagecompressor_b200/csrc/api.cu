@@ -168,7 +168,7 @@ static void make_quant(int quality, QuantDev *q) {
             if (v > 255) v = 255;
             const uint32_t d = 8u * (uint32_t)v;
             q->q[t][i] = (uint16_t)v;
-            q->finv[t][i] = (float)((1.0 / (double)d) * (1.0 + 1.0 / 1048576.0));   // see k_fdct: exact for |c| <= 2^18
+            q->finv[t][i] = (float)((1.0 / (double)d) * (1.0 + 1.0 / 1048576.0)) * 4096.0f;   // see k_fdct: exact for |c| <= 2^18
         }
 }
 

@@ -105,7 +105,7 @@ __device__ __constant__ const uint8_t c_zigzag_nat[64] = {0,  1,  8,  16, 9,  2,
 __device__ __forceinline__ int zigzag_nat_rt(int k) { return c_zigzag_nat[k]; }
 
 // ---- device-side tables -------------------------------------------------------------------------------
-struct QuantDev {          // forward: q = low half of fma(c, finv, 1.5 * 2^23), natural order; [0] luma, [1] chroma
+struct QuantDev {          // forward: q = low half of fma(c, finv, 1.5 * 2^35), finv = 4096 (1 + 2^-20) / (8 q); natural order; [0] luma, [1] chroma
     float finv[2][64];
     uint16_t q[2][64];     // natural order quant values (dequantisation + DQT marker)
 };

@@ -388,14 +388,16 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
         v[0] -= 8192;  // 64 samples x 128: the only output the -128 level shift changes (exact: multiple of 4)
 
         // quantise (jcdctmgr.c): q = sign(c) * ((|c| + d/2) / d), d = 8*qtbl, on the FMA pipes, which the integer
-        // transform leaves idle: with finv = fl32((1 + 2^-20) / d) the single rounding of fma(c, finv, 1.5 * 2^23) lands
-        // on exactly that quotient for every divisor and |c| <= 2^18 (ties of |c|/d go away from zero because finv is a
-        // little large, everything else is further than |c| * 2^-20 from a tie; checked exhaustively on the CPU,
-        // tests/cpp/quant_exhaustive.c). The quotient is the low half of the result's bit pattern; results are kept
-        // as 16-bit pairs in zig-zag order (they live across the CTA scan below); the non-zero AC coefficients are
-        // counted on the way (one token each) as saturate(q * q), also on the FMA pipes.
+        // transform leaves idle. The table holds finv = fl32((1 + 2^-20) / d) * 4096: the single rounding of
+        // fma(c, finv, 1.5 * 2^35) lands on 4096 * that quotient for every divisor and |c| <= 2^18 (ties of |c|/d go away
+        // from zero because finv is a little large, everything else is further than |c| * 2^-20 from a tie), i.e. the
+        // quotient is the low half of the result's bit pattern. The same table value counts the non-zero AC
+        // coefficients (one token each) with ONE saturating FMA: |c| * finv - 2047 is >= 1 from |c| = d/2 on and
+        // negative below. Both checked exhaustively on the CPU (tests/cpp/quant_exhaustive.c). Results are kept as
+        // 16-bit pairs in zig-zag order (they live across the CTA scan below).
         const float4 *qt = reinterpret_cast<const float4 *>(qs + ((C::HV > 1 && !real) ? 2 : tbl) * 64);
-        constexpr float MAGIC = 12582912.0f;   // 1.5 * 2^23
+        constexpr float MAGIC = 12582912.0f;        // 1.5 * 2^23: int -> float
+        constexpr float MAGICK = 51539607552.0f;    // 1.5 * 2^35: bit pattern 0x51400000 + quotient
         float nnzf = 0.0f;
 #pragma unroll
         for (int n4 = 0; n4 < 16; n4++) {
@@ -405,12 +407,11 @@ k_fdct(const uint8_t *__restrict__ img, size_t step, Geom g, const QuantDev *__r
             for (int j = 0; j < 4; j++) {
                 const int n = n4 * 4 + j;
                 const float xf = __int_as_float(v[n] + 0x4B400000) - MAGIC;   // exact int -> float for |c| < 2^22
-                const float r = fmaf(xf, qq[j], MAGIC);
-                if (n != 0) { const float zf = r - MAGIC; nnzf += __saturatef(zf * zf); }
-                v[n] = __float_as_int(r);
+                if (n != 0) nnzf += __saturatef(fmaf(fabsf(xf), qq[j], -2047.0f));
+                v[n] = __float_as_int(fmaf(xf, qq[j], MAGICK));
             }
         }
-        mydc = v[0] - 0x4B400000;
+        mydc = v[0] - 0x51400000;
 #pragma unroll
         for (int k = 0; k < 64; k += 2) pk[k >> 1] = __byte_perm((uint32_t)v[zigzag_nat(k)], (uint32_t)v[zigzag_nat(k + 1)], 0x5410);
         ntok = 1 + (int)nnzf + ((pk[31] >> 16) == 0u ? 1 : 0);   // DC, one per non-zero AC, EOB iff the last coefficient is zero

@@ -440,16 +440,23 @@ __device__ __forceinline__ int pack_scatter(const SH &sh, uint32_t *buf, uint32_
         for (int k = 0; k < PACK_K; k++) {
             uint32_t n = L[k];
             const uint32_t nz = (w[k] >> 26) & 3u;
-            if (nz) {   // ZRL symbols ahead of this coefficient (about one token in sixty)
-                const uint32_t zr = (bin_table((w[k] >> 16) & 0x3FFu) & 2u) ? zr_c : zr_y;
-                n -= nz * (zr & 31u);
-                e.put(zr >> 8, zr & 31u);
-                if (nz > 1u) {
-                    e.put(zr >> 8, zr & 31u);
-                    if (nz > 2u) e.put(zr >> 8, zr & 31u);
+            uint32_t b = bits[k];
+            if (nz) {   // ZRL symbols ahead of this coefficient (about one token in sixty, i.e. one lane in most steps)
+                // AC tokens: tcode 0 luma / 1 chroma, and the table field holds (tcode + run) & 3 (common.cuh)
+                const uint32_t zr = (((w[k] >> 16) - (w[k] >> 22)) & 1u) ? zr_c : zr_y;
+                const uint32_t zl = zr & 31u, tl = n - nz * zl;
+                if (nz == 1u && n <= 32u) {   // the usual case: the ZRL code rides on top of the token's bits
+                    b |= (zr >> 8) << tl;
+                } else {
+                    n = tl;
+                    e.put(zr >> 8, zl);
+                    if (nz > 1u) {
+                        e.put(zr >> 8, zl);
+                        if (nz > 2u) e.put(zr >> 8, zl);
+                    }
                 }
             }
-            e.put(bits[k], n);
+            e.put(b, n);
         }
         if (!WINDOWED) __syncwarp();   // every whole word of this step is stored: now the pieces that do not fill a word
         e.finish();
