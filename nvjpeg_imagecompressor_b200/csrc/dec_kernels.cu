@@ -956,27 +956,37 @@ k_upcolor(const uint8_t *__restrict__ py, const uint8_t *__restrict__ pcb, const
     if (x0 >= 8 && x0 + 16 <= g.W && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         const uint2 yw = *reinterpret_cast<const uint2 *>(py + (size_t)y * ys + x0);
         int cbv[8], crv[8];
+        uint32_t o32[6];
         chroma8_interior<HS, VS>(pcb, cs, rlo, rhi, x0, y, cbv);
         chroma8_interior<HS, VS>(pcr, cs, rlo, rhi, x0, y, crv);
+        // jdcolor.c ycc_rgb_convert with the tables written out: r = y + ((91881 (cr - 128) + 32768) >> 16) etc. Here y sits
+        // at bit 16 of the accumulator, the -128 and the rounding are one constant per channel, the sum is clamped to
+        // [0, 255.99..] and the result is byte 2 of the word: same integers, a third fewer instructions per pixel.
+        uint32_t B[8], G[8], R[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int Y = (int)(((i < 4 ? yw.x : yw.y) >> (8 * (i & 3))) & 0xFF);
-            const int cb = cbv[i] - 128, cr = crv[i] - 128;
-            const int r = Y + ((91881 * cr + 32768) >> 16);
-            const int b = Y + ((116130 * cb + 32768) >> 16);
-            const int gg = Y + ((-22554 * cb - 46802 * cr + 32768) >> 16);
-            o[3 * i] = (uint8_t)min(255, max(0, b));
-            o[3 * i + 1] = (uint8_t)min(255, max(0, gg));
-            o[3 * i + 2] = (uint8_t)min(255, max(0, r));
+            const int Y16 = (int)__byte_perm(i < 4 ? yw.x : yw.y, 0u, 0x4044u | ((uint32_t)(i & 3) << 8));   // y << 16
+            const int cb = cbv[i], cr = crv[i];
+            const int r = 91881 * cr + Y16 + (32768 - 128 * 91881);
+            const int b = 116130 * cb + Y16 + (32768 - 128 * 116130);
+            const int gg = -22554 * cb - 46802 * cr + Y16 + (32768 + 128 * (22554 + 46802));
+            R[i] = (uint32_t)min(0x00FFFFFF, max(0, r));
+            B[i] = (uint32_t)min(0x00FFFFFF, max(0, b));
+            G[i] = (uint32_t)min(0x00FFFFFF, max(0, gg));
         }
+        // bytes b g r b | g r b g | r b g r per four pixels, every one byte 2 of its word
         uint2 *d2 = reinterpret_cast<uint2 *>(dst);
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) { lo |= (uint32_t)o[8 * j + c] << (8 * c); hi |= (uint32_t)o[8 * j + 4 + c] << (8 * c); }
-            d2[j] = make_uint2(lo, hi);
+        for (int h = 0; h < 2; h++) {
+            const int k = 4 * h;
+            const uint32_t w0 = __byte_perm(__byte_perm(B[k], G[k], 0x0062), __byte_perm(R[k], B[k + 1], 0x0062), 0x5410);
+            const uint32_t w1 = __byte_perm(__byte_perm(G[k + 1], R[k + 1], 0x0062), __byte_perm(B[k + 2], G[k + 2], 0x0062), 0x5410);
+            const uint32_t w2 = __byte_perm(__byte_perm(R[k + 2], B[k + 3], 0x0062), __byte_perm(G[k + 3], R[k + 3], 0x0062), 0x5410);
+            o32[3 * h] = w0; o32[3 * h + 1] = w1; o32[3 * h + 2] = w2;
         }
+        d2[0] = make_uint2(o32[0], o32[1]);
+        d2[1] = make_uint2(o32[2], o32[3]);
+        d2[2] = make_uint2(o32[4], o32[5]);
         return;
     }
 #pragma unroll
