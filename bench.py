@@ -34,12 +34,12 @@ PUBLISHED_MPIX_S = 1652.0   # BASELINE.md section 1 (reference README.md:48): 33
 
 
 def kernel_source_digest():
-    """sha256 over the CUDA sources of the library: profiles/traffic.json carries the digest of the code it was captured on
-    (scripts/ncu_export.py); a capture of other code is not reported as this run's traffic."""
-    import glob
+    """sha256 over the CUDA sources of the ENCODE kernels (the ones profiles/traffic.json holds): the file carries the
+    digest of the code it was captured on (scripts/ncu_export.py); a capture of other code is not reported as this run's
+    traffic. Decoder-only sources do not count."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "nvjpeg_imagecompressor_b200", "csrc", "*"))):
+    for f in [os.path.join(ROOT, "nvjpeg_imagecompressor_b200", "csrc", n) for n in ("common.cuh", "enc_fdct.cu", "enc_huff.cu")]:
         with open(f, "rb") as fh:
             h.update(os.path.basename(f).encode() + b"\0" + fh.read())
     return h.hexdigest()[:16]

@@ -30,9 +30,9 @@ for r in rows[2:]:
                   "ncu_ms": round(to_ms(r[ix["gpu__time_duration.sum"]], units[ix["gpu__time_duration.sum"]]), 4),
                   "warp_instructions": int(float(r[ix["smsp__inst_executed.sum"]])),
                   "issue_active_pct": round(float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]), 1)}
-import glob, hashlib
-_h = hashlib.sha256()
-for _f in sorted(glob.glob(os.path.join(root, "nvjpeg_imagecompressor_b200", "csrc", "*"))):
+import hashlib
+_h = hashlib.sha256()   # the encode kernels' sources, as bench.py kernel_source_digest()
+for _f in [os.path.join(root, "nvjpeg_imagecompressor_b200", "csrc", n) for n in ("common.cuh", "enc_fdct.cu", "enc_huff.cu")]:
     _h.update(os.path.basename(_f).encode() + b"\0" + open(_f, "rb").read())
 json.dump({"source": f"profiles/{tag}_raw.csv (ncu --set full --clock-control none, headline config, one launch each)",
            "source_digest": _h.hexdigest()[:16],   # bench.py reports `traffic` only for the code this was captured on
