@@ -790,71 +790,104 @@ __device__ __forceinline__ void idct8(int &i0, int &i1, int &i2, int &i3, int &i
     i3 = (t13 + a0 + RND) >> SH; i4 = (t13 - a0 + RND) >> SH;
 }
 
+// Persistent CTAs (two per SM: 128 registers per thread) walk tiles of 256 blocks; the tile's 32 KB of coefficients
+// arrive by cp.async (16 bytes per request, written straight to their bank-swizzled place) into one of two shared
+// buffers while the previous tile is transformed, so the load latency that used to sit in front of every tile's
+// arithmetic is hidden. The de-quantisation table is kept as 32-bit words in zig-zag order (one 16-byte load per four
+// coefficients); samples are clamped with the fused add-min/max and packed with byte permutes.
+constexpr int IDCT_TILE = 256;
+constexpr int IDCT_SMEM = 2 * IDCT_TILE * 8 * 16;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256, 2)
 k_idct(const int16_t *__restrict__ coef, const int16_t *__restrict__ dcarr, Geom g, const DecTables *__restrict__ tb,
        uint8_t *__restrict__ py, uint8_t *__restrict__ pcb, uint8_t *__restrict__ pcr, int rst_mcus) {
-    __shared__ __align__(16) uint4 s_c[256 * 8];
-    __shared__ uint16_t s_q[2][64];
+    extern __shared__ __align__(16) uint4 s_c[];   // [2][IDCT_TILE * 8], chunk c of block b at b * 8 + (c ^ (b & 7))
+    __shared__ __align__(16) int s_q[2][64];       // zig-zag order
     const int tid = threadIdx.x;
-    const int b0 = blockIdx.x * 256;
-    const int nb = min(256, g.nblocks - b0);
-    for (int i = tid; i < nb * 8; i += 256) {
-        const int b = i >> 3, c = i & 7;
-        s_c[b * 8 + (c ^ (b & 7))] = ld_nc_v4(reinterpret_cast<const uint4 *>(coef) + (size_t)b0 * 8 + i);
-    }
-    if (tid < 128) s_q[tid >> 6][tid & 63] = tb->q[tid >> 6][tid & 63];
-    __syncthreads();
-    if (tid >= nb) return;
-    const int b = b0 + tid;
+    const int ntile = (g.nblocks + IDCT_TILE - 1) / IDCT_TILE;
+    const uint4 *coef4 = reinterpret_cast<const uint4 *>(coef);
+    auto issue = [&](int tile, int buf) {
+        const int b0 = tile * IDCT_TILE, nb = min(IDCT_TILE, g.nblocks - b0);
+        uint4 *dstb = s_c + buf * (IDCT_TILE * 8);
+        for (int i = tid; i < nb * 8; i += 256) {
+            const int b = i >> 3, c = i & 7;
+            cp_async16(dstb + b * 8 + (c ^ (b & 7)), coef4 + (size_t)b0 * 8 + i);
+        }
+        cp_async_commit();
+    };
+    int t = blockIdx.x;
+    if (t < ntile) issue(t, 0);
+    if (tid < 128) s_q[tid >> 6][tid & 63] = (int)tb->q[tid >> 6][zigzag_nat_rt(tid & 63)];
     const int hv = g.bpm - 2;
-    const int m = b / g.bpm, bn = b - m * g.bpm;
-    const int my = m / g.mcux, mx = m - my * g.mcux;
-    const bool isY = bn < hv;
-    const uint16_t *q = s_q[isY ? 0 : 1];
-    int v[64];
+    for (int k = 0; t < ntile; t += gridDim.x, k++) {
+        const int tn = t + gridDim.x;
+        if (tn < ntile) { issue(tn, (k + 1) & 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();   // tile t has landed (every thread waited for its own requests)
+        const int b0 = t * IDCT_TILE, nb = min(IDCT_TILE, g.nblocks - b0);
+        if (tid < nb) {
+            const uint4 *sc = s_c + (k & 1) * (IDCT_TILE * 8);
+            const int b = b0 + tid;
+            const int m = b / g.bpm, bn = b - m * g.bpm;
+            const int my = m / g.mcux, mx = m - my * g.mcux;
+            const bool isY = bn < hv;
+            const int4 *q4 = reinterpret_cast<const int4 *>(s_q[isY ? 0 : 1]);
+            int v[64];
+            int c0raw = 0;
 #pragma unroll
-    for (int ch = 0; ch < 8; ch++) {
-        const uint4 w = s_c[tid * 8 + (ch ^ (tid & 7))];
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            for (int ch = 0; ch < 8; ch++) {
+                const uint4 w = sc[tid * 8 + (ch ^ (tid & 7))];
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                const int4 qa = q4[2 * ch], qb = q4[2 * ch + 1];
+                const int qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                if (ch == 0) c0raw = (int)(int16_t)(w.x & 0xFFFFu);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = ch * 8 + j;
-            const int n = zigzag_nat(k);
-            const int cv = (j & 1) ? ((int)ww[j >> 1] >> 16) : (int)(int16_t)(ww[j >> 1] & 0xFFFFu);
-            v[n] = cv * (int)q[n];
+                for (int j = 0; j < 8; j++) {
+                    const int n = zigzag_nat(ch * 8 + j);
+                    const int cv = (j & 1) ? ((int)ww[j >> 1] >> 16) : (int)(int16_t)(ww[j >> 1] & 0xFFFFu);
+                    v[n] = cv * qq[j];
+                }
+            }
+            // the un-differenced DC (the coefficient array holds the difference): k_dc_scan's running sum, taken from the
+            // start of the block's restart interval (predictors return to 0 there; 16-bit modular differences are exact)
+            // (dcarr == NULL: the blocks come from the encoder and hold the quantised DC itself -- b2j_reconstruct_*)
+            int dcv = dcarr ? (int)dcarr[b] : c0raw;
+            if (dcarr && rst_mcus > 0 && m >= rst_mcus) {
+                const int pm = (m / rst_mcus) * rst_mcus - 1;   // last MCU of the previous interval
+                dcv = (int16_t)(dcv - (int)dcarr[pm * g.bpm + (isY ? hv - 1 : bn)]);
+            }
+            v[0] = dcv * s_q[isY ? 0 : 1][0];
+#pragma unroll
+            for (int c = 0; c < 8; c++) idct8<11>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+            uint8_t *dst;
+            size_t stride;
+            if (isY) {
+                const int by = bn / g.hs, bx = bn - by * g.hs;
+                stride = (size_t)g.mcux * 8 * g.hs;
+                dst = py + ((size_t)(my * g.vs + by) * 8) * stride + (size_t)(mx * g.hs + bx) * 8;
+            } else {
+                stride = (size_t)g.mcux * 8;
+                dst = (bn == hv ? pcb : pcr) + ((size_t)my * 8) * stride + (size_t)mx * 8;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                idct8<18>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+                uint32_t x[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) x[c] = (uint32_t)min(255, max(0, v[r * 8 + c] + 128));
+                const uint32_t lo = __byte_perm(__byte_perm(x[0], x[1], 0x0040), __byte_perm(x[2], x[3], 0x0040), 0x5410);
+                const uint32_t hi = __byte_perm(__byte_perm(x[4], x[5], 0x0040), __byte_perm(x[6], x[7], 0x0040), 0x5410);
+                *reinterpret_cast<uint2 *>(dst + r * stride) = make_uint2(lo, hi);
+            }
         }
-    }
-    // the un-differenced DC (the coefficient array holds the difference): k_dc_scan's running sum, taken from the start
-    // of the block's restart interval (predictors return to 0 there; 16-bit modular differences are exact)
-    // (dcarr == NULL: the blocks come from the encoder and hold the quantised DC itself -- b2j_reconstruct_device)
-    int dcv = dcarr ? (int)dcarr[b] : (int)(int16_t)(s_c[tid * 8 + (0 ^ (tid & 7))].x & 0xFFFFu);
-    if (dcarr && rst_mcus > 0 && m >= rst_mcus) {
-        const int pm = (m / rst_mcus) * rst_mcus - 1;   // last MCU of the previous interval
-        dcv = (int16_t)(dcv - (int)dcarr[pm * g.bpm + (isY ? hv - 1 : bn)]);
-    }
-    v[0] = dcv * (int)q[0];
-#pragma unroll
-    for (int c = 0; c < 8; c++) idct8<11>(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
-    uint8_t *dst;
-    size_t stride;
-    if (isY) {
-        const int by = bn / g.hs, bx = bn - by * g.hs;
-        stride = (size_t)g.mcux * 8 * g.hs;
-        dst = py + ((size_t)(my * g.vs + by) * 8) * stride + (size_t)(mx * g.hs + bx) * 8;
-    } else {
-        stride = (size_t)g.mcux * 8;
-        dst = (bn == hv ? pcb : pcr) + ((size_t)my * 8) * stride + (size_t)mx * 8;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        idct8<18>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            lo |= (uint32_t)min(255, max(0, v[r * 8 + c] + 128)) << (8 * c);
-            hi |= (uint32_t)min(255, max(0, v[r * 8 + 4 + c] + 128)) << (8 * c);
-        }
-        *reinterpret_cast<uint2 *>(dst + r * stride) = make_uint2(lo, hi);
+        __syncthreads();   // buffer k & 1 is free for the tile after next
     }
 }
 
@@ -1091,7 +1124,19 @@ cudaError_t launch_dc_scan(int16_t *coef, const Geom &g, uint64_t *desc, uint32_
 
 cudaError_t launch_idct(const int16_t *coef, const int16_t *dcarr, const Geom &g, const void *tb, uint8_t *py, uint8_t *pcb,
                         uint8_t *pcr, int rst_mcus, cudaStream_t s) {
-    k_idct<<<g.ntiles, 256, 0, s>>>(coef, dcarr, g, (const DecTables *)tb, py, pcb, pcr, rst_mcus);
+    // the dynamic shared-memory attribute is per device: one bit per device ordinal
+    static std::atomic<uint64_t> attr_done{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+        e = cudaFuncSetAttribute(k_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, IDCT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done.fetch_or(bit, std::memory_order_release);
+    }
+    const int ntile = (g.nblocks + IDCT_TILE - 1) / IDCT_TILE;
+    k_idct<<<std::max(1, std::min(ntile, 148 * 2)), 256, IDCT_SMEM, s>>>(coef, dcarr, g, (const DecTables *)tb, py, pcb, pcr, rst_mcus);
     return cudaGetLastError();
 }
 
