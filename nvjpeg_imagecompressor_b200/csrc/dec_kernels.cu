@@ -145,10 +145,13 @@ constexpr int SUB_BITS = 1024;                 // subsequence length
 constexpr int SUB_WORDS = SUB_BITS / 32;
 constexpr int DEC_THREADS = 256;               // subsequences per CTA
 constexpr int DEC_FIRST_SKIP = 512;            // bits of every subsequence the first synchronisation pass does not decode
-constexpr int DEC_SMEM_WORDS = SUB_WORDS * (DEC_THREADS + 1);
+// The chunk's words live at g + (g >> 5): one pad word per subsequence, so threads that stand at the same word of their
+// own subsequences hit 32 different banks, and the address is one shift and one add per load.
+constexpr int DEC_SMEM_WORDS = SUB_WORDS * DEC_THREADS + DEC_THREADS + 8;
+__device__ __forceinline__ uint32_t dec_widx(uint32_t g) { return g + (g >> 5); }
 
 struct DecShared {
-    uint32_t words[DEC_SMEM_WORDS];            // [word-in-subsequence][subsequence(+1 overflow column)]
+    uint32_t words[DEC_SMEM_WORDS];            // word g of the chunk (+ 2 of overflow) at dec_widx(g)
     uint16_t lut[4][1 << DEC_LUT_BITS];
     int32_t maxcode[4][18];
     int32_t valoff[4][17];
@@ -221,9 +224,8 @@ __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t c
     while (q < stop) {
         if (RST && q >= rt.lim) { c = 0; k = 0; rt.next(); }   // an interval begins here
         const uint32_t g = q >> 5, o = q & 31u;
-        const uint32_t w0 = sh.words[(g & 31u) * (DEC_THREADS + 1) + (g >> 5)];
-        const uint32_t g1 = g + 1;
-        const uint32_t w1 = sh.words[(g1 & 31u) * (DEC_THREADS + 1) + (g1 >> 5)];
+        const uint32_t w0 = sh.words[dec_widx(g)];
+        const uint32_t w1 = sh.words[dec_widx(g + 1)];
         const uint32_t win = __funnelshift_l(w1, w0, o);  // 32 bits starting at q
         const bool dc = k == 0;
         const uint32_t t = (c < hv ? 0u : 2u) + (dc ? 0u : 1u);
@@ -269,7 +271,7 @@ __device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__r
     for (int i = tid; i < SUB_WORDS * DEC_THREADS + 2; i += DEC_THREADS) {
         const size_t gw = w0 + i;
         const uint32_t w = gw < nwords ? uw[gw] : 0xFFFFFFFFu;
-        sh.words[(i & 31) * (DEC_THREADS + 1) + (i >> 5)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
+        sh.words[dec_widx((uint32_t)i)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
     }
     for (int i = tid; i < 4 * (1 << DEC_LUT_BITS); i += DEC_THREADS) (&sh.lut[0][0])[i] = (&tb->lut[0][0])[i];
     for (int i = tid; i < 4 * 18; i += DEC_THREADS) (&sh.maxcode[0][0])[i] = (&tb->maxcode[0][0])[i];
@@ -520,9 +522,8 @@ k_dec_sync_long(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_le
 // collects the block's coefficients in a 128-byte cell of shared memory; the warp runs in lock step, one symbol per
 // lane and iteration, and after every iteration the lanes that completed a block have it written out by the whole
 // warp: one coalesced 128-byte store per block, zeros included -- no memset of the array, no scattered 2-byte stores.
-constexpr int WR_STRIDE = DEC_THREADS + 3;           // columns: 256 subsequences + 2 of lookahead, odd stride
 struct DecWriteShared {
-    uint32_t words[SUB_WORDS * WR_STRIDE];           // [word-in-subsequence][subsequence]
+    uint32_t words[SUB_WORDS * (DEC_THREADS + 2) + DEC_THREADS + 2 + 8];   // 256 subsequences + 2 of lookahead, word g at dec_widx(g)
     uint16_t lut[4][1 << DEC_LUT_BITS];
     int32_t maxcode[4][18];
     int32_t valoff[4][17];
@@ -551,7 +552,7 @@ k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, c
         for (int i = tid; i < SUB_WORDS * (DEC_THREADS + 2); i += DEC_THREADS) {
             const size_t gw = w0 + i;
             const uint32_t w = gw < nwords ? uw[gw] : 0xFFFFFFFFu;
-            sh.words[(i & 31) * WR_STRIDE + (i >> 5)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
+            sh.words[dec_widx((uint32_t)i)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
         }
         for (int i = tid; i < 4 * (1 << DEC_LUT_BITS); i += DEC_THREADS) (&sh.lut[0][0])[i] = (&tb->lut[0][0])[i];
         for (int i = tid; i < 4 * 18; i += DEC_THREADS) (&sh.maxcode[0][0])[i] = (&tb->maxcode[0][0])[i];
@@ -584,9 +585,8 @@ k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, c
         if (active) {
             if (RST && q >= rt.lim) { c = 0; k = 0; rt.next(); }   // an interval begins here (states are synchronised: nothing pending)
             const uint32_t g = q >> 5, o = q & 31u;
-            const uint32_t w0 = sh.words[(g & 31u) * WR_STRIDE + (g >> 5)];
-            const uint32_t g1 = g + 1;
-            const uint32_t w1 = sh.words[(g1 & 31u) * WR_STRIDE + (g1 >> 5)];
+            const uint32_t w0 = sh.words[dec_widx(g)];
+            const uint32_t w1 = sh.words[dec_widx(g + 1)];
             const uint32_t win = __funnelshift_l(w1, w0, o);
             const bool dc = k == 0;
             const uint32_t t = (c < hv ? 0u : 2u) + (dc ? 0u : 1u);
