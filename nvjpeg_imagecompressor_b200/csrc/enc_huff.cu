@@ -322,7 +322,8 @@ k_tables(const uint32_t *hist /* the predecessor's output: no __restrict__, load
 //      OR-ed into a per-boundary cell that thread 0 writes after the NEXT tile's barrier (cells double-buffered)
 // Dense tiles (more tokens than the warp buffers are sure to hold, or a buffer that overflowed) take the two-pass
 // path: lengths first, then the bits are scattered window by window into one tile-wide buffer.
-// Raw-DC tokens were resolved by k_dc_edge_hist; ZRL prefixes (token bits 29:28) are emitted in a side branch.
+// Raw-DC tokens were resolved by k_dc_edge_hist; ZRL prefixes (token bits 27:26) ride on the token when there is one and
+// the bits fit a word, and are emitted in a side branch otherwise.
 constexpr int WIN_WORDS = 2048;                  // dense tiles: 64 kbit window of the tile's bit string
 constexpr int SUB_WORDS = 512;                   // per-warp bit buffer: 16 kbit (a typical share is ~7.5 kbit)
 constexpr int PACK_THREADS = 128;                // one CTA per tile at a time, PACK_WARPS contiguous shares
