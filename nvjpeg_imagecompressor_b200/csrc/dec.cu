@@ -191,13 +191,13 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
     // ---- front end, pipelined: the scan goes up in pieces on its own stream; every piece is de-stuffed as soon as it
     // has landed and the first synchronisation pass runs on the decoder chunks whose bytes are complete, so most of
     // that pass hides behind the upload (large scans, speculative mode).
-    const int nch = (int)((n + 4095) / 4096);
+    const uint8_t *scan_in = d_scan_src ? d_scan_src : d->d_scan;
+    const int nch = destuff_chunks(scan_in, n);   // d_scan is 256-byte aligned: pieces below fall on chunk borders
     // restart markers: one piece (a marker's two bytes may straddle pieces: k_destuff looks one byte ahead)
     const int npieces = (spec && n >= (16u << 20) && !rst && !d_scan_src) ? 8 : 1;   // fewer, larger pieces: a piece should fill the GPU
-    const uint8_t *scan_in = d_scan_src ? d_scan_src : d->d_scan;
     uint32_t *bnd = rst ? d->d_bnd : nullptr;
     const uint32_t *nmark = rst ? &d->d_ctrl->nmark : nullptr;
-    const size_t piece = ((n + npieces - 1) / npieces + 4095) & ~(size_t)4095;
+    const size_t piece = ((n + npieces - 1) / npieces + DS_CHUNK - 1) & ~(size_t)(DS_CHUNK - 1);
     DCK(cudaEventRecord(d->ev_up[32], s));                       // the scan buffer is free once earlier work on s is done
     DCK(cudaStreamWaitEvent(d->up_stream, d->ev_up[32], 0));
     for (int j = 0; j < npieces; j++) {
@@ -212,7 +212,7 @@ int dec_run(Decoder *d, const uint8_t *jpg, size_t len, const JpegInfo &info, co
         }
         DCK(cudaEventRecord(d->ev_up[j], d->up_stream));
         DCK(cudaStreamWaitEvent(s, d->ev_up[j], 0));
-        const int c0 = (int)(b0 / 4096), c1 = j == npieces - 1 ? nch : (int)(b1 / 4096);
+        const int c0 = (int)(b0 / DS_CHUNK), c1 = j == npieces - 1 ? nch : (int)(b1 / DS_CHUNK);
         if (c1 > c0) {
             DCK(launch_destuff(scan_in, n, d->d_u, d->d_desc, &d->d_ctrl->dticket[j], c0, c1, &d->d_ctrl->u_len, &d->d_ctrl->avail,
                                bnd, (uint32_t)d->bnd_cap, &d->d_ctrl->nmark, &d->d_ctrl->err, s));

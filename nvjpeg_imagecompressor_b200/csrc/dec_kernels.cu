@@ -17,91 +17,195 @@
 namespace b2j {
 
 // ------------------------------------------------------------------------------------------------------
-// k_destuff: drop the 0x00 that follows every 0xFF. 16 bytes per thread, 4 KB per chunk, persistent CTAs with
-// ticketed chunks and a decoupled look-back over the kept-byte counts. Output is padded with 0xFF bytes (1-bits).
-// One launch handles the 4 KB chunks [c0, c1) of the scan (the bytes before them are already there: a byte only looks
-// at its predecessor), so the scan can be de-stuffed piece by piece while it is still being uploaded; look-back
+// k_destuff: drop the 0x00 that follows every 0xFF. Persistent CTAs take 16 KB chunks by ticket: every thread loads four
+// 16-byte vectors (piece p of all threads, then piece p + 1: the stream order), finds the dropped bytes with byte-lane
+// arithmetic on the words, the kept-byte counts are scanned across the CTA and chained by a decoupled look-back, the
+// kept bytes are compacted word by word with a 16-entry table of PRMT selectors into a zeroed staging buffer and
+// copied out as 16-byte vectors. Output is padded with 0xFF bytes (1-bits).
+// The input may start at any address: the chunk grid is laid over the 16-byte aligned stream that begins up to 15
+// bytes earlier (bytes outside [in, in + n) count as absent), so every load is an aligned vector.
+// One launch handles the chunks [c0, c1) of the scan (the bytes before them are already there: a byte only looks at
+// its predecessor), so the scan can be de-stuffed piece by piece while it is still being uploaded; look-back
 // descriptors carry over, `ticket` is a fresh counter per launch, *avail = bytes produced up to the end of the launch.
 // RST (streams with restart markers, jdmarker.c read_restart_marker): the two bytes of every FF Dn are dropped as well
 // and the output offset where the next interval begins goes to bnd[j], j = ordinal of the marker (the look-back
 // carries the marker count in the upper bits of its sums); bnd[number of markers] = 0xFFFFFFFF closes the list.
 constexpr int DS_MK_SHIFT = 38;   // look-back value: kept bytes | markers << 38
+constexpr int DS_THREADS = 256, DS_NP = 4;
+static_assert(DS_THREADS * 16 * DS_NP == DS_CHUNK, "chunk = four 16-byte pieces per thread");
+constexpr int DS_OUT_WORDS = (DS_CHUNK + 64) / 4;
+
+// bit 7 of every byte lane: the byte is 0xFF / is 0x00
+__device__ __forceinline__ uint32_t lanes_ff(uint32_t w) { return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u; }
+__device__ __forceinline__ uint32_t lanes_zero(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u; }
+// bits 7, 15, 23, 31 -> bits 0..3
+__device__ __forceinline__ uint32_t lanes_to_bits(uint32_t m) { return ((m >> 7) * 0x01020408u) >> 24 & 15u; }
+
 template <bool RST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DS_THREADS)
 k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint64_t *__restrict__ desc,
           uint32_t *__restrict__ ticket, int c0, int c1, uint64_t *__restrict__ out_len, uint64_t *__restrict__ avail,
           uint32_t *__restrict__ bnd, uint32_t bnd_cap, uint32_t *__restrict__ nmark, uint32_t *__restrict__ err) {
     __shared__ int s_chunk;
-    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_warp[DS_NP][DS_THREADS / 32];
     __shared__ uint64_t s_goff;
-    __shared__ uint8_t s_out[4096];
+    __shared__ uint32_t s_lut[16];
+    __shared__ __align__(16) uint32_t s_out32[DS_OUT_WORDS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nchunks = (int)((n + 4095) / 4096);
+    const uint32_t sbase = smem_u32(s_out32);
+    const size_t lo = reinterpret_cast<uintptr_t>(in) & 15, hi = lo + n;   // the stream's bytes in the aligned stream
+    const uint8_t *ina = in - lo;
+    const int nchunks = (int)((hi + DS_CHUNK - 1) / DS_CHUNK);
+    if (tid < 16) {   // PRMT selectors: the bytes of a word that are not dropped (bit i of tid: byte i is), in order, zero fill
+        uint32_t sel = 0;
+        int k = 0;
+        for (int i = 0; i < 4; i++)
+            if (!(tid & (1 << i))) sel |= (uint32_t)i << (4 * k++);
+        for (; k < 4; k++) sel |= 4u << (4 * k);
+        s_lut[tid] = sel;
+    }
+    for (int i = tid; i < DS_OUT_WORDS; i += DS_THREADS) s_out32[i] = 0;
+    __syncthreads();
     for (;;) {
         if (tid == 0) s_chunk = c0 + (int)atomicAdd(ticket, 1u);
         __syncthreads();
         const int ch = s_chunk;
         if (ch >= c1) break;
-        const size_t base = (size_t)ch * 4096 + (size_t)tid * 16;
-        uint8_t b[18];
-        b[0] = base > 0 && base <= n ? in[base - 1] : 0;
+        uint32_t x[DS_NP][4], keep[DS_NP], mark[DS_NP], cnt[DS_NP], inc[DS_NP];
 #pragma unroll
-        for (int i = 0; i < 16; i++) b[i + 1] = base + i < n ? in[base + i] : 0;
-        b[17] = (RST && base + 16 < n) ? in[base + 16] : 0;
-        uint32_t keep = 0, mark = 0;   // mark: bit i = byte i is the second byte of a restart marker
+        for (int p = 0; p < DS_NP; p++) {
+            const size_t base = (size_t)ch * DS_CHUNK + (size_t)p * (DS_THREADS * 16) + (size_t)tid * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            uint32_t valid = 0;   // bit i: byte i of the piece belongs to the stream
+            if (base < hi && base + 16 > lo) {
+                v = *reinterpret_cast<const uint4 *>(ina + base);
+                const uint32_t b0 = base < lo ? (uint32_t)(lo - base) : 0u, b1 = base + 16 > hi ? (uint32_t)(hi - base) : 16u;
+                valid = ((1u << b1) - 1u) & ~((1u << b0) - 1u);
+                if (valid != 0xFFFFu) {   // absent bytes read as zero
+                    uint32_t *w = &v.x;
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            if (base + i >= n) continue;
-            bool k = !(b[i + 1] == 0 && b[i] == 0xFF);
-            if (RST) {
-                const bool second = b[i] == 0xFF && (b[i + 1] & 0xF8) == 0xD0;
-                const bool first = b[i + 1] == 0xFF && (b[i + 2] & 0xF8) == 0xD0 && base + i + 1 < n;
-                if (second) mark |= 1u << i;
-                k = k && !second && !first;
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t vb = (valid >> (4 * q)) & 15u;
+                        w[q] &= ((vb * 0x00204081u) & 0x01010101u) * 0xFFu;
+                    }
+                }
             }
-            if (k) keep |= 1u << i;
+            x[p][0] = v.x; x[p][1] = v.y; x[p][2] = v.z; x[p][3] = v.w;
+            // the byte before the piece / after it: the neighbour lane's, or one byte load at the warp's ends
+            uint32_t prevb = __shfl_up_sync(0xffffffffu, v.w >> 24, 1);
+            if (lane == 0) prevb = (base > lo && base - 1 < hi) ? ina[base - 1] : 0u;
+            uint32_t nextb = 0;
+            if (RST) {
+                nextb = __shfl_down_sync(0xffffffffu, v.x & 0xFFu, 1);
+                if (lane == 31) nextb = (base + 16 >= lo && base + 16 < hi) ? ina[base + 16] : 0u;
+            }
+            uint32_t ff[4], drop[4], sec[4] = {0, 0, 0, 0}, d0[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ff[q] = lanes_ff(x[p][q]);
+                if (RST) d0[q] = lanes_zero((x[p][q] & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);   // bytes D0 .. D7
+            }
+            const uint32_t ffprev = prevb == 0xFFu ? 0x80000000u : 0u;
+            const uint32_t d0next = (nextb & 0xF8u) == 0xD0u ? 0x80u : 0u;
+            uint32_t k16 = 0, m16 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t pf = __funnelshift_l(q ? ff[q - 1] : ffprev, ff[q], 8);          // the byte before is 0xFF
+                drop[q] = lanes_zero(x[p][q]) & pf;
+                if (RST) {
+                    sec[q] = pf & d0[q];                                                        // second byte of FF Dn
+                    const uint32_t nd = __funnelshift_r(d0[q], q < 3 ? d0[q + 1] : d0next, 8);  // the byte after is Dn
+                    drop[q] |= sec[q] | (ff[q] & nd);                                           // ... and its first byte
+                    m16 |= lanes_to_bits(sec[q]) << (4 * q);
+                }
+                k16 |= lanes_to_bits(drop[q] ^ 0x80808080u) << (4 * q);
+            }
+            // (absent bytes read as zero, so an 0xFF that ends the stream is data: a marker needs both of its bytes)
+            keep[p] = k16 & valid;
+            mark[p] = m16 & valid;
+            cnt[p] = __popc(keep[p]) | (RST ? (uint32_t)__popc(mark[p]) << 16 : 0u);   // kept bytes | markers << 16
+            inc[p] = cnt[p];
         }
-        const uint32_t cnt = __popc(keep) | (RST ? (uint32_t)__popc(mark) << 16 : 0u);   // kept bytes | markers << 16
-        uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += y;
+#pragma unroll
+            for (int p = 0; p < DS_NP; p++) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc[p], o);
+                if (lane >= o) inc[p] += y;
+            }
         }
-        if (lane == 31) s_warp[wid] = inc;
+        if (lane == 31) {
+#pragma unroll
+            for (int p = 0; p < DS_NP; p++) s_warp[p][wid] = inc[p];
+        }
         __syncthreads();
-        uint32_t wbase = 0, total = 0;
+        uint32_t ex[DS_NP], total = 0;   // exclusive prefix in stream order (piece-major): kept bytes | markers << 16
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t x = s_warp[i];
-            if (i < wid) wbase += x;
-            total += x;
+        for (int p = 0; p < DS_NP; p++) {
+            uint32_t wb = 0, tt = 0;
+#pragma unroll
+            for (int k = 0; k < DS_THREADS / 32; k++) {
+                const uint32_t y = s_warp[p][k];
+                if (k < wid) wb += y;
+                tt += y;
+            }
+            ex[p] = total + wb + inc[p] - cnt[p];
+            total += tt;
         }
-        const uint32_t ex = wbase + inc - cnt;   // exclusive: kept bytes | markers << 16 before this thread
-        uint32_t o = ex & 0xFFFFu;
-        const uint32_t o0 = o;
-#pragma unroll
-        for (int i = 0; i < 16; i++)
-            if (keep & (1u << i)) s_out[o++] = b[i + 1];
-        if (wid == 0) {
+        if (wid == 0) {   // the other warps compact meanwhile
             const uint64_t local = (uint64_t)(total & 0xFFFFu) | ((uint64_t)(total >> 16) << DS_MK_SHIFT);
             const uint64_t pre = lookback_exclusive(desc, ch, local, err);
             if (lane == 0) s_goff = pre;
+        }
+        // ---- the kept bytes of every word, compacted, OR-ed into the zeroed staging buffer at their chunk-local offset
+#pragma unroll
+        for (int p = 0; p < DS_NP; p++) {
+            uint32_t o = ex[p] & 0xFFFFu;
+            if (keep[p]) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t d4 = (~keep[p] >> (4 * q)) & 15u;
+                    const uint32_t bytes = __byte_perm(x[p][q], 0u, s_lut[d4]);
+                    const uint32_t bs = (o & 3u) * 8u, addr = sbase + (o & ~3u);
+                    const uint32_t y0 = bytes << bs, y1 = __funnelshift_l(bytes, 0u, bs);
+                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(y0) : "memory");
+                    if (y1) asm volatile("red.shared.or.b32 [%0+4], %1;" ::"r"(addr), "r"(y1) : "memory");
+                    o += 4u - __popc(d4);
+                }
+            }
         }
         __syncthreads();
         const uint64_t goff = s_goff & ((1ull << DS_MK_SHIFT) - 1);
         const uint32_t tkept = total & 0xFFFFu;
         uint8_t *dst = out + goff;
-        for (uint32_t i = tid; i < tkept; i += 256) dst[i] = s_out[i];
-        if (RST && mark) {   // the interval after marker j begins at the output offset of the first byte kept after it
-            uint32_t j = (uint32_t)(s_goff >> DS_MK_SHIFT) + (ex >> 16), oo = o0;
+        {   // copy out: bytes up to the first 16-byte boundary and behind the last one singly, 16-byte vectors between
+            const uint8_t *s_out = reinterpret_cast<const uint8_t *>(s_out32);
+            const uint32_t head = min(tkept, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+            const uint32_t nvec = (tkept - head) >> 4, tail0 = head + 16u * nvec;
+            if ((uint32_t)tid < head) dst[tid] = s_out[tid];
+            if (tail0 + (uint32_t)tid < tkept) dst[tail0 + tid] = s_out[tail0 + tid];
+            for (uint32_t v = tid; v < nvec; v += DS_THREADS) {
+                const uint32_t k0 = head + 16u * v, wi = k0 >> 2, bs = (k0 & 3u) * 8u;
+                const uint32_t a0 = s_out32[wi], a1 = s_out32[wi + 1], a2 = s_out32[wi + 2], a3 = s_out32[wi + 3], a4 = s_out32[wi + 4];
+                uint4 o4;
+                o4.x = __funnelshift_r(a0, a1, bs); o4.y = __funnelshift_r(a1, a2, bs);
+                o4.z = __funnelshift_r(a2, a3, bs); o4.w = __funnelshift_r(a3, a4, bs);
+                *reinterpret_cast<uint4 *>(dst + k0) = o4;
+            }
+        }
+        if (RST) {   // the interval after marker j begins at the output offset of the first byte kept after it
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (mark & (1u << i)) {
-                    if (j < bnd_cap) bnd[j] = (uint32_t)(goff + oo); else atomicOr(err, 16u);
-                    j++;
+            for (int p = 0; p < DS_NP; p++) {
+                if (mark[p]) {
+                    uint32_t j = (uint32_t)(s_goff >> DS_MK_SHIFT) + (ex[p] >> 16), oo = ex[p] & 0xFFFFu;
+                    for (int i = 0; i < 16; i++) {
+                        if (mark[p] & (1u << i)) {
+                            if (j < bnd_cap) bnd[j] = (uint32_t)(goff + oo); else atomicOr(err, 16u);
+                            j++;
+                        }
+                        if (keep[p] & (1u << i)) oo++;
+                    }
                 }
-                if (keep & (1u << i)) oo++;
             }
         }
         if (ch == c1 - 1 && tid == 0) *avail = goff + tkept;
@@ -117,6 +221,7 @@ k_destuff(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, u
             }
         }
         __syncthreads();
+        for (uint32_t i = tid; i * 16 < tkept + 20; i += DS_THREADS) reinterpret_cast<uint4 *>(s_out32)[i] = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -1045,7 +1150,7 @@ size_t dec_sync_smem() { return sizeof(DecShared); }
 cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,
                            uint64_t *out_len, uint64_t *avail, uint32_t *bnd, uint32_t bnd_cap, uint32_t *nmark, uint32_t *err,
                            cudaStream_t s) {
-    const int grid = std::max(1, std::min(148 * 6, c1 - c0));
+    const int grid = std::max(1, std::min(148 * 4, c1 - c0));
     if (bnd) k_destuff<true><<<grid, 256, 0, s>>>(in, n, out, desc, ticket, c0, c1, out_len, avail, bnd, bnd_cap, nmark, err);
     else k_destuff<false><<<grid, 256, 0, s>>>(in, n, out, desc, ticket, c0, c1, out_len, avail, nullptr, 0, nullptr, err);
     return cudaGetLastError();

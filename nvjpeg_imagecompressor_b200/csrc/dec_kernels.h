@@ -19,9 +19,12 @@ size_t dec_tables_size();
 // host side (dec_parse.cpp); B2J_EFORMAT for a table with more codes than its lengths allow
 int dec_build_tables(const JpegInfo &info, void *dst_host);
 
-// 4 KB chunks [c0, c1) of the n-byte scan; `ticket`: a zeroed counter per launch; *avail = bytes produced so far
+// Chunks [c0, c1) of the n-byte scan (DS_CHUNK bytes of the 16-byte aligned stream that contains `in`: destuff_chunks()
+// of them in all); `ticket`: a zeroed counter per launch; *avail = bytes produced so far
 // bnd != NULL (restart markers): FF Dn pairs are dropped too; bnd[j] = output offset where interval j + 1 begins,
 // bnd[*nmark] = 0xFFFFFFFF (bnd_cap entries available)
+constexpr int DS_CHUNK = 16384;
+inline int destuff_chunks(const void *in, size_t n) { return (int)(((reinterpret_cast<uintptr_t>(in) & 15) + n + DS_CHUNK - 1) / DS_CHUNK); }
 cudaError_t launch_destuff(const uint8_t *in, size_t n, uint8_t *out, uint64_t *desc, uint32_t *ticket, int c0, int c1,
                            uint64_t *out_len, uint64_t *avail, uint32_t *bnd, uint32_t bnd_cap, uint32_t *nmark, uint32_t *err,
                            cudaStream_t s);

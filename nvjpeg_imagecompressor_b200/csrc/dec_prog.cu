@@ -383,7 +383,7 @@ int dec_progressive(const uint8_t *jpg, size_t len, const ProgInfo &info, const 
         // front end: stuffing and RSTn markers out, interval starts recorded (the baseline decoder's kernel)
         PCK(cudaMemsetAsync(d_ctl, 0, sizeof(ProgCtl), s));
         PCK(cudaMemsetAsync(d_desc, 0, (ps.seg_len / 4096 + 8) * 8, s));
-        PCK(launch_destuff(d_file + ps.seg_off, ps.seg_len, d_u, d_desc, &d_ctl->ticket, 0, (int)((ps.seg_len + 4095) / 4096), &d_ctl->u_len,
+        PCK(launch_destuff(d_file + ps.seg_off, ps.seg_len, d_u, d_desc, &d_ctl->ticket, 0, destuff_chunks(d_file + ps.seg_off, ps.seg_len), &d_ctl->u_len,
                            &d_ctl->avail, d_bnd, (uint32_t)(max_int + 2), &d_ctl->nmark, &d_ctl->err, s));
         uint64_t *cm = d_tmp, *corr = d_tmp + max_units, *newm = d_tmp + 2 * max_units, *news = d_tmp + 3 * max_units;
         const bool refine_ac = sd.Ss > 0 && sd.Ah > 0;
