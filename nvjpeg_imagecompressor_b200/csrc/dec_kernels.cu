@@ -252,11 +252,11 @@ constexpr int DEC_THREADS = 256;               // subsequences per CTA
 constexpr int DEC_FIRST_SKIP = 512;            // bits of every subsequence the first synchronisation pass does not decode
 // The chunk's words live at g + (g >> 5): one pad word per subsequence, so threads that stand at the same word of their
 // own subsequences hit 32 different banks, and the address is one shift and one add per load.
-constexpr int DEC_SMEM_WORDS = SUB_WORDS * DEC_THREADS + DEC_THREADS + 8;
+constexpr int DEC_SMEM_WORDS = SUB_WORDS * (DEC_THREADS + 1) + DEC_THREADS + 1 + 8;   // + one subsequence of lead-in (k_dec_sync)
 __device__ __forceinline__ uint32_t dec_widx(uint32_t g) { return g + (g >> 5); }
 
 struct DecShared {
-    uint32_t words[DEC_SMEM_WORDS];            // word g of the chunk (+ 2 of overflow) at dec_widx(g)
+    uint32_t words[DEC_SMEM_WORDS];            // word g of the staged bits (lead-in + chunk + 2 of overflow) at dec_widx(g)
     uint16_t lut[4][1 << DEC_LUT_BITS];
     int32_t maxcode[4][18];
     int32_t valoff[4][17];
@@ -368,12 +368,11 @@ __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t c
 }
 
 __device__ __forceinline__ void dec_load_chunk(DecShared &sh, const uint8_t *__restrict__ u, uint64_t nbytes_padded,
-                                               size_t cta, const DecTables *__restrict__ tb) {
+                                               size_t w0, int count, const DecTables *__restrict__ tb) {
     const int tid = threadIdx.x;
     const uint32_t *uw = reinterpret_cast<const uint32_t *>(u);
-    const size_t w0 = cta * (size_t)(SUB_WORDS * DEC_THREADS);
     const size_t nwords = (size_t)(nbytes_padded >> 2);
-    for (int i = tid; i < SUB_WORDS * DEC_THREADS + 2; i += DEC_THREADS) {
+    for (int i = tid; i < count; i += DEC_THREADS) {
         const size_t gw = w0 + i;
         const uint32_t w = gw < nwords ? uw[gw] : 0xFFFFFFFFu;
         sh.words[dec_widx((uint32_t)i)] = __byte_perm(w, 0, 0x0123);  // big-endian bit order
@@ -414,12 +413,26 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
     const uint64_t total_bits = nbytes * 8;
     if (chunk_bit0 >= total_bits) return;
     const uint32_t nmark = RST ? *nmark_p : 0u;
-    dec_load_chunk(sh, u, mode == 1 ? *u_len & ~(uint64_t)3 : (nbytes + 64) & ~(uint64_t)3, cta, tb);
     const size_t i = cta * DEC_THREADS + tid;
+    const uint64_t my_bit0_pre = chunk_bit0 + (uint64_t)tid * SUB_BITS;
+    // A later launch has work only where a start state differs from the one the subsequence was last decoded from:
+    // nothing of the chunk is loaded before that is known (after the first launch most chunks have nothing left to do).
+    if (!first_launch) {
+        const bool need0 = my_bit0_pre < total_bits && (i == 0 ? pack_state(0, 0, 0) : st_out[i - 1]) != st_in[i];
+        if (!__syncthreads_or(need0)) return;
+    }
+    // The staged bits begin one subsequence before the chunk (lead-in): in the first round thread 0 decodes the second
+    // half of it from a guess, which almost always ends in step, so the chunk's own first subsequence starts from the
+    // right state in this very launch instead of waiting for the previous chunk's result in the next one.
+    const int lead = cta ? 1 : 0;
+    const uint64_t base_bit0 = chunk_bit0 - (uint64_t)lead * SUB_BITS;
+    dec_load_chunk(sh, u, mode == 1 ? *u_len & ~(uint64_t)3 : (nbytes + 64) & ~(uint64_t)3, (size_t)(base_bit0 >> 5),
+                   SUB_WORDS * (DEC_THREADS + lead) + 2, tb);
     const uint64_t my_bit0 = chunk_bit0 + (uint64_t)tid * SUB_BITS;
     const uint64_t my_end = my_bit0 + SUB_BITS;
     const bool live = my_bit0 < total_bits;
-    // incoming state of the CTA's first subsequence; initial guess = "a block starts exactly at my first bit"
+    // incoming state of the CTA's first subsequence; first launch: found in round 0 from the lead-in (until then the
+    // guess "a block starts exactly at my first bit")
     if (tid == 0) sh.state[0] = cta == 0 ? pack_state(0, 0, 0) : (first_launch ? pack_state(chunk_bit0, 0, 0) : st_out[i - 1]);
     sh.used[tid] = first_launch ? ~0ull : st_in[i];
     const uint64_t before = first_launch ? pack_state(my_end, 0, 0) : st_out[i];
@@ -443,26 +456,35 @@ k_dec_sync(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, co
         uint64_t outst = 0, in = 0;
         uint32_t nb = 0;
         int t = -1;
+        bool leadin = false;
         if ((uint32_t)tid < total) {
             t = sh.list[tid];
             in = sh.state[t];
-            const uint64_t t_end = chunk_bit0 + (uint64_t)(t + 1) * SUB_BITS;
+            uint64_t t_end = chunk_bit0 + (uint64_t)(t + 1) * SUB_BITS;
             uint64_t from = in;
             // The very first pass only looks for a synchronisation point: every start state is a guess and the block
             // counts are thrown away (the next round decodes again from the real states), so it decodes the second half
             // of the subsequence only -- a decoder is in step after one or two hundred bits on ordinary streams.
+            // Thread 0 of a chunk other than the first spends that pass on the lead-in: its end is the chunk's start state.
             if (first_launch && round == 0 && !(cta == 0 && t == 0)) {
-                from = pack_state(chunk_bit0 + (uint64_t)t * SUB_BITS + DEC_FIRST_SKIP, 0, 0);
+                leadin = t == 0;
+                from = pack_state(chunk_bit0 + (uint64_t)t * SUB_BITS + DEC_FIRST_SKIP - (leadin ? (uint64_t)SUB_BITS : 0), 0, 0);
+                if (leadin) t_end = chunk_bit0;
                 in = ~0ull;
             }
-            outst = decode_range<false, RST>(sh, chunk_bit0, from, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0, bnd, nmark);
+            outst = decode_range<false, RST>(sh, base_bit0, from, t_end, total_bits, bpm, hv, nb, nullptr, 0, 0, bnd, nmark);
         }
         __syncthreads();
         if (t >= 0) {
-            ch = outst != sh.state[t + 1];
-            sh.state[t + 1] = outst;
-            sh.used[t] = in;
-            sh.nblk[t] = nb;
+            if (leadin) {   // the chunk's start state; subsequence 0 itself is decoded from it in the next round
+                sh.state[0] = outst;
+                ch = 1;
+            } else {
+                ch = outst != sh.state[t + 1];
+                sh.state[t + 1] = outst;
+                sh.used[t] = in;
+                sh.nblk[t] = nb;
+            }
         }
         any = __syncthreads_or(ch);
     }
