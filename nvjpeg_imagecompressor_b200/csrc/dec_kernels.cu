@@ -360,7 +360,8 @@ __device__ __forceinline__ uint64_t decode_range(const DecShared &sh, uint64_t c
         }
         const bool done = knew > 63;
         k = done ? 0 : knew;
-        c = done ? (c + 1 == bpm ? 0 : c + 1) : c;
+        c += done ? 1 : 0;
+        c = c == bpm ? 0 : c;
         nblk += done ? 1u : 0u;
     }
     nblk_out = nblk;
@@ -742,14 +743,15 @@ k_dec_write(const uint8_t *__restrict__ u, const uint64_t *__restrict__ u_len, c
                     const int idx = dc ? 0 : k + (int)r;
                     if (idx < 64) reinterpret_cast<int16_t *>(&cell[(idx >> 1) ^ lane])[idx & 1] = (int16_t)val;
                 }
+                // a block ends about once in twenty symbols, i.e. in some lane of the warp in most iterations: no branch here
                 const bool done = knew > 63;
                 k = done ? 0 : knew;
-                c = done ? (c + 1 == bpm ? 0 : c + 1) : c;
-                if (done) {
-                    flush = owning;
-                    if (!owning) { b_cur++; owning = true; }   // my predecessor's block is over; the next one is mine
-                    if (q >= stop) active = false;             // blocks that start at or past my last bit are not mine
-                }
+                c += done ? 1 : 0;
+                c = c == bpm ? 0 : c;
+                flush = done && owning;
+                b_cur += (done && !owning) ? 1u : 0u;          // my predecessor's block is over; the next one is mine
+                owning = owning || done;
+                active = !(done && q >= stop);                 // blocks that start at or past my last bit are not mine
             }
             if (!crossed && q >= stop) { crossed = true; end_state = pack_state(chunk_bit0 + q, c, k); }
         }
