@@ -1,30 +1,44 @@
-import sys, os
+"""Randomised parity run against the checker (development aid, needs a B200): random sizes up to 2000 x 1500, all
+samplings, qualities, both Huffman modes; every encode also through the fused entropy kernel (debug flag 8), with
+restart rows now and then, and every stream decoded back and compared with the checker's decode.
+    python scripts/dev/stress.py [cases] [seed]"""
+import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import nvjpeg_imagecompressor_b200 as P
-from nvjpeg_imagecompressor_b200 import _native as N
 import oracle as O
-rng = np.random.default_rng(1)
-nfail = 0; ntot = 0
-for css in range(5):
-    for q, opt in ((95, 1), (75, 0), (100, 1)):
-        eng = P.Engine(300, 160, q, bool(opt), css)
-        for trial in range(12):
-            W = int(rng.integers(1, 300)); H = int(rng.integers(1, 160))
-            img = O.synth(W, H, W * 31 + H, 8)
-            want = O.encode(img, css, q, opt)
-            for rep in range(3):
-                jpg = eng.encode(img)
-                ntot += 1
-                ok = jpg.size == want.size and bool(np.array_equal(jpg, want))
-                if not ok:
-                    nfail += 1
-                    recs = eng.debug_read(N.DBG_TILE_RECS, np.uint8).reshape(-1, 24)
-                    a = [int(x) & 3 for x in recs[:, :4].view(np.uint32).ravel()]
-                    cnt = [int(x) for x in recs[:, 4:8].view(np.uint32).ravel()]
-                    n = min(jpg.size, want.size)
-                    d = np.nonzero(jpg[:n] != want[:n])[0]
-                    if nfail <= 12:
-                        print(f"FAIL css{css} q{q} opt{opt} {W}x{H} rep{rep} len {jpg.size}/{want.size} firstdiff {d[:1]} a={a[:10]} cnt={cnt[:10]}")
-        eng.close()
-print("total", ntot, "fail", nfail)
+ncase = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
+CAPW, CAPH = 2000, 1500
+engs = {}
+nfail = ntot = 0
+t0 = time.time()
+for case in range(ncase):
+    css = int(rng.integers(0, 5)); q = int(rng.choice([30, 60, 75, 90, 95, 98, 100])); opt = int(rng.integers(0, 2))
+    small = rng.random() < 0.5
+    W = int(rng.integers(1, 200 if small else CAPW)); H = int(rng.integers(1, 200 if small else CAPH))
+    kind = rng.random()
+    if kind < 0.6: img = O.synth(W, H, case, int(rng.choice([0, 2, 8, 40])))
+    elif kind < 0.8: img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    else: img = np.full((H, W, 3), int(rng.integers(0, 256)), np.uint8)
+    key = (css, q, opt)
+    if key not in engs: engs[key] = P.Engine(CAPW, CAPH, q, bool(opt), css)
+    eng = engs[key]
+    g = O.geometry(W, H, css)
+    rows = int(rng.integers(1, 4)) if rng.random() < 0.25 and rng.integers(1, 4) * g.mcux <= 65535 else 0
+    want = O.encode(img, css, q, opt, rows * g.mcux) if rows else O.encode(img, css, q, opt)
+    for dbg in ((0,) if rows else (0, 8, 2, 10)):
+        eng.set_debug(dbg); eng.set_restart_rows(rows)
+        jpg = eng.encode(img)
+        ntot += 1
+        if not (jpg.size == want.size and np.array_equal(jpg, want)):
+            nfail += 1
+            print(f"ENCODE FAIL case{case} css{css} q{q} opt{opt} {W}x{H} rows{rows} dbg{dbg} len {jpg.size}/{want.size}")
+    eng.set_debug(0); eng.set_restart_rows(0)
+    dec = eng.decode(want)
+    ntot += 1
+    if not np.array_equal(dec, O.decode(want)):
+        nfail += 1
+        print(f"DECODE FAIL case{case} css{css} q{q} opt{opt} {W}x{H} rows{rows}")
+print({"checks": ntot, "fail": nfail, "seconds": round(time.time() - t0, 1)})
+sys.exit(1 if nfail else 0)
