@@ -122,7 +122,10 @@ B2J_API int b2j_decode_device(b2j_ctx *ctx, const uint8_t *jpg, size_t len, uint
 /* A baseline JPEG whose entropy-coded segment is already in DEVICE memory: hdr = the file's bytes from SOI up to and
  * including the SOS header (host, a few hundred bytes), d_scan = the stuffed scan bytes up to the terminating marker
  * (device). height_override > 0 replaces the frame height: whole restart intervals of whole MCU rows decode as an image
- * of their own (one image decoded by several GPUs: strips.StripDecoder). Synchronous and validated. */
+ * of their own (one image decoded by several GPUs: strips.StripDecoder). Synchronous and validated.
+ * d_scan may have any alignment; the de-stuffing kernel reads whole 16-byte aligned vectors, i.e. up to 15 bytes in front
+ * of d_scan and behind d_scan + scan_len are read (never interpreted) -- inside the same 16-byte block of the same
+ * allocation, which every CUDA allocation granule (>= 256 bytes) contains. */
 B2J_API int b2j_decode_scan_device(b2j_ctx *ctx, const uint8_t *hdr, size_t hdr_len, const uint8_t *d_scan, size_t scan_len,
                                    int height_override, uint8_t *d_bgr, size_t step, int *width, int *height);
 /* Completes the last b2j_decode_device: waits for it and validates it. The decode runs a fixed schedule of Huffman
